@@ -1,0 +1,104 @@
+/* stp_b200.h -- C ABI of libstp_b200.so, the sm_100a implementation of the pool-based BO hot path
+ * (fit -> predict -> acquire, batched over independent campaigns) of standw7/STPBenchmark.
+ *
+ * The reference is pure Python and has no FFI of its own; the seam this library sits behind is
+ * the arithmetic the reference reaches through gpytorch / botorch / scipy.  Each entry point
+ * cites the reference call site whose arithmetic it replaces (paths relative to the reference
+ * checkout).  INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory (e.g. torch.Tensor.data_ptr()),
+ *     except `opts`, `prior`, `lower`, `upper`, which are small HOST arrays read at call time;
+ *   - tensors are contiguous, row-major, batch-major; fp64 values, int32 indices, uint8 masks;
+ *   - B = number of campaigns in the batch; one CTA owns one campaign;
+ *   - `n` (int32[B], may be NULL = all n_cap) is the number of training points per campaign;
+ *     X is [B, n_cap, d], y is [B, n_cap]; rows >= n[b] are ignored;
+ *   - theta is [B, d+3] = (noise, constant, outputscale, lengthscale_1..d): the order botorch's
+ *     fit hands the parameters of models.ExactGP to scipy (models.py:319-358);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     asynchronous and stream-ordered; nothing allocates, nothing synchronises;
+ *   - return value: 0 = launched, negative = rejected (see stp_last_error_string());
+ *   - status[b] (int32): 0 ok, 1 matrix not positive definite, 2 non-finite parameter or
+ *     objective, 3 fit stopped on a non-finite objective, 4 iteration / evaluation cap reached,
+ *     5 abnormal line-search termination.  No exception crosses the boundary.
+ *   - limits: 1 <= d <= STP_MAX_D, n_cap <= STP_MAX_N.
+ */
+#ifndef STP_B200_H
+#define STP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STP_MAX_D 8
+#define STP_MAX_N 160
+#define STP_ABI_VERSION 1
+
+/* L-BFGS-B options; scipy.optimize.minimize(method="L-BFGS-B") defaults are
+ * {10, 15000, 15000, 20, ftol / DBL_EPSILON with ftol = 2.220446049250313e-09, 1e-5}. */
+typedef struct stp_lbfgsb_opts {
+  int32_t m;
+  int32_t maxiter;
+  int32_t maxfun;
+  int32_t maxls;
+  double factr;
+  double pgtol;
+} stp_lbfgsb_opts;
+
+/* Likelihood of a variational model (models.py: VarGP :166, VarTGP :76, VarLGP :262). */
+enum { STP_LIK_GAUSSIAN = 0, STP_LIK_STUDENT_T = 1, STP_LIK_LAPLACE = 2 };
+
+int stp_version(void);
+const char* stp_last_error_string(void);
+
+/* Negative exact marginal log-likelihood (+ log-priors) / n and its gradient for B campaigns.
+ * Replaces one closure call of botorch.fit.fit_gpytorch_mll -> ExactMarginalLogLikelihood
+ * (optim.py:31-32) on models.ExactGP (models.py:300-395).  prior = {noise_loc, noise_scale,
+ * os_loc, os_scale, ls_loc, ls_scale} of the LogNormal priors.  f: [B], g: [B, d+3]. */
+int stp_exact_mll_fg(int B, int n_cap, int d, const double* X, const double* y, const int32_t* n,
+                     const double* theta, const double* prior, double* f, double* g, int32_t* status,
+                     void* stream);
+
+/* Device-resident L-BFGS-B fit of theta (in/out) for B campaigns: train_exact_model_botorch
+ * (optim.py:11-32).  lower/upper: host arrays [d+3], +-HUGE_VAL = unbounded.
+ * f_out [B], nit [B], nfev [B] may be NULL. */
+int stp_exact_fit(int B, int n_cap, int d, const double* X, const double* y, const int32_t* n, double* theta,
+                  const double* lower, const double* upper, const double* prior, const stp_lbfgsb_opts* opts,
+                  double* f_out, int32_t* nit, int32_t* nfev, int32_t* status, void* stream);
+
+/* Fused predictive + LogEI + argmax over the pool at fixed theta: ExactGP.posterior
+ * (models.py:387-395) + botorch LogExpectedImprovement.forward + argmax (runners.py:88-95).
+ * pool: [G, N, d]; pool_id: int32[B] (NULL = pool 0); mask: uint8[B, N], non-zero = candidate
+ * still available (NULL = all); best_f: [B] (NULL = predictive only).  out_idx [B] receives the
+ * POOL index of the first maximal LogEI among available candidates (-1 if none / failure),
+ * out_acq [B] its value.  mean / var / acq: optional [B, N] outputs for every pool point. */
+int stp_exact_acq(int B, int n_cap, int d, int N, const double* pool, const int32_t* pool_id, const uint8_t* mask,
+                  const double* X, const double* y, const int32_t* n, const double* theta, const double* best_f,
+                  int32_t* out_idx, double* out_acq, double* mean, double* var, double* acq, int32_t* status,
+                  void* stream);
+
+/* One whole BO iteration (the loop body runners.py:64-109) for B campaigns in ONE launch:
+ * fresh theta0 -> L-BFGS-B fit -> factorise -> pool pass -> argmax -> append the pick to
+ * (X, y, n, trace) and clear its mask byte.  pool_y: [G, N].  trace: int32[B, n_cap] receives
+ * the picked pool index at position n[b] (before the increment).  theta0: host [d+3] start
+ * (the prior modes, models.py:326,334,347,357); theta_out [B, d+3] fitted values.
+ * Campaigns whose status[b] is non-zero on entry are skipped (frozen, like the reference's
+ * try/except at runners.py:113-115); n[b] >= n_cap is rejected by status 2. */
+int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const double* pool_y,
+                      const int32_t* pool_id, uint8_t* mask, double* X, double* y, int32_t* n, int32_t* trace,
+                      const double* theta0, const double* lower, const double* upper, const double* prior,
+                      const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
+                      int32_t* status, void* stream);
+
+/* Sustained FP64 FMA throughput probe (roofline denominator; MEASURED_PEAKS.json has no FP64
+ * figure).  Runs `iters` dependent-chain-free DFMA batches on every SM; *flops_out (device,
+ * double) receives the number of floating-point operations executed. */
+int stp_fp64_probe(int iters, double* sink, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STP_B200_H */

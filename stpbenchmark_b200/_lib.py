@@ -1,0 +1,163 @@
+"""ctypes binding of libstp_b200.so (C ABI: include/stp_b200.h).
+
+The only compute path of the package.  There is NO CPU fallback: if the library is missing,
+or no CUDA device is visible, every operator raises.  Arguments are torch CUDA tensors; the
+raw device pointers and the current CUDA stream are handed to the library.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from typing import Optional
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libstp_b200.so")
+_lib = None
+
+MAX_D = 8
+MAX_N = 160
+
+STATUS_TEXT = {
+    0: "ok", 1: "matrix not positive definite", 2: "non-finite parameter or objective",
+    3: "fit stopped on a non-finite objective", 4: "iteration/evaluation cap reached",
+    5: "abnormal line-search termination",
+}
+
+
+class LbfgsbOpts(ctypes.Structure):
+    """scipy.optimize.minimize(method='L-BFGS-B') defaults."""
+
+    _fields_ = [("m", ctypes.c_int32), ("maxiter", ctypes.c_int32), ("maxfun", ctypes.c_int32),
+                ("maxls", ctypes.c_int32), ("factr", ctypes.c_double), ("pgtol", ctypes.c_double)]
+
+    @staticmethod
+    def scipy_defaults() -> "LbfgsbOpts":
+        eps = 2.220446049250313e-16
+        return LbfgsbOpts(10, 15000, 15000, 20, 2.220446049250313e-09 / eps, 1e-5)
+
+
+def lib():
+    """Load libstp_b200.so; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m stpbenchmark_b200.build` "
+                "(nvcc, sm_100a). stpbenchmark_b200 has no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.stp_version.restype = ctypes.c_int
+        L.stp_last_error_string.restype = ctypes.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {lib().stp_last_error_string().decode()}")
+
+
+def _require_cuda(*tensors):
+    if not torch.cuda.is_available():
+        raise RuntimeError("stpbenchmark_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    for t in tensors:
+        if t is not None and (not t.is_cuda or not t.is_contiguous()):
+            raise ValueError("expected contiguous CUDA tensors")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _host(vals):
+    arr = (ctypes.c_double * len(vals))(*[float(v) for v in vals])
+    return arr
+
+
+def _bounds(lower, upper, np_):
+    lo = [(-math.inf if v is None else float(v)) for v in (lower if lower is not None else [None] * np_)]
+    hi = [(math.inf if v is None else float(v)) for v in (upper if upper is not None else [None] * np_)]
+    return _host(lo), _host(hi)
+
+
+def exact_mll_fg(X, y, theta, prior, n=None):
+    """f [B], g [B, d+3], status [B] for X [B, n_cap, d], y [B, n_cap], theta [B, d+3]."""
+    _require_cuda(X, y, theta, n)
+    B, n_cap, d = X.shape
+    f = torch.empty(B, dtype=torch.double, device=X.device)
+    g = torch.empty(B, d + 3, dtype=torch.double, device=X.device)
+    status = torch.zeros(B, dtype=torch.int32, device=X.device)
+    _check(lib().stp_exact_mll_fg(B, n_cap, d, _p(X), _p(y), _p(n), _p(theta), _host(prior), _p(f), _p(g),
+                                  _p(status), _stream()), "stp_exact_mll_fg")
+    return f, g, status
+
+
+def exact_fit(X, y, theta, lower, upper, prior, n=None, opts: Optional[LbfgsbOpts] = None):
+    """In-place device L-BFGS-B fit of theta [B, d+3]; returns (f, nit, nfev, status)."""
+    _require_cuda(X, y, theta, n)
+    B, n_cap, d = X.shape
+    f = torch.empty(B, dtype=torch.double, device=X.device)
+    nit = torch.zeros(B, dtype=torch.int32, device=X.device)
+    nfev = torch.zeros(B, dtype=torch.int32, device=X.device)
+    status = torch.zeros(B, dtype=torch.int32, device=X.device)
+    lo, hi = _bounds(lower, upper, d + 3)
+    o = opts or LbfgsbOpts.scipy_defaults()
+    _check(lib().stp_exact_fit(B, n_cap, d, _p(X), _p(y), _p(n), _p(theta), lo, hi, _host(prior), ctypes.byref(o),
+                               _p(f), _p(nit), _p(nfev), _p(status), _stream()), "stp_exact_fit")
+    return f, nit, nfev, status
+
+
+def exact_acq(pool, X, y, theta, best_f=None, mask=None, pool_id=None, n=None, want_pointwise=False):
+    """Fused predictive + LogEI + argmax.  pool [G, N, d].  Returns dict(idx, acq_best, status
+    [, mean, var, acq])."""
+    _require_cuda(pool, X, y, theta, best_f, mask, pool_id, n)
+    B, n_cap, d = X.shape
+    N = pool.shape[-2]
+    dev = X.device
+    idx = torch.full((B,), -1, dtype=torch.int32, device=dev)
+    best = torch.empty(B, dtype=torch.double, device=dev)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    mean = var = acq = None
+    if want_pointwise:
+        mean = torch.empty(B, N, dtype=torch.double, device=dev)
+        var = torch.empty(B, N, dtype=torch.double, device=dev)
+        acq = torch.empty(B, N, dtype=torch.double, device=dev)
+    _check(lib().stp_exact_acq(B, n_cap, d, N, _p(pool), _p(pool_id), _p(mask), _p(X), _p(y), _p(n), _p(theta),
+                               _p(best_f), _p(idx), _p(best), _p(mean), _p(var), _p(acq), _p(status), _stream()),
+           "stp_exact_acq")
+    return {"idx": idx, "acq_best": best, "status": status, "mean": mean, "var": var, "acq": acq}
+
+
+def exact_bo_step(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upper, prior, status,
+                  theta_out=None, acq_out=None, nit=None, nfev=None, opts: Optional[LbfgsbOpts] = None):
+    """One BO iteration for every campaign, in place (see stp_exact_bo_step)."""
+    _require_cuda(pool, pool_y, pool_id, mask, X, y, n, trace, status, theta_out, acq_out, nit, nfev)
+    B, n_cap, d = X.shape
+    N = pool.shape[-2]
+    lo, hi = _bounds(lower, upper, d + 3)
+    o = opts or LbfgsbOpts.scipy_defaults()
+    _check(lib().stp_exact_bo_step(B, n_cap, d, N, _p(pool), _p(pool_y), _p(pool_id), _p(mask), _p(X), _p(y), _p(n),
+                                   _p(trace), _host(theta0), lo, hi, _host(prior), ctypes.byref(o), _p(theta_out),
+                                   _p(acq_out), _p(nit), _p(nfev), _p(status), _stream()), "stp_exact_bo_step")
+
+
+def fp64_probe(iters: int = 4096) -> float:
+    """Measured FP64 FMA throughput of the current device in TFLOP/s (roofline denominator)."""
+    _require_cuda()
+    sink = torch.zeros(1, dtype=torch.double, device="cuda")
+    L = lib()
+    _check(L.stp_fp64_probe(64, _p(sink), _stream()), "stp_fp64_probe")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _check(L.stp_fp64_probe(iters, _p(sink), _stream()), "stp_fp64_probe")
+    e1.record()
+    torch.cuda.synchronize()
+    flops = 148 * 8 * 256 * float(iters) * 16 * 8 * 2
+    return flops / (e0.elapsed_time(e1) * 1e-3) / 1e12

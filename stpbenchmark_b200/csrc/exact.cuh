@@ -1,0 +1,313 @@
+// Exact-GP pieces of the BO hot path, one campaign per team (CTA):
+//   exact_mll_fg      K1+K3+K4+K5  loss = -(log N(y|c, K+s2 I) + log-priors)/n and its analytic
+//                                   gradient (what botorch's closure hands to L-BFGS-B at
+//                                   optim.py:31-32; formulas SURVEY.md App. A.3)
+//   exact_factorize   K1+K3+K4      L^-1 and alpha = (K+s2 I)^-1 (y-c) at the fitted theta
+//   exact_acquire     K2+K10+K12+K13 fused cross-covariance, predictive mean/variance
+//                                   (models.py:387-395), LogEI (runners.py:88-90) and the
+//                                   first-index argmax over the remaining pool (runners.py:95)
+// theta layout (botorch parameter order): [noise, constant, outputscale, lengthscale_0..d-1].
+#pragma once
+#include "linalg.cuh"
+#include "logei.cuh"
+#include "team.cuh"
+
+namespace stp {
+
+constexpr int kMaxD = 8;          // input dimensions supported by the unrolled ARD loops
+constexpr double kLog2Pi = 1.83787706640934548356;
+
+struct ExactPrior {               // LogNormal(loc, scale) on noise, outputscale, lengthscale
+  double noise_loc, noise_scale, os_loc, os_scale, ls_loc, ls_scale;
+};
+
+STP_HD double lognormal_logpdf(double x, double loc, double scale) {
+  const double lx = log(x);
+  const double z = lx - loc;
+  return -lx - log(scale) - 0.5 * kLog2Pi - z * z / (2.0 * scale * scale);
+}
+STP_HD double lognormal_dlogpdf(double x, double loc, double scale) {
+  return -(1.0 + (log(x) - loc) / (scale * scale)) / x;
+}
+
+// Shared-memory carve-up of one exact-GP campaign with room for `cap` training points.
+struct ExactSmem {
+  double* A;      // (cap+1) x ld : lower = working matrix, strict upper = noise-free K (fit only)
+  double* Xt;     // d x cap      : training inputs, transposed (conflict-free across points)
+  double* y;      // cap
+  double* c0;     // cap+1
+  double* c1;     // cap+1
+  double* piv;    // cap+1 (pivots; reused as tmp by the triangular inverse)
+  double* alpha;  // cap
+  double* tile;   // acquisition: cap x TC cross-covariances + TC x (kMaxD) staged candidates
+  double* part;   // acquisition: nwarps x TC x 2 partial sums
+  double* small;  // 64 doubles: theta (<=11), gradient (<=11), misc
+  double* red;    // kRedDoubles reduction scratch
+  int ld, cap;
+};
+
+STP_HD size_t exact_smem_doubles(int cap, int d, int tc, int nwarps) {
+  const int ld = odd_ld(cap + 1);
+  return (size_t)(cap + 1) * ld + (size_t)d * cap + cap + 3 * (size_t)(cap + 1) + cap +
+         (size_t)cap * tc + (size_t)tc * kMaxD + (size_t)nwarps * tc * 2 + 64 + 16 * kMaxWarps;
+}
+
+STP_HD ExactSmem exact_smem_carve(double* base, int cap, int d, int tc, int nwarps) {
+  ExactSmem s;
+  s.cap = cap;
+  s.ld = odd_ld(cap + 1);
+  double* p = base;
+  s.A = p;      p += (size_t)(cap + 1) * s.ld;
+  s.Xt = p;     p += (size_t)d * cap;
+  s.y = p;      p += cap;
+  s.c0 = p;     p += cap + 1;
+  s.c1 = p;     p += cap + 1;
+  s.piv = p;    p += cap + 1;
+  s.alpha = p;  p += cap;
+  s.tile = p;   p += (size_t)cap * tc + (size_t)tc * kMaxD;
+  s.part = p;   p += (size_t)nwarps * tc * 2;
+  s.small = p;  p += 64;
+  s.red = p;
+  return s;
+}
+
+// Copy one campaign's training set into shared memory (X row-major [n,d] -> Xt [d][cap]).
+template <class Team>
+STP_HD void exact_load(const Team& tm, const ExactSmem& s, int n, int d, const double* X, const double* y) {
+  for (int idx = tm.rank(); idx < n * d; idx += tm.size()) {
+    const int i = idx / d, k = idx - i * d;
+    s.Xt[k * s.cap + i] = X[idx];
+  }
+  for (int i = tm.rank(); i < n; i += tm.size()) s.y[i] = y[i];
+  tm.sync();
+}
+
+// noise-free kernel value between training points i and j (direct differences, App. A.1)
+STP_HD double ard_rbf_tt(const double* Xt, int cap, int d, const double* invl, int i, int j, double os) {
+  double r2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < kMaxD; ++k)
+    if (k < d) {
+      const double t = (Xt[k * cap + i] - Xt[k * cap + j]) * invl[k];
+      r2 += t * t;
+    }
+  return os * exp(-0.5 * r2);
+}
+
+// ---------------------------------------------------------------------------------------
+// One L-BFGS-B closure call.  Every thread returns the same status and loss; the gradient
+// (d+3 doubles) is left in `g` (shared memory), valid after the call for every thread.
+// status: 0 ok, 1 matrix not positive definite, 2 non-finite parameter / objective.
+// Work: n^3/2 MAC (sweep) + n^2 (3d+8)/2 flop (kernel build + gradient contraction).
+// ---------------------------------------------------------------------------------------
+template <class Team>
+STP_HD int exact_mll_fg(const Team& tm, const ExactSmem& s, int n, int d, const double* theta,
+                        const ExactPrior& pr, double* f_out, double* g) {
+  const int ld = s.ld, cap = s.cap, W = tm.warp_width();
+  const double noise = theta[0], cst = theta[1], os = theta[2];
+  double* invl = s.small + 32;  // d doubles
+  tm.sync();
+  for (int k = tm.rank(); k < d; k += tm.size()) invl[k] = 1.0 / theta[3 + k];
+  int bad = !(noise > 0.0) || !(os > 0.0) || !(cst == cst);
+  for (int k = 0; k < d; ++k) bad |= !(theta[3 + k] > 0.0);
+  if (bad) { *f_out = NAN; return 2; }
+  tm.sync();
+  // K1: lower = K + noise I (to be swept), strict upper = K (kept for the gradient), border = y - c
+  for (int i = tm.warp(); i <= n; i += tm.nwarps()) {
+    double* row = s.A + i * ld;
+    if (i < n) {
+      for (int j = tm.lane(); j <= i; j += W) {
+        if (j == i) row[j] = os + noise;
+        else {
+          const double kij = ard_rbf_tt(s.Xt, cap, d, invl, i, j, os);
+          row[j] = kij;
+          s.A[j * ld + i] = kij;
+        }
+      }
+    } else {
+      for (int j = tm.lane(); j <= n; j += W) row[j] = (j < n) ? (s.y[j] - cst) : 0.0;
+    }
+  }
+  tm.sync();
+  // K3+K4: bordered sweep -> -Kinv, alpha, -quad, pivots
+  const int fail = sweep_bordered(tm, s.A, ld, n + 1, n, s.c0, s.c1, s.piv);
+  if (fail) { *f_out = NAN; return 1; }
+  const double* arow = s.A + n * ld;  // alpha
+  // K5: reductions
+  double acc[kMaxD + 4];
+#pragma unroll
+  for (int q = 0; q < kMaxD + 4; ++q) acc[q] = 0.0;
+  // acc[0] = sum log piv, acc[1] = sum W_ii, acc[2] = sum alpha, acc[3] = sum_{i>j} W_ij K_ij,
+  // acc[4+k] = sum_{i>j} W_ij K_ij (x_ik - x_jk)^2
+  for (int i = tm.rank(); i < n; i += tm.size()) {
+    const double ai = arow[i];
+    acc[0] += log(s.piv[i]);
+    acc[1] += ai * ai + s.A[i * ld + i];
+    acc[2] += ai;
+  }
+  for (int i = 1 + tm.warp(); i < n; i += tm.nwarps()) {
+    const double ai = arow[i];
+    const double* row = s.A + i * ld;
+    double xi[kMaxD];
+#pragma unroll
+    for (int k = 0; k < kMaxD; ++k) xi[k] = (k < d) ? s.Xt[k * cap + i] : 0.0;
+    for (int j = tm.lane(); j < i; j += W) {
+      const double t = (ai * arow[j] + row[j]) * s.A[j * ld + i];
+      acc[3] += t;
+#pragma unroll
+      for (int k = 0; k < kMaxD; ++k)
+        if (k < d) {
+          const double dx = xi[k] - s.Xt[k * cap + j];
+          acc[4 + k] += t * dx * dx;
+        }
+    }
+  }
+  tm.sum_vec(acc, 4 + d);
+  const double quad = -s.A[n * ld + n];
+  const double logN = -0.5 * (quad + acc[0] + n * kLog2Pi);
+  double total = logN + lognormal_logpdf(noise, pr.noise_loc, pr.noise_scale) +
+                 lognormal_logpdf(os, pr.os_loc, pr.os_scale);
+  for (int k = 0; k < d; ++k) total += lognormal_logpdf(theta[3 + k], pr.ls_loc, pr.ls_scale);
+  const double scale = -1.0 / n;
+  const double f = total * scale;
+  tm.sync();
+  if (tm.rank() == 0) {
+    g[0] = scale * (0.5 * acc[1] + lognormal_dlogpdf(noise, pr.noise_loc, pr.noise_scale));
+    g[1] = scale * acc[2];
+    g[2] = scale * (acc[3] / os + 0.5 * acc[1] + lognormal_dlogpdf(os, pr.os_loc, pr.os_scale));
+  }
+  for (int k = tm.rank(); k < d; k += tm.size()) {
+    const double l = theta[3 + k];
+    g[3 + k] = scale * (acc[4 + k] / (l * l * l) + lognormal_dlogpdf(l, pr.ls_loc, pr.ls_scale));
+  }
+  tm.sync();
+  *f_out = f;
+  int st = !(f == f) || !(fabs(f) <= 1.79e308);
+  for (int k = 0; k < d + 3; ++k) st |= !(g[k] == g[k]);
+  return st ? 2 : 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Factorise at the fitted theta: A(lower) <- L^-1 with K + noise I = L L^T, alpha <- K^-1 (y-c).
+// Returns 0 or 1 (not PD).
+// ---------------------------------------------------------------------------------------
+template <class Team>
+STP_HD int exact_factorize(const Team& tm, const ExactSmem& s, int n, int d, const double* theta) {
+  const int ld = s.ld, cap = s.cap, W = tm.warp_width();
+  const double noise = theta[0], cst = theta[1], os = theta[2];
+  double* invl = s.small + 32;
+  tm.sync();
+  for (int k = tm.rank(); k < d; k += tm.size()) invl[k] = 1.0 / theta[3 + k];
+  tm.sync();
+  for (int i = tm.warp(); i < n; i += tm.nwarps()) {
+    double* row = s.A + i * ld;
+    for (int j = tm.lane(); j <= i; j += W)
+      row[j] = (j == i) ? os + noise : ard_rbf_tt(s.Xt, cap, d, invl, i, j, os);
+  }
+  if (cholesky_lower(tm, s.A, ld, n, s.c0)) return 1;
+  tri_inverse_lower(tm, s.A, ld, n, s.piv);
+  // z = Linv (y - c)  -> c0 ;  alpha = Linv^T z
+  for (int i = tm.rank(); i < n; i += tm.size()) {
+    const double* row = s.A + i * ld;
+    double z = 0.0;
+    for (int j = 0; j <= i; ++j) z += row[j] * (s.y[j] - cst);
+    s.c0[i] = z;
+  }
+  tm.sync();
+  for (int j = tm.rank(); j < n; j += tm.size()) {
+    double a = 0.0;
+    for (int i = j; i < n; ++i) a += s.A[i * ld + j] * s.c0[i];
+    s.alpha[j] = a;
+  }
+  tm.sync();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused pool pass.  For every pool point c (N of them, row-major [N,d] in global memory):
+//   k_j = os exp(-1/2 ||(x_c - x_j)/l||^2),  mean = cst + k.alpha,
+//   var = os - ||Linv k||^2 + noise          (observation noise included, App. D-3)
+//   acq = LogEI(mean, var, best_f)
+// and the argmax over the points whose mask byte is non-zero.  Tiles of TC = warp-width
+// candidates are staged in shared memory; each warp owns an interleaved quarter of the rows
+// of Linv, so Linv[i][j] is a broadcast read and the tile column is conflict-free.
+// Optional per-point outputs (may be null): mean_out, var_out, acq_out [N].
+// best_f may be NAN when only the predictive is wanted (acq_out then holds NaN).
+// ---------------------------------------------------------------------------------------
+template <class Team>
+STP_HD void exact_acquire(const Team& tm, const ExactSmem& s, int n, int d, const double* theta,
+                          const double* pool, int N, const uint8_t* mask, double best_f,
+                          int* best_idx, double* best_acq, double* mean_out, double* var_out,
+                          double* acq_out) {
+  const int ld = s.ld, cap = s.cap, TC = tm.warp_width(), nw = tm.nwarps();
+  const double noise = theta[0], cst = theta[1], os = theta[2];
+  const double* invl = s.small + 32;
+  double* xc = s.tile + (size_t)cap * TC;  // [kMaxD][TC]
+  double run_v = -INFINITY;
+  int run_i = -1;
+  for (int base = 0; base < N; base += TC) {
+    const int cnt = (N - base < TC) ? (N - base) : TC;
+    tm.sync();
+    for (int idx = tm.rank(); idx < cnt * d; idx += tm.size()) {
+      const int c = idx / d, k = idx - c * d;
+      xc[k * TC + c] = pool[(size_t)base * d + idx];
+    }
+    tm.sync();
+    for (int idx = tm.rank(); idx < n * TC; idx += tm.size()) {
+      const int j = idx / TC, c = idx - j * TC;
+      double v = 0.0;
+      if (c < cnt) {
+        double r2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < kMaxD; ++k)
+          if (k < d) {
+            const double t = (xc[k * TC + c] - s.Xt[k * cap + j]) * invl[k];
+            r2 += t * t;
+          }
+        v = os * exp(-0.5 * r2);
+      }
+      s.tile[j * TC + c] = v;
+    }
+    tm.sync();
+    {
+      const int c = tm.lane();
+      double ssq = 0.0, mu = 0.0;
+      for (int i = tm.warp(); i < n; i += nw) {
+        const double* row = s.A + i * ld;
+        double v0 = 0.0, v1 = 0.0;
+        int j = 0;
+        for (; j + 1 <= i; j += 2) {
+          v0 += row[j] * s.tile[j * TC + c];
+          v1 += row[j + 1] * s.tile[(j + 1) * TC + c];
+        }
+        if (j <= i) v0 += row[j] * s.tile[j * TC + c];
+        const double v = v0 + v1;
+        ssq += v * v;
+        mu += s.alpha[i] * s.tile[i * TC + c];
+      }
+      s.part[(tm.warp() * TC + c) * 2 + 0] = ssq;
+      s.part[(tm.warp() * TC + c) * 2 + 1] = mu;
+    }
+    tm.sync();
+    for (int c = tm.rank(); c < cnt; c += tm.size()) {
+      double ssq = 0.0, mu = 0.0;
+      for (int w = 0; w < nw; ++w) {
+        ssq += s.part[(w * TC + c) * 2 + 0];
+        mu += s.part[(w * TC + c) * 2 + 1];
+      }
+      const double mean = cst + mu;
+      const double var = os - ssq + noise;
+      const double a = log_ei(mean, var, best_f);
+      const int gi = base + c;
+      if (mean_out) mean_out[gi] = mean;
+      if (var_out) var_out[gi] = var;
+      if (acq_out) acq_out[gi] = a;
+      if ((!mask || mask[gi]) && acq_better(a, gi, run_v, run_i)) { run_v = a; run_i = gi; }
+    }
+  }
+  tm.argmax(run_v, run_i);
+  *best_idx = run_i;
+  *best_acq = run_v;
+}
+
+}  // namespace stp

@@ -1,0 +1,315 @@
+// libstp_b200.so -- sm_100a kernels and C ABI (include/stp_b200.h) of the batched BO hot path.
+// One CTA owns one campaign; every matrix of a campaign stays in shared memory for the whole
+// launch (<= 64 KB per campaign at n = 89, so three campaigns are resident per SM).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/stp_b200.h"
+#include "exact_campaign.cuh"
+#include "variational.cuh"
+
+using namespace stp;
+
+namespace {
+
+thread_local char g_err[256] = "";
+int fail(const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return -1;
+}
+int fail_cuda(const char* where, cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return -2;
+}
+
+constexpr int kTC = 32;  // acquisition tile: one candidate per lane
+
+int threads_for(int n_cap) {
+  const char* env = getenv("STP_THREADS");
+  if (env) {
+    const int t = atoi(env);
+    if (t >= 32 && t <= 1024 && t % 32 == 0) return t;
+  }
+  return n_cap <= 48 ? 128 : 256;
+}
+
+size_t exact_smem_bytes(int n_cap, int d, int threads, bool with_optimizer) {
+  size_t b = exact_smem_doubles(n_cap, d, kTC, threads / 32) * sizeof(double);
+  if (with_optimizer) b += sizeof(LbfgsbState) + 16;
+  return b;
+}
+
+struct PriorArg { double v[6]; };
+struct BoundsArg { double lb[kMaxP], ub[kMaxP], theta0[kMaxP]; };
+
+__device__ __forceinline__ ExactPrior to_prior(const PriorArg& p) {
+  return ExactPrior{p.v[0], p.v[1], p.v[2], p.v[3], p.v[4], p.v[5]};
+}
+
+__device__ __forceinline__ int fit_status_code(int s) {  // optimiser status -> ABI status
+  return s == 0 ? 0 : (s == 1 ? 4 : (s == 2 ? 5 : 3));
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_exact_mll_fg(int n_cap, int d, const double* __restrict__ X, const double* __restrict__ y,
+                               const int32_t* __restrict__ n_arr, const double* __restrict__ theta, PriorArg prior,
+                               double* __restrict__ f, double* __restrict__ g, int32_t* __restrict__ status) {
+  extern __shared__ double smem[];
+  const int b = blockIdx.x;
+  const int n = n_arr ? n_arr[b] : n_cap;
+  const ExactSmem s = exact_smem_carve(smem, n_cap, d, kTC, blockDim.x >> 5);
+  CtaTeam tm{s.red};
+  const int np = d + 3;
+  exact_load(tm, s, n, d, X + (size_t)b * n_cap * d, y + (size_t)b * n_cap);
+  if (threadIdx.x < np) s.small[threadIdx.x] = theta[b * np + threadIdx.x];
+  __syncthreads();
+  double fv;
+  const int st = exact_mll_fg(tm, s, n, d, s.small, to_prior(prior), &fv, s.small + 16);
+  if (threadIdx.x == 0) { f[b] = fv; status[b] = st; }
+  if (threadIdx.x < np) g[b * np + threadIdx.x] = st ? NAN : s.small[16 + threadIdx.x];
+}
+
+__global__ void k_exact_fit(int n_cap, int d, const double* __restrict__ X, const double* __restrict__ y,
+                            const int32_t* __restrict__ n_arr, double* __restrict__ theta, BoundsArg bnd,
+                            PriorArg prior, LbfgsbOpts opts, double* __restrict__ f_out, int32_t* __restrict__ nit,
+                            int32_t* __restrict__ nfev, int32_t* __restrict__ status) {
+  extern __shared__ double smem[];
+  const int b = blockIdx.x;
+  const int n = n_arr ? n_arr[b] : n_cap;
+  const int nw = blockDim.x >> 5;
+  const ExactSmem s = exact_smem_carve(smem, n_cap, d, kTC, nw);
+  LbfgsbState* S = reinterpret_cast<LbfgsbState*>(smem + exact_smem_doubles(n_cap, d, kTC, nw));
+  int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(S) + sizeof(LbfgsbState));
+  CtaTeam tm{s.red};
+  const int np = d + 3;
+  exact_load(tm, s, n, d, X + (size_t)b * n_cap * d, y + (size_t)b * n_cap);
+  double* th = s.small;
+  if (threadIdx.x < np) th[threadIdx.x] = theta[b * np + threadIdx.x];
+  __syncthreads();
+  const ExactFitResult r = exact_fit_run(tm, s, S, flag, n, d, th, bnd.lb, bnd.ub, to_prior(prior), opts);
+  if (threadIdx.x < np) theta[b * np + threadIdx.x] = th[threadIdx.x];
+  if (threadIdx.x == 0) {
+    if (f_out) f_out[b] = r.f;
+    if (nit) nit[b] = r.nit;
+    if (nfev) nfev[b] = r.nfev;
+    status[b] = fit_status_code(r.status);
+  }
+}
+
+__global__ void k_exact_acq(int n_cap, int d, int N, const double* __restrict__ pool,
+                            const int32_t* __restrict__ pool_id, const uint8_t* __restrict__ mask,
+                            const double* __restrict__ X, const double* __restrict__ y,
+                            const int32_t* __restrict__ n_arr, const double* __restrict__ theta,
+                            const double* __restrict__ best_f, int32_t* __restrict__ out_idx,
+                            double* __restrict__ out_acq, double* __restrict__ mean, double* __restrict__ var,
+                            double* __restrict__ acq, int32_t* __restrict__ status) {
+  extern __shared__ double smem[];
+  const int b = blockIdx.x;
+  const int n = n_arr ? n_arr[b] : n_cap;
+  const ExactSmem s = exact_smem_carve(smem, n_cap, d, kTC, blockDim.x >> 5);
+  CtaTeam tm{s.red};
+  const int np = d + 3;
+  exact_load(tm, s, n, d, X + (size_t)b * n_cap * d, y + (size_t)b * n_cap);
+  if (threadIdx.x < np) s.small[threadIdx.x] = theta[b * np + threadIdx.x];
+  __syncthreads();
+  const int st = exact_factorize(tm, s, n, d, s.small);
+  if (st) {
+    if (threadIdx.x == 0) { status[b] = 1; if (out_idx) out_idx[b] = -1; if (out_acq) out_acq[b] = NAN; }
+    return;
+  }
+  int bi; double bv;
+  const double* P = pool + (size_t)(pool_id ? pool_id[b] : 0) * N * d;
+  exact_acquire(tm, s, n, d, s.small, P, N, mask ? mask + (size_t)b * N : nullptr, best_f ? best_f[b] : NAN, &bi,
+                &bv, mean ? mean + (size_t)b * N : nullptr, var ? var + (size_t)b * N : nullptr,
+                acq ? acq + (size_t)b * N : nullptr);
+  if (threadIdx.x == 0) { status[b] = 0; if (out_idx) out_idx[b] = bi; if (out_acq) out_acq[b] = bv; }
+}
+
+// The whole loop body runners.py:64-109 for one campaign.
+__global__ void k_exact_bo_step(int n_cap, int d, int N, const double* __restrict__ pool,
+                                const double* __restrict__ pool_y, const int32_t* __restrict__ pool_id,
+                                uint8_t* __restrict__ mask, double* __restrict__ X, double* __restrict__ y,
+                                int32_t* __restrict__ n_arr, int32_t* __restrict__ trace, BoundsArg bnd,
+                                PriorArg prior, LbfgsbOpts opts, double* __restrict__ theta_out,
+                                double* __restrict__ acq_out, int32_t* __restrict__ nit, int32_t* __restrict__ nfev,
+                                int32_t* __restrict__ status) {
+  extern __shared__ double smem[];
+  const int b = blockIdx.x;
+  if (status[b] != 0) return;  // frozen campaign
+  const int n = n_arr[b];
+  if (n >= n_cap || n < 1) { if (threadIdx.x == 0) status[b] = 2; return; }
+  const int nw = blockDim.x >> 5;
+  const ExactSmem s = exact_smem_carve(smem, n_cap, d, kTC, nw);
+  LbfgsbState* S = reinterpret_cast<LbfgsbState*>(smem + exact_smem_doubles(n_cap, d, kTC, nw));
+  int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(S) + sizeof(LbfgsbState));
+  CtaTeam tm{s.red};
+  const int np = d + 3;
+  double* Xb = X + (size_t)b * n_cap * d;
+  double* yb = y + (size_t)b * n_cap;
+  exact_load(tm, s, n, d, Xb, yb);
+  double* th = s.small;
+  if (threadIdx.x < np) th[threadIdx.x] = bnd.theta0[threadIdx.x];  // no warm start (App. D-7)
+  __syncthreads();
+  const ExactFitResult r = exact_fit_run(tm, s, S, flag, n, d, th, bnd.lb, bnd.ub, to_prior(prior), opts);
+  if (threadIdx.x < np && theta_out) theta_out[b * np + threadIdx.x] = th[threadIdx.x];
+  if (threadIdx.x == 0) { if (nit) nit[b] = r.nit; if (nfev) nfev[b] = r.nfev; }
+  if (r.status == 3) { if (threadIdx.x == 0) status[b] = 3; return; }
+  if (exact_factorize(tm, s, n, d, th)) { if (threadIdx.x == 0) status[b] = 1; return; }
+  double best = -INFINITY;                      // best_f = y_train.max(), raw (runners.py:89)
+  for (int i = 0; i < n; ++i) best = fmax(best, s.y[i]);
+  int bi; double bv;
+  const int pid = pool_id ? pool_id[b] : 0;
+  const double* P = pool + (size_t)pid * N * d;
+  uint8_t* mb = mask + (size_t)b * N;
+  exact_acquire(tm, s, n, d, th, P, N, mb, best, &bi, &bv, nullptr, nullptr, nullptr);
+  if (bi < 0) { if (threadIdx.x == 0) status[b] = 2; return; }
+  // runners.py:98-109: record the pick, append it to the training set, drop it from the pool
+  if (threadIdx.x < d) Xb[(size_t)n * d + threadIdx.x] = P[(size_t)bi * d + threadIdx.x];
+  if (threadIdx.x == 0) {
+    yb[n] = pool_y[(size_t)pid * N + bi];
+    trace[(size_t)b * n_cap + n] = bi;
+    mb[bi] = 0;
+    n_arr[b] = n + 1;
+    if (acq_out) acq_out[b] = bv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 FMA throughput probe: 8 independent accumulator chains per thread.
+__global__ void k_fp64_probe(int iters, double* sink) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (r == 12345.678) sink[0] = r;  // keeps the loop alive; never true in practice
+}
+
+template <class K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 227 * 1024) return fail("campaign does not fit in shared memory (n_cap too large)");
+  if (bytes > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail_cuda("cudaFuncSetAttribute", e);
+  }
+  return 0;
+}
+
+int check_dims(int B, int n_cap, int d) {
+  if (B < 0) return fail("B < 0");
+  if (d < 1 || d > STP_MAX_D) return fail("d out of range [1, STP_MAX_D]");
+  if (n_cap < 1 || n_cap > STP_MAX_N) return fail("n_cap out of range [1, STP_MAX_N]");
+  return 0;
+}
+
+int fill_bounds(BoundsArg& b, int d, const double* lower, const double* upper, const double* theta0) {
+  for (int k = 0; k < kMaxP; ++k) { b.lb[k] = -HUGE_VAL; b.ub[k] = HUGE_VAL; b.theta0[k] = 0.0; }
+  for (int k = 0; k < d + 3; ++k) {
+    if (lower) b.lb[k] = lower[k];
+    if (upper) b.ub[k] = upper[k];
+    if (theta0) b.theta0[k] = theta0[k];
+  }
+  return 0;
+}
+
+LbfgsbOpts to_opts(const stp_lbfgsb_opts* o) {
+  LbfgsbOpts r{10, 15000, 15000, 20, 2.220446049250313e-09 / 2.220446049250313e-16, 1e-5};
+  if (o) { r.m = o->m; r.maxiter = o->maxiter; r.maxfun = o->maxfun; r.maxls = o->maxls; r.factr = o->factr; r.pgtol = o->pgtol; }
+  if (r.m < 1) r.m = 1;
+  if (r.m > kHist) r.m = kHist;
+  return r;
+}
+
+int after_launch(const char* name) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(name, e);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int stp_version(void) { return STP_ABI_VERSION; }
+const char* stp_last_error_string(void) { return g_err; }
+
+int stp_exact_mll_fg(int B, int n_cap, int d, const double* X, const double* y, const int32_t* n,
+                     const double* theta, const double* prior, double* f, double* g, int32_t* status,
+                     void* stream) {
+  if (check_dims(B, n_cap, d)) return -1;
+  if (!X || !y || !theta || !prior || !f || !g || !status) return fail("null argument");
+  if (B == 0) return 0;
+  const int threads = threads_for(n_cap);
+  const size_t smem = exact_smem_bytes(n_cap, d, threads, false);
+  if (set_smem(k_exact_mll_fg, smem)) return -1;
+  PriorArg p; memcpy(p.v, prior, sizeof(p.v));
+  k_exact_mll_fg<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, theta, p, f, g, status);
+  return after_launch("stp_exact_mll_fg");
+}
+
+int stp_exact_fit(int B, int n_cap, int d, const double* X, const double* y, const int32_t* n, double* theta,
+                  const double* lower, const double* upper, const double* prior, const stp_lbfgsb_opts* opts,
+                  double* f_out, int32_t* nit, int32_t* nfev, int32_t* status, void* stream) {
+  if (check_dims(B, n_cap, d)) return -1;
+  if (!X || !y || !theta || !prior || !status) return fail("null argument");
+  if (B == 0) return 0;
+  const int threads = threads_for(n_cap);
+  const size_t smem = exact_smem_bytes(n_cap, d, threads, true);
+  if (set_smem(k_exact_fit, smem)) return -1;
+  PriorArg p; memcpy(p.v, prior, sizeof(p.v));
+  BoundsArg bnd; fill_bounds(bnd, d, lower, upper, nullptr);
+  k_exact_fit<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, theta, bnd, p, to_opts(opts), f_out, nit,
+                                                          nfev, status);
+  return after_launch("stp_exact_fit");
+}
+
+int stp_exact_acq(int B, int n_cap, int d, int N, const double* pool, const int32_t* pool_id, const uint8_t* mask,
+                  const double* X, const double* y, const int32_t* n, const double* theta, const double* best_f,
+                  int32_t* out_idx, double* out_acq, double* mean, double* var, double* acq, int32_t* status,
+                  void* stream) {
+  if (check_dims(B, n_cap, d)) return -1;
+  if (N < 0) return fail("N < 0");
+  if (!pool || !X || !y || !theta || !status) return fail("null argument");
+  if (B == 0) return 0;
+  const int threads = threads_for(n_cap);
+  const size_t smem = exact_smem_bytes(n_cap, d, threads, false);
+  if (set_smem(k_exact_acq, smem)) return -1;
+  k_exact_acq<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, N, pool, pool_id, mask, X, y, n, theta, best_f,
+                                                          out_idx, out_acq, mean, var, acq, status);
+  return after_launch("stp_exact_acq");
+}
+
+int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const double* pool_y,
+                      const int32_t* pool_id, uint8_t* mask, double* X, double* y, int32_t* n, int32_t* trace,
+                      const double* theta0, const double* lower, const double* upper, const double* prior,
+                      const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
+                      int32_t* status, void* stream) {
+  if (check_dims(B, n_cap, d)) return -1;
+  if (N < 1) return fail("N < 1");
+  if (!pool || !pool_y || !mask || !X || !y || !n || !trace || !theta0 || !prior || !status) return fail("null argument");
+  if (B == 0) return 0;
+  const int threads = threads_for(n_cap);
+  const size_t smem = exact_smem_bytes(n_cap, d, threads, true);
+  if (set_smem(k_exact_bo_step, smem)) return -1;
+  PriorArg p; memcpy(p.v, prior, sizeof(p.v));
+  BoundsArg bnd; fill_bounds(bnd, d, lower, upper, theta0);
+  k_exact_bo_step<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, N, pool, pool_y, pool_id, mask, X, y, n, trace,
+                                                              bnd, p, to_opts(opts), theta_out, acq_out, nit, nfev,
+                                                              status);
+  return after_launch("stp_exact_bo_step");
+}
+
+int stp_fp64_probe(int iters, double* sink, void* stream) {
+  if (iters < 1 || !sink) return fail("bad argument");
+  k_fp64_probe<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+  return after_launch("stp_fp64_probe");
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// Thread-team abstraction shared by every per-campaign routine.
+//
+// One BO campaign is owned by one CTA.  The numerical routines (kernel matrices, symmetric
+// sweep, Cholesky, MLL/ELBO, L-BFGS-B, fused acquisition) are written once against a "team"
+// with rank()/size()/sync()/sum(): on the device the team is the CTA (CtaTeam: __syncthreads
+// and warp-shuffle reductions); in tests/hostemu the same source is compiled by g++ with a
+// one-thread team (SoloTeam) so that the algebra can be checked on a CPU-only box.  The host
+// build is test scaffolding only: the shipped library contains device code exclusively.
+#pragma once
+
+#if defined(__CUDACC__)
+#define STP_HD __host__ __device__ __forceinline__
+#define STP_D __device__ __forceinline__
+#else
+#define STP_HD inline
+#define STP_D inline
+#endif
+
+#include <math.h>
+#include <stdint.h>
+
+namespace stp {
+
+constexpr int kMaxWarps = 32;
+
+// ---------------------------------------------------------------------------------------
+// One-thread team: host emulation (tests/hostemu) and trivially-serial device sections.
+// ---------------------------------------------------------------------------------------
+struct SoloTeam {
+  STP_HD int rank() const { return 0; }
+  STP_HD int size() const { return 1; }
+  STP_HD int lane() const { return 0; }
+  STP_HD int warp() const { return 0; }
+  STP_HD int nwarps() const { return 1; }
+  STP_HD int warp_width() const { return 1; }
+  STP_HD void sync() const {}
+  STP_HD double sum(double v) const { return v; }
+  STP_HD double warp_sum(double v) const { return v; }
+  template <int KMAX>
+  STP_HD void sum_vec(double (&v)[KMAX], int k) const {}
+  // argmax with torch semantics (first maximal index; NaN wins, first NaN wins)
+  STP_HD void argmax(double& v, int& idx) const {}
+  STP_HD int any(int p) const { return p; }
+};
+
+// torch.argmax ordering: NaN beats everything; ties resolved towards the smaller index.
+STP_HD bool acq_better(double v, int i, double w, int j) {
+  const bool vn = (v != v), wn = (w != w);
+  if (j < 0) return i >= 0;
+  if (i < 0) return false;
+  if (vn || wn) {
+    if (vn && wn) return i < j;
+    return vn;
+  }
+  if (v > w) return true;
+  if (v < w) return false;
+  return i < j;
+}
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------
+// CTA team.  `red` points at >= 2*kMaxWarps doubles of shared scratch.
+// ---------------------------------------------------------------------------------------
+struct CtaTeam {
+  double* red;
+  __device__ __forceinline__ int rank() const { return threadIdx.x; }
+  __device__ __forceinline__ int size() const { return blockDim.x; }
+  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int warp() const { return threadIdx.x >> 5; }
+  __device__ __forceinline__ int nwarps() const { return blockDim.x >> 5; }
+  __device__ __forceinline__ int warp_width() const { return 32; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+
+  __device__ __forceinline__ double warp_sum(double v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  // Block-wide sum, result returned to every thread.  Deterministic for a fixed block size.
+  __device__ __forceinline__ double sum(double v) const {
+    v = warp_sum(v);
+    __syncthreads();  // protect `red` against the previous reduction's readers
+    if (lane() == 0) red[warp()] = v;
+    __syncthreads();
+    double t = 0.0;
+    const int nw = nwarps();
+    for (int w = 0; w < nw; ++w) t += red[w];
+    return t;
+  }
+  // K simultaneous block-wide sums (K <= 16), in place, every thread gets all of them.
+  template <int KMAX>
+  __device__ __forceinline__ void sum_vec(double (&v)[KMAX], int k) const {
+    static_assert(KMAX <= 16, "reduction scratch holds 16 x kMaxWarps doubles");
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q)
+      if (q < k) v[q] = warp_sum(v[q]);
+    __syncthreads();
+    const int nw = nwarps();
+    if (lane() == 0) {
+#pragma unroll
+      for (int q = 0; q < KMAX; ++q)
+        if (q < k) red[q * kMaxWarps + warp()] = v[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q)
+      if (q < k) {
+        double t = 0.0;
+        for (int w = 0; w < nw; ++w) t += red[q * kMaxWarps + w];
+        v[q] = t;
+      }
+  }
+  __device__ __forceinline__ void argmax(double& v, int& idx) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double w = __shfl_xor_sync(0xffffffffu, v, o);
+      const int j = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (acq_better(w, j, v, idx)) { v = w; idx = j; }
+    }
+    __syncthreads();
+    int* ired = reinterpret_cast<int*>(red + kMaxWarps);
+    if (lane() == 0) { red[warp()] = v; ired[warp()] = idx; }
+    __syncthreads();
+    const int nw = nwarps();
+    v = red[0]; idx = ired[0];
+    for (int w = 1; w < nw; ++w)
+      if (acq_better(red[w], ired[w], v, idx)) { v = red[w]; idx = ired[w]; }
+  }
+  __device__ __forceinline__ int any(int p) const { return __syncthreads_or(p); }
+};
+constexpr int kRedDoubles = 16 * kMaxWarps;  // scratch a CtaTeam needs
+#endif
+
+}  // namespace stp
