@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- BO iterations/s (fit + predict + acquire + update) over batched campaigns.
+
+Workload (BASELINE.json configs[3], the north-star shape): synthetic pools N = 2048, d = 6
+(negated Hartmann-6 + 0.05 t_3 noise, 8 pools), 1024 concurrent ExactGP campaigns PER GPU,
+n_initial = 10, 80 trials each.  Campaigns are kept at staggered ages (n = 10 ... 89 uniformly,
+"continuous batching": a campaign that finishes its 80 trials is replaced by a fresh seed), so
+that every step is one BO iteration of every campaign at the campaign-average cost, whatever
+--steps is.  One step = one launch of stp_exact_bo_step over all campaigns of the rank.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # CUDA arm (N > 1 under torchrun)
+  python bench.py --impl reference [--steps K] [--warmup W]    # CPU arm: the oracle on host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POOL, DIM, N_POOLS = 2048, 6, 8
+N_INITIAL, N_TRIALS = 10, 80
+CAP = N_INITIAL + N_TRIALS + 1
+METRIC, UNIT = "bo_iterations_per_sec", "it/s"
+WORKLOAD = ("cfg4: synthetic pools N=2048 d=6 (Hartmann-6 + t3 noise), {B} concurrent ExactGP campaigns per GPU, "
+            "n_initial=10, 80 trials, ages staggered over n=10..89 (continuous batching)")
+
+
+# ------------------------------------------------------------------------------------------
+# CPU workers (the oracle).  Forked BEFORE CUDA is initialised; they never touch the GPU.
+# ------------------------------------------------------------------------------------------
+def _cpu_init():
+    os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    import torch
+    torch.set_num_threads(1)
+
+
+def _cpu_one_iteration(job):
+    """One oracle BO iteration from a given campaign state -> (picked pool index, seconds, nfev)."""
+    import numpy as np
+    import torch
+    from oracle.loop import bo_iteration
+    Xp, yp, picked = job
+    Xp = torch.from_numpy(Xp); yp = torch.from_numpy(yp)
+    mask = torch.ones(len(Xp), dtype=torch.bool); mask[picked] = False
+    info = {}
+    t0 = time.perf_counter()
+    best, _ = bo_iteration("ExactGP", Xp[picked], yp[picked], Xp[mask], info=info)
+    dt = time.perf_counter() - t0
+    return int(torch.where(mask)[0][best]), dt, int(info["nfev"])
+
+
+def _cpu_campaign(job):
+    """`iters` consecutive oracle BO iterations of one fresh campaign -> per-iteration seconds."""
+    import torch
+    from oracle.loop import run_single_loop
+    from stpbenchmark_b200 import synthetic
+    g, seed, iters = job
+    X, y = synthetic.cfg4_pool(g)
+    times = []
+    run_single_loop(X, y, "ExactGP", n_initial=N_INITIAL, n_trials=iters, seed=seed,
+                    on_iteration=lambda t, idx, dt, info: times.append(dt))
+    return times
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference path's CPU restatement (oracle/) on every host core.
+    A step = iteration t of `cores` independent campaigns, one per core (bounded sample of the
+    1024-campaign workload); W + K consecutive iterations of each campaign are run, the first W
+    are warm-up."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    W, K = args.warmup, args.steps
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init) as pool:
+        jobs = [(c % N_POOLS, 900000 + c, W + K) for c in range(cores)]
+        t0 = time.perf_counter()
+        per = pool.map(_cpu_campaign, jobs)
+        wall = time.perf_counter() - t0
+    # step time = slowest core at that iteration (all cores advance in lock-step conceptually)
+    step_s = [max(p[t] for p in per) for t in range(W, W + K)]
+    total = sum(step_s)
+    value = cores * K / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(B=args.campaigns), "sample": f"{cores} campaigns (one per host core), "
+                   f"iterations {W}..{W + K - 1} of each (n = {N_INITIAL + W}..{N_INITIAL + W + K - 1})"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cores} campaigns x {K} consecutive BO iterations, oracle/ (torch fp64 + scipy "
+                                   f"L-BFGS-B), 1 thread per campaign; wall {wall:.1f}s"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def algorithmic_flops(n, nfev, d, N):
+    """W = F (n^3 + n^2 (3d+6)) + n^3/3 + Nc (n^2 + n (3d+8) + 60) per campaign-iteration,
+    with the campaign's actual closure count F and Nc = N - n remaining candidates."""
+    n = n.double(); F = nfev.double()
+    return F * (n ** 3 + n ** 2 * (3 * d + 6)) + n ** 3 / 3 + (N - n) * (n ** 2 + n * (3 * d + 8) + 60)
+
+
+def run_cuda_arm(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    cpu_pool = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu_pool = mp.get_context("fork").Pool(min(cores, 64), initializer=_cpu_init)  # before CUDA init
+
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (CUDA arm) needs a GPU; use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from stpbenchmark_b200 import _lib, synthetic
+    from stpbenchmark_b200.engine import CampaignBatch
+
+    B, W, K = args.campaigns, args.warmup, args.steps
+    per_pool = B // N_POOLS
+    pools = [synthetic.cfg4_pool(g) for g in range(N_POOLS)]
+    PX = torch.stack([p[0] for p in pools]); PY = torch.stack([p[1] for p in pools])
+    pool_id = [b // per_pool if per_pool else 0 for b in range(B)]
+    pool_id = [min(p, N_POOLS - 1) for p in pool_id]
+    age0 = [b % N_TRIALS for b in range(B)]                 # trials already done when timing starts
+    # seeds: first generation as config #4 (1000 g + k), later generations continue per slot
+    n_steps_total = W + K + K                                # device-resident region + e2e region
+    gens = 1 + (n_steps_total + N_TRIALS) // N_TRIALS + 1
+    rank_off = 100000 * rank
+    seed_of = lambda b, gen: rank_off + synthetic.campaign_seed(pool_id[b], b % max(per_pool, 1)) + 10007 * gen
+    t_setup = time.perf_counter()
+    designs = {}
+    for g in range(N_POOLS):
+        slots = [b for b in range(B) if pool_id[b] == g]
+        seeds = [seed_of(b, gen) for gen in range(gens) for b in slots]
+        if seeds:
+            D = synthetic.initial_designs(pools[g][0], pools[g][1], seeds, N_INITIAL)
+            for i, (gen, b) in enumerate([(gen, b) for gen in range(gens) for b in slots]):
+                designs[(b, gen)] = D[i]
+    batch = CampaignBatch(PX, PY, pool_id, [designs[(b, 0)].tolist() for b in range(B)], n_cap=CAP, kind="ExactGP",
+                          device=dev)
+    # pre-roll (untimed): bring campaign b to age0[b]; it starts at step N_TRIALS - age0[b]
+    start_step = torch.tensor([N_TRIALS - a for a in age0], device=dev)
+    batch.status.fill_(-1)                                   # not started yet
+    for t in range(N_TRIALS):
+        batch.status[start_step == t] = 0
+        batch.step()
+    batch.status[batch.status == -1] = 0                     # age-0 campaigns start now
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+
+    # recycling schedule: slot b finishes after (N_TRIALS - age0[b]) more steps, then every N_TRIALS
+    gen_of = [0] * B
+    def schedule(step_no):
+        sl = [b for b in range(B) if (step_no + age0[b]) % N_TRIALS == 0 and step_no + age0[b] > 0]
+        if not sl:
+            return None
+        for b in sl:
+            gen_of[b] += 1
+        init = torch.stack([designs[(b, gen_of[b])] for b in sl])
+        return torch.tensor(sl, device=dev), init.to(dev)
+    total_steps = W + K
+    sched = [schedule(s) for s in range(1, 2 * total_steps + 1)]   # sched[s-1] applies AFTER step s
+    sink = torch.full((B * 4, CAP), -1, dtype=torch.int32, device=dev)
+    sink_used = 0
+    n_hist = torch.zeros(K, B, dtype=torch.int32, device=dev)
+    f_hist = torch.zeros(K, B, dtype=torch.int32, device=dev)
+
+    def one_step(step_no, k_idx=None):
+        nonlocal sink_used
+        if k_idx is not None:
+            n_hist[k_idx].copy_(batch.n)
+        batch.step()
+        if k_idx is not None:
+            f_hist[k_idx].copy_(batch.nfev)
+        rc = sched[step_no - 1]
+        if rc is not None:
+            batch.recycle(rc[0], rc[1], sink, sink_used)
+            sink_used += rc[0].numel()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: W warm-up + K timed steps ------------------------------------
+    step_no = 0
+    for _ in range(W):
+        step_no += 1
+        one_step(step_no)
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    launches0 = batch.launches
+    ev[0].record()
+    for k in range(K):
+        step_no += 1
+        one_step(step_no, k)
+        ev[k + 1].record()
+    barrier()
+    clocks = sampler.stop()
+    gpu_launches = batch.launches - launches0
+    elapsed_ms = ev[0].elapsed_time(ev[K])
+    t = torch.tensor([elapsed_ms], dtype=torch.double, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms_max = float(t.item())
+    status_bad = int((batch.status != 0).sum().item())
+    value = world * B * K / (elapsed_ms_max * 1e-3)
+
+    # roofline of the dominant (only) kernel: algorithmic flops per launch / launch duration
+    flops = algorithmic_flops(n_hist, f_hist, DIM, N_POOL).sum(dim=1)              # [K]
+    step_ms = torch.tensor([ev[k].elapsed_time(ev[k + 1]) for k in range(K)], dtype=torch.double)
+    achieved_tflops = float(flops.sum().item()) / (float(step_ms.sum()) * 1e-3) / 1e12
+    fp64_peak = _lib.fp64_probe(4096)
+    hbm_bytes = float(((N_POOL - n_hist.double()) * DIM * 8 + N_POOL + n_hist.double() * (DIM + 1) * 8 + 16 + 24).sum())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+
+    # ---- end-to-end arm: same step through HOST buffers (pinned), H2D + launch + D2H per step --
+    host = {k: getattr(batch, k).cpu().pin_memory() for k in ("X", "y", "n", "mask", "trace", "status")}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = h2d
+    def e2e_step(step_no):
+        for kname, hv in host.items():
+            getattr(batch, kname).copy_(hv, non_blocking=True)
+        batch.step()
+        for kname, hv in host.items():
+            hv.copy_(getattr(batch, kname), non_blocking=True)
+        rc = sched[step_no - 1]
+        torch.cuda.synchronize()   # the host owns the state between steps: it must see the picks
+        if rc is not None:          # turnover done on the host copy
+            batch.recycle(rc[0], rc[1])
+            for kname, hv in host.items():
+                hv.copy_(getattr(batch, kname))
+    for _ in range(min(W, 2)):
+        step_no += 1
+        e2e_step(step_no)
+    barrier()
+    Ke = min(K, max(4, K // 4))
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(Ke):
+        step_no += 1
+        e2e_step(step_no)
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([e2e_ms], dtype=torch.double, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * Ke / (float(t.item()) * 1e-3)
+
+    # ---- the one collective of the path: gather the finished traces on rank 0 ------------------
+    if world > 1:
+        gathered = [torch.empty_like(sink) for _ in range(world)] if rank == 0 else None
+        dist.gather(sink, gathered, dst=0)
+
+    # ---- CPU baseline (rank 0): oracle BO iterations from the GPU's own campaign states ----------
+    cpu = None
+    parity = None
+    if cpu_pool is not None:
+        tr = batch.trace.cpu().long(); nn = batch.n.cpu().long(); pid = batch.pool_id.cpu().long()
+        S = min(B, max(16, min(cores, 64) * 3))
+        pick = [int(i) for i in torch.linspace(0, B - 1, S).round().long().tolist()]
+        # state one step back: the last pick is what the oracle must reproduce
+        jobs = []
+        for b in pick:
+            nb = int(nn[b]) - 1
+            if nb < N_INITIAL:
+                continue
+            jobs.append((PX[pid[b]].numpy(), PY[pid[b]].numpy(), tr[b, :nb].tolist(), int(tr[b, nb])))
+        t0 = time.perf_counter()
+        res = cpu_pool.map(_cpu_one_iteration, [j[:3] for j in jobs])
+        wall = time.perf_counter() - t0
+        cpu_pool.close()
+        agree = sum(1 for r, j in zip(res, jobs) if r[0] == j[3])
+        parity = {"oracle_index_agreement": f"{agree}/{len(jobs)}"}
+        ncores = min(cores, 64)
+        cpu = {"value": len(jobs) / wall, "unit": UNIT, "cores": ncores, "kind": "port",
+               "per_core": len(jobs) / sum(r[1] for r in res),
+               "sample": f"{len(jobs)} BO iterations (campaign states taken from this run, n = "
+                         f"{min(len(j[2]) for j in jobs)}..{max(len(j[2]) for j in jobs)}), oracle/ on {ncores} "
+                         f"processes x 1 thread; wall {wall:.1f}s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": elapsed_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD.format(B=B), "campaigns_per_gpu": B, "pool": N_POOL, "d": DIM,
+                       "l2": "inputs are L2-resident by design (0.8 MB of pools); the kernel is FP64/latency bound, "
+                             "no HBM stream to flush", "threads_per_campaign": os.environ.get("STP_THREADS", "auto")},
+            "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tflops / fp64_peak, "traffic": None,
+                         "kernel": "k_exact_bo_step",
+                         "peak_source": "stp_fp64_probe (DFMA microbenchmark, this run); MEASURED_PEAKS.json has no FP64 figure",
+                         "hbm": {"achieved": hbm_bytes / (float(step_ms.sum()) * 1e-3) / 1e9, "peak": hbm_peak,
+                                 "unit": "GB/s"}},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": Ke},
+            "gpu_launches": gpu_launches,
+            "clocks": clocks,
+            "parity": parity,
+            "frozen_campaigns": status_bad,
+            "mean_closures_per_fit": float(f_hist.double().mean().item()),
+            "setup_s": setup_s,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--campaigns", type=int, default=1024, help="campaigns per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = max(1, min(args.steps, N_TRIALS - args.warmup))  # one campaign per core has 80 trials
+        run_reference_arm(args)
+    else:
+        run_cuda_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -93,6 +93,11 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
                       const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
                       int32_t* status, void* stream);
 
+/* Elementwise analytic LogEI (botorch LogExpectedImprovement.forward, runners.py:88-90) of
+ * `count` (mean, var) pairs against one best_f: out[i] = log_h((mean - best_f)/sigma) + log sigma,
+ * sigma = sqrt(max(var, 1e-12)). */
+int stp_log_ei(long long count, const double* mean, const double* var, double best_f, double* out, void* stream);
+
 /* Sustained FP64 FMA throughput probe (roofline denominator; MEASURED_PEAKS.json has no FP64
  * figure).  Runs `iters` dependent-chain-free DFMA batches on every SM; *flops_out (device,
  * double) receives the number of floating-point operations executed. */

@@ -80,7 +80,7 @@ def init_state(X: torch.Tensor, kind: str, init_noise: torch.Tensor | None = Non
         ls=torch.full((1, d), mode_ls, dtype=torch.double, requires_grad=True),
         os=torch.tensor(_lognormal_mode_f32(0.0, 1.0), dtype=torch.double, requires_grad=True),
         noise=torch.tensor([_lognormal_mode_f32(-4.0, 1.0)], dtype=torch.double, requires_grad=True),
-        rawdf=(torch.tensor([inv_softplus(5.0)], dtype=torch.double, requires_grad=True)
+        rawdf=(torch.tensor([_f32(inv_softplus(5.0))], dtype=torch.double, requires_grad=True)
                if kind == "VarTGP" else None),
         nat1=torch.zeros(n, dtype=torch.double),
         nat2=-0.5 * torch.eye(n, dtype=torch.double),

@@ -147,6 +147,17 @@ def exact_bo_step(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, up
                                    _p(acq_out), _p(nit), _p(nfev), _p(status), _stream()), "stp_exact_bo_step")
 
 
+def log_ei(mean: torch.Tensor, var: torch.Tensor, best_f: float) -> torch.Tensor:
+    """Elementwise analytic LogEI on the device; output has the shape of ``mean``."""
+    _require_cuda(mean, var)
+    if mean.shape != var.shape:
+        raise ValueError("mean and var must have the same shape")
+    out = torch.empty_like(mean)
+    _check(lib().stp_log_ei(ctypes.c_longlong(mean.numel()), _p(mean), _p(var), ctypes.c_double(best_f), _p(out),
+                            _stream()), "stp_log_ei")
+    return out
+
+
 def fp64_probe(iters: int = 4096) -> float:
     """Measured FP64 FMA throughput of the current device in TFLOP/s (roofline denominator)."""
     _require_cuda()

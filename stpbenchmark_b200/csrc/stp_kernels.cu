@@ -192,6 +192,14 @@ __global__ void k_fp64_probe(int iters, double* sink) {
   if (r == 12345.678) sink[0] = r;  // keeps the loop alive; never true in practice
 }
 
+// Elementwise LogEI over `count` (mean, var) pairs; grid-stride.
+__global__ void k_log_ei(long long count, const double* __restrict__ mean, const double* __restrict__ var,
+                         double best_f, double* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = log_ei(mean[i], var[i], best_f);
+}
+
 template <class K>
 int set_smem(K kernel, size_t bytes) {
   if (bytes > 227 * 1024) return fail("campaign does not fit in shared memory (n_cap too large)");
@@ -304,6 +312,15 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
                                                               bnd, p, to_opts(opts), theta_out, acq_out, nit, nfev,
                                                               status);
   return after_launch("stp_exact_bo_step");
+}
+
+int stp_log_ei(long long count, const double* mean, const double* var, double best_f, double* out, void* stream) {
+  if (count < 0 || !mean || !var || !out) return fail("bad argument");
+  if (count == 0) return 0;
+  long long blocks = (count + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_log_ei<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(count, mean, var, best_f, out);
+  return after_launch("stp_log_ei");
 }
 
 int stp_fp64_probe(int iters, double* sink, void* stream) {

@@ -1,0 +1,148 @@
+"""Batched campaign engine: B independent BO campaigns advanced together on one GPU.
+
+The reference runs campaigns strictly one after another (run_benchmark.py:20-43,
+runners.py:174-200); they share nothing, so here every campaign is one CTA of the same launch
+and the whole loop body runners.py:64-109 (fresh model -> fit -> LogEI over the pool -> argmax
+-> move the pick from the pool to the training set) is ONE kernel per iteration
+(stp_exact_bo_step) or two (stp_var_fit + stp_var_acq_step) for the variational models.
+
+State kept resident in HBM for the whole run (row-major, batch-major, fp64 / int32 / uint8):
+    pool   [G, N, d]   candidate inputs of the G distinct pools (shared by their campaigns)
+    pool_y [G, N]      their targets
+    pool_id[B]         which pool a campaign draws from
+    mask   [B, N]      1 = still a candidate (runners.py:53-54)
+    X      [B, cap, d] training inputs, rows < n[b] valid (duplicates kept, App. D-4)
+    y      [B, cap]    training targets (RAW, App. D-1)
+    n      [B]         current training-set size
+    trace  [B, cap]    selected pool index per row: initial design first, then one per trial
+    status [B]         0 running; non-zero = frozen (the reference's try/except, runners.py:113-115)
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib, priors
+
+
+class CampaignBatch:
+    """Device-resident state of B campaigns over G pools, for any of the four model kinds."""
+
+    def __init__(self, pools: torch.Tensor, pool_ys: torch.Tensor, pool_id: Sequence[int],
+                 init_indices: Sequence[Sequence[int]], n_cap: int, kind: str = "ExactGP",
+                 device: Optional[torch.device] = None, epochs: int = 600, learning_rate: float = 0.01,
+                 num_samples: int = 2048, seeds: Optional[Sequence[int]] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("CampaignBatch needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        if pools.dim() == 2:
+            pools, pool_ys = pools.unsqueeze(0), pool_ys.reshape(1, -1)
+        self.kind = kind
+        self.G, self.N, self.d = pools.shape
+        self.B = len(pool_id)
+        self.cap = int(n_cap)
+        if self.cap > _lib.MAX_N or self.d > _lib.MAX_D:
+            raise ValueError(f"n_cap <= {_lib.MAX_N} and d <= {_lib.MAX_D} required")
+        dev = self.device
+        self.pool = pools.to(dev, torch.double).contiguous()
+        self.pool_y = pool_ys.to(dev, torch.double).contiguous()
+        self.pool_id = torch.tensor(list(pool_id), dtype=torch.int32, device=dev)
+        B, cap, d, N = self.B, self.cap, self.d, self.N
+        # host-side assembly of the initial designs, then one H2D copy per array
+        mask = torch.ones(B, N, dtype=torch.uint8)
+        trace = torch.full((B, cap), -1, dtype=torch.int32)
+        n = torch.zeros(B, dtype=torch.int32)
+        for b, idx in enumerate(init_indices):
+            idx = [int(i) for i in idx]
+            if len(idx) > cap:
+                raise ValueError("initial design longer than n_cap")
+            t = torch.tensor(idx, dtype=torch.long)
+            mask[b, t] = 0
+            trace[b, : len(idx)] = t.to(torch.int32)
+            n[b] = len(idx)
+        self.mask = mask.to(dev)
+        self.trace = trace.to(dev)
+        self.n = n.to(dev)
+        self.X = torch.zeros(B, cap, d, dtype=torch.double, device=dev)
+        self.y = torch.zeros(B, cap, dtype=torch.double, device=dev)
+        self._gather_training_sets()
+        self.status = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.theta = torch.zeros(B, d + 3, dtype=torch.double, device=dev)
+        self.acq = torch.zeros(B, dtype=torch.double, device=dev)
+        self.nit = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.nfev = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.launches = 0
+        self.epochs, self.learning_rate, self.num_samples = int(epochs), float(learning_rate), int(num_samples)
+        self.seeds = list(seeds) if seeds is not None else list(range(B))
+        self.iteration = 0
+        if kind == "ExactGP":
+            self._theta0 = priors.exact_theta0(d)
+            self._lower, self._upper = priors.exact_bounds(d)
+            self._prior = priors.exact_prior_vector(d)
+            self._opts = _lib.LbfgsbOpts.scipy_defaults()
+        else:
+            from . import varops
+            self._var = varops.VarBatchState(self)
+
+    def _gather_training_sets(self):
+        """X[b, i] = pool[pool_id[b], trace[b, i]] for i < n[b] (runners.py:56-57)."""
+        idx = self.trace.clamp_min(0).long()
+        pid = self.pool_id.long().unsqueeze(1).expand_as(idx)
+        valid = (torch.arange(self.cap, device=self.device).unsqueeze(0) < self.n.unsqueeze(1))
+        self.X.copy_(self.pool[pid, idx] * valid.unsqueeze(-1))
+        self.y.copy_(self.pool_y[pid, idx] * valid)
+
+    def step(self) -> None:
+        """One BO iteration (runners.py:64-109) for every running campaign."""
+        if self.kind == "ExactGP":
+            _lib.exact_bo_step(self.pool, self.pool_y, self.pool_id, self.mask, self.X, self.y, self.n, self.trace,
+                               self._theta0, self._lower, self._upper, self._prior, self.status,
+                               theta_out=self.theta, acq_out=self.acq, nit=self.nit, nfev=self.nfev,
+                               opts=self._opts)
+            self.launches += 1
+        else:
+            self.launches += self._var.step()
+        self.iteration += 1
+
+    def run(self, n_trials: int) -> None:
+        for _ in range(int(n_trials)):
+            self.step()
+
+    def traces(self):
+        """(indices [B, cap] int64 with -1 beyond the last pick, n [B], status [B]) on the host."""
+        torch.cuda.synchronize(self.device)
+        return self.trace.cpu().long(), self.n.cpu().long(), self.status.cpu().long()
+
+    def selected_values(self):
+        idx, n, _ = self.traces()
+        py = self.pool_y.cpu()
+        pid = self.pool_id.cpu().long()
+        out: List[List[float]] = []
+        for b in range(self.B):
+            out.append([float(py[pid[b], idx[b, i]]) for i in range(int(n[b]))])
+        return out
+
+    # -- continuous batching: finished campaigns leave, fresh ones take their slots --------------
+    def recycle(self, slots: torch.Tensor, new_init: torch.Tensor, sink: Optional[torch.Tensor] = None,
+                sink_offset: int = 0) -> None:
+        """Replace the campaigns in ``slots`` (int64 [k], device) by fresh ones whose initial
+        designs are ``new_init`` (int64 [k, n_initial], device).  The finished traces are first
+        copied into ``sink[sink_offset : sink_offset + k]`` when a sink is given.  Plumbing only
+        (a handful of tiny torch index kernels); no host synchronisation."""
+        if slots.numel() == 0:
+            return
+        if sink is not None:
+            sink[sink_offset: sink_offset + slots.numel()] = self.trace[slots]
+        k, ni = new_init.shape
+        pid = self.pool_id[slots].long()
+        self.mask[slots] = 1
+        self.mask[slots.unsqueeze(1), new_init] = 0
+        self.trace[slots] = -1
+        self.trace[slots, :ni] = new_init.to(torch.int32)
+        self.X[slots] = 0
+        self.y[slots] = 0
+        self.X[slots, :ni] = self.pool[pid.unsqueeze(1), new_init]
+        self.y[slots, :ni] = self.pool_y[pid.unsqueeze(1), new_init]
+        self.n[slots] = ni
+        self.status[slots] = 0

@@ -1,0 +1,76 @@
+"""Pins the CPU oracle against the reference's checked-in traces."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _fixtures import EXACT_KAT, GOLDEN, dataset, trace
+from oracle import acq as oacq, exact as oexact, loop as oloop
+
+torch.set_num_threads(1)
+
+
+def test_cfg1_exactgp_agnp_seed45_smoke_trace():
+    """BASELINE config #1: ExactGP on AgNP, seed 45, SMOKE length == results/ExactGP_AgNP_dataset_traces_SMOKE.csv."""
+    X, y = dataset("AgNP")
+    sel, vals = oloop.run_single_loop(X, y, "ExactGP", n_initial=10, n_trials=30, seed=45)
+    assert sel == trace("smoke", "ExactGP", "AgNP", 45)
+    assert sel == trace("gold1", "ExactGP", "AgNP", 45)[:40]
+    assert len(vals) == 40 and vals[0] == float(y[sel[0]])
+
+
+@pytest.mark.parametrize("name,seed", [("Perovskite", 359), ("AutoAM", 102)])
+def test_exactgp_gold1_prefix(name, seed):
+    """First 12 BO picks of two more known-answer campaigns of gold_runs/benchmark_1."""
+    X, y = dataset(name)
+    sel, _ = oloop.run_single_loop(X, y, "ExactGP", n_initial=10, n_trials=12, seed=seed)
+    assert sel == trace("gold1", "ExactGP", name, seed)[:22]
+
+
+def test_full_kat_report_is_consistent_with_survey():
+    """tools/validate_oracle_golden.py re-ran all 250 ExactGP campaigns (90 rows) with this oracle;
+    the committed report must list at least the traces the survey found index-exact."""
+    path = os.path.join(GOLDEN, "oracle_kat_report_ExactGP_gold1.json")
+    if not os.path.exists(path):
+        pytest.skip("full KAT report not generated yet")
+    rep = json.load(open(path))
+    assert sum(rep["exact_traces"].values()) >= 100
+    for name, kat in EXACT_KAT.items():
+        got = {int(s) for s, v in rep["first_divergence"][name].items() if v >= 90}
+        assert len(got & set(kat)) >= 0.8 * len(kat), (name, sorted(set(kat) - got))
+
+
+def test_autograd_and_analytic_gradients_agree():
+    X, y = dataset("AgNP")
+    sel = trace("gold1", "ExactGP", "AgNP", 359)[:23]
+    sel[5] = sel[2]  # one duplicated row, as the Sobol designs produce
+    Xt, yt = X[sel], y[sel]
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        th = oexact.initial_theta(X.shape[1]) * rng.uniform(0.5, 2.0, X.shape[1] + 3) + np.r_[0, 0.3, np.zeros(X.shape[1] + 1)]
+        f1, g1 = oexact.mll_value_and_grad(th, Xt, yt)
+        f2, g2 = oexact.mll_value_and_grad_analytic(th, Xt, yt)
+        assert abs(f1 - f2) < 1e-12 * max(1, abs(f1))
+        assert np.abs(g1 - g2).max() < 1e-10 * np.abs(g1).max()
+
+
+def test_log_ei_helper_branches_are_continuous_and_match_naive():
+    u = torch.tensor([-1e7, -1e6 - 1, -1e6 + 1, -50.0, -5.0, -1.0 - 1e-12, -1.0 + 1e-12, 0.0, 3.0], dtype=torch.double)
+    v = oacq.log_ei_helper(u)
+    assert torch.isfinite(v).all()
+    naive = torch.log(torch.exp(-0.5 * u[4:] ** 2) / np.sqrt(2 * np.pi) + u[4:] * 0.5 * torch.erfc(-u[4:] / np.sqrt(2)))
+    assert torch.allclose(v[4:], naive, rtol=1e-9, atol=0)
+    tail = v + 0.5 * u * u  # remove the Gaussian factor before comparing across the -1e6 branch point
+    assert abs(v[5] - v[6]) < 1e-10 and abs(tail[1] - tail[2]) < 1e-3
+    assert oacq.first_argmax(torch.tensor([1.0, 3.0, 3.0, float("nan"), 2.0])) == 3  # NaN wins
+    assert oacq.first_argmax(torch.tensor([1.0, 3.0, 3.0])) == 1                      # first maximal index
+
+
+def test_posterior_includes_observation_noise():
+    X, y = dataset("AutoAM")
+    sel = trace("gold1", "ExactGP", "AutoAM", 45)[:15]
+    th = oexact.initial_theta(X.shape[1])
+    mean, var = oexact.posterior_exact(th, X[sel], y[sel], X[sel])
+    assert (var > th[0] * 0.999).all() and torch.allclose(mean, y[sel], atol=0.2 * float(y.std()))
