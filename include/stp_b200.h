@@ -93,6 +93,54 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
                       const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
                       int32_t* status, void* stream);
 
+/* ---- variational models: VarGP / VarTGP / VarLGP (models.py:114-202, 18-111, 205-297) ---------------
+ * State arrays (device, caller-owned, batch-major): Z [B, n_cap, d] inducing locations, hyp [B, d+4] =
+ * (constant, lengthscale_1..d, outputscale, noise, raw_deg_free), nat1 [B, n_cap], nat2 [B, n_cap, n_cap]
+ * natural parameters of the whitened q(u), adam_m / adam_v [B, n_cap*d + d + 4] Adam moments laid out as
+ * (Z | hyp).  work: device scratch of stp_var_workspace_bytes(B, n_cap) bytes.
+ * Host tables: hyp0 [d+4] construction values; prior [8] = (ls_loc, ls_scale, os_loc, os_scale, noise_loc,
+ * noise_scale, df_concentration, df_rate); gh [40] = 20 Gauss-Hermite nodes then 20 weights. */
+size_t stp_var_workspace_bytes(int B, int n_cap);
+
+/* train_natural_variational_model (optim.py:105-181): `epochs` full-batch steps in ONE persistent launch --
+ * ELBO forward (20-point Gauss-Hermite for Student-T / Laplace), hand-derived backward, natural-gradient step
+ * lr_ngd * n on (nat1, nat2) (gpytorch.optim.NGD, optim.py:132-134) and Adam(lr_adam; optim.py:136-141) on
+ * (Z, hyp).  y is standardised inside (optim.py:126-127).  fresh != 0 first builds a new model
+ * (runners.py:66-74): Z = X, hyp = hyp0, nat1 = 1e-3 * init_noise (init_noise [B, n_cap]; NULL = Philox(seed)),
+ * nat2 = -I/2, Adam moments 0; fresh == 0 continues from the given state with Adam step offset t0.
+ * loss_hist: optional [B, epochs].  Campaigns with status != 0 on entry are skipped. */
+int stp_var_fit(int B, int n_cap, int d, int lik, int epochs, double lr_ngd, double lr_adam, int fresh, int t0,
+                const double* X, const double* y, const int32_t* n, const double* init_noise, unsigned long long seed,
+                const double* hyp0, const double* prior, const double* gh, double* Z, double* hyp, double* nat1,
+                double* nat2, double* adam_m, double* adam_v, double* loss_hist, int32_t* status, double* work,
+                void* stream);
+
+/* One evaluation of -ELBO/n (VariationalELBO, optim.py:143, 153-154) and its raw gradients at a given state,
+ * nothing updated.  grads [B, G], G = n_cap + n_cap^2 + n_cap*d + d + 4, laid out as
+ * (natural gradient of nat1 | of nat2 | dZ | d hyp).  standardise != 0 standardises y first. */
+int stp_var_elbo_fg(int B, int n_cap, int d, int lik, int standardise, const double* X, const double* y,
+                    const int32_t* n, const double* Z, const double* hyp, const double* nat1, const double* nat2,
+                    const double* prior, const double* gh, double* loss, double* grads, int32_t* status, double* work,
+                    void* stream);
+
+/* Fused pool pass of a trained variational model: Var*.posterior (models.py:95-111, 187-202, 280-297) +
+ * LogExpectedImprovement + mean over the S likelihood samples + argmax (runners.py:88-95).  mean / var
+ * (optional [B, N]) receive the latent q(f) moments; acq (optional [B, N]) the acquisition.  Gaussian: analytic
+ * LogEI on N(m, v + noise).  Student-T / Laplace: mean over S samples f = m + sqrt(v) eps of LogEI with the
+ * constant likelihood sigma; eps [B, N, S] if non-NULL, else Philox4x32-10(seed, stream = campaign,
+ * counter = candidate * ceil(S/2) + pair) -- stp_philox_normal reproduces that stream.  best_f [B] or NULL
+ * (= max of y[b, :n], raw).  update != 0 additionally performs runners.py:98-109 (append the pick to X, y, n,
+ * trace; clear its mask byte). */
+int stp_var_acq(int B, int n_cap, int d, int N, int lik, const double* pool, const int32_t* pool_id, uint8_t* mask,
+                const double* Z, const double* hyp, const double* nat1, const double* nat2, int32_t* n,
+                const double* best_f, int S, const double* eps, unsigned long long seed, int32_t* out_idx,
+                double* out_acq, double* mean, double* var, double* acq, int update, const double* pool_y, double* X,
+                double* y, int32_t* trace, int32_t* status, double* work, void* stream);
+
+/* 2 * pairs standard normals of the in-kernel generator: out[2q], out[2q+1] for counters counter0 + q. */
+int stp_philox_normal(unsigned long long seed, unsigned long long stream_id, unsigned long long counter0,
+                      long long pairs, double* out, void* stream);
+
 /* Elementwise analytic LogEI (botorch LogExpectedImprovement.forward, runners.py:88-90) of
  * `count` (mean, var) pairs against one best_f: out[i] = log_h((mean - best_f)/sigma) + log sigma,
  * sigma = sqrt(max(var, 1e-12)). */

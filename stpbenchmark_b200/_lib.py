@@ -172,3 +172,80 @@ def fp64_probe(iters: int = 4096) -> float:
     torch.cuda.synchronize()
     flops = 148 * 8 * 256 * float(iters) * 16 * 8 * 2
     return flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+
+# ---------------------------------------------------------------------------------------------
+# variational models
+# ---------------------------------------------------------------------------------------------
+LIK = {"gaussian": 0, "student_t": 1, "laplace": 2, "VarGP": 0, "VarTGP": 1, "VarLGP": 2}
+
+
+def var_workspace(B: int, n_cap: int, device) -> torch.Tensor:
+    L = lib()
+    L.stp_var_workspace_bytes.restype = ctypes.c_size_t
+    nbytes = L.stp_var_workspace_bytes(B, n_cap)
+    return torch.empty(nbytes // 8, dtype=torch.double, device=device)
+
+
+def _u64(v: int):
+    return ctypes.c_ulonglong(int(v) & 0xFFFFFFFFFFFFFFFF)
+
+
+def var_fit(X, y, n, state: dict, lik: int, epochs: int, lr_ngd: float, lr_adam: float, hyp0, prior, gh, status,
+            work, fresh: bool = True, t0: int = 0, init_noise=None, seed: int = 0, loss_hist=None):
+    """stp_var_fit on the state dict {Z, hyp, nat1, nat2, adam_m, adam_v} (in place)."""
+    _require_cuda(X, y, n, init_noise, status, work, loss_hist, *state.values())
+    B, n_cap, d = X.shape
+    _check(lib().stp_var_fit(B, n_cap, d, int(lik), int(epochs), ctypes.c_double(lr_ngd), ctypes.c_double(lr_adam),
+                             int(bool(fresh)), int(t0), _p(X), _p(y), _p(n), _p(init_noise), _u64(seed), _host(hyp0),
+                             _host(prior), _host(gh), _p(state["Z"]), _p(state["hyp"]), _p(state["nat1"]),
+                             _p(state["nat2"]), _p(state["adam_m"]), _p(state["adam_v"]), _p(loss_hist), _p(status),
+                             _p(work), _stream()), "stp_var_fit")
+
+
+def var_elbo_fg(X, y, n, state: dict, lik: int, prior, gh, work, standardise: bool = True):
+    """Loss [B] and raw gradients [B, G] at the given state (nothing updated)."""
+    _require_cuda(X, y, n, work, *[state[k] for k in ("Z", "hyp", "nat1", "nat2")])
+    B, n_cap, d = X.shape
+    G = n_cap + n_cap * n_cap + n_cap * d + d + 4
+    loss = torch.empty(B, dtype=torch.double, device=X.device)
+    grads = torch.zeros(B, G, dtype=torch.double, device=X.device)
+    status = torch.zeros(B, dtype=torch.int32, device=X.device)
+    _check(lib().stp_var_elbo_fg(B, n_cap, d, int(lik), int(bool(standardise)), _p(X), _p(y), _p(n), _p(state["Z"]),
+                                 _p(state["hyp"]), _p(state["nat1"]), _p(state["nat2"]), _host(prior), _host(gh),
+                                 _p(loss), _p(grads), _p(status), _p(work), _stream()), "stp_var_elbo_fg")
+    return loss, grads, status
+
+
+def var_acq(pool, state: dict, n, lik: int, status, work, best_f=None, mask=None, pool_id=None, S: int = 2048, eps=None,
+            seed: int = 0, want_pointwise: bool = False, update=None):
+    """stp_var_acq.  ``update`` = dict(pool_y, X, y, trace) performs the append of runners.py:98-109."""
+    _require_cuda(pool, n, status, work, best_f, mask, pool_id, eps, *[state[k] for k in ("Z", "hyp", "nat1", "nat2")])
+    B, n_cap, d = state["Z"].shape
+    N = pool.shape[-2]
+    dev = pool.device
+    idx = torch.full((B,), -1, dtype=torch.int32, device=dev)
+    best = torch.empty(B, dtype=torch.double, device=dev)
+    mean = var = acq = None
+    if want_pointwise:
+        mean = torch.empty(B, N, dtype=torch.double, device=dev)
+        var = torch.empty(B, N, dtype=torch.double, device=dev)
+        acq = torch.empty(B, N, dtype=torch.double, device=dev)
+    u = update or {}
+    _require_cuda(*u.values())
+    _check(lib().stp_var_acq(B, n_cap, d, N, int(lik), _p(pool), _p(pool_id), _p(mask), _p(state["Z"]), _p(state["hyp"]),
+                             _p(state["nat1"]), _p(state["nat2"]), _p(n), _p(best_f), int(S), _p(eps), _u64(seed),
+                             _p(idx), _p(best), _p(mean), _p(var), _p(acq), int(update is not None), _p(u.get("pool_y")),
+                             _p(u.get("X")), _p(u.get("y")), _p(u.get("trace")), _p(status), _p(work), _stream()),
+           "stp_var_acq")
+    return {"idx": idx, "acq_best": best, "mean": mean, "var": var, "acq": acq}
+
+
+def philox_normal(seed: int, stream_id: int, counter0: int, count: int, device="cuda") -> torch.Tensor:
+    """The in-kernel N(0,1) stream: ``count`` (even) draws for counters counter0 .. counter0 + count/2 - 1."""
+    _require_cuda()
+    pairs = (count + 1) // 2
+    out = torch.empty(2 * pairs, dtype=torch.double, device=device)
+    _check(lib().stp_philox_normal(_u64(seed), _u64(stream_id), _u64(counter0), ctypes.c_longlong(pairs), _p(out),
+                                   _stream()), "stp_philox_normal")
+    return out[:count]

@@ -40,7 +40,7 @@ struct ExactSmem {
   double* piv;    // cap+1 (pivots; reused as tmp by the triangular inverse)
   double* alpha;  // cap
   double* tile;   // acquisition: cap x TC cross-covariances + TC x (kMaxD) staged candidates
-  double* part;   // acquisition: nwarps x TC x 2 partial sums
+  double* part;   // acquisition: nwarps x TC x 2 partial sums (ALIASES `red`: never live together)
   double* small;  // 64 doubles: theta (<=11), gradient (<=11), misc
   double* red;    // kRedDoubles reduction scratch
   int ld, cap;
@@ -49,7 +49,7 @@ struct ExactSmem {
 STP_HD size_t exact_smem_doubles(int cap, int d, int tc, int nwarps) {
   const int ld = odd_ld(cap + 1);
   return (size_t)(cap + 1) * ld + (size_t)d * cap + cap + 3 * (size_t)(cap + 1) + cap +
-         (size_t)cap * tc + (size_t)tc * kMaxD + (size_t)nwarps * tc * 2 + 64 + 16 * kMaxWarps;
+         (size_t)cap * tc + (size_t)tc * kMaxD + 64 + 16 * kMaxWarps;  // nwarps*tc*2 <= 16*kMaxWarps
 }
 
 STP_HD ExactSmem exact_smem_carve(double* base, int cap, int d, int tc, int nwarps) {
@@ -65,9 +65,9 @@ STP_HD ExactSmem exact_smem_carve(double* base, int cap, int d, int tc, int nwar
   s.piv = p;    p += cap + 1;
   s.alpha = p;  p += cap;
   s.tile = p;   p += (size_t)cap * tc + (size_t)tc * kMaxD;
-  s.part = p;   p += (size_t)nwarps * tc * 2;
   s.small = p;  p += 64;
   s.red = p;
+  s.part = p;   // block reductions and the acquisition partials are never in flight together
   return s;
 }
 

@@ -33,9 +33,15 @@ STP_HD ExactFitResult exact_fit_run(const Team& tm, const ExactSmem& s, LbfgsbSt
     tm.sync();
     if (tm.rank() == 0) {
       if (st) { f = NAN; for (int k = 0; k < np; ++k) g[k] = NAN; }
-      *flag = lbfgsb_advance(*S, f, g);
+      *flag = lbfgsb_advance_split(*S, f, g);
     }
     tm.sync();
+    while (*flag == 3) {            // the optimiser wants the dense B: formed by warp 0, one lane per row
+      lb_build_B_team(tm, *S);
+      tm.sync();
+      if (tm.rank() == 0) *flag = lbfgsb_resume(*S);
+      tm.sync();
+    }
   }
   for (int k = tm.rank(); k < np; k += tm.size()) theta[k] = S->x[k];
   tm.sync();

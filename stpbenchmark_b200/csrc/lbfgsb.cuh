@@ -57,6 +57,7 @@ struct LbfgsbState {
   int brackt, stage;
   double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1;
   int phase;                      // 0 waiting for f(x0); 1 inside a line search
+  int B_ready;                    // the dense B of the current memory has been formed (possibly by the team)
   int status;
 };
 
@@ -414,7 +415,7 @@ STP_HD void lbfgsb_init(LbfgsbState& S, int np, const double* x0, const double* 
   }
   lb_reset_memory(S);
   S.iter = 0; S.nfev = 0; S.nskip = 0; S.iback = 0; S.ifun = 0; S.info = 0;
-  S.phase = 0; S.status = -1; S.f = 0.0; S.fold = 0.0; S.sbgnrm = 0.0; S.stp = 0.0;
+  S.phase = 0; S.status = -1; S.f = 0.0; S.fold = 0.0; S.sbgnrm = 0.0; S.stp = 0.0; S.B_ready = 0;
 }
 
 // Start (or restart) an iteration at the current x: Cauchy point, subspace step, direction,
@@ -423,7 +424,9 @@ STP_HD void lbfgsb_init(LbfgsbState& S, int np, const double* x0, const double* 
 STP_HD int lb_begin_iteration(LbfgsbState& S) {
   const int n = S.np;
   for (int guard = 0; guard < 4; ++guard) {
-    if (S.col > 0 && lb_build_B(S)) { lb_reset_memory(S); continue; }
+    if (S.col > 0 && !S.B_ready) return 3;      // caller forms B (lb_build_B or its team version), then re-enters
+    if (S.col > 0 && S.B_ready == 2) { lb_reset_memory(S); S.B_ready = 0; continue; }   // breakdown while forming B
+    S.B_ready = 0;
     if (S.col == 0)
       for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) S.B[i][j] = (i == j) ? S.theta : 0.0;
@@ -568,7 +571,9 @@ STP_HD int lb_advance_once(LbfgsbState& S, double f, const double* g) {
 // Feed the objective at S.x.  Returns 1 if S.x now holds a new point to evaluate, else 0.
 // scipy's ScalarFunction does not re-evaluate (or count) a point equal to the previous one;
 // neither do we.
-STP_HD int lbfgsb_advance(LbfgsbState& S, double f, const double* g) {
+// Return codes: 0 finished, 1 evaluate S.x, 3 form the dense B (S.B_ready = lb_build_B(S) ? 2 : 1, or the
+// team version) and call lbfgsb_resume(S).
+STP_HD int lbfgsb_advance_split(LbfgsbState& S, double f, const double* g) {
   double gc[kMaxP];
   for (int i = 0; i < S.np; ++i) gc[i] = g[i];
   for (;;) {
@@ -576,5 +581,59 @@ STP_HD int lbfgsb_advance(LbfgsbState& S, double f, const double* g) {
     if (r != 2) return r;
   }
 }
+STP_HD int lbfgsb_resume(LbfgsbState& S) {
+  for (;;) {
+    const int r = lb_begin_iteration(S);
+    if (r != 2) return r;
+  }
+}
+STP_HD int lbfgsb_advance(LbfgsbState& S, double f, const double* g) {
+  int r = lbfgsb_advance_split(S, f, g);
+  while (r == 3) {
+    S.B_ready = lb_build_B(S) ? 2 : 1;
+    r = lbfgsb_resume(S);
+  }
+  return r;
+}
+
+// Team version of lb_build_B: one lane per row of B (np <= 11 rows), pairs replayed with warp shuffles.
+STP_HD void lb_build_B_team(const SoloTeam&, LbfgsbState& S) { S.B_ready = lb_build_B(S) ? 2 : 1; }
+#if defined(__CUDACC__)
+__device__ __forceinline__ void lb_build_B_team(const CtaTeam& tm, LbfgsbState& S) {
+  if (tm.warp() != 0) return;
+  const int n = S.np, r = tm.lane();
+  const bool live = r < n;
+  double Brow[kMaxP];
+#pragma unroll
+  for (int c = 0; c < kMaxP; ++c) Brow[c] = (live && c == r) ? S.theta : 0.0;
+  int broke = 0;
+  for (int q = 0; q < S.col; ++q) {
+    const int p = (S.head + q) % S.m;
+    const double* s = S.ws[p];
+    const double* y = S.wy[p];
+    double Bs = 0.0;
+#pragma unroll
+    for (int c = 0; c < kMaxP; ++c)
+      if (c < n) Bs += Brow[c] * s[c];
+    const double sr = live ? s[r] : 0.0, yr = live ? y[r] : 0.0;
+    const double sBs = tm.warp_sum(sr * Bs), ys = tm.warp_sum(sr * yr);
+    if (!(sBs > 0.0) || !(ys > 0.0)) { broke = 1; break; }
+    const double ia = 1.0 / sBs, ib = 1.0 / ys;
+#pragma unroll
+    for (int c = 0; c < kMaxP; ++c)
+      if (c < n) {
+        const double Bsc = __shfl_sync(0xffffffffu, Bs, c);
+        Brow[c] += yr * y[c] * ib - Bs * Bsc * ia;
+      }
+  }
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < kMaxP; ++c)
+      if (c < n) S.B[r][c] = Brow[c];
+  }
+  __syncwarp();
+  if (r == 0) S.B_ready = broke ? 2 : 1;
+}
+#endif
 
 }  // namespace stp

@@ -37,16 +37,19 @@ STP_HD int sweep_bordered(const Team& tm, double* A, int ld, int m, int npiv, do
     if (tm.rank() == 0) piv[k] = p;
     const double invp = 1.0 / p;
     for (int i = tm.warp(); i < m; i += tm.nwarps()) {
-      const double ti = cur[i] * invp;
       double* row = A + i * ld;
-      for (int j = tm.lane(); j <= i; j += W) {
-        double a;
-        if (i == k) a = (j == k) ? -invp : cur[j] * invp;
-        else if (j == k) a = ti;
-        else a = row[j] - ti * cur[j];
-        row[j] = a;
-        if (j == k + 1) nxt[i] = a;
-        if (i == k + 1) nxt[j] = a;
+      if (i == k) {  // pivot row (warp-uniform branch): a_kj / p, and -1/p on the diagonal
+        for (int j = tm.lane(); j <= i; j += W) row[j] = (j == k) ? -invp : cur[j] * invp;
+      } else {       // generic rows, branch-free body: a_ij - a_ik a_kj / p, pivot column gets a_ik / p
+        const double ti = cur[i] * invp;
+        const bool next_row = (i == k + 1);
+        for (int j = tm.lane(); j <= i; j += W) {
+          double a = fma(-ti, cur[j], row[j]);
+          a = (j == k) ? ti : a;
+          row[j] = a;
+          if (j == k + 1) nxt[i] = a;
+          if (next_row) nxt[j] = a;
+        }
       }
     }
     tm.sync();

@@ -7,7 +7,7 @@
 
 #include "../../include/stp_b200.h"
 #include "exact_campaign.cuh"
-#include "variational.cuh"
+#include "var_campaign.cuh"
 
 using namespace stp;
 
@@ -29,7 +29,7 @@ int threads_for(int n_cap) {
   const char* env = getenv("STP_THREADS");
   if (env) {
     const int t = atoi(env);
-    if (t >= 32 && t <= 1024 && t % 32 == 0) return t;
+    if (t >= 32 && t <= 256 && t % 32 == 0) return t;
   }
   return n_cap <= 48 ? 128 : 256;
 }
@@ -70,7 +70,7 @@ __global__ void k_exact_mll_fg(int n_cap, int d, const double* __restrict__ X, c
   if (threadIdx.x < np) g[b * np + threadIdx.x] = st ? NAN : s.small[16 + threadIdx.x];
 }
 
-__global__ void k_exact_fit(int n_cap, int d, const double* __restrict__ X, const double* __restrict__ y,
+__global__ void __launch_bounds__(256, 2) k_exact_fit(int n_cap, int d, const double* __restrict__ X, const double* __restrict__ y,
                             const int32_t* __restrict__ n_arr, double* __restrict__ theta, BoundsArg bnd,
                             PriorArg prior, LbfgsbOpts opts, double* __restrict__ f_out, int32_t* __restrict__ nit,
                             int32_t* __restrict__ nfev, int32_t* __restrict__ status) {
@@ -127,7 +127,7 @@ __global__ void k_exact_acq(int n_cap, int d, int N, const double* __restrict__ 
 }
 
 // The whole loop body runners.py:64-109 for one campaign.
-__global__ void k_exact_bo_step(int n_cap, int d, int N, const double* __restrict__ pool,
+__global__ void __launch_bounds__(256, 2) k_exact_bo_step(int n_cap, int d, int N, const double* __restrict__ pool,
                                 const double* __restrict__ pool_y, const int32_t* __restrict__ pool_id,
                                 uint8_t* __restrict__ mask, double* __restrict__ X, double* __restrict__ y,
                                 int32_t* __restrict__ n_arr, int32_t* __restrict__ trace, BoundsArg bnd,
@@ -173,6 +173,120 @@ __global__ void k_exact_bo_step(int n_cap, int d, int N, const double* __restric
     n_arr[b] = n + 1;
     if (acq_out) acq_out[b] = bv;
   }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Variational models.  State arrays are batch-major: Z [B, cap, d], hyp [B, d+4], nat1 [B, cap],
+// nat2 [B, cap, cap], adam_m / adam_v [B, cap*d + d + 4]; work [B, var_work_doubles(cap)].
+// ------------------------------------------------------------------------------------------
+struct VarPtrs { double *Z, *hyp, *nat1, *nat2, *adam_m, *adam_v; };
+
+__device__ __forceinline__ VarModel var_model_of(const VarPtrs& P, int b, int cap, int d) {
+  const size_t na = (size_t)cap * d + d + 4;
+  return VarModel{P.Z + (size_t)b * cap * d, P.hyp + (size_t)b * (d + 4), P.nat1 + (size_t)b * cap,
+                  P.nat2 + (size_t)b * cap * cap, P.adam_m ? P.adam_m + b * na : nullptr,
+                  P.adam_v ? P.adam_v + b * na : nullptr};
+}
+
+__global__ void __launch_bounds__(256) k_var_fit(int n_cap, int d, const double* __restrict__ X,
+                                                 const double* __restrict__ y, const int32_t* __restrict__ n_arr,
+                                                 const double* __restrict__ init_noise, VarFitArgs args, int t0,
+                                                 VarPtrs P, double* __restrict__ loss_hist, int32_t* __restrict__ status,
+                                                 double* __restrict__ work) {
+  extern __shared__ double smem[];
+  const int b = blockIdx.x;
+  if (status[b] != 0) return;
+  const int n = n_arr ? n_arr[b] : n_cap;
+  if (n < 1 || n > n_cap) { if (threadIdx.x == 0) status[b] = 2; return; }
+  const VarSmem s = var_smem_carve(smem, n_cap, d);
+  CtaTeam tm{s.red};
+  const VarWork w = var_work_carve(work + (size_t)b * var_work_doubles(n_cap), n_cap);
+  const VarModel M = var_model_of(P, b, n_cap, d);
+  const double* Xb = X + (size_t)b * n_cap * d;
+  var_load(tm, s, n, d, Xb, y + (size_t)b * n_cap, 1);
+  if (args.fresh) var_init_state(tm, M, n, d, n_cap, Xb, init_noise ? init_noise + (size_t)b * n_cap : nullptr, args, b);
+  int st = 0;
+  for (int e = 0; e < args.epochs; ++e) {
+    const VarEpochOut r = var_epoch(tm, s, w, M, n, d, args.lik, args.prior, args.gh_x, args.gh_w, t0 + e + 1,
+                                    args.lr_ngd, args.lr_adam, 1, (double*)nullptr);
+    if (r.status) { st = r.status; break; }
+    if (loss_hist && threadIdx.x == 0) loss_hist[(size_t)b * args.epochs + e] = r.loss;
+  }
+  if (threadIdx.x == 0) status[b] = st;
+}
+
+__global__ void __launch_bounds__(256) k_var_elbo_fg(int n_cap, int d, int lik, int standardise,
+                                                     const double* __restrict__ X, const double* __restrict__ y,
+                                                     const int32_t* __restrict__ n_arr, VarFitArgs args, VarPtrs P,
+                                                     double* __restrict__ loss, double* __restrict__ grads,
+                                                     int32_t* __restrict__ status, double* __restrict__ work) {
+  extern __shared__ double smem[];
+  const int b = blockIdx.x;
+  const int n = n_arr ? n_arr[b] : n_cap;
+  const VarSmem s = var_smem_carve(smem, n_cap, d);
+  CtaTeam tm{s.red};
+  const VarWork w = var_work_carve(work + (size_t)b * var_work_doubles(n_cap), n_cap);
+  const VarModel M = var_model_of(P, b, n_cap, d);
+  var_load(tm, s, n, d, X + (size_t)b * n_cap * d, y + (size_t)b * n_cap, standardise);
+  const size_t G = (size_t)n_cap + (size_t)n_cap * n_cap + (size_t)n_cap * d + d + 4;
+  const VarEpochOut r = var_epoch(tm, s, w, M, n, d, lik, args.prior, args.gh_x, args.gh_w, 1, 0.0, 0.0, 0,
+                                  grads + (size_t)b * G);
+  if (threadIdx.x == 0) { loss[b] = r.loss; status[b] = r.status; }
+}
+
+__global__ void __launch_bounds__(256) k_var_acq(int n_cap, int d, int N, int lik, const double* __restrict__ pool,
+                                                 const int32_t* __restrict__ pool_id, uint8_t* __restrict__ mask,
+                                                 VarPtrs P, int32_t* __restrict__ n_arr, const double* __restrict__ best_f,
+                                                 int S, const double* __restrict__ eps, unsigned long long seed,
+                                                 int32_t* __restrict__ out_idx, double* __restrict__ out_acq,
+                                                 double* __restrict__ mean, double* __restrict__ var,
+                                                 double* __restrict__ acq, int update, const double* __restrict__ pool_y,
+                                                 double* __restrict__ X, double* __restrict__ y, int32_t* __restrict__ trace,
+                                                 int32_t* __restrict__ status, double* __restrict__ work) {
+  extern __shared__ double smem[];
+  const int b = blockIdx.x;
+  if (status[b] != 0) { if (threadIdx.x == 0 && out_idx) out_idx[b] = -1; return; }
+  const int n = n_arr ? n_arr[b] : n_cap;
+  if (n < 1 || n > n_cap || (update && n >= n_cap)) { if (threadIdx.x == 0) status[b] = 2; return; }
+  const int nw = blockDim.x >> 5;
+  const VarSmem s = var_smem_carve(smem, n_cap, d);
+  double* tile = smem + var_smem_doubles(n_cap, d);
+  double* part = tile + (size_t)n_cap * kTC + (size_t)kMaxD * kTC;
+  CtaTeam tm{s.red};
+  const VarWork w = var_work_carve(work + (size_t)b * var_work_doubles(n_cap), n_cap);
+  const VarModel M = var_model_of(P, b, n_cap, d);
+  const int st = var_prepare(tm, s, w, M, n, d);
+  if (st) { if (threadIdx.x == 0) { status[b] = st; if (out_idx) out_idx[b] = -1; if (out_acq) out_acq[b] = NAN; } return; }
+  double best;
+  if (best_f) best = best_f[b];
+  else {                                             // best_f = y_train.max(), RAW (runners.py:89, App. D-2)
+    best = -INFINITY;
+    for (int i = 0; i < n; ++i) best = fmax(best, y[(size_t)b * n_cap + i]);
+  }
+  const int pid = pool_id ? pool_id[b] : 0;
+  const double* Pl = pool + (size_t)pid * N * d;
+  uint8_t* mb = mask ? mask + (size_t)b * N : nullptr;
+  int bi; double bv;
+  var_acquire(tm, s, w, n, d, lik, tile, part, Pl, N, mb, best, S, eps ? eps + (size_t)b * N * S : nullptr, seed,
+              (unsigned long long)b, &bi, &bv, mean ? mean + (size_t)b * N : nullptr,
+              var ? var + (size_t)b * N : nullptr, acq ? acq + (size_t)b * N : nullptr);
+  if (threadIdx.x == 0) { if (out_idx) out_idx[b] = bi; if (out_acq) out_acq[b] = bv; }
+  if (!update) return;
+  if (bi < 0) { if (threadIdx.x == 0) status[b] = 2; return; }
+  if (threadIdx.x < d) X[((size_t)b * n_cap + n) * d + threadIdx.x] = Pl[(size_t)bi * d + threadIdx.x];
+  if (threadIdx.x == 0) {
+    y[(size_t)b * n_cap + n] = pool_y[(size_t)pid * N + bi];
+    trace[(size_t)b * n_cap + n] = bi;
+    mb[bi] = 0;
+    n_arr[b] = n + 1;
+  }
+}
+
+__global__ void k_philox_normal(unsigned long long seed, unsigned long long stream, unsigned long long counter0,
+                                long long pairs, double* __restrict__ out) {
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < pairs; q += (long long)gridDim.x * blockDim.x)
+    philox_normal2(seed, stream, counter0 + q, out[2 * q], out[2 * q + 1]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -312,6 +426,93 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
                                                               bnd, p, to_opts(opts), theta_out, acq_out, nit, nfev,
                                                               status);
   return after_launch("stp_exact_bo_step");
+}
+
+
+static int fill_var_args(VarFitArgs& a, int d, int lik, int epochs, int fresh, double lr_ngd, double lr_adam,
+                         const double* hyp0, const double* prior, const double* gh, unsigned long long seed) {
+  if (lik < 0 || lik > 2) return fail("lik must be 0 (gaussian), 1 (student-t) or 2 (laplace)");
+  if (!prior || !gh) return fail("null prior / gauss-hermite table");
+  a.lik = lik; a.epochs = epochs; a.fresh = fresh; a.lr_ngd = lr_ngd; a.lr_adam = lr_adam; a.seed = seed;
+  for (int k = 0; k < kMaxD + 4; ++k) a.hyp0[k] = (hyp0 && k < d + 4) ? hyp0[k] : 0.0;
+  a.prior = VarHyperPrior{prior[0], prior[1], prior[2], prior[3], prior[4], prior[5], prior[6], prior[7]};
+  for (int q = 0; q < kGH; ++q) { a.gh_x[q] = gh[q]; a.gh_w[q] = gh[kGH + q]; }
+  return 0;
+}
+
+size_t stp_var_workspace_bytes(int B, int n_cap) {
+  if (B < 0 || n_cap < 1) return 0;
+  return (size_t)B * var_work_doubles(n_cap) * sizeof(double);
+}
+
+int stp_var_fit(int B, int n_cap, int d, int lik, int epochs, double lr_ngd, double lr_adam, int fresh, int t0,
+                const double* X, const double* y, const int32_t* n, const double* init_noise, unsigned long long seed,
+                const double* hyp0, const double* prior, const double* gh, double* Z, double* hyp, double* nat1,
+                double* nat2, double* adam_m, double* adam_v, double* loss_hist, int32_t* status, double* work,
+                void* stream) {
+  if (check_dims(B, n_cap, d)) return -1;
+  if (epochs < 0) return fail("epochs < 0");
+  if (!X || !y || !Z || !hyp || !nat1 || !nat2 || !adam_m || !adam_v || !status || !work) return fail("null argument");
+  if (fresh && !hyp0) return fail("fresh model needs hyp0");
+  if (B == 0) return 0;
+  VarFitArgs a;
+  if (fill_var_args(a, d, lik, epochs, fresh, lr_ngd, lr_adam, hyp0, prior, gh, seed)) return -1;
+  const size_t smem = var_smem_doubles(n_cap, d) * sizeof(double);
+  if (set_smem(k_var_fit, smem)) return -1;
+  k_var_fit<<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, init_noise, a, t0,
+                                                    VarPtrs{Z, hyp, nat1, nat2, adam_m, adam_v}, loss_hist, status, work);
+  return after_launch("stp_var_fit");
+}
+
+int stp_var_elbo_fg(int B, int n_cap, int d, int lik, int standardise, const double* X, const double* y,
+                    const int32_t* n, const double* Z, const double* hyp, const double* nat1, const double* nat2,
+                    const double* prior, const double* gh, double* loss, double* grads, int32_t* status, double* work,
+                    void* stream) {
+  if (check_dims(B, n_cap, d)) return -1;
+  if (!X || !y || !Z || !hyp || !nat1 || !nat2 || !loss || !grads || !status || !work) return fail("null argument");
+  if (B == 0) return 0;
+  VarFitArgs a;
+  if (fill_var_args(a, d, lik, 1, 0, 0.0, 0.0, nullptr, prior, gh, 0)) return -1;
+  const size_t smem = var_smem_doubles(n_cap, d) * sizeof(double);
+  if (set_smem(k_var_elbo_fg, smem)) return -1;
+  k_var_elbo_fg<<<B, 256, smem, (cudaStream_t)stream>>>(
+      n_cap, d, lik, standardise, X, y, n, a,
+      VarPtrs{const_cast<double*>(Z), const_cast<double*>(hyp), const_cast<double*>(nat1), const_cast<double*>(nat2),
+              nullptr, nullptr},
+      loss, grads, status, work);
+  return after_launch("stp_var_elbo_fg");
+}
+
+int stp_var_acq(int B, int n_cap, int d, int N, int lik, const double* pool, const int32_t* pool_id, uint8_t* mask,
+                const double* Z, const double* hyp, const double* nat1, const double* nat2, int32_t* n,
+                const double* best_f, int S, const double* eps, unsigned long long seed, int32_t* out_idx,
+                double* out_acq, double* mean, double* var, double* acq, int update, const double* pool_y, double* X,
+                double* y, int32_t* trace, int32_t* status, double* work, void* stream) {
+  if (check_dims(B, n_cap, d)) return -1;
+  if (N < 0 || S < 1) return fail("N < 0 or S < 1");
+  if (lik < 0 || lik > 2) return fail("lik must be 0, 1 or 2");
+  if (!pool || !Z || !hyp || !nat1 || !nat2 || !status || !work) return fail("null argument");
+  if (update && (!pool_y || !X || !y || !trace || !mask || !n)) return fail("update needs pool_y, X, y, n, trace and mask");
+  if (!best_f && !y) return fail("best_f or y required");
+  if (B == 0) return 0;
+  const size_t smem = (var_smem_doubles(n_cap, d) + (size_t)n_cap * kTC + (size_t)kMaxD * kTC + 8 * kTC * 3) * sizeof(double);
+  if (set_smem(k_var_acq, smem)) return -1;
+  k_var_acq<<<B, 256, smem, (cudaStream_t)stream>>>(
+      n_cap, d, N, lik, pool, pool_id, mask,
+      VarPtrs{const_cast<double*>(Z), const_cast<double*>(hyp), const_cast<double*>(nat1), const_cast<double*>(nat2),
+              nullptr, nullptr},
+      n, best_f, S, eps, seed, out_idx, out_acq, mean, var, acq, update, pool_y, X, y, trace, status, work);
+  return after_launch("stp_var_acq");
+}
+
+int stp_philox_normal(unsigned long long seed, unsigned long long stream_id, unsigned long long counter0,
+                      long long pairs, double* out, void* stream) {
+  if (pairs < 0 || !out) return fail("bad argument");
+  if (pairs == 0) return 0;
+  long long blocks = (pairs + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_philox_normal<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(seed, stream_id, counter0, pairs, out);
+  return after_launch("stp_philox_normal");
 }
 
 int stp_log_ei(long long count, const double* mean, const double* var, double best_f, double* out, void* stream) {

@@ -1,3 +1,804 @@
-// placeholder: variational (SVGP) campaign routines -- filled in below
+// Whitened SVGP (VarGP / VarTGP / VarLGP) pieces of the BO hot path, one campaign per team:
+//   var_epoch     K7+K8+K9  one pass of the loop body optim.py:150-170: ELBO forward, the
+//                           hand-derived backward, the natural-gradient
+//                           step on (theta1, Theta2) and the Adam step on (Z, c, l, os, noise[, rho])
+//   var_prepare   K3+K4     Linv_K, G = L_P^-1 Linv_K, w = Linv_K^T mu for the pool pass
+//   var_acquire   K2+K10-13 fused cross-covariance, q(f) mean / variance at every pool point,
+//                           analytic LogEI (VarGP) or the S-sample Monte-Carlo mean of LogEI
+//                           (VarTGP / VarLGP, models.py:95-111 / 280-297 + runners.py:88-93)
+//                           and the first-index argmax.
+//
+// Layout.  All n x n work matrices are ROW-PER-DATA-POINT ("t" = transposed w.r.t. the maths of
+// App. A.4): At[c][k] = A[k][c] etc., so that every O(n^3) contraction reads one operand as a
+// warp-wide broadcast and the other as consecutive doubles.  They live in a per-campaign
+// workspace in global memory (L1/L2-resident: 6 squares of (cap+1) x ld doubles); vectors and the
+// transposed point sets live in shared memory.
 #pragma once
 #include "exact.cuh"
+#include "linalg.cuh"
+#include "logei.cuh"
+#include "team.cuh"
+
+namespace stp {
+
+enum { kLikGaussian = 0, kLikStudentT = 1, kLikLaplace = 2 };
+constexpr int kGH = 20;
+constexpr double kVarJitter = 1e-6;  // gpytorch's variational Cholesky jitter in fp64
+
+struct VarHyperPrior {   // LogNormal on lengthscale / outputscale / noise, Gamma(conc, rate) on nu
+  double ls_loc, ls_scale, os_loc, os_scale, noise_loc, noise_scale, df_conc, df_rate;
+};
+
+// digamma for x > 0: upward recurrence to x >= 10, then the asymptotic series (|err| < 1e-15).
+STP_HD double digamma_pos(double x) {
+  double r = 0.0;
+  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  const double f = 1.0 / (x * x);
+  const double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 + f * (-1.0 / 132.0 +
+                   f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
+  return r + log(x) - 0.5 / x + t;
+}
+
+STP_HD double softplus(double x) { return x > 30.0 ? x : log1p(exp(x)); }
+STP_HD double sigmoid(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+// ---- Philox4x32-10 counter-based generator -> standard normals (Box-Muller, fp64) ----------
+STP_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                          uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Two independent N(0,1) draws for (seed, stream, counter): stream = campaign, counter = (candidate, pair).
+STP_HD void philox_normal2(uint64_t seed, uint64_t stream, uint64_t counter, double& z0, double& z1) {
+  uint32_t o[4];
+  philox4x32_10((uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)stream, (uint32_t)(stream >> 32),
+                (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  const double u0 = (((uint64_t)o[0] << 21) ^ (uint64_t)(o[1] >> 11)) * (1.0 / 9007199254740992.0);  // [0,1)
+  const double u1 = (((uint64_t)o[2] << 21) ^ (uint64_t)(o[3] >> 11)) * (1.0 / 9007199254740992.0);
+  const double rad = sqrt(-2.0 * log(1.0 - u0));   // 1 - u0 in (0, 1]
+  const double ang = 6.283185307179586476925 * u1;
+  z0 = rad * cos(ang);
+  z1 = rad * sin(ang);
+}
+
+// ------------------------------------------------------------------------------------------
+// State of one variational campaign (pointers into global memory, caller-owned).
+// Adam moments are laid out like the parameters: [Z (n*d, row-major, stride d) | c | ls (d) | os | noise | rho].
+// ------------------------------------------------------------------------------------------
+struct VarModel {
+  double* Z;      // [cap, d]
+  double* hyp;    // [d + 4]: c, ls_0..d-1, os, noise, rho (rho unused unless Student-T)
+  double* nat1;   // [cap]
+  double* nat2;   // [cap, cap] row-major, stride cap
+  double* adam_m; // [cap*d + d + 4]
+  double* adam_v; // [cap*d + d + 4]
+};
+
+struct VarSmem {
+  double* Xt;    // d x cap   training inputs (transposed)
+  double* Zt;    // d x cap   inducing inputs (transposed), refreshed every epoch
+  double* ys;    // cap       standardised targets
+  double* mu;    // cap+1
+  double* c0;    // cap+1
+  double* c1;    // cap+1
+  double* piv;   // cap+1
+  double* fm;    // cap       q(f) mean at the training points
+  double* fv;    // cap       q(f) variance
+  double* dm;    // cap
+  double* dv;    // cap
+  double* gmu;   // cap
+  double* gsm;   // cap       G_S mu
+  double* gZ;    // cap x d   gradient w.r.t. Z (row-major)
+  double* small; // 96
+  double* red;   // 16 * kMaxWarps
+  int cap, ld;
+};
+
+STP_HD size_t var_smem_doubles(int cap, int d) {
+  return (size_t)2 * d * cap + (size_t)cap * 8 + 4 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
+}
+
+STP_HD VarSmem var_smem_carve(double* base, int cap, int d) {
+  VarSmem s;
+  s.cap = cap; s.ld = odd_ld(cap + 1);
+  double* p = base;
+  s.Xt = p; p += (size_t)d * cap;
+  s.Zt = p; p += (size_t)d * cap;
+  s.ys = p; p += cap;
+  s.mu = p; p += cap + 1;
+  s.c0 = p; p += cap + 1;
+  s.c1 = p; p += cap + 1;
+  s.piv = p; p += cap + 1;
+  s.fm = p; p += cap;
+  s.fv = p; p += cap;
+  s.dm = p; p += cap;
+  s.dv = p; p += cap;
+  s.gmu = p; p += cap;
+  s.gsm = p; p += cap;
+  s.gZ = p; p += (size_t)cap * d;
+  s.small = p; p += 96;
+  s.red = p;
+  return s;
+}
+
+// Per-campaign global workspace: 6 squares of (cap+1) rows x ld doubles.
+STP_HD size_t var_work_doubles(int cap) { return (size_t)6 * (cap + 1) * odd_ld(cap + 1); }
+
+struct VarWork {
+  double* R[6];
+  int ld;
+};
+STP_HD VarWork var_work_carve(double* base, int cap) {
+  VarWork w;
+  w.ld = odd_ld(cap + 1);
+  for (int q = 0; q < 6; ++q) w.R[q] = base + (size_t)q * (cap + 1) * w.ld;
+  return w;
+}
+
+// Cholesky factor kept in the lower triangle, inverse written MIRRORED into `Linv` (full square:
+// Linv[i][j] = Linv[j][i] = (L^-1)_{max,min}) so that both L^-1 and L^-T rows are contiguous.
+template <class Team>
+STP_HD void tri_inverse_mirrored(const Team& tm, const double* L, double* Linv, int ld, int n, double* tmp) {
+  for (int j = n - 1; j >= 0; --j) {
+    const double invd = 1.0 / L[j * ld + j];
+    for (int i = j + 1 + tm.rank(); i < n; i += tm.size()) {
+      const double* row = Linv + i * ld;
+      double s0 = 0.0, s1 = 0.0;
+      int k = j + 1;
+      for (; k + 1 <= i; k += 2) {
+        s0 += row[k] * L[k * ld + j];
+        s1 += row[k + 1] * L[(k + 1) * ld + j];
+      }
+      if (k <= i) s0 += row[k] * L[k * ld + j];
+      tmp[i] = -(s0 + s1) * invd;
+    }
+    tm.sync();
+    for (int i = j + tm.rank(); i < n; i += tm.size()) {
+      const double v = (i == j) ? invd : tmp[i];
+      Linv[i * ld + j] = v;
+      Linv[j * ld + i] = v;
+    }
+    tm.sync();
+  }
+}
+
+// log p(y | f) and its derivatives for one quadrature node.
+struct LikConst {   // per-epoch constants of the likelihood
+  int lik;
+  double noise, nu, lg_const;   // lg_const: lgamma((nu+1)/2) - lgamma(nu/2) - 0.5 log(nu pi) - 0.5 log noise
+  double dnu_const;             // 0.5 psi((nu+1)/2) - 0.5 psi(nu/2) - 1/(2 nu)
+};
+
+STP_HD void lik_node(const LikConst& L, double r, double& lp, double& dlf, double& dln, double& dlnu) {
+  if (L.lik == kLikStudentT) {
+    const double r2 = r * r;
+    const double den = L.nu * L.noise + r2;
+    const double z2n = r2 / (L.noise * L.nu);
+    lp = L.lg_const - 0.5 * (L.nu + 1.0) * log1p(z2n);
+    dlf = (L.nu + 1.0) * r / den;
+    dln = -0.5 / L.noise + (L.nu + 1.0) * r2 / (2.0 * L.noise * den);
+    dlnu = L.dnu_const - 0.5 * log1p(z2n) + 0.5 * (L.nu + 1.0) * (z2n / L.nu) / (1.0 + z2n);
+  } else {  // Laplace, b = sqrt(noise)
+    const double b = sqrt(L.noise);
+    const double a = fabs(r);
+    lp = -log(2.0 * b) - a / b;
+    dlf = (r > 0.0 ? 1.0 : (r < 0.0 ? -1.0 : 0.0)) / b;
+    dln = -0.5 / L.noise + a / (2.0 * L.noise * b);
+    dlnu = 0.0;
+  }
+}
+
+struct VarEpochOut {
+  double loss;
+  int status;   // 0 ok, 1 not PD (P or K_ZZ), 2 non-finite
+};
+
+// ------------------------------------------------------------------------------------------
+// One training epoch.  gh_x / gh_w: the 20 Gauss-Hermite nodes / weights (fp32-rounded, App. D-9).
+// `t` is the 1-based Adam step.  lr_ngd is the reference's `lr` argument (scaled by n inside, App.
+// D-10); lr_adam is the hard-coded 0.01 of optim.py:140.  If `apply` is 0 the parameters are left
+// untouched and the raw gradients are exported through `dbg` (tests): layout
+// [g_nat1 (cap) | g_nat2 (cap*cap) | gZ (cap*d) | g_c | g_ls (d) | g_os | g_noise | g_rho].
+// ------------------------------------------------------------------------------------------
+template <class Team>
+STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w, const VarModel& M, int n, int d,
+                             int lik, const VarHyperPrior& pr, const double* gh_x, const double* gh_w, int t,
+                             double lr_ngd, double lr_adam, int apply, double* dbg) {
+  const int ld = w.ld, cap = s.cap, W = tm.warp_width(), nw = tm.nwarps();
+  VarEpochOut out; out.loss = NAN; out.status = 0;
+  double* S = w.R[0];    // P -> -S (lower, bordered) -> full S ; later G_S ; later Cbar_t
+  double* LK = w.R[1];   // L_K (lower)
+  double* LI = w.R[2];   // Linv_K mirrored (full)
+  double* Ct = w.R[3];   // Ct[c][j] = k(x_c, z_j)
+  double* At = w.R[4];   // At[c][k] ; later Phi ; later Kbar'
+  double* Dt = w.R[5];   // Tt -> Dt -> Abar_t ; later Lbar ; later U
+  double* hyp = s.small;          // c, ls[d], os, noise, rho  (d + 4)
+  double* invl = s.small + 16;    // d
+  double* ghyp = s.small + 32;    // gradient of hyp (d + 4)
+  const int nh = d + 4;
+  tm.sync();
+  for (int k = tm.rank(); k < nh; k += tm.size()) hyp[k] = M.hyp[k];
+  for (int idx = tm.rank(); idx < n * d; idx += tm.size()) {
+    const int i = idx / d, k = idx - i * d;
+    s.Zt[k * cap + i] = M.Z[idx];
+  }
+  tm.sync();
+  const double cst = hyp[0], os = hyp[1 + d], noise = hyp[2 + d], rho = hyp[3 + d];
+  for (int k = tm.rank(); k < d; k += tm.size()) invl[k] = 1.0 / hyp[1 + k];
+  int bad = !(os == os) || !(noise == noise) || !(cst == cst);
+  for (int k = 0; k < d; ++k) bad |= !(hyp[1 + k] == hyp[1 + k]) || hyp[1 + k] == 0.0;
+  if (bad) { out.status = 2; return out; }
+  tm.sync();
+
+  // (1) P = -2 Theta2, bordered with theta1; sweep -> -S, mu = S theta1, pivots
+  for (int i = tm.warp(); i <= n; i += nw) {
+    double* row = S + i * ld;
+    if (i < n) for (int j = tm.lane(); j <= i; j += W) row[j] = -2.0 * M.nat2[(size_t)i * cap + j];
+    else for (int j = tm.lane(); j <= n; j += W) row[j] = (j < n) ? M.nat1[j] : 0.0;
+  }
+  tm.sync();
+  if (sweep_bordered(tm, S, ld, n + 1, n, s.c0, s.c1, s.piv)) { out.status = 1; return out; }
+  double kl_acc[4] = {0.0, 0.0, 0.0, 0.0};   // sum log piv(P), tr S, mu.mu
+  for (int i = tm.rank(); i < n; i += tm.size()) {
+    const double m = S[n * ld + i];
+    s.mu[i] = m;
+    kl_acc[0] += log(s.piv[i]);
+    kl_acc[1] += -S[i * ld + i];
+    kl_acc[2] += m * m;
+  }
+  tm.sum_vec(kl_acc, 3);
+  // full symmetric S = -(swept)
+  for (int i = tm.warp(); i < n; i += nw)
+    for (int j = tm.lane(); j <= i; j += W) {
+      const double v = -S[i * ld + j];
+      S[i * ld + j] = v;
+      S[j * ld + i] = v;
+    }
+  // (2) K_ZZ + jitter -> L_K ; Linv mirrored ; Ct
+  for (int i = tm.warp(); i < n; i += nw) {
+    double* row = LK + i * ld;
+    for (int j = tm.lane(); j <= i; j += W)
+      row[j] = (j == i) ? os + kVarJitter : ard_rbf_tt(s.Zt, cap, d, invl, i, j, os);
+  }
+  for (int c = tm.warp(); c < n; c += nw) {
+    double* row = Ct + c * ld;
+    for (int j = tm.lane(); j < n; j += W) {
+      double r2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < kMaxD; ++k)
+        if (k < d) {
+          const double tt = (s.Xt[k * cap + c] - s.Zt[k * cap + j]) * invl[k];
+          r2 += tt * tt;
+        }
+      row[j] = os * exp(-0.5 * r2);
+    }
+  }
+  if (cholesky_lower(tm, LK, ld, n, s.c0)) { out.status = 1; return out; }
+  tri_inverse_mirrored(tm, LK, LI, ld, n, s.c0);
+  // (3) At[c][k] = sum_{j<=k} Ct[c][j] Linv[k][j]   (row k of the mirrored inverse, columns j <= k)
+  for (int c = tm.warp(); c < n; c += nw) {
+    const double* crow = Ct + c * ld;
+    double* arow = At + c * ld;
+    for (int k = tm.lane(); k < n; k += W) {
+      double a0 = 0.0, a1 = 0.0;
+      int j = 0;
+      for (; j + 1 <= k; j += 2) {
+        a0 += crow[j] * LI[j * ld + k];
+        a1 += crow[j + 1] * LI[(j + 1) * ld + k];
+      }
+      if (j <= k) a0 += crow[j] * LI[j * ld + k];
+      arow[k] = a0 + a1;
+    }
+  }
+  tm.sync();
+  // (4) Tt = At S ; Dt = Tt - At ; q(f): m_c = cst + At[c].mu ; v_c = os + jitter + At[c].Dt[c]
+  for (int c = tm.warp(); c < n; c += nw) {
+    const double* arow = At + c * ld;
+    double* drow = Dt + c * ld;
+    double pm = 0.0, pv = 0.0;
+    for (int k = tm.lane(); k < n; k += W) {
+      double t0 = 0.0, t1 = 0.0;
+      int r = 0;
+      for (; r + 1 < n; r += 2) {
+        t0 += arow[r] * S[r * ld + k];
+        t1 += arow[r + 1] * S[(r + 1) * ld + k];
+      }
+      if (r < n) t0 += arow[r] * S[r * ld + k];
+      const double a = arow[k];
+      const double dd = (t0 + t1) - a;
+      drow[k] = dd;
+      pm += a * s.mu[k];
+      pv += a * dd;
+    }
+    pm = tm.warp_sum(pm);
+    pv = tm.warp_sum(pv);
+    if (tm.lane() == 0) { s.fm[c] = cst + pm; s.fv[c] = os + kVarJitter + pv; }
+  }
+  tm.sync();
+  // (5) expected log-likelihood and its derivatives per training point
+  LikConst LC; LC.lik = lik; LC.noise = noise; LC.nu = 0.0; LC.lg_const = 0.0; LC.dnu_const = 0.0;
+  double nu = 0.0;
+  if (lik == kLikStudentT) {
+    nu = 2.0 + softplus(rho);
+    LC.nu = nu;
+    LC.lg_const = lgamma(0.5 * (nu + 1.0)) - lgamma(0.5 * nu) - 0.5 * log(nu * 3.14159265358979323846) - 0.5 * log(noise);
+    LC.dnu_const = 0.5 * digamma_pos(0.5 * (nu + 1.0)) - 0.5 * digamma_pos(0.5 * nu) - 0.5 / nu;
+  }
+  const double inv_n = 1.0 / n;
+  double lk_acc[4] = {0.0, 0.0, 0.0, 0.0};   // ell, d ell / d noise, d ell / d nu, sum dv
+  for (int i = tm.rank(); i < n; i += tm.size()) {
+    const double m = s.fm[i], v = s.fv[i], yy = s.ys[i];
+    double ell, dm_, dv_, dn_ = 0.0, dnu_ = 0.0;
+    if (lik == kLikGaussian) {
+      const double r = yy - m;
+      ell = -0.5 * ((r * r + v) / noise + log(noise) + kLog2Pi);
+      dm_ = r / noise;
+      dv_ = -0.5 / noise;
+      dn_ = 0.5 * ((r * r + v) / (noise * noise) - 1.0 / noise);
+    } else {
+      const double sq = sqrt(2.0 * v);
+      const double kInvSqrtPi = 0.56418958354775628695;
+      ell = 0.0; dm_ = 0.0; dv_ = 0.0;
+      for (int q = 0; q < kGH; ++q) {
+        const double f = sq * gh_x[q] + m;
+        double lp, dlf, dln, dlnu;
+        lik_node(LC, yy - f, lp, dlf, dln, dlnu);
+        const double wq = kInvSqrtPi * gh_w[q];
+        ell += wq * lp;
+        dm_ += wq * dlf;
+        dv_ += wq * dlf * gh_x[q];
+        dn_ += wq * dln;
+        dnu_ += wq * dlnu;
+      }
+      dv_ /= sq;
+    }
+    s.dm[i] = -inv_n * dm_;
+    s.dv[i] = -inv_n * dv_;
+    lk_acc[0] += ell; lk_acc[1] += dn_; lk_acc[2] += dnu_; lk_acc[3] += -inv_n * dv_;
+  }
+  tm.sum_vec(lk_acc, 4);
+  // loss
+  const double logdetS = -kl_acc[0];
+  const double kl = 0.5 * (-logdetS + kl_acc[1] + kl_acc[2] - n);
+  double lprior = lognormal_logpdf(os, pr.os_loc, pr.os_scale) + lognormal_logpdf(noise, pr.noise_loc, pr.noise_scale);
+  for (int k = 0; k < d; ++k) lprior += lognormal_logpdf(hyp[1 + k], pr.ls_loc, pr.ls_scale);
+  if (lik == kLikStudentT)
+    lprior += pr.df_conc * log(pr.df_rate) + (pr.df_conc - 1.0) * log(nu) - pr.df_rate * nu - lgamma(pr.df_conc);
+  out.loss = -(lk_acc[0] - kl + lprior) * inv_n;
+  if (!(out.loss == out.loss) || !(fabs(out.loss) <= 1.79e308)) { out.status = 2; return out; }
+
+  // (6) variational gradients: g_mu = A dm + mu/n ; G_S = A diag(dv) A^T + (I - P)/(2n)  (into R0)
+  for (int k = tm.rank(); k < n; k += tm.size()) {
+    double a = 0.0;
+    for (int c = 0; c < n; ++c) a += At[c * ld + k] * s.dm[c];
+    s.gmu[k] = a + s.mu[k] * inv_n;
+  }
+  double* GS = S;
+  tm.sync();   // every reader of S (step 4) is done
+  for (int i = tm.warp(); i < n; i += nw) {
+    for (int k = tm.lane(); k <= i; k += W) {
+      double g0 = 0.0, g1 = 0.0;
+      int c = 0;
+      for (; c + 1 < n; c += 2) {
+        g0 += At[c * ld + i] * s.dv[c] * At[c * ld + k];
+        g1 += At[(c + 1) * ld + i] * s.dv[c + 1] * At[(c + 1) * ld + k];
+      }
+      if (c < n) g0 += At[c * ld + i] * s.dv[c] * At[c * ld + k];
+      const double P = -2.0 * M.nat2[(size_t)i * cap + k];
+      const double g = (g0 + g1) + ((i == k ? 1.0 : 0.0) - P) * (0.5 * inv_n);
+      GS[i * ld + k] = g;
+      GS[k * ld + i] = g;
+    }
+  }
+  tm.sync();
+  for (int i = tm.warp(); i < n; i += nw) {
+    double a = 0.0;
+    for (int k = tm.lane(); k < n; k += W) a += GS[i * ld + k] * s.mu[k];
+    a = tm.warp_sum(a);
+    if (tm.lane() == 0) s.gsm[i] = a;
+  }
+  tm.sync();
+  if (dbg) {
+    for (int i = tm.rank(); i < n; i += tm.size()) dbg[i] = s.gmu[i] - 2.0 * s.gsm[i];
+    for (int idx = tm.rank(); idx < n * n; idx += tm.size()) {
+      const int i = idx / n, k = idx - i * n;
+      dbg[cap + (size_t)i * cap + k] = GS[i * ld + k];
+    }
+  }
+  if (apply) {
+    // natural-gradient step (optim.py:132-134, 169): theta <- theta - lr * n * grad
+    const double step = lr_ngd * n;
+    for (int i = tm.rank(); i < n; i += tm.size()) M.nat1[i] -= step * (s.gmu[i] - 2.0 * s.gsm[i]);
+    for (int i = tm.warp(); i < n; i += nw)
+      for (int k = tm.lane(); k < n; k += W) M.nat2[(size_t)i * cap + k] -= step * GS[i * ld + k];
+  }
+  tm.sync();
+  // (7) Abar_t[c][k] = mu_k dm_c + 2 Dt[c][k] dv_c   (in place over Dt)
+  for (int c = tm.warp(); c < n; c += nw) {
+    double* drow = Dt + c * ld;
+    const double dmc = s.dm[c], dvc2 = 2.0 * s.dv[c];
+    for (int k = tm.lane(); k < n; k += W) drow[k] = s.mu[k] * dmc + drow[k] * dvc2;
+  }
+  tm.sync();
+  // (8) Cbar_t[c][j] = sum_{i>=j} Abar_t[c][i] Linv[i][j]   (into R0)
+  double* CBt = S;
+  for (int c = tm.warp(); c < n; c += nw) {
+    const double* arow = Dt + c * ld;
+    double* crow = CBt + c * ld;
+    for (int j = tm.lane(); j < n; j += W) {
+      double a0 = 0.0, a1 = 0.0;
+      int i = j;
+      for (; i + 1 < n; i += 2) {
+        a0 += arow[i] * LI[i * ld + j];
+        a1 += arow[i + 1] * LI[(i + 1) * ld + j];
+      }
+      if (i < n) a0 += arow[i] * LI[i * ld + j];
+      crow[j] = a0 + a1;
+    }
+  }
+  tm.sync();
+  // (9) Lbar[i][k] = -sum_c Cbar_t[c][i] At[c][k], i >= k   (into R5, Abar_t is dead)
+  double* LB = Dt;
+  for (int i = tm.warp(); i < n; i += nw) {
+    double* lrow = LB + i * ld;
+    for (int k = tm.lane(); k <= i; k += W) {
+      double a0 = 0.0, a1 = 0.0;
+      int c = 0;
+      for (; c + 1 < n; c += 2) {
+        a0 += CBt[c * ld + i] * At[c * ld + k];
+        a1 += CBt[(c + 1) * ld + i] * At[(c + 1) * ld + k];
+      }
+      if (c < n) a0 += CBt[c * ld + i] * At[c * ld + k];
+      lrow[k] = -(a0 + a1);
+    }
+  }
+  tm.sync();
+  // (10) Phi[i][k] = sum_{r>=i} L[r][i] Lbar[r][k], i >= k, diagonal halved   (into R4, At is dead)
+  double* PH = At;
+  for (int i = tm.warp(); i < n; i += nw) {
+    double* prow = PH + i * ld;
+    for (int k = tm.lane(); k <= i; k += W) {
+      double a0 = 0.0, a1 = 0.0;
+      int r = i;
+      for (; r + 1 < n; r += 2) {
+        a0 += LK[r * ld + i] * LB[r * ld + k];
+        a1 += LK[(r + 1) * ld + i] * LB[(r + 1) * ld + k];
+      }
+      if (r < n) a0 += LK[r * ld + i] * LB[r * ld + k];
+      prow[k] = (i == k) ? 0.5 * (a0 + a1) : (a0 + a1);
+    }
+  }
+  tm.sync();
+  // (11) U[i][k] = sum_{k<=r<=i} Phi[i][r] Linv[r][k]   (into R5, Lbar is dead)
+  double* U = Dt;
+  for (int i = tm.warp(); i < n; i += nw) {
+    const double* prow = PH + i * ld;
+    double* urow = U + i * ld;
+    for (int k = tm.lane(); k <= i; k += W) {
+      double a0 = 0.0, a1 = 0.0;
+      int r = k;
+      for (; r + 1 <= i; r += 2) {
+        a0 += prow[r] * LI[r * ld + k];
+        a1 += prow[r + 1] * LI[(r + 1) * ld + k];
+      }
+      if (r <= i) a0 += prow[r] * LI[r * ld + k];
+      urow[k] = a0 + a1;
+    }
+  }
+  tm.sync();
+  // (12) Kbar'[j][k] = sum_{i>=max(j,k)} Linv[i][j] U[i][k]   (into R4, Phi is dead)
+  double* KB = At;
+  for (int j = tm.warp(); j < n; j += nw) {
+    double* krow = KB + j * ld;
+    for (int k = tm.lane(); k < n; k += W) {
+      double a0 = 0.0;
+      for (int i = (j > k ? j : k); i < n; ++i) a0 += LI[j * ld + i] * U[i * ld + k];
+      krow[k] = a0;
+    }
+  }
+  tm.sync();
+  // (13) kernel-parameter gradients.  Kbar = sym(Kbar'); K0 and C are re-evaluated on the fly.
+  double acc[kMaxD + 4];
+#pragma unroll
+  for (int q = 0; q < kMaxD + 4; ++q) acc[q] = 0.0;   // acc[0]: sum (Kbar.K0 + Cbar.C); acc[1+k]: lengthscale sums
+  for (int idx = tm.rank(); idx < n * d; idx += tm.size()) s.gZ[idx] = 0.0;
+  tm.sync();
+  for (int i = tm.warp(); i < n; i += nw) {
+    double gz[kMaxD];
+#pragma unroll
+    for (int k = 0; k < kMaxD; ++k) gz[k] = 0.0;
+    for (int j = tm.lane(); j < n; j += W) {
+      // K part: pair (i, j) of inducing points, i != j (the diagonal has no dependence on l or Z)
+      if (j != i) {
+        const double kb = 0.5 * (KB[i * ld + j] + KB[j * ld + i]);
+        const double k0 = ard_rbf_tt(s.Zt, cap, d, invl, i, j, os);
+        const double tK = kb * k0;
+        acc[0] += tK;
+#pragma unroll
+        for (int k = 0; k < kMaxD; ++k)
+          if (k < d) {
+            const double dz = s.Zt[k * cap + i] - s.Zt[k * cap + j];
+            acc[1 + k] += tK * dz * dz;
+            gz[k] += 2.0 * tK * dz;
+          }
+      } else {
+        acc[0] += KB[i * ld + i] * os;
+      }
+      // C part: inducing point i against data point j : (Cbar . C)[i][j] = Cbar_t[j][i] Ct[j][i]
+      const double tC = CBt[j * ld + i] * Ct[j * ld + i];
+      acc[0] += tC;
+#pragma unroll
+      for (int k = 0; k < kMaxD; ++k)
+        if (k < d) {
+          const double dz = s.Zt[k * cap + i] - s.Xt[k * cap + j];
+          acc[1 + k] += tC * dz * dz;
+          gz[k] += tC * dz;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxD; ++k)
+      if (k < d) {
+        const double gsum = tm.warp_sum(gz[k]);
+        if (tm.lane() == 0) s.gZ[i * d + k] = -gsum * invl[k] * invl[k];
+      }
+  }
+  tm.sum_vec(acc, 1 + d);
+  double csum = 0.0;
+  for (int i = tm.rank(); i < n; i += tm.size()) csum += s.dm[i];
+  csum = tm.sum(csum);
+  tm.sync();
+  if (tm.rank() == 0) {
+    ghyp[0] = csum;
+    for (int k = 0; k < d; ++k) {
+      const double l = hyp[1 + k];
+      ghyp[1 + k] = acc[1 + k] / (l * l * l) - inv_n * lognormal_dlogpdf(l, pr.ls_loc, pr.ls_scale);
+    }
+    ghyp[1 + d] = lk_acc[3] + acc[0] / os - inv_n * lognormal_dlogpdf(os, pr.os_loc, pr.os_scale);
+    ghyp[2 + d] = -inv_n * lk_acc[1] - inv_n * lognormal_dlogpdf(noise, pr.noise_loc, pr.noise_scale);
+    double grho = 0.0;
+    if (lik == kLikStudentT) {
+      const double dnu = -inv_n * lk_acc[2] - inv_n * ((pr.df_conc - 1.0) / nu - pr.df_rate);
+      grho = dnu * sigmoid(rho);
+    }
+    ghyp[3 + d] = grho;
+  }
+  tm.sync();
+  if (dbg) {
+    double* g = dbg + cap + (size_t)cap * cap;
+    for (int idx = tm.rank(); idx < n * d; idx += tm.size()) g[idx] = s.gZ[idx];
+    for (int k = tm.rank(); k < nh; k += tm.size()) g[(size_t)cap * d + k] = ghyp[k];
+  }
+  if (apply) {
+    // (14) Adam (torch.optim.Adam defaults; lr = 0.01 hard-coded at optim.py:140)
+    const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    const double bc1 = 1.0 - pow(b1, (double)t), bc2s = sqrt(1.0 - pow(b2, (double)t));
+    const double step_size = lr_adam / bc1;
+    const int nadam = (lik == kLikStudentT) ? nh : nh - 1;
+    for (int idx = tm.rank(); idx < n * d + nadam; idx += tm.size()) {
+      const int isz = idx < n * d;
+      const double g = isz ? s.gZ[idx] : ghyp[idx - n * d];
+      const size_t slot = isz ? (size_t)idx : (size_t)cap * d + (idx - n * d);
+      double m = M.adam_m[slot], v = M.adam_v[slot];
+      m = m + (g - m) * (1.0 - b1);              // exp_avg.lerp_(grad, 1 - beta1)
+      v = v * b2 + (1.0 - b2) * g * g;
+      M.adam_m[slot] = m; M.adam_v[slot] = v;
+      const double denom = sqrt(v) / bc2s + eps;
+      const double upd = step_size * (m / denom);
+      if (isz) M.Z[idx] -= upd; else M.hyp[idx - n * d] -= upd;
+    }
+  }
+  tm.sync();
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------
+// Prepare the pool pass at the trained state:
+//   R1 <- Linv_K mirrored, R2 <- G = L_P^-1 Linv_K (lower), s.gmu <- w = Linv_K^T mu, s.mu <- mu.
+// v_* = os + jitter + ||G k||^2 - ||Linv_K k||^2, m_* = cst + k.w   (App. A.4 step 3 at a candidate)
+// Returns 0, 1 (not PD) or 2 (non-finite hyper-parameter).
+// ------------------------------------------------------------------------------------------
+template <class Team>
+STP_HD int var_prepare(const Team& tm, const VarSmem& s, const VarWork& w, const VarModel& M, int n, int d) {
+  const int ld = w.ld, cap = s.cap, W = tm.warp_width(), nw = tm.nwarps();
+  double* LP = w.R[0];    // chol(P), then its mirrored inverse in R3
+  double* LI = w.R[1];    // Linv_K mirrored
+  double* G = w.R[2];
+  double* LPI = w.R[3];
+  double* LK = w.R[4];
+  double* hyp = s.small;
+  double* invl = s.small + 16;
+  const int nh = d + 4;
+  tm.sync();
+  for (int k = tm.rank(); k < nh; k += tm.size()) hyp[k] = M.hyp[k];
+  for (int idx = tm.rank(); idx < n * d; idx += tm.size()) {
+    const int i = idx / d, k = idx - i * d;
+    s.Zt[k * cap + i] = M.Z[idx];
+  }
+  tm.sync();
+  const double os = hyp[1 + d];
+  for (int k = tm.rank(); k < d; k += tm.size()) invl[k] = 1.0 / hyp[1 + k];
+  int bad = !(os == os) || !(hyp[2 + d] == hyp[2 + d]) || !(hyp[0] == hyp[0]);
+  for (int k = 0; k < d; ++k) bad |= !(hyp[1 + k] == hyp[1 + k]) || hyp[1 + k] == 0.0;
+  if (bad) return 2;
+  tm.sync();
+  for (int i = tm.warp(); i < n; i += nw) {
+    for (int j = tm.lane(); j <= i; j += W) {
+      LP[i * ld + j] = -2.0 * M.nat2[(size_t)i * cap + j];
+      LK[i * ld + j] = (j == i) ? os + kVarJitter : ard_rbf_tt(s.Zt, cap, d, invl, i, j, os);
+    }
+  }
+  if (cholesky_lower(tm, LP, ld, n, s.c0)) return 1;
+  if (cholesky_lower(tm, LK, ld, n, s.c0)) return 1;
+  tri_inverse_mirrored(tm, LP, LPI, ld, n, s.c0);
+  tri_inverse_mirrored(tm, LK, LI, ld, n, s.c0);
+  // mu = S theta1 = LPI^T (LPI theta1)
+  for (int i = tm.rank(); i < n; i += tm.size()) {
+    double a = 0.0;
+    for (int j = 0; j <= i; ++j) a += LPI[i * ld + j] * M.nat1[j];
+    s.c1[i] = a;
+  }
+  tm.sync();
+  for (int j = tm.rank(); j < n; j += tm.size()) {
+    double a = 0.0;
+    for (int i = j; i < n; ++i) a += LPI[j * ld + i] * s.c1[i];
+    s.mu[j] = a;
+  }
+  tm.sync();
+  // w = Linv_K^T mu ; G[i][k] = sum_{k<=r<=i} LPI[i][r] Linv_K[r][k]
+  for (int j = tm.rank(); j < n; j += tm.size()) {
+    double a = 0.0;
+    for (int i = j; i < n; ++i) a += LI[j * ld + i] * s.mu[i];
+    s.gmu[j] = a;
+  }
+  for (int i = tm.warp(); i < n; i += nw) {
+    for (int k = tm.lane(); k <= i; k += W) {
+      double a = 0.0;
+      for (int r = k; r <= i; ++r) a += LPI[i * ld + r] * LI[r * ld + k];
+      G[i * ld + k] = a;
+    }
+  }
+  tm.sync();
+  return 0;
+}
+
+// Likelihood scale used by the acquisition (App. A.5): sqrt(max(var_lik, 1e-12)).
+STP_HD double var_lik_variance(int lik, double noise, double rho) {
+  if (lik == kLikStudentT) { const double nu = 2.0 + softplus(rho); return noise * nu / (nu - 2.0); }
+  if (lik == kLikLaplace) return 2.0 * noise;
+  return noise;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused pool pass of a variational model (after var_prepare).  `tile`: cap x TC + kMaxD x TC doubles
+// and `part`: nwarps x TC x 3 doubles of shared memory.  MC models: `eps` (global, [N, S]) if non-null,
+// else Philox(seed, stream = campaign id, counter = candidate * (S/2) + pair).
+// Optional outputs (may be null): mean_out / var_out = q(f) moments (no likelihood noise), acq_out.
+// ------------------------------------------------------------------------------------------
+template <class Team>
+STP_HD void var_acquire(const Team& tm, const VarSmem& s, const VarWork& w, int n, int d, int lik, double* tile,
+                        double* part, const double* pool, int N, const uint8_t* mask, double best_f, int S,
+                        const double* eps, uint64_t seed, uint64_t stream, int* best_idx, double* best_acq,
+                        double* mean_out, double* var_out, double* acq_out) {
+  const int ld = w.ld, cap = s.cap, TC = tm.warp_width(), nw = tm.nwarps();
+  const double* LI = w.R[1];
+  const double* G = w.R[2];
+  const double* hyp = s.small;
+  const double* invl = s.small + 16;
+  const double cst = hyp[0], os = hyp[1 + d], noise = hyp[2 + d], rho = hyp[3 + d];
+  double* xc = tile + (size_t)cap * TC;
+  const double lik_var = var_lik_variance(lik, noise, rho);
+  const double sig_l = sqrt(lik_var > 1e-12 ? lik_var : 1e-12);
+  const double log_sig_l = log(sig_l);
+  double run_v = -INFINITY;
+  int run_i = -1;
+  for (int base = 0; base < N; base += TC) {
+    const int cnt = (N - base < TC) ? (N - base) : TC;
+    tm.sync();
+    for (int idx = tm.rank(); idx < cnt * d; idx += tm.size()) {
+      const int c = idx / d, k = idx - c * d;
+      xc[k * TC + c] = pool[(size_t)base * d + idx];
+    }
+    tm.sync();
+    for (int idx = tm.rank(); idx < n * TC; idx += tm.size()) {
+      const int j = idx / TC, c = idx - j * TC;
+      double v = 0.0;
+      if (c < cnt) {
+        double r2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < kMaxD; ++k)
+          if (k < d) {
+            const double tt = (xc[k * TC + c] - s.Zt[k * cap + j]) * invl[k];
+            r2 += tt * tt;
+          }
+        v = os * exp(-0.5 * r2);
+      }
+      tile[j * TC + c] = v;
+    }
+    tm.sync();
+    {
+      const int c = tm.lane();
+      double sa = 0.0, sb = 0.0, mu = 0.0;
+      for (int i = tm.warp(); i < n; i += nw) {
+        const double* r1 = LI + i * ld;
+        const double* r2 = G + i * ld;
+        double a = 0.0, b = 0.0;
+        for (int j = 0; j <= i; ++j) {
+          const double kj = tile[j * TC + c];
+          a += r1[j] * kj;
+          b += r2[j] * kj;
+        }
+        sa += a * a;
+        sb += b * b;
+        mu += s.gmu[i] * tile[i * TC + c];
+      }
+      part[(tm.warp() * TC + c) * 3 + 0] = sa;
+      part[(tm.warp() * TC + c) * 3 + 1] = sb;
+      part[(tm.warp() * TC + c) * 3 + 2] = mu;
+    }
+    tm.sync();
+    for (int c = tm.rank(); c < cnt; c += tm.size()) {
+      double sa = 0.0, sb = 0.0, mu = 0.0;
+      for (int ww = 0; ww < nw; ++ww) {
+        sa += part[(ww * TC + c) * 3 + 0];
+        sb += part[(ww * TC + c) * 3 + 1];
+        mu += part[(ww * TC + c) * 3 + 2];
+      }
+      const int gi = base + c;
+      const double mean = cst + mu;
+      const double var = os + kVarJitter + (sb - sa);
+      if (mean_out) mean_out[gi] = mean;
+      if (var_out) var_out[gi] = var;
+      part[c * 3 + 0] = mean;   // warp 0's slots are dead now; reuse them to hand (mean, var) over
+      part[c * 3 + 1] = var;
+    }
+    tm.sync();
+    if (lik == kLikGaussian) {
+      for (int c = tm.rank(); c < cnt; c += tm.size()) {
+        const int gi = base + c;
+        const double a = log_ei(part[c * 3 + 0], part[c * 3 + 1] + noise, best_f);
+        if (acq_out) acq_out[gi] = a;
+        if ((!mask || mask[gi]) && acq_better(a, gi, run_v, run_i)) { run_v = a; run_i = gi; }
+      }
+    } else {
+      // Monte-Carlo mean of LogEI over S latent samples; one warp per candidate, lanes split the samples
+      for (int c = tm.warp(); c < cnt; c += nw) {
+        const int gi = base + c;
+        if (mask && !mask[gi] && !acq_out) continue;
+        const double mean = part[c * 3 + 0], sd = sqrt(part[c * 3 + 1]);
+        double a = 0.0;
+        if (eps) {
+          const double* e = eps + (size_t)gi * S;
+          for (int q = tm.lane(); q < S; q += TC) a += log_h(((mean + sd * e[q]) - best_f) / sig_l);
+        } else {
+          for (int q = tm.lane(); 2 * q < S; q += TC) {
+            double z0, z1;
+            philox_normal2(seed, stream, (uint64_t)gi * (uint64_t)((S + 1) / 2) + q, z0, z1);
+            a += log_h(((mean + sd * z0) - best_f) / sig_l);
+            if (2 * q + 1 < S) a += log_h(((mean + sd * z1) - best_f) / sig_l);
+          }
+        }
+        a = tm.warp_sum(a) / S + log_sig_l;
+        if (tm.lane() == 0) {
+          if (acq_out) acq_out[gi] = a;
+          if ((!mask || mask[gi]) && acq_better(a, gi, run_v, run_i)) { run_v = a; run_i = gi; }
+        }
+      }
+    }
+  }
+  tm.argmax(run_v, run_i);
+  *best_idx = run_i;
+  *best_acq = run_v;
+}
+
+}  // namespace stp

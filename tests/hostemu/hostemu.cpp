@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "../../stpbenchmark_b200/csrc/exact_campaign.cuh"
-#include "../../stpbenchmark_b200/csrc/variational.cuh"
+#include "../../stpbenchmark_b200/csrc/var_campaign.cuh"
 
 using namespace stp;
 

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     text = open(os.path.join(ROOT, "include", "stp_b200.h")).read()
-    return sorted(set(re.findall(r"^(?:int|const char\*)\s+(stp_\w+)\s*\(", text, flags=re.M)))
+    return sorted(set(re.findall(r"^(?:int|size_t|const char\*)\s+(stp_\w+)\s*\(", text, flags=re.M)))
 
 
 @pytest.fixture(scope="module")
