@@ -378,6 +378,82 @@ def run_cuda_arm(args):
         dist.destroy_process_group()
 
 
+def run_var_arm(args):
+    """Secondary workload: B concurrent VarGP / VarTGP / VarLGP campaigns (pool 2048, d = 6, ages staggered over
+    n = 10..89, 600 epochs, S = 2048 Monte-Carlo samples, in-kernel Philox).  Training sets of age a are the Sobol
+    initial design + a random distinct pool points (no BO pre-roll: a pre-roll alone would take minutes); every
+    step is a real BO iteration (fresh model -> stp_var_fit -> stp_var_acq with the update)."""
+    import torch
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from stpbenchmark_b200 import _lib, synthetic
+    from stpbenchmark_b200.engine import CampaignBatch
+    B, W, K = args.campaigns, args.warmup, args.steps
+    per_pool = max(B // N_POOLS, 1)
+    pools = [synthetic.cfg4_pool(g) for g in range(N_POOLS)]
+    PX = torch.stack([p[0] for p in pools]); PY = torch.stack([p[1] for p in pools])
+    pool_id = [min(b // per_pool, N_POOLS - 1) for b in range(B)]
+    gen = torch.Generator().manual_seed(4242 + rank)
+    init = []
+    for b in range(B):
+        g = pool_id[b]
+        d0 = synthetic.initial_designs(pools[g][0], pools[g][1], [100000 * rank + synthetic.campaign_seed(g, b % per_pool)], N_INITIAL)[0].tolist()
+        age = (b * N_TRIALS // B + b) % (N_TRIALS - W - K) if N_TRIALS - W - K > 0 else 0
+        rest = [i for i in torch.randperm(N_POOL, generator=gen).tolist() if i not in set(d0)][:age]
+        init.append(d0 + rest)
+    batch = CampaignBatch(PX, PY, pool_id, init, n_cap=CAP, kind=args.model, device=dev, epochs=args.epochs,
+                          learning_rate=0.01, num_samples=2048)
+    n0 = batch.n.clone()
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(W):
+        batch.step()
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = batch.launches
+    n_before = batch.n.clone()
+    e0.record()
+    for _ in range(K):
+        batch.step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.double, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    bad = int((batch.status != 0).sum().item())
+    E, S, d = args.epochs, 2048, DIM
+    nn = n_before.double() + (K - 1) / 2.0
+    C = 60.0 if args.model == "VarGP" else S * 80.0
+    flops = float((E * (9 * nn ** 3 + nn ** 2 * (14 * d + 12) + 800 * nn) + 3 * nn ** 3 +
+                   (N_POOL - nn) * (nn * (3 * d + 4) + 2 * nn ** 2 + C)).sum()) * K
+    peak = _lib.fp64_probe(4096)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": world * B * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"{B} concurrent {args.model} campaigns per GPU, synthetic pools N=2048 d=6, n staggered over "
+                                   f"{int(n0.min())}..{int(n0.max())} (+{W + K} steps), {E} epochs, S=2048 (in-kernel Philox)",
+                       "campaigns_per_gpu": B},
+            "roofline": {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None, "kernel": "k_var_fit + k_var_acq"},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": batch.launches - l0, "clocks": clocks,
+            "frozen_campaigns": bad}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -386,10 +462,16 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--campaigns", type=int, default=1024, help="campaigns per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="ExactGP", choices=["ExactGP", "VarGP", "VarTGP", "VarLGP"],
+                    help="ExactGP = the headline workload; the others run the secondary variational workload")
+    ap.add_argument("--epochs", type=int, default=600)
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = max(1, min(args.steps, N_TRIALS - args.warmup))  # one campaign per core has 80 trials
         run_reference_arm(args)
+    elif args.model != "ExactGP":
+        args.steps = min(args.steps, 10)
+        run_var_arm(args)
     else:
         run_cuda_arm(args)
 

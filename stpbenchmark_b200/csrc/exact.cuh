@@ -35,9 +35,9 @@ struct ExactSmem {
   double* A;      // (cap+1) x ld : lower = working matrix, strict upper = noise-free K (fit only)
   double* Xt;     // d x cap      : training inputs, transposed (conflict-free across points)
   double* y;      // cap
-  double* c0;     // cap+1
-  double* c1;     // cap+1
-  double* piv;    // cap+1 (pivots; reused as tmp by the triangular inverse)
+  double* c0;     // cap+5
+  double* c1;     // cap+5
+  double* piv;    // cap+5 (pivots; reused as tmp by the triangular inverse)
   double* alpha;  // cap
   double* tile;   // acquisition: cap x TC cross-covariances + TC x (kMaxD) staged candidates
   double* part;   // acquisition: nwarps x TC x 2 partial sums (ALIASES `red`: never live together)
@@ -48,7 +48,7 @@ struct ExactSmem {
 
 STP_HD size_t exact_smem_doubles(int cap, int d, int tc, int nwarps) {
   const int ld = odd_ld(cap + 1);
-  return (size_t)(cap + 1) * ld + (size_t)d * cap + cap + 3 * (size_t)(cap + 1) + cap +
+  return (size_t)(cap + 1) * ld + (size_t)d * cap + cap + 3 * (size_t)(cap + 5) + cap +
          (size_t)cap * tc + (size_t)tc * kMaxD + 64 + 16 * kMaxWarps;  // nwarps*tc*2 <= 16*kMaxWarps
 }
 
@@ -60,9 +60,9 @@ STP_HD ExactSmem exact_smem_carve(double* base, int cap, int d, int tc, int nwar
   s.A = p;      p += (size_t)(cap + 1) * s.ld;
   s.Xt = p;     p += (size_t)d * cap;
   s.y = p;      p += cap;
-  s.c0 = p;     p += cap + 1;
-  s.c1 = p;     p += cap + 1;
-  s.piv = p;    p += cap + 1;
+  s.c0 = p;     p += cap + 5;   // (cap + 1) rounded up to a multiple of 4 for the register-blocked sweep
+  s.c1 = p;     p += cap + 5;
+  s.piv = p;    p += cap + 5;
   s.alpha = p;  p += cap;
   s.tile = p;   p += (size_t)cap * tc + (size_t)tc * kMaxD;
   s.small = p;  p += 64;
@@ -205,7 +205,7 @@ STP_HD int exact_factorize(const Team& tm, const ExactSmem& s, int n, int d, con
       row[j] = (j == i) ? os + noise : ard_rbf_tt(s.Xt, cap, d, invl, i, j, os);
   }
   if (cholesky_lower(tm, s.A, ld, n, s.c0)) return 1;
-  tri_inverse_lower(tm, s.A, ld, n, s.piv);
+  tri_inverse_rl_inplace(tm, s.A, ld, n, s.piv);
   // z = Linv (y - c)  -> c0 ;  alpha = Linv^T z
   for (int i = tm.rank(); i < n; i += tm.size()) {
     const double* row = s.A + i * ld;
@@ -240,6 +240,7 @@ STP_HD void exact_acquire(const Team& tm, const ExactSmem& s, int n, int d, cons
                           int* best_idx, double* best_acq, double* mean_out, double* var_out,
                           double* acq_out) {
   const int ld = s.ld, cap = s.cap, TC = tm.warp_width(), nw = tm.nwarps();
+  const int nwa = nw < 8 ? nw : 8;
   const double noise = theta[0], cst = theta[1], os = theta[2];
   const double* invl = s.small + 32;
   double* xc = s.tile + (size_t)cap * TC;  // [kMaxD][TC]
@@ -269,10 +270,10 @@ STP_HD void exact_acquire(const Team& tm, const ExactSmem& s, int n, int d, cons
       s.tile[j * TC + c] = v;
     }
     tm.sync();
-    {
+    if (tm.warp() < nwa) {   // at most 8 warps: the partials live in the 512-double reduction scratch
       const int c = tm.lane();
       double ssq = 0.0, mu = 0.0;
-      for (int i = tm.warp(); i < n; i += nw) {
+      for (int i = tm.warp(); i < n; i += nwa) {
         const double* row = s.A + i * ld;
         double v0 = 0.0, v1 = 0.0;
         int j = 0;
@@ -291,7 +292,7 @@ STP_HD void exact_acquire(const Team& tm, const ExactSmem& s, int n, int d, cons
     tm.sync();
     for (int c = tm.rank(); c < cnt; c += tm.size()) {
       double ssq = 0.0, mu = 0.0;
-      for (int w = 0; w < nw; ++w) {
+      for (int w = 0; w < nwa; ++w) {
         ssq += s.part[(w * TC + c) * 2 + 0];
         mu += s.part[(w * TC + c) * 2 + 1];
       }

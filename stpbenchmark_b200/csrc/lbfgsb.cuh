@@ -58,6 +58,11 @@ struct LbfgsbState {
   double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1;
   int phase;                      // 0 waiting for f(x0); 1 inside a line search
   int B_ready;                    // the dense B of the current memory has been formed (possibly by the team)
+  // scratch of the serial routines: kept in the (shared-memory) state on purpose -- with ~220 KB of the SM's
+  // 228 KB carved out as shared memory there is next to no L1 left, and thread-local arrays would turn every
+  // access of the optimiser thread into an L2 round trip
+  double sc_a[kMaxP], sc_b[kMaxP], sc_c[kMaxP], sc_d[kMaxP], sc_C[kMaxP][kMaxP];
+  int sc_i[kMaxP], sc_j[kMaxP];
   int status;
 };
 
@@ -94,7 +99,7 @@ STP_HD int lb_build_B(LbfgsbState& S) {
     const int p = (S.head + q) % S.m;
     const double* s = S.ws[p];
     const double* y = S.wy[p];
-    double Bs[kMaxP];
+    double* Bs = S.sc_a;
     double sBs = 0.0, ys = 0.0;
     for (int i = 0; i < n; ++i) {
       double a = 0.0;
@@ -115,8 +120,8 @@ STP_HD int lb_build_B(LbfgsbState& S) {
 STP_HD void lb_cauchy(LbfgsbState& S) {
   const int n = S.np;
   double* xcp = S.z;
-  double dvec[kMaxP], tbrk[kMaxP], zz[kMaxP];
-  int order[kMaxP];
+  double* dvec = S.sc_a; double* tbrk = S.sc_b; double* zz = S.sc_c;
+  int* order = S.sc_i;
   int nbreak = 0;
   if (S.sbgnrm <= 0.0) { for (int i = 0; i < n; ++i) xcp[i] = S.x[i]; return; }
   for (int i = 0; i < n; ++i) {
@@ -200,11 +205,12 @@ STP_HD void lb_cauchy(LbfgsbState& S) {
 // On entry S.z = x^cp; on exit S.z = the subspace minimiser.  Returns 1 if B_FF is not PD.
 STP_HD int lb_subsm(LbfgsbState& S) {
   const int n = S.np;
-  int ind[kMaxP];
+  int* ind = S.sc_j;
   int nf = 0;
   for (int i = 0; i < n; ++i) if (S.iwhere[i] <= 0) ind[nf++] = i;
   if (nf == 0 || S.col == 0) return 0;
-  double rr[kMaxP], C[kMaxP][kMaxP], dd[kMaxP];
+  double* rr = S.sc_a; double* dd = S.sc_b;
+  double (*C)[kMaxP] = S.sc_C;
   for (int a = 0; a < nf; ++a) {
     const int i = ind[a];
     double bz = 0.0;
@@ -574,7 +580,7 @@ STP_HD int lb_advance_once(LbfgsbState& S, double f, const double* g) {
 // Return codes: 0 finished, 1 evaluate S.x, 3 form the dense B (S.B_ready = lb_build_B(S) ? 2 : 1, or the
 // team version) and call lbfgsb_resume(S).
 STP_HD int lbfgsb_advance_split(LbfgsbState& S, double f, const double* g) {
-  double gc[kMaxP];
+  double* gc = S.sc_d;
   for (int i = 0; i < S.np; ++i) gc[i] = g[i];
   for (;;) {
     const int r = lb_advance_once(S, f, gc);

@@ -113,4 +113,210 @@ STP_HD void tri_inverse_lower(const Team& tm, double* A, int ld, int n, double* 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Right-looking inverse of a lower-triangular matrix, out of place: X = L^-1 (lower, strict upper
+// zero-filled) and, optionally, XT = L^-T (upper, strict lower zero-filled).  Step k subtracts
+// (L[i][k] / L[k][k]) * X[k][:] from every later row: n steps, one barrier each, every step fully
+// parallel over (i > k, c <= k) -- no per-thread substitution chain.  n^3/6 MAC.
+// ---------------------------------------------------------------------------------------
+template <class Team>
+STP_HD void tri_inverse_rl(const Team& tm, const double* L, int ld, int n, double* X, double* XT) {
+  const int W = tm.warp_width(), nw = tm.nwarps();
+  for (int i = tm.warp(); i < n; i += nw) {
+    double* row = X + i * ld;
+    for (int c = tm.lane(); c < n; c += W) row[c] = (c == i) ? 1.0 : 0.0;
+  }
+  tm.sync();
+  for (int k = 0; k < n - 1; ++k) {
+    const double invd = 1.0 / L[k * ld + k];
+    const double* xk = X + k * ld;
+    for (int i = k + 1 + tm.warp(); i < n; i += nw) {
+      const double f = L[i * ld + k] * invd;
+      double* row = X + i * ld;
+      for (int c = tm.lane(); c <= k; c += W) row[c] = fma(-f, xk[c], row[c]);
+    }
+    tm.sync();
+  }
+  for (int i = tm.warp(); i < n; i += nw) {
+    const double invd = 1.0 / L[i * ld + i];
+    double* row = X + i * ld;
+    for (int c = tm.lane(); c < n; c += W) {
+      const double v = (c <= i) ? row[c] * invd : 0.0;
+      row[c] = v;
+      if (XT) XT[c * ld + i] = v;
+    }
+  }
+  tm.sync();
+}
+
+// ---------------------------------------------------------------------------------------
+// Register-tiled contraction  out(i, k) = sum_{r = r0}^{r1 - 1} Lf(i, r) * Rf(r, k).
+// A warp owns RB consecutive rows, a lane CQ columns 32 apart: RB + CQ loads feed RB * CQ FMAs
+// with RB * CQ independent accumulators.  Lf(i, r) is the same address for the whole warp (broadcast),
+// Rf(r, k) is consecutive across lanes when R is row-major.  `range(i_lo, i_hi, k_lo, k_hi, r0, r1)` gives
+// a common reduction range for the tile; operands must be ZERO (not just ignored) outside their own
+// support inside that range.  `store(i, k, v)` is called for every in-bounds (i, k) of every tile.
+// ---------------------------------------------------------------------------------------
+template <int RB, int CQ, class Team, class LF, class RF, class RangeF, class StoreF>
+STP_HD void contract(const Team& tm, int n_rows, int n_cols, LF Lf, RF Rf, RangeF range, StoreF store) {
+  const int W = tm.warp_width(), nw = tm.nwarps();
+  for (int ib = tm.warp() * RB; ib < n_rows; ib += nw * RB) {
+    int ri[RB];
+#pragma unroll
+    for (int a = 0; a < RB; ++a) ri[a] = (ib + a < n_rows) ? ib + a : n_rows - 1;
+    for (int kb = 0; kb < n_cols; kb += W * CQ) {
+      int kk[CQ];
+#pragma unroll
+      for (int q = 0; q < CQ; ++q) { const int k = kb + tm.lane() + q * W; kk[q] = (k < n_cols) ? k : n_cols - 1; }
+      int r0 = 0, r1 = 0;
+      range(ib, ri[RB - 1], kb, (kb + W * CQ - 1 < n_cols) ? kb + W * CQ - 1 : n_cols - 1, r0, r1);
+      double acc[RB][CQ];
+#pragma unroll
+      for (int a = 0; a < RB; ++a)
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) acc[a][q] = 0.0;
+      for (int r = r0; r < r1; ++r) {
+        double l[RB], rr[CQ];
+#pragma unroll
+        for (int a = 0; a < RB; ++a) l[a] = Lf(ri[a], r);
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) rr[q] = Rf(r, kk[q]);
+#pragma unroll
+        for (int a = 0; a < RB; ++a)
+#pragma unroll
+          for (int q = 0; q < CQ; ++q) acc[a][q] = fma(l[a], rr[q], acc[a][q]);
+      }
+#pragma unroll
+      for (int a = 0; a < RB; ++a)
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) {
+          const int k = kb + tm.lane() + q * W;
+          if (ib + a < n_rows && k < n_cols) store(ib + a, k, acc[a][q]);
+        }
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Pointer form of `contract`:  out(i, k) = sum_r L(i, r) * [scale(r)] * R(r, k)  with
+//   L(i, r) = Lp[i * l_si + r * l_sr]   (LT = false: l_sr == 1, row-major;  LT = true: l_si == 1, read down a column)
+//   R(r, k) = Rp[r * ld_r + k]
+// The reduction loop is unrolled by 4 with running pointers, so the inner body is loads + DFMA only.
+// ---------------------------------------------------------------------------------------
+template <int RB, int CQ, bool LT, bool SCALE, class Team, class RangeF, class StoreF>
+STP_HD void contract_p(const Team& tm, int n_rows, int n_cols, const double* Lp, int ld_l, const double* Rp, int ld_r,
+                       const double* scale, RangeF range, StoreF store) {
+  const int W = tm.warp_width(), nw = tm.nwarps();
+  const int l_si = LT ? 1 : ld_l, l_sr = LT ? ld_l : 1;
+  for (int ib = tm.warp() * RB; ib < n_rows; ib += nw * RB) {
+    int ri[RB];
+#pragma unroll
+    for (int a = 0; a < RB; ++a) ri[a] = (ib + a < n_rows) ? ib + a : n_rows - 1;
+    for (int kb = 0; kb < n_cols; kb += W * CQ) {
+      int kk[CQ];
+#pragma unroll
+      for (int q = 0; q < CQ; ++q) { const int k = kb + tm.lane() + q * W; kk[q] = (k < n_cols) ? k : n_cols - 1; }
+      int r0 = 0, r1 = 0;
+      range(ib, ri[RB - 1], kb, (kb + W * CQ - 1 < n_cols) ? kb + W * CQ - 1 : n_cols - 1, r0, r1);
+      double acc[RB][CQ];
+#pragma unroll
+      for (int a = 0; a < RB; ++a)
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) acc[a][q] = 0.0;
+      const double* lp[RB];
+      const double* rp[CQ];
+#pragma unroll
+      for (int a = 0; a < RB; ++a) lp[a] = Lp + (size_t)ri[a] * l_si + (size_t)r0 * l_sr;
+#pragma unroll
+      for (int q = 0; q < CQ; ++q) rp[q] = Rp + (size_t)r0 * ld_r + kk[q];
+      const double* sp = SCALE ? scale + r0 : nullptr;
+      int r = r0;
+      for (; r + 4 <= r1; r += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          double l[RB], rr[CQ];
+#pragma unroll
+          for (int a = 0; a < RB; ++a) l[a] = lp[a][u * l_sr];
+#pragma unroll
+          for (int q = 0; q < CQ; ++q) rr[q] = rp[q][u * ld_r];
+          if (SCALE) {
+            const double sc = sp[u];
+#pragma unroll
+            for (int q = 0; q < CQ; ++q) rr[q] *= sc;
+          }
+#pragma unroll
+          for (int a = 0; a < RB; ++a)
+#pragma unroll
+            for (int q = 0; q < CQ; ++q) acc[a][q] = fma(l[a], rr[q], acc[a][q]);
+        }
+#pragma unroll
+        for (int a = 0; a < RB; ++a) lp[a] += 4 * l_sr;
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) rp[q] += 4 * ld_r;
+        if (SCALE) sp += 4;
+      }
+      for (; r < r1; ++r) {
+        double l[RB], rr[CQ];
+#pragma unroll
+        for (int a = 0; a < RB; ++a) { l[a] = *lp[a]; lp[a] += l_sr; }
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) { rr[q] = *rp[q]; rp[q] += ld_r; }
+        if (SCALE) {
+          const double sc = *sp++;
+#pragma unroll
+          for (int q = 0; q < CQ; ++q) rr[q] *= sc;
+        }
+#pragma unroll
+        for (int a = 0; a < RB; ++a)
+#pragma unroll
+          for (int q = 0; q < CQ; ++q) acc[a][q] = fma(l[a], rr[q], acc[a][q]);
+      }
+#pragma unroll
+      for (int a = 0; a < RB; ++a)
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) {
+          const int k = kb + tm.lane() + q * W;
+          if (ib + a < n_rows && k < n_cols) store(ib + a, k, acc[a][q]);
+        }
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// In-place right-looking inverse of a lower-triangular matrix: on exit A (lower, diagonal included) holds
+// L^-1.  Step k consumes column k of L and replaces it by column k of the (unscaled) inverse, so no second
+// buffer is needed; one barrier per step, every step parallel over (i > k, c <= k).  `invd`: n doubles.
+// ---------------------------------------------------------------------------------------
+template <class Team>
+STP_HD void tri_inverse_rl_inplace(const Team& tm, double* A, int ld, int n, double* invd) {
+  const int W = tm.warp_width(), nw = tm.nwarps();
+  for (int i = tm.rank(); i < n; i += tm.size()) invd[i] = 1.0 / A[i * ld + i];
+  tm.sync();
+  // X starts as the identity in the positions already "consumed": column k of L is read at step k only.
+  for (int k = 0; k < n - 1; ++k) {
+    const double ik = invd[k];
+    const double* xk = A + k * ld;            // row k of X: X[k][c], c < k (unscaled), X[k][k] = 1 implied
+    for (int i = k + 1 + tm.warp(); i < n; i += nw) {
+      double* row = A + i * ld;
+      const double f = row[k] * ik;           // L[i][k] / L[k][k]: every lane reads it before lane k % W overwrites it
+      tm.sync_warp();
+      for (int c = tm.lane(); c <= k; c += W) {
+        const double xkc = (c == k) ? 1.0 : xk[c];
+        const double old = (c == k) ? 0.0 : row[c];
+        row[c] = fma(-f, xkc, old);
+      }
+    }
+    tm.sync();
+  }
+  for (int i = tm.warp(); i < n; i += nw) {
+    double* row = A + i * ld;
+    const double di = invd[i];
+    for (int c = tm.lane(); c <= i; c += W) row[c] = ((c == i) ? 1.0 : row[c]) * di;
+  }
+  tm.sync();
+}
+
 }  // namespace stp

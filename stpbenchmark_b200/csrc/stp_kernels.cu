@@ -25,12 +25,32 @@ int fail_cuda(const char* where, cudaError_t e) {
 
 constexpr int kTC = 32;  // acquisition tile: one candidate per lane
 
+// STP_EXACT_REGS = 1 selects the register-blocked closure (exact_regs.cuh; one thread per 4 x 4 block, up to
+// 288 threads).  Measured on B200 it does not beat the shared-memory sweep yet (13.1k vs 14.5k it/s on the
+// headline workload: the 96-register cap of 2 CTAs/SM x 288 threads spills), so it is off by default.
+#ifndef STP_EXACT_REGS
+#define STP_EXACT_REGS 0
+#endif
+#ifndef STP_EXACT_MINB
+#define STP_EXACT_MINB 2
+#endif
+#if STP_EXACT_REGS
+#define STP_EXACT_MAXT 288
+#else
+#define STP_EXACT_MAXT 256
+#endif
+
 int threads_for(int n_cap) {
   const char* env = getenv("STP_THREADS");
   if (env) {
     const int t = atoi(env);
-    if (t >= 32 && t <= 256 && t % 32 == 0) return t;
+    if (t >= 32 && t <= STP_EXACT_MAXT && t % 32 == 0) return t;
   }
+  // one thread per 4 x 4 block of the bordered matrix (register-blocked sweep) when that fits in 288 threads (n_cap <= 91)
+#if STP_EXACT_REGS
+  const int blocks = reg_blocks_for(n_cap + 1);
+  if (blocks <= 288) { const int t = (blocks + 31) / 32 * 32; return t < 128 ? 128 : t; }
+#endif
   return n_cap <= 48 ? 128 : 256;
 }
 
@@ -65,12 +85,12 @@ __global__ void k_exact_mll_fg(int n_cap, int d, const double* __restrict__ X, c
   if (threadIdx.x < np) s.small[threadIdx.x] = theta[b * np + threadIdx.x];
   __syncthreads();
   double fv;
-  const int st = exact_mll_fg(tm, s, n, d, s.small, to_prior(prior), &fv, s.small + 16);
+  const int st = exact_closure(tm, s, n, d, s.small, to_prior(prior), &fv, s.small + 16);
   if (threadIdx.x == 0) { f[b] = fv; status[b] = st; }
   if (threadIdx.x < np) g[b * np + threadIdx.x] = st ? NAN : s.small[16 + threadIdx.x];
 }
 
-__global__ void __launch_bounds__(256, 2) k_exact_fit(int n_cap, int d, const double* __restrict__ X, const double* __restrict__ y,
+__global__ void __launch_bounds__(STP_EXACT_MAXT, STP_EXACT_MINB) k_exact_fit(int n_cap, int d, const double* __restrict__ X, const double* __restrict__ y,
                             const int32_t* __restrict__ n_arr, double* __restrict__ theta, BoundsArg bnd,
                             PriorArg prior, LbfgsbOpts opts, double* __restrict__ f_out, int32_t* __restrict__ nit,
                             int32_t* __restrict__ nfev, int32_t* __restrict__ status) {
@@ -127,7 +147,7 @@ __global__ void k_exact_acq(int n_cap, int d, int N, const double* __restrict__ 
 }
 
 // The whole loop body runners.py:64-109 for one campaign.
-__global__ void __launch_bounds__(256, 2) k_exact_bo_step(int n_cap, int d, int N, const double* __restrict__ pool,
+__global__ void __launch_bounds__(STP_EXACT_MAXT, STP_EXACT_MINB) k_exact_bo_step(int n_cap, int d, int N, const double* __restrict__ pool,
                                 const double* __restrict__ pool_y, const int32_t* __restrict__ pool_id,
                                 uint8_t* __restrict__ mask, double* __restrict__ X, double* __restrict__ y,
                                 int32_t* __restrict__ n_arr, int32_t* __restrict__ trace, BoundsArg bnd,
@@ -189,7 +209,10 @@ __device__ __forceinline__ VarModel var_model_of(const VarPtrs& P, int b, int ca
                   P.adam_v ? P.adam_v + b * na : nullptr};
 }
 
-__global__ void __launch_bounds__(256) k_var_fit(int n_cap, int d, const double* __restrict__ X,
+#ifndef STP_VAR_MINB
+#define STP_VAR_MINB 2
+#endif
+__global__ void __launch_bounds__(256, STP_VAR_MINB) k_var_fit(int n_cap, int d, const double* __restrict__ X,
                                                  const double* __restrict__ y, const int32_t* __restrict__ n_arr,
                                                  const double* __restrict__ init_noise, VarFitArgs args, int t0,
                                                  VarPtrs P, double* __restrict__ loss_hist, int32_t* __restrict__ status,

@@ -34,6 +34,7 @@ struct SoloTeam {
   STP_HD int nwarps() const { return 1; }
   STP_HD int warp_width() const { return 1; }
   STP_HD void sync() const {}
+  STP_HD void sync_warp() const {}
   STP_HD double sum(double v) const { return v; }
   STP_HD double warp_sum(double v) const { return v; }
   template <int KMAX>
@@ -70,6 +71,7 @@ struct CtaTeam {
   __device__ __forceinline__ int nwarps() const { return blockDim.x >> 5; }
   __device__ __forceinline__ int warp_width() const { return 32; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
+  __device__ __forceinline__ void sync_warp() const { __syncwarp(); }
 
   __device__ __forceinline__ double warp_sum(double v) const {
 #pragma unroll

@@ -11,7 +11,7 @@
 // Layout.  All n x n work matrices are ROW-PER-DATA-POINT ("t" = transposed w.r.t. the maths of
 // App. A.4): At[c][k] = A[k][c] etc., so that every O(n^3) contraction reads one operand as a
 // warp-wide broadcast and the other as consecutive doubles.  They live in a per-campaign
-// workspace in global memory (L1/L2-resident: 6 squares of (cap+1) x ld doubles); vectors and the
+// workspace in global memory (L1/L2-resident: 7 squares of (cap+1) x ld doubles); vectors and the
 // transposed point sets live in shared memory.
 #pragma once
 #include "exact.cuh"
@@ -102,11 +102,12 @@ struct VarSmem {
   double* gZ;    // cap x d   gradient w.r.t. Z (row-major)
   double* small; // 96
   double* red;   // 16 * kMaxWarps
+  double* M0;    // (cap+1) x ld: the step-sequential routines (sweep, Cholesky, triangular inverse) run here
   int cap, ld;
 };
 
 STP_HD size_t var_smem_doubles(int cap, int d) {
-  return (size_t)2 * d * cap + (size_t)cap * 8 + 4 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
+  return (size_t)(cap + 1) * odd_ld(cap + 1) + (size_t)2 * d * cap + (size_t)cap * 8 + 4 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
 }
 
 STP_HD VarSmem var_smem_carve(double* base, int cap, int d) {
@@ -128,49 +129,24 @@ STP_HD VarSmem var_smem_carve(double* base, int cap, int d) {
   s.gsm = p; p += cap;
   s.gZ = p; p += (size_t)cap * d;
   s.small = p; p += 96;
-  s.red = p;
+  s.red = p; p += 16 * kMaxWarps;
+  s.M0 = p;
   return s;
 }
 
-// Per-campaign global workspace: 6 squares of (cap+1) rows x ld doubles.
-STP_HD size_t var_work_doubles(int cap) { return (size_t)6 * (cap + 1) * odd_ld(cap + 1); }
+// Per-campaign global workspace: 7 squares of (cap+1) rows x ld doubles.
+constexpr int kVarSquares = 7;
+STP_HD size_t var_work_doubles(int cap) { return (size_t)kVarSquares * (cap + 1) * odd_ld(cap + 1); }
 
 struct VarWork {
-  double* R[6];
+  double* R[kVarSquares];
   int ld;
 };
 STP_HD VarWork var_work_carve(double* base, int cap) {
   VarWork w;
   w.ld = odd_ld(cap + 1);
-  for (int q = 0; q < 6; ++q) w.R[q] = base + (size_t)q * (cap + 1) * w.ld;
+  for (int q = 0; q < kVarSquares; ++q) w.R[q] = base + (size_t)q * (cap + 1) * w.ld;
   return w;
-}
-
-// Cholesky factor kept in the lower triangle, inverse written MIRRORED into `Linv` (full square:
-// Linv[i][j] = Linv[j][i] = (L^-1)_{max,min}) so that both L^-1 and L^-T rows are contiguous.
-template <class Team>
-STP_HD void tri_inverse_mirrored(const Team& tm, const double* L, double* Linv, int ld, int n, double* tmp) {
-  for (int j = n - 1; j >= 0; --j) {
-    const double invd = 1.0 / L[j * ld + j];
-    for (int i = j + 1 + tm.rank(); i < n; i += tm.size()) {
-      const double* row = Linv + i * ld;
-      double s0 = 0.0, s1 = 0.0;
-      int k = j + 1;
-      for (; k + 1 <= i; k += 2) {
-        s0 += row[k] * L[k * ld + j];
-        s1 += row[k + 1] * L[(k + 1) * ld + j];
-      }
-      if (k <= i) s0 += row[k] * L[k * ld + j];
-      tmp[i] = -(s0 + s1) * invd;
-    }
-    tm.sync();
-    for (int i = j + tm.rank(); i < n; i += tm.size()) {
-      const double v = (i == j) ? invd : tmp[i];
-      Linv[i * ld + j] = v;
-      Linv[j * ld + i] = v;
-    }
-    tm.sync();
-  }
 }
 
 // log p(y | f) and its derivatives for one quadrature node.
@@ -219,7 +195,8 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   VarEpochOut out; out.loss = NAN; out.status = 0;
   double* S = w.R[0];    // P -> -S (lower, bordered) -> full S ; later G_S ; later Cbar_t
   double* LK = w.R[1];   // L_K (lower)
-  double* LI = w.R[2];   // Linv_K mirrored (full)
+  double* LI = w.R[2];   // Linv_K (lower, strict upper zero)
+  double* LT = w.R[6];   // Linv_K^T (upper, strict lower zero)
   double* Ct = w.R[3];   // Ct[c][j] = k(x_c, z_j)
   double* At = w.R[4];   // At[c][k] ; later Phi ; later Kbar'
   double* Dt = w.R[5];   // Tt -> Dt -> Abar_t ; later Lbar ; later U
@@ -241,35 +218,34 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   if (bad) { out.status = 2; return out; }
   tm.sync();
 
-  // (1) P = -2 Theta2, bordered with theta1; sweep -> -S, mu = S theta1, pivots
+  // (1) P = -2 Theta2, bordered with theta1; sweep IN SHARED MEMORY -> -S, mu = S theta1, pivots
+  double* M0 = s.M0;
   for (int i = tm.warp(); i <= n; i += nw) {
-    double* row = S + i * ld;
+    double* row = M0 + i * ld;
     if (i < n) for (int j = tm.lane(); j <= i; j += W) row[j] = -2.0 * M.nat2[(size_t)i * cap + j];
     else for (int j = tm.lane(); j <= n; j += W) row[j] = (j < n) ? M.nat1[j] : 0.0;
   }
   tm.sync();
-  if (sweep_bordered(tm, S, ld, n + 1, n, s.c0, s.c1, s.piv)) { out.status = 1; return out; }
+  if (sweep_bordered(tm, M0, ld, n + 1, n, s.c0, s.c1, s.piv)) { out.status = 1; return out; }
   double kl_acc[4] = {0.0, 0.0, 0.0, 0.0};   // sum log piv(P), tr S, mu.mu
   for (int i = tm.rank(); i < n; i += tm.size()) {
-    const double m = S[n * ld + i];
+    const double m = M0[n * ld + i];
     s.mu[i] = m;
     kl_acc[0] += log(s.piv[i]);
-    kl_acc[1] += -S[i * ld + i];
+    kl_acc[1] += -M0[i * ld + i];
     kl_acc[2] += m * m;
   }
   tm.sum_vec(kl_acc, 3);
-  // full symmetric S = -(swept)
+  // full symmetric S = -(swept) into global memory (operand of the Tt contraction)
   for (int i = tm.warp(); i < n; i += nw)
-    for (int j = tm.lane(); j <= i; j += W) {
-      const double v = -S[i * ld + j];
-      S[i * ld + j] = v;
-      S[j * ld + i] = v;
-    }
-  // (2) K_ZZ + jitter -> L_K ; Linv mirrored ; Ct
+    for (int j = tm.lane(); j < n; j += W) S[i * ld + j] = (j <= i) ? -M0[i * ld + j] : -M0[j * ld + i];
+  tm.sync();
+  // (2) K_ZZ + jitter -> L_K by Cholesky in shared memory; copy L_K out (strict upper zero-filled); invert in
+  //     place (right-looking) and write Linv (lower) and Linv^T (upper), zero-filled, to global memory; Ct
   for (int i = tm.warp(); i < n; i += nw) {
-    double* row = LK + i * ld;
+    double* row = M0 + i * ld;
     for (int j = tm.lane(); j <= i; j += W)
-      row[j] = (j == i) ? os + kVarJitter : ard_rbf_tt(s.Zt, cap, d, invl, i, j, os);
+      row[j] = (j < i) ? ard_rbf_tt(s.Zt, cap, d, invl, i, j, os) : os + kVarJitter;
   }
   for (int c = tm.warp(); c < n; c += nw) {
     double* row = Ct + c * ld;
@@ -284,42 +260,34 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
       row[j] = os * exp(-0.5 * r2);
     }
   }
-  if (cholesky_lower(tm, LK, ld, n, s.c0)) { out.status = 1; return out; }
-  tri_inverse_mirrored(tm, LK, LI, ld, n, s.c0);
-  // (3) At[c][k] = sum_{j<=k} Ct[c][j] Linv[k][j]   (row k of the mirrored inverse, columns j <= k)
-  for (int c = tm.warp(); c < n; c += nw) {
-    const double* crow = Ct + c * ld;
-    double* arow = At + c * ld;
-    for (int k = tm.lane(); k < n; k += W) {
-      double a0 = 0.0, a1 = 0.0;
-      int j = 0;
-      for (; j + 1 <= k; j += 2) {
-        a0 += crow[j] * LI[j * ld + k];
-        a1 += crow[j + 1] * LI[(j + 1) * ld + k];
-      }
-      if (j <= k) a0 += crow[j] * LI[j * ld + k];
-      arow[k] = a0 + a1;
+  if (cholesky_lower(tm, M0, ld, n, s.c0)) { out.status = 1; return out; }
+  for (int i = tm.warp(); i < n; i += nw)
+    for (int j = tm.lane(); j < n; j += W) LK[i * ld + j] = (j <= i) ? M0[i * ld + j] : 0.0;
+  tri_inverse_rl_inplace(tm, M0, ld, n, s.c0);
+  for (int i = tm.warp(); i < n; i += nw)
+    for (int j = tm.lane(); j < n; j += W) {
+      LI[i * ld + j] = (j <= i) ? M0[i * ld + j] : 0.0;
+      LT[i * ld + j] = (j >= i) ? M0[j * ld + i] : 0.0;
     }
-  }
+  tm.sync();
+  // (3) At[c][k] = sum_{j<=k} Ct[c][j] Linv^T[j][k]
+  contract_p<4, 2, false, false>(tm, n, n, Ct, ld, LT, ld, (const double*)nullptr,
+                 [=](int, int, int, int k_hi, int& r0, int& r1) { r0 = 0; r1 = k_hi + 1; },
+                 [=](int c, int k, double v) { At[c * ld + k] = v; });
   tm.sync();
   // (4) Tt = At S ; Dt = Tt - At ; q(f): m_c = cst + At[c].mu ; v_c = os + jitter + At[c].Dt[c]
+  contract_p<4, 2, false, false>(tm, n, n, At, ld, S, ld, (const double*)nullptr,
+                 [=](int, int, int, int, int& r0, int& r1) { r0 = 0; r1 = n; },
+                 [=](int c, int k, double v) { Dt[c * ld + k] = v - At[c * ld + k]; });
+  tm.sync();
   for (int c = tm.warp(); c < n; c += nw) {
     const double* arow = At + c * ld;
-    double* drow = Dt + c * ld;
+    const double* drow = Dt + c * ld;
     double pm = 0.0, pv = 0.0;
     for (int k = tm.lane(); k < n; k += W) {
-      double t0 = 0.0, t1 = 0.0;
-      int r = 0;
-      for (; r + 1 < n; r += 2) {
-        t0 += arow[r] * S[r * ld + k];
-        t1 += arow[r + 1] * S[(r + 1) * ld + k];
-      }
-      if (r < n) t0 += arow[r] * S[r * ld + k];
       const double a = arow[k];
-      const double dd = (t0 + t1) - a;
-      drow[k] = dd;
       pm += a * s.mu[k];
-      pv += a * dd;
+      pv += a * drow[k];
     }
     pm = tm.warp_sum(pm);
     pv = tm.warp_sum(pv);
@@ -386,20 +354,19 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   }
   double* GS = S;
   tm.sync();   // every reader of S (step 4) is done
-  for (int i = tm.warp(); i < n; i += nw) {
-    for (int k = tm.lane(); k <= i; k += W) {
-      double g0 = 0.0, g1 = 0.0;
-      int c = 0;
-      for (; c + 1 < n; c += 2) {
-        g0 += At[c * ld + i] * s.dv[c] * At[c * ld + k];
-        g1 += At[(c + 1) * ld + i] * s.dv[c + 1] * At[(c + 1) * ld + k];
-      }
-      if (c < n) g0 += At[c * ld + i] * s.dv[c] * At[c * ld + k];
-      const double P = -2.0 * M.nat2[(size_t)i * cap + k];
-      const double g = (g0 + g1) + ((i == k ? 1.0 : 0.0) - P) * (0.5 * inv_n);
-      GS[i * ld + k] = g;
-      GS[k * ld + i] = g;
-    }
+  {
+    const double* dvv = s.dv;
+    const double* nat2 = M.nat2;
+    contract_p<4, 2, true, true>(tm, n, n, At, ld, At, ld, dvv,
+                   [=](int, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = 0; r1 = (k_lo > i_hi) ? 0 : n; },
+                   [=](int i, int k, double v) {
+                     if (k <= i) {
+                       const double P = -2.0 * nat2[(size_t)i * cap + k];
+                       const double g = v + ((i == k ? 1.0 : 0.0) - P) * (0.5 * inv_n);
+                       GS[i * ld + k] = g;
+                       GS[k * ld + i] = g;
+                     }
+                   });
   }
   tm.sync();
   for (int i = tm.warp(); i < n; i += nw) {
@@ -431,82 +398,35 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
     for (int k = tm.lane(); k < n; k += W) drow[k] = s.mu[k] * dmc + drow[k] * dvc2;
   }
   tm.sync();
-  // (8) Cbar_t[c][j] = sum_{i>=j} Abar_t[c][i] Linv[i][j]   (into R0)
+  // (8) Cbar_t[c][j] = sum_{i>=j} Abar_t[c][i] Linv[i][j]   (into R0; G_S is dead)
   double* CBt = S;
-  for (int c = tm.warp(); c < n; c += nw) {
-    const double* arow = Dt + c * ld;
-    double* crow = CBt + c * ld;
-    for (int j = tm.lane(); j < n; j += W) {
-      double a0 = 0.0, a1 = 0.0;
-      int i = j;
-      for (; i + 1 < n; i += 2) {
-        a0 += arow[i] * LI[i * ld + j];
-        a1 += arow[i + 1] * LI[(i + 1) * ld + j];
-      }
-      if (i < n) a0 += arow[i] * LI[i * ld + j];
-      crow[j] = a0 + a1;
-    }
-  }
+  contract_p<4, 2, false, false>(tm, n, n, Dt, ld, LI, ld, (const double*)nullptr,
+                 [=](int, int, int k_lo, int, int& r0, int& r1) { r0 = k_lo; r1 = n; },
+                 [=](int c, int j, double v) { CBt[c * ld + j] = v; });
   tm.sync();
-  // (9) Lbar[i][k] = -sum_c Cbar_t[c][i] At[c][k], i >= k   (into R5, Abar_t is dead)
+  // (9) Lbar[i][k] = -sum_c Cbar_t[c][i] At[c][k], i >= k, zero above   (into R5, Abar_t is dead)
   double* LB = Dt;
-  for (int i = tm.warp(); i < n; i += nw) {
-    double* lrow = LB + i * ld;
-    for (int k = tm.lane(); k <= i; k += W) {
-      double a0 = 0.0, a1 = 0.0;
-      int c = 0;
-      for (; c + 1 < n; c += 2) {
-        a0 += CBt[c * ld + i] * At[c * ld + k];
-        a1 += CBt[(c + 1) * ld + i] * At[(c + 1) * ld + k];
-      }
-      if (c < n) a0 += CBt[c * ld + i] * At[c * ld + k];
-      lrow[k] = -(a0 + a1);
-    }
-  }
+  contract_p<4, 2, true, false>(tm, n, n, CBt, ld, At, ld, (const double*)nullptr,
+                 [=](int, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = 0; r1 = (k_lo > i_hi) ? 0 : n; },
+                 [=](int i, int k, double v) { LB[i * ld + k] = (k <= i) ? -v : 0.0; });
   tm.sync();
-  // (10) Phi[i][k] = sum_{r>=i} L[r][i] Lbar[r][k], i >= k, diagonal halved   (into R4, At is dead)
+  // (10) Phi[i][k] = sum_{r>=i} L[r][i] Lbar[r][k], i >= k, diagonal halved, zero above   (into R4, At is dead)
   double* PH = At;
-  for (int i = tm.warp(); i < n; i += nw) {
-    double* prow = PH + i * ld;
-    for (int k = tm.lane(); k <= i; k += W) {
-      double a0 = 0.0, a1 = 0.0;
-      int r = i;
-      for (; r + 1 < n; r += 2) {
-        a0 += LK[r * ld + i] * LB[r * ld + k];
-        a1 += LK[(r + 1) * ld + i] * LB[(r + 1) * ld + k];
-      }
-      if (r < n) a0 += LK[r * ld + i] * LB[r * ld + k];
-      prow[k] = (i == k) ? 0.5 * (a0 + a1) : (a0 + a1);
-    }
-  }
+  contract_p<4, 2, true, false>(tm, n, n, LK, ld, LB, ld, (const double*)nullptr,
+                 [=](int i_lo, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = i_lo; r1 = (k_lo > i_hi) ? i_lo : n; },
+                 [=](int i, int k, double v) { PH[i * ld + k] = (k < i) ? v : (k == i ? 0.5 * v : 0.0); });
   tm.sync();
-  // (11) U[i][k] = sum_{k<=r<=i} Phi[i][r] Linv[r][k]   (into R5, Lbar is dead)
+  // (11) U[i][k] = sum_{k<=r<=i} Phi[i][r] Linv[r][k], zero above   (into R5, Lbar is dead)
   double* U = Dt;
-  for (int i = tm.warp(); i < n; i += nw) {
-    const double* prow = PH + i * ld;
-    double* urow = U + i * ld;
-    for (int k = tm.lane(); k <= i; k += W) {
-      double a0 = 0.0, a1 = 0.0;
-      int r = k;
-      for (; r + 1 <= i; r += 2) {
-        a0 += prow[r] * LI[r * ld + k];
-        a1 += prow[r + 1] * LI[(r + 1) * ld + k];
-      }
-      if (r <= i) a0 += prow[r] * LI[r * ld + k];
-      urow[k] = a0 + a1;
-    }
-  }
+  contract_p<4, 2, false, false>(tm, n, n, PH, ld, LI, ld, (const double*)nullptr,
+                 [=](int, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = k_lo; r1 = (k_lo > i_hi) ? k_lo : i_hi + 1; },
+                 [=](int i, int k, double v) { U[i * ld + k] = (k <= i) ? v : 0.0; });
   tm.sync();
   // (12) Kbar'[j][k] = sum_{i>=max(j,k)} Linv[i][j] U[i][k]   (into R4, Phi is dead)
   double* KB = At;
-  for (int j = tm.warp(); j < n; j += nw) {
-    double* krow = KB + j * ld;
-    for (int k = tm.lane(); k < n; k += W) {
-      double a0 = 0.0;
-      for (int i = (j > k ? j : k); i < n; ++i) a0 += LI[j * ld + i] * U[i * ld + k];
-      krow[k] = a0;
-    }
-  }
+  contract_p<4, 2, true, false>(tm, n, n, LI, ld, U, ld, (const double*)nullptr,
+                 [=](int j_lo, int, int k_lo, int, int& r0, int& r1) { r0 = (j_lo > k_lo) ? j_lo : k_lo; r1 = n; },
+                 [=](int j, int k, double v) { KB[j * ld + k] = v; });
   tm.sync();
   // (13) kernel-parameter gradients.  Kbar = sym(Kbar'); K0 and C are re-evaluated on the fly.
   double acc[kMaxD + 4];
@@ -611,11 +531,9 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
 template <class Team>
 STP_HD int var_prepare(const Team& tm, const VarSmem& s, const VarWork& w, const VarModel& M, int n, int d) {
   const int ld = w.ld, cap = s.cap, W = tm.warp_width(), nw = tm.nwarps();
-  double* LP = w.R[0];    // chol(P), then its mirrored inverse in R3
   double* LI = w.R[1];    // Linv_K mirrored
   double* G = w.R[2];
   double* LPI = w.R[3];
-  double* LK = w.R[4];
   double* hyp = s.small;
   double* invl = s.small + 16;
   const int nh = d + 4;
@@ -632,16 +550,22 @@ STP_HD int var_prepare(const Team& tm, const VarSmem& s, const VarWork& w, const
   for (int k = 0; k < d; ++k) bad |= !(hyp[1 + k] == hyp[1 + k]) || hyp[1 + k] == 0.0;
   if (bad) return 2;
   tm.sync();
-  for (int i = tm.warp(); i < n; i += nw) {
-    for (int j = tm.lane(); j <= i; j += W) {
-      LP[i * ld + j] = -2.0 * M.nat2[(size_t)i * cap + j];
-      LK[i * ld + j] = (j == i) ? os + kVarJitter : ard_rbf_tt(s.Zt, cap, d, invl, i, j, os);
+  // chol(P)^-1 and chol(K_ZZ + jitter I)^-1, each factorised and inverted in shared memory, written out zero-filled
+  double* M0 = s.M0;
+  for (int pass = 0; pass < 2; ++pass) {
+    double* dst = pass == 0 ? LPI : LI;
+    for (int i = tm.warp(); i < n; i += nw) {
+      double* row = M0 + i * ld;
+      for (int j = tm.lane(); j <= i; j += W)
+        row[j] = pass == 0 ? -2.0 * M.nat2[(size_t)i * cap + j]
+                           : ((j == i) ? os + kVarJitter : ard_rbf_tt(s.Zt, cap, d, invl, i, j, os));
     }
+    if (cholesky_lower(tm, M0, ld, n, s.c0)) return 1;
+    tri_inverse_rl_inplace(tm, M0, ld, n, s.c0);
+    for (int i = tm.warp(); i < n; i += nw)
+      for (int j = tm.lane(); j < n; j += W) dst[i * ld + j] = (j <= i) ? M0[i * ld + j] : 0.0;
+    tm.sync();
   }
-  if (cholesky_lower(tm, LP, ld, n, s.c0)) return 1;
-  if (cholesky_lower(tm, LK, ld, n, s.c0)) return 1;
-  tri_inverse_mirrored(tm, LP, LPI, ld, n, s.c0);
-  tri_inverse_mirrored(tm, LK, LI, ld, n, s.c0);
   // mu = S theta1 = LPI^T (LPI theta1)
   for (int i = tm.rank(); i < n; i += tm.size()) {
     double a = 0.0;
@@ -651,23 +575,19 @@ STP_HD int var_prepare(const Team& tm, const VarSmem& s, const VarWork& w, const
   tm.sync();
   for (int j = tm.rank(); j < n; j += tm.size()) {
     double a = 0.0;
-    for (int i = j; i < n; ++i) a += LPI[j * ld + i] * s.c1[i];
+    for (int i = j; i < n; ++i) a += LPI[i * ld + j] * s.c1[i];
     s.mu[j] = a;
   }
   tm.sync();
-  // w = Linv_K^T mu ; G[i][k] = sum_{k<=r<=i} LPI[i][r] Linv_K[r][k]
+  // w = Linv_K^T mu ; G[i][k] = sum_{k<=r<=i} LPI[i][r] Linv_K[r][k]  (lower, zero above)
   for (int j = tm.rank(); j < n; j += tm.size()) {
     double a = 0.0;
-    for (int i = j; i < n; ++i) a += LI[j * ld + i] * s.mu[i];
+    for (int i = j; i < n; ++i) a += LI[i * ld + j] * s.mu[i];
     s.gmu[j] = a;
   }
-  for (int i = tm.warp(); i < n; i += nw) {
-    for (int k = tm.lane(); k <= i; k += W) {
-      double a = 0.0;
-      for (int r = k; r <= i; ++r) a += LPI[i * ld + r] * LI[r * ld + k];
-      G[i * ld + k] = a;
-    }
-  }
+  contract_p<4, 2, false, false>(tm, n, n, LPI, ld, LI, ld, (const double*)nullptr,
+                 [=](int, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = k_lo; r1 = (k_lo > i_hi) ? k_lo : i_hi + 1; },
+                 [=](int i, int k, double v) { G[i * ld + k] = (k <= i) ? v : 0.0; });
   tm.sync();
   return 0;
 }
