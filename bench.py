@@ -200,6 +200,7 @@ def run_cuda_arm(args):
                 designs[(b, gen)] = D[i]
     batch = CampaignBatch(PX, PY, pool_id, [designs[(b, 0)].tolist() for b in range(B)], n_cap=CAP, kind="ExactGP",
                           device=dev)
+    batch.ragged = True                                      # ages differ: longest fits are scheduled first
     # pre-roll (untimed): bring campaign b to age0[b]; it starts at step N_TRIALS - age0[b]
     start_step = torch.tensor([N_TRIALS - a for a in age0], device=dev)
     batch.status.fill_(-1)                                   # not started yet

@@ -86,12 +86,15 @@ int stp_exact_acq(int B, int n_cap, int d, int N, const double* pool, const int3
  * the picked pool index at position n[b] (before the increment).  theta0: host [d+3] start
  * (the prior modes, models.py:326,334,347,357); theta_out [B, d+3] fitted values.
  * Campaigns whose status[b] is non-zero on entry are skipped (frozen, like the reference's
- * try/except at runners.py:113-115); n[b] >= n_cap is rejected by status 2. */
+ * try/except at runners.py:113-115); n[b] >= n_cap is rejected by status 2.
+ * order: optional int32[B] permutation (NULL = identity): CTA i works on campaign order[i].  CTAs are issued in
+ * index order, so passing the campaigns sorted by decreasing n (longest fits first) shortens the tail of the
+ * launch when the batch mixes training-set sizes. */
 int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const double* pool_y,
                       const int32_t* pool_id, uint8_t* mask, double* X, double* y, int32_t* n, int32_t* trace,
                       const double* theta0, const double* lower, const double* upper, const double* prior,
                       const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
-                      int32_t* status, void* stream);
+                      int32_t* status, const int32_t* order, void* stream);
 
 /* ---- variational models: VarGP / VarTGP / VarLGP (models.py:114-202, 18-111, 205-297) ---------------
  * State arrays (device, caller-owned, batch-major): Z [B, n_cap, d] inducing locations, hyp [B, d+4] =

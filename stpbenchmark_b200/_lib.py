@@ -135,16 +135,16 @@ def exact_acq(pool, X, y, theta, best_f=None, mask=None, pool_id=None, n=None, w
 
 
 def exact_bo_step(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upper, prior, status,
-                  theta_out=None, acq_out=None, nit=None, nfev=None, opts: Optional[LbfgsbOpts] = None):
+                  theta_out=None, acq_out=None, nit=None, nfev=None, opts: Optional[LbfgsbOpts] = None, order=None):
     """One BO iteration for every campaign, in place (see stp_exact_bo_step)."""
-    _require_cuda(pool, pool_y, pool_id, mask, X, y, n, trace, status, theta_out, acq_out, nit, nfev)
+    _require_cuda(pool, pool_y, pool_id, mask, X, y, n, trace, status, theta_out, acq_out, nit, nfev, order)
     B, n_cap, d = X.shape
     N = pool.shape[-2]
     lo, hi = _bounds(lower, upper, d + 3)
     o = opts or LbfgsbOpts.scipy_defaults()
     _check(lib().stp_exact_bo_step(B, n_cap, d, N, _p(pool), _p(pool_y), _p(pool_id), _p(mask), _p(X), _p(y), _p(n),
                                    _p(trace), _host(theta0), lo, hi, _host(prior), ctypes.byref(o), _p(theta_out),
-                                   _p(acq_out), _p(nit), _p(nfev), _p(status), _stream()), "stp_exact_bo_step")
+                                   _p(acq_out), _p(nit), _p(nfev), _p(status), _p(order), _stream()), "stp_exact_bo_step")
 
 
 def log_ei(mean: torch.Tensor, var: torch.Tensor, best_f: float) -> torch.Tensor:

@@ -48,7 +48,7 @@ struct ExactSmem {
 
 STP_HD size_t exact_smem_doubles(int cap, int d, int tc, int nwarps) {
   const int ld = odd_ld(cap + 1);
-  return (size_t)(cap + 1) * ld + (size_t)d * cap + cap + 3 * (size_t)(cap + 5) + cap +
+  return (size_t)(cap + 1) * ld + (size_t)d * cap + cap + 3 * (size_t)(cap + 9) + cap +
          (size_t)cap * tc + (size_t)tc * kMaxD + 64 + 16 * kMaxWarps;  // nwarps*tc*2 <= 16*kMaxWarps
 }
 
@@ -60,9 +60,9 @@ STP_HD ExactSmem exact_smem_carve(double* base, int cap, int d, int tc, int nwar
   s.A = p;      p += (size_t)(cap + 1) * s.ld;
   s.Xt = p;     p += (size_t)d * cap;
   s.y = p;      p += cap;
-  s.c0 = p;     p += cap + 5;   // (cap + 1) rounded up to a multiple of 4 for the register-blocked sweep
-  s.c1 = p;     p += cap + 5;
-  s.piv = p;    p += cap + 5;
+  s.c0 = p;     p += cap + 9;   // (cap + 1) rounded up to a multiple of the register-block edge (<= 8)
+  s.c1 = p;     p += cap + 9;
+  s.piv = p;    p += cap + 9;
   s.alpha = p;  p += cap;
   s.tile = p;   p += (size_t)cap * tc + (size_t)tc * kMaxD;
   s.small = p;  p += 64;

@@ -2,7 +2,7 @@
 //
 // Same mathematics as exact_mll_fg (exact.cuh) -- bordered symmetric sweep of [K + s2 I, y - c; (y - c)^T, 0],
 // then the gradient contraction 1/2 tr((alpha alpha^T - K^-1) dK) -- but the matrix never touches shared
-// memory: thread t owns one 4 x 4 block (bi >= bj) of the lower triangle in REGISTERS for the whole sweep.
+// memory: thread t owns one BS x BS block (BS = STP_REG_BS, bi >= bj) of the lower triangle in REGISTERS for the whole sweep.
 // Per pivot a thread loads the 4 + 4 pivot-column entries it needs (two LDS.128 each), issues 16 DFMA, and
 // the owners of row / column k+1 publish the next pivot column; one barrier per pivot.  ~1.5 instructions per
 // matrix element per pivot instead of ~10 for the shared-memory loop, and no bank traffic for the matrix.
@@ -13,8 +13,11 @@
 #if defined(__CUDACC__)
 namespace stp {
 
+#ifndef STP_REG_BS
+#define STP_REG_BS 6            // edge of the square register block owned by one thread
+#endif
 __host__ __device__ __forceinline__ int reg_blocks_for(int m) {
-  const int mb = (m + 3) >> 2;
+  const int mb = (m + STP_REG_BS - 1) / STP_REG_BS;
   return mb * (mb + 1) / 2;
 }
 
@@ -28,6 +31,7 @@ __device__ __forceinline__ double bordered_entry(const ExactSmem& s, int n, int 
   return ard_rbf_tt(s.Xt, s.cap, d, invl, i, j, os);
 }
 
+template <int BS>
 __device__ __forceinline__ int exact_mll_fg_regs(const CtaTeam& tm, const ExactSmem& s, int n, int d,
                                                  const double* theta, const ExactPrior& pr, double* f_out, double* g) {
   const int cap = s.cap;
@@ -39,7 +43,7 @@ __device__ __forceinline__ int exact_mll_fg_regs(const CtaTeam& tm, const ExactS
   for (int k = 0; k < d; ++k) bad |= !(theta[3 + k] > 0.0);
   if (bad) { *f_out = NAN; return 2; }
   tm.sync();
-  const int m = n + 1, mb = (m + 3) >> 2, nblk = mb * (mb + 1) / 2, mp = mb << 2;
+  const int m = n + 1, mb = (m + BS - 1) / BS, nblk = mb * (mb + 1) / 2, mp = mb * BS;
   const int t = tm.rank();
   const bool live = t < nblk;
   // block coordinates: largest bi with bi (bi + 1) / 2 <= t
@@ -47,19 +51,19 @@ __device__ __forceinline__ int exact_mll_fg_regs(const CtaTeam& tm, const ExactS
   while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
   while (bi * (bi + 1) / 2 > t) --bi;
   const int bj = t - bi * (bi + 1) / 2;
-  const int i0 = bi << 2, j0 = bj << 2;
-  double A[4][4];
+  const int i0 = bi * BS, j0 = bj * BS;
+  double A[BS][BS];
   if (live) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < BS; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) A[a][b] = bordered_entry(s, n, d, invl, os, noise, cst, i0 + a, j0 + b);
+      for (int b = 0; b < BS; ++b) A[a][b] = bordered_entry(s, n, d, invl, os, noise, cst, i0 + a, j0 + b);
   }
   double* cur = s.c0;   // mp <= cap + 4 doubles each: c0 / c1 / piv are contiguous, see exact_smem_carve
   double* nxt = s.c1;
   if (live && bj == 0) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a) cur[i0 + a] = A[a][0];
+    for (int a = 0; a < BS; ++a) cur[i0 + a] = A[a][0];
   }
   tm.sync();
   const int kb_i = i0, kb_j = j0;
@@ -69,47 +73,47 @@ __device__ __forceinline__ int exact_mll_fg_regs(const CtaTeam& tm, const ExactS
     const double invp = 1.0 / p;
     if (t == 0) s.piv[k] = p;
     if (live) {
-      double ci[4], cj[4], ti[4];
+      double ci[BS], cj[BS], ti[BS];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) { ci[a] = cur[kb_i + a]; cj[a] = cur[kb_j + a]; ti[a] = ci[a] * invp; }
+      for (int a = 0; a < BS; ++a) { ci[a] = cur[kb_i + a]; cj[a] = cur[kb_j + a]; ti[a] = ci[a] * invp; }
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < BS; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) A[a][b] = fma(-ti[a], cj[b], A[a][b]);
+        for (int b = 0; b < BS; ++b) A[a][b] = fma(-ti[a], cj[b], A[a][b]);
       const int ka = k - i0, kc = k - j0;   // position of the pivot inside this block's rows / columns
-      if ((unsigned)ka < 4u) {              // pivot row: a_kj / p, diagonal -1 / p
+      if ((unsigned)ka < (unsigned)BS) {              // pivot row: a_kj / p, diagonal -1 / p
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < BS; ++a)
           if (a == ka) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) A[a][b] = (b == kc) ? -invp : cj[b] * invp;
+            for (int b = 0; b < BS; ++b) A[a][b] = (b == kc) ? -invp : cj[b] * invp;
           }
       }
-      if ((unsigned)kc < 4u) {              // pivot column: a_ik / p
+      if ((unsigned)kc < (unsigned)BS) {              // pivot column: a_ik / p
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
+        for (int b = 0; b < BS; ++b)
           if (b == kc) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < BS; ++a)
               if (a != ka) A[a][b] = ti[a];
           }
       }
       const int na = k + 1 - i0, nc = k + 1 - j0;   // publish column k + 1 (rows >= k + 1) and row k + 1 (cols <= k + 1)
-      if ((unsigned)nc < 4u) {
+      if ((unsigned)nc < (unsigned)BS) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
+        for (int b = 0; b < BS; ++b)
           if (b == nc) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < BS; ++a)
               if (i0 + a >= k + 1) nxt[i0 + a] = A[a][b];
           }
       }
-      if ((unsigned)na < 4u) {
+      if ((unsigned)na < (unsigned)BS) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < BS; ++a)
           if (a == na) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
+            for (int b = 0; b < BS; ++b)
               if (j0 + b <= k + 1) nxt[j0 + b] = A[a][b];
           }
       }
@@ -118,13 +122,13 @@ __device__ __forceinline__ int exact_mll_fg_regs(const CtaTeam& tm, const ExactS
     double* tt = cur; cur = nxt; nxt = tt;
   }
   // border row -> alpha (shared), corner -> -quad
-  const int bn = n >> 2, an = n & 3;
+  const int bn = n / BS, an = n - bn * BS;
   if (live && bi == bn) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < BS; ++a)
       if (a == an) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < BS; ++b) {
           const int j = j0 + b;
           if (j < n) s.alpha[j] = A[a][b];
           else if (j == n) s.small[40] = -A[a][b];
@@ -142,12 +146,12 @@ __device__ __forceinline__ int exact_mll_fg_regs(const CtaTeam& tm, const ExactS
   }
   if (live) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < BS; ++a) {
       const int i = i0 + a;
       if (i < n) {
         const double ai = s.alpha[i];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < BS; ++b) {
           const int j = j0 + b;
           if (j < i) {
             double r2 = 0.0, dx2[kMaxD];
@@ -199,7 +203,7 @@ __device__ __forceinline__ int exact_mll_fg_regs(const CtaTeam& tm, const ExactS
 __device__ __forceinline__ int exact_closure(const CtaTeam& tm, const ExactSmem& s, int n, int d, const double* theta,
                                              const ExactPrior& pr, double* f_out, double* g) {
 #if defined(STP_EXACT_REGS) && STP_EXACT_REGS
-  if (reg_blocks_for(n + 1) <= tm.size()) return exact_mll_fg_regs(tm, s, n, d, theta, pr, f_out, g);
+  if (reg_blocks_for(n + 1) <= tm.size()) return exact_mll_fg_regs<STP_REG_BS>(tm, s, n, d, theta, pr, f_out, g);
 #endif
   return exact_mll_fg(tm, s, n, d, theta, pr, f_out, g);
 }

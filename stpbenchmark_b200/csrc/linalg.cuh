@@ -23,9 +23,69 @@ STP_HD int odd_ld(int n) { return n | 1; }
 // `c0`, `c1`: two scratch vectors of m doubles (ping-pong copies of the pivot column).
 // Returns 0, or 1 + k if pivot k is not positive / not finite (matrix not PD).
 // ---------------------------------------------------------------------------------------
+// Fast path: every lane owns CQ fixed columns (lane + q W, q < CQ) whose pivot-column entries stay in
+// registers for the whole step; a warp walks its rows with a running row pointer, so the body per element is
+// load / DFMA / select / store plus predicated publishes (no per-element index arithmetic or branches).
+template <int CQ, class Team>
+STP_HD int sweep_bordered_cf(const Team& tm, double* A, int ld, int m, int npiv, double* c0, double* c1,
+                             double* piv) {
+  const int W = tm.warp_width(), lane = tm.lane(), nw = tm.nwarps();
+  for (int i = tm.rank(); i < m; i += tm.size()) c0[i] = A[i * ld];
+  tm.sync();
+  double* cur = c0;
+  double* nxt = c1;
+  for (int k = 0; k < npiv; ++k) {
+    const double p = cur[k];
+    if (!(p > 0.0) || !(p <= 1.79e308)) return 1 + k;
+    if (tm.rank() == 0) piv[k] = p;
+    const double invp = 1.0 / p;
+    double cj[CQ];
+    bool own_k[CQ], own_n[CQ];
+#pragma unroll
+    for (int q = 0; q < CQ; ++q) {
+      const int j = lane + q * W;
+      cj[q] = (j < m) ? cur[j] : 0.0;
+      own_k[q] = (j == k);
+      own_n[q] = (j == k + 1);
+    }
+    for (int i = tm.warp(); i < m; i += nw) {
+      double* row = A + i * ld;
+      if (i == k) {
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) {
+          const int j = lane + q * W;
+          if (j <= i) row[j] = own_k[q] ? -invp : cj[q] * invp;
+        }
+      } else {
+        const double ti = cur[i] * invp;
+        const bool next_row = (i == k + 1);
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) {
+          const int j = lane + q * W;
+          if (j <= i) {
+            double a = fma(-ti, cj[q], row[j]);
+            a = own_k[q] ? ti : a;
+            row[j] = a;
+            if (own_n[q]) nxt[i] = a;
+            if (next_row) nxt[j] = a;
+          }
+        }
+      }
+    }
+    tm.sync();
+    double* t = cur; cur = nxt; nxt = t;
+  }
+  return 0;
+}
+
 template <class Team>
 STP_HD int sweep_bordered(const Team& tm, double* A, int ld, int m, int npiv, double* c0, double* c1,
                           double* piv) {
+  if (tm.warp_width() > 1) {
+    if (m <= 1 * tm.warp_width()) return sweep_bordered_cf<1>(tm, A, ld, m, npiv, c0, c1, piv);
+    if (m <= 2 * tm.warp_width()) return sweep_bordered_cf<2>(tm, A, ld, m, npiv, c0, c1, piv);
+    if (m <= 3 * tm.warp_width()) return sweep_bordered_cf<3>(tm, A, ld, m, npiv, c0, c1, piv);
+  }
   for (int i = tm.rank(); i < m; i += tm.size()) c0[i] = A[i * ld];
   tm.sync();
   double* cur = c0;

@@ -34,8 +34,9 @@ constexpr int kTC = 32;  // acquisition tile: one candidate per lane
 #ifndef STP_EXACT_MINB
 #define STP_EXACT_MINB 2
 #endif
-#if STP_EXACT_REGS
-#define STP_EXACT_MAXT 288
+#if defined(STP_EXACT_MAXT)
+#elif STP_EXACT_REGS
+#define STP_EXACT_MAXT 160      // 6 x 6 register blocks: 136 blocks at n_cap = 91; leaves ~200 registers per thread
 #else
 #define STP_EXACT_MAXT 256
 #endif
@@ -49,7 +50,7 @@ int threads_for(int n_cap) {
   // one thread per 4 x 4 block of the bordered matrix (register-blocked sweep) when that fits in 288 threads (n_cap <= 91)
 #if STP_EXACT_REGS
   const int blocks = reg_blocks_for(n_cap + 1);
-  if (blocks <= 288) { const int t = (blocks + 31) / 32 * 32; return t < 128 ? 128 : t; }
+  if (blocks <= STP_EXACT_MAXT) { const int t = (blocks + 31) / 32 * 32; return t < 128 ? 128 : t; }
 #endif
   return n_cap <= 48 ? 128 : 256;
 }
@@ -153,9 +154,9 @@ __global__ void __launch_bounds__(STP_EXACT_MAXT, STP_EXACT_MINB) k_exact_bo_ste
                                 int32_t* __restrict__ n_arr, int32_t* __restrict__ trace, BoundsArg bnd,
                                 PriorArg prior, LbfgsbOpts opts, double* __restrict__ theta_out,
                                 double* __restrict__ acq_out, int32_t* __restrict__ nit, int32_t* __restrict__ nfev,
-                                int32_t* __restrict__ status) {
+                                int32_t* __restrict__ status, const int32_t* __restrict__ order) {
   extern __shared__ double smem[];
-  const int b = blockIdx.x;
+  const int b = order ? order[blockIdx.x] : blockIdx.x;   // longest-first scheduling: CTAs are issued in blockIdx order
   if (status[b] != 0) return;  // frozen campaign
   const int n = n_arr[b];
   if (n >= n_cap || n < 1) { if (threadIdx.x == 0) status[b] = 2; return; }
@@ -435,7 +436,7 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
                       const int32_t* pool_id, uint8_t* mask, double* X, double* y, int32_t* n, int32_t* trace,
                       const double* theta0, const double* lower, const double* upper, const double* prior,
                       const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
-                      int32_t* status, void* stream) {
+                      int32_t* status, const int32_t* order, void* stream) {
   if (check_dims(B, n_cap, d)) return -1;
   if (N < 1) return fail("N < 1");
   if (!pool || !pool_y || !mask || !X || !y || !n || !trace || !theta0 || !prior || !status) return fail("null argument");
@@ -447,7 +448,7 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
   BoundsArg bnd; fill_bounds(bnd, d, lower, upper, theta0);
   k_exact_bo_step<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, N, pool, pool_y, pool_id, mask, X, y, n, trace,
                                                               bnd, p, to_opts(opts), theta_out, acq_out, nit, nfev,
-                                                              status);
+                                                              status, order);
   return after_launch("stp_exact_bo_step");
 }
 

@@ -76,6 +76,7 @@ class CampaignBatch:
         self.epochs, self.learning_rate, self.num_samples = int(epochs), float(learning_rate), int(num_samples)
         self.seeds = list(seeds) if seeds is not None else list(range(B))
         self.iteration = 0
+        self.ragged = len({len(i) for i in init_indices}) > 1   # campaigns of different ages: schedule longest first
         if kind == "ExactGP":
             self._theta0 = priors.exact_theta0(d)
             self._lower, self._upper = priors.exact_bounds(d)
@@ -96,10 +97,12 @@ class CampaignBatch:
     def step(self) -> None:
         """One BO iteration (runners.py:64-109) for every running campaign."""
         if self.kind == "ExactGP":
+            # longest-first: a fit costs ~ closures x n^3, so the biggest training sets go first (no host sync)
+            order = torch.argsort(self.n, descending=True, stable=True).to(torch.int32) if self.ragged else None
             _lib.exact_bo_step(self.pool, self.pool_y, self.pool_id, self.mask, self.X, self.y, self.n, self.trace,
                                self._theta0, self._lower, self._upper, self._prior, self.status,
                                theta_out=self.theta, acq_out=self.acq, nit=self.nit, nfev=self.nfev,
-                               opts=self._opts)
+                               opts=self._opts, order=order)
             self.launches += 1
         else:
             self.launches += self._var.step()
