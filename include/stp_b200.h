@@ -111,12 +111,13 @@ size_t stp_var_workspace_bytes(int B, int n_cap);
  * (Z, hyp).  y is standardised inside (optim.py:126-127).  fresh != 0 first builds a new model
  * (runners.py:66-74): Z = X, hyp = hyp0, nat1 = 1e-3 * init_noise (init_noise [B, n_cap]; NULL = Philox(seed)),
  * nat2 = -I/2, Adam moments 0; fresh == 0 continues from the given state with Adam step offset t0.
- * loss_hist: optional [B, epochs].  Campaigns with status != 0 on entry are skipped. */
+ * loss_hist: optional [B, epochs].  Campaigns with status != 0 on entry are skipped.  order: optional int32[B]
+ * CTA -> campaign permutation (longest first), as for stp_exact_bo_step. */
 int stp_var_fit(int B, int n_cap, int d, int lik, int epochs, double lr_ngd, double lr_adam, int fresh, int t0,
                 const double* X, const double* y, const int32_t* n, const double* init_noise, unsigned long long seed,
                 const double* hyp0, const double* prior, const double* gh, double* Z, double* hyp, double* nat1,
                 double* nat2, double* adam_m, double* adam_v, double* loss_hist, int32_t* status, double* work,
-                void* stream);
+                const int32_t* order, void* stream);
 
 /* One evaluation of -ELBO/n (VariationalELBO, optim.py:143, 153-154) and its raw gradients at a given state,
  * nothing updated.  grads [B, G], G = n_cap + n_cap^2 + n_cap*d + d + 4, laid out as
@@ -138,7 +139,7 @@ int stp_var_acq(int B, int n_cap, int d, int N, int lik, const double* pool, con
                 const double* Z, const double* hyp, const double* nat1, const double* nat2, int32_t* n,
                 const double* best_f, int S, const double* eps, unsigned long long seed, int32_t* out_idx,
                 double* out_acq, double* mean, double* var, double* acq, int update, const double* pool_y, double* X,
-                double* y, int32_t* trace, int32_t* status, double* work, void* stream);
+                double* y, int32_t* trace, int32_t* status, double* work, const int32_t* order, void* stream);
 
 /* 2 * pairs standard normals of the in-kernel generator: out[2q], out[2q+1] for counters counter0 + q. */
 int stp_philox_normal(unsigned long long seed, unsigned long long stream_id, unsigned long long counter0,

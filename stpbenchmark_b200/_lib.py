@@ -192,15 +192,15 @@ def _u64(v: int):
 
 
 def var_fit(X, y, n, state: dict, lik: int, epochs: int, lr_ngd: float, lr_adam: float, hyp0, prior, gh, status,
-            work, fresh: bool = True, t0: int = 0, init_noise=None, seed: int = 0, loss_hist=None):
+            work, fresh: bool = True, t0: int = 0, init_noise=None, seed: int = 0, loss_hist=None, order=None):
     """stp_var_fit on the state dict {Z, hyp, nat1, nat2, adam_m, adam_v} (in place)."""
-    _require_cuda(X, y, n, init_noise, status, work, loss_hist, *state.values())
+    _require_cuda(X, y, n, init_noise, status, work, loss_hist, order, *state.values())
     B, n_cap, d = X.shape
     _check(lib().stp_var_fit(B, n_cap, d, int(lik), int(epochs), ctypes.c_double(lr_ngd), ctypes.c_double(lr_adam),
                              int(bool(fresh)), int(t0), _p(X), _p(y), _p(n), _p(init_noise), _u64(seed), _host(hyp0),
                              _host(prior), _host(gh), _p(state["Z"]), _p(state["hyp"]), _p(state["nat1"]),
                              _p(state["nat2"]), _p(state["adam_m"]), _p(state["adam_v"]), _p(loss_hist), _p(status),
-                             _p(work), _stream()), "stp_var_fit")
+                             _p(work), _p(order), _stream()), "stp_var_fit")
 
 
 def var_elbo_fg(X, y, n, state: dict, lik: int, prior, gh, work, standardise: bool = True):
@@ -218,7 +218,7 @@ def var_elbo_fg(X, y, n, state: dict, lik: int, prior, gh, work, standardise: bo
 
 
 def var_acq(pool, state: dict, n, lik: int, status, work, best_f=None, mask=None, pool_id=None, S: int = 2048, eps=None,
-            seed: int = 0, want_pointwise: bool = False, update=None):
+            seed: int = 0, want_pointwise: bool = False, update=None, order=None):
     """stp_var_acq.  ``update`` = dict(pool_y, X, y, trace) performs the append of runners.py:98-109."""
     _require_cuda(pool, n, status, work, best_f, mask, pool_id, eps, *[state[k] for k in ("Z", "hyp", "nat1", "nat2")])
     B, n_cap, d = state["Z"].shape
@@ -236,7 +236,7 @@ def var_acq(pool, state: dict, n, lik: int, status, work, best_f=None, mask=None
     _check(lib().stp_var_acq(B, n_cap, d, N, int(lik), _p(pool), _p(pool_id), _p(mask), _p(state["Z"]), _p(state["hyp"]),
                              _p(state["nat1"]), _p(state["nat2"]), _p(n), _p(best_f), int(S), _p(eps), _u64(seed),
                              _p(idx), _p(best), _p(mean), _p(var), _p(acq), int(update is not None), _p(u.get("pool_y")),
-                             _p(u.get("X")), _p(u.get("y")), _p(u.get("trace")), _p(status), _p(work), _stream()),
+                             _p(u.get("X")), _p(u.get("y")), _p(u.get("trace")), _p(status), _p(work), _p(order), _stream()),
            "stp_var_acq")
     return {"idx": idx, "acq_best": best, "mean": mean, "var": var, "acq": acq}
 

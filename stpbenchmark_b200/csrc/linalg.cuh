@@ -10,6 +10,11 @@ namespace stp {
 
 STP_HD int odd_ld(int n) { return n | 1; }
 
+// Row offset of a lower-triangular matrix: square storage (row i at i * ld) or packed rows (row i at i (i + 1) / 2,
+// half the shared memory; rows stay contiguous, which is all the sweep / Cholesky / inverse / pool pass need).
+template <bool TRI>
+STP_HD int row_off(int i, int ld) { return TRI ? (i * (i + 1)) / 2 : i * ld; }
+
 // ---------------------------------------------------------------------------------------
 // Symmetric sweep (Goodnight 1979) of the leading `npiv` pivots of an m x m symmetric matrix
 // whose LOWER triangle (i >= j) lives in A.  With the bordered input
@@ -26,11 +31,11 @@ STP_HD int odd_ld(int n) { return n | 1; }
 // Fast path: every lane owns CQ fixed columns (lane + q W, q < CQ) whose pivot-column entries stay in
 // registers for the whole step; a warp walks its rows with a running row pointer, so the body per element is
 // load / DFMA / select / store plus predicated publishes (no per-element index arithmetic or branches).
-template <int CQ, class Team>
+template <int CQ, bool TRI, class Team>
 STP_HD int sweep_bordered_cf(const Team& tm, double* A, int ld, int m, int npiv, double* c0, double* c1,
                              double* piv) {
   const int W = tm.warp_width(), lane = tm.lane(), nw = tm.nwarps();
-  for (int i = tm.rank(); i < m; i += tm.size()) c0[i] = A[i * ld];
+  for (int i = tm.rank(); i < m; i += tm.size()) c0[i] = A[row_off<TRI>(i, ld)];
   tm.sync();
   double* cur = c0;
   double* nxt = c1;
@@ -49,7 +54,7 @@ STP_HD int sweep_bordered_cf(const Team& tm, double* A, int ld, int m, int npiv,
       own_n[q] = (j == k + 1);
     }
     for (int i = tm.warp(); i < m; i += nw) {
-      double* row = A + i * ld;
+      double* row = A + row_off<TRI>(i, ld);
       if (i == k) {
 #pragma unroll
         for (int q = 0; q < CQ; ++q) {
@@ -78,15 +83,15 @@ STP_HD int sweep_bordered_cf(const Team& tm, double* A, int ld, int m, int npiv,
   return 0;
 }
 
-template <class Team>
+template <bool TRI = false, class Team>
 STP_HD int sweep_bordered(const Team& tm, double* A, int ld, int m, int npiv, double* c0, double* c1,
                           double* piv) {
   if (tm.warp_width() > 1) {
-    if (m <= 1 * tm.warp_width()) return sweep_bordered_cf<1>(tm, A, ld, m, npiv, c0, c1, piv);
-    if (m <= 2 * tm.warp_width()) return sweep_bordered_cf<2>(tm, A, ld, m, npiv, c0, c1, piv);
-    if (m <= 3 * tm.warp_width()) return sweep_bordered_cf<3>(tm, A, ld, m, npiv, c0, c1, piv);
+    if (m <= 1 * tm.warp_width()) return sweep_bordered_cf<1, TRI>(tm, A, ld, m, npiv, c0, c1, piv);
+    if (m <= 2 * tm.warp_width()) return sweep_bordered_cf<2, TRI>(tm, A, ld, m, npiv, c0, c1, piv);
+    if (m <= 3 * tm.warp_width()) return sweep_bordered_cf<3, TRI>(tm, A, ld, m, npiv, c0, c1, piv);
   }
-  for (int i = tm.rank(); i < m; i += tm.size()) c0[i] = A[i * ld];
+  for (int i = tm.rank(); i < m; i += tm.size()) c0[i] = A[row_off<TRI>(i, ld)];
   tm.sync();
   double* cur = c0;
   double* nxt = c1;
@@ -97,7 +102,7 @@ STP_HD int sweep_bordered(const Team& tm, double* A, int ld, int m, int npiv, do
     if (tm.rank() == 0) piv[k] = p;
     const double invp = 1.0 / p;
     for (int i = tm.warp(); i < m; i += tm.nwarps()) {
-      double* row = A + i * ld;
+      double* row = A + row_off<TRI>(i, ld);
       if (i == k) {  // pivot row (warp-uniform branch): a_kj / p, and -1/p on the diagonal
         for (int j = tm.lane(); j <= i; j += W) row[j] = (j == k) ? -invp : cur[j] * invp;
       } else {       // generic rows, branch-free body: a_ij - a_ik a_kj / p, pivot column gets a_ik / p
@@ -123,25 +128,25 @@ STP_HD int sweep_bordered(const Team& tm, double* A, int ld, int m, int npiv, do
 // deferred to the end (the loop works on l_ij * l_jj), hence one barrier per column.
 // `sd` : n doubles of scratch.  Returns 0 or 1 + j for a non-positive pivot.
 // ---------------------------------------------------------------------------------------
-template <class Team>
+template <bool TRI = false, class Team>
 STP_HD int cholesky_lower(const Team& tm, double* A, int ld, int n, double* sd) {
   const int W = tm.warp_width();
   for (int j = 0; j < n; ++j) {
     tm.sync();
-    const double dj = A[j * ld + j];
+    const double dj = A[row_off<TRI>(j, ld) + j];
     if (!(dj > 0.0) || !(dj <= 1.79e308)) return 1 + j;
     const double inv = 1.0 / dj;
     for (int i = j + 1 + tm.warp(); i < n; i += tm.nwarps()) {
-      double* row = A + i * ld;
+      double* row = A + row_off<TRI>(i, ld);
       const double lij = row[j] * inv;
-      for (int k = j + 1 + tm.lane(); k <= i; k += W) row[k] -= lij * A[k * ld + j];
+      for (int k = j + 1 + tm.lane(); k <= i; k += W) row[k] -= lij * A[row_off<TRI>(k, ld) + j];
     }
   }
   tm.sync();
-  for (int j = tm.rank(); j < n; j += tm.size()) sd[j] = sqrt(A[j * ld + j]);
+  for (int j = tm.rank(); j < n; j += tm.size()) sd[j] = sqrt(A[row_off<TRI>(j, ld) + j]);
   tm.sync();
   for (int i = tm.warp(); i < n; i += tm.nwarps()) {
-    double* row = A + i * ld;
+    double* row = A + row_off<TRI>(i, ld);
     for (int j = tm.lane(); j <= i; j += W) row[j] = (j == i) ? sd[j] : row[j] / sd[j];
   }
   tm.sync();
@@ -149,120 +154,13 @@ STP_HD int cholesky_lower(const Team& tm, double* A, int ld, int n, double* sd) 
 }
 
 // ---------------------------------------------------------------------------------------
-// In-place inverse of a lower-triangular matrix (unblocked, right-to-left columns):
-//   Linv[j][j] = 1 / L[j][j];  Linv[j+1:, j] = -Linv[j+1:, j+1:] L[j+1:, j] / L[j][j].
-// ---------------------------------------------------------------------------------------
-template <class Team>
-STP_HD void tri_inverse_lower(const Team& tm, double* A, int ld, int n, double* tmp) {
-  for (int j = n - 1; j >= 0; --j) {
-    const double invd = 1.0 / A[j * ld + j];
-    for (int i = j + 1 + tm.rank(); i < n; i += tm.size()) {
-      const double* row = A + i * ld;
-      double s0 = 0.0, s1 = 0.0;
-      int k = j + 1;
-      for (; k + 1 <= i; k += 2) {
-        s0 += row[k] * A[k * ld + j];
-        s1 += row[k + 1] * A[(k + 1) * ld + j];
-      }
-      if (k <= i) s0 += row[k] * A[k * ld + j];
-      tmp[i] = -(s0 + s1) * invd;
-    }
-    tm.sync();
-    for (int i = j + tm.rank(); i < n; i += tm.size()) A[i * ld + j] = (i == j) ? invd : tmp[i];
-    tm.sync();
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------
-// Right-looking inverse of a lower-triangular matrix, out of place: X = L^-1 (lower, strict upper
-// zero-filled) and, optionally, XT = L^-T (upper, strict lower zero-filled).  Step k subtracts
-// (L[i][k] / L[k][k]) * X[k][:] from every later row: n steps, one barrier each, every step fully
-// parallel over (i > k, c <= k) -- no per-thread substitution chain.  n^3/6 MAC.
-// ---------------------------------------------------------------------------------------
-template <class Team>
-STP_HD void tri_inverse_rl(const Team& tm, const double* L, int ld, int n, double* X, double* XT) {
-  const int W = tm.warp_width(), nw = tm.nwarps();
-  for (int i = tm.warp(); i < n; i += nw) {
-    double* row = X + i * ld;
-    for (int c = tm.lane(); c < n; c += W) row[c] = (c == i) ? 1.0 : 0.0;
-  }
-  tm.sync();
-  for (int k = 0; k < n - 1; ++k) {
-    const double invd = 1.0 / L[k * ld + k];
-    const double* xk = X + k * ld;
-    for (int i = k + 1 + tm.warp(); i < n; i += nw) {
-      const double f = L[i * ld + k] * invd;
-      double* row = X + i * ld;
-      for (int c = tm.lane(); c <= k; c += W) row[c] = fma(-f, xk[c], row[c]);
-    }
-    tm.sync();
-  }
-  for (int i = tm.warp(); i < n; i += nw) {
-    const double invd = 1.0 / L[i * ld + i];
-    double* row = X + i * ld;
-    for (int c = tm.lane(); c < n; c += W) {
-      const double v = (c <= i) ? row[c] * invd : 0.0;
-      row[c] = v;
-      if (XT) XT[c * ld + i] = v;
-    }
-  }
-  tm.sync();
-}
-
-// ---------------------------------------------------------------------------------------
-// Register-tiled contraction  out(i, k) = sum_{r = r0}^{r1 - 1} Lf(i, r) * Rf(r, k).
-// A warp owns RB consecutive rows, a lane CQ columns 32 apart: RB + CQ loads feed RB * CQ FMAs
-// with RB * CQ independent accumulators.  Lf(i, r) is the same address for the whole warp (broadcast),
-// Rf(r, k) is consecutive across lanes when R is row-major.  `range(i_lo, i_hi, k_lo, k_hi, r0, r1)` gives
-// a common reduction range for the tile; operands must be ZERO (not just ignored) outside their own
-// support inside that range.  `store(i, k, v)` is called for every in-bounds (i, k) of every tile.
-// ---------------------------------------------------------------------------------------
-template <int RB, int CQ, class Team, class LF, class RF, class RangeF, class StoreF>
-STP_HD void contract(const Team& tm, int n_rows, int n_cols, LF Lf, RF Rf, RangeF range, StoreF store) {
-  const int W = tm.warp_width(), nw = tm.nwarps();
-  for (int ib = tm.warp() * RB; ib < n_rows; ib += nw * RB) {
-    int ri[RB];
-#pragma unroll
-    for (int a = 0; a < RB; ++a) ri[a] = (ib + a < n_rows) ? ib + a : n_rows - 1;
-    for (int kb = 0; kb < n_cols; kb += W * CQ) {
-      int kk[CQ];
-#pragma unroll
-      for (int q = 0; q < CQ; ++q) { const int k = kb + tm.lane() + q * W; kk[q] = (k < n_cols) ? k : n_cols - 1; }
-      int r0 = 0, r1 = 0;
-      range(ib, ri[RB - 1], kb, (kb + W * CQ - 1 < n_cols) ? kb + W * CQ - 1 : n_cols - 1, r0, r1);
-      double acc[RB][CQ];
-#pragma unroll
-      for (int a = 0; a < RB; ++a)
-#pragma unroll
-        for (int q = 0; q < CQ; ++q) acc[a][q] = 0.0;
-      for (int r = r0; r < r1; ++r) {
-        double l[RB], rr[CQ];
-#pragma unroll
-        for (int a = 0; a < RB; ++a) l[a] = Lf(ri[a], r);
-#pragma unroll
-        for (int q = 0; q < CQ; ++q) rr[q] = Rf(r, kk[q]);
-#pragma unroll
-        for (int a = 0; a < RB; ++a)
-#pragma unroll
-          for (int q = 0; q < CQ; ++q) acc[a][q] = fma(l[a], rr[q], acc[a][q]);
-      }
-#pragma unroll
-      for (int a = 0; a < RB; ++a)
-#pragma unroll
-        for (int q = 0; q < CQ; ++q) {
-          const int k = kb + tm.lane() + q * W;
-          if (ib + a < n_rows && k < n_cols) store(ib + a, k, acc[a][q]);
-        }
-    }
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------
-// Pointer form of `contract`:  out(i, k) = sum_r L(i, r) * [scale(r)] * R(r, k)  with
+// Register-tiled contraction  out(i, k) = sum_{r = r0}^{r1 - 1} L(i, r) * [scale(r)] * R(r, k)  with
 //   L(i, r) = Lp[i * l_si + r * l_sr]   (LT = false: l_sr == 1, row-major;  LT = true: l_si == 1, read down a column)
 //   R(r, k) = Rp[r * ld_r + k]
+// A warp owns RB consecutive rows, a lane CQ columns 32 apart: RB + CQ loads feed RB * CQ DFMAs with RB * CQ
+// independent accumulators; L(i, r) is a warp-wide broadcast, R(r, k) is consecutive across lanes.
+// `range(i_lo, i_hi, k_lo, k_hi, r0, r1)` gives one reduction range per tile: operands must be ZERO (not just
+// ignored) outside their own support inside it.  `store(i, k, v)` is called for every in-bounds (i, k).
 // The reduction loop is unrolled by 4 with running pointers, so the inner body is loads + DFMA only.
 // ---------------------------------------------------------------------------------------
 template <int RB, int CQ, bool LT, bool SCALE, class Team, class RangeF, class StoreF>
@@ -350,17 +248,17 @@ STP_HD void contract_p(const Team& tm, int n_rows, int n_cols, const double* Lp,
 // L^-1.  Step k consumes column k of L and replaces it by column k of the (unscaled) inverse, so no second
 // buffer is needed; one barrier per step, every step parallel over (i > k, c <= k).  `invd`: n doubles.
 // ---------------------------------------------------------------------------------------
-template <class Team>
+template <bool TRI = false, class Team>
 STP_HD void tri_inverse_rl_inplace(const Team& tm, double* A, int ld, int n, double* invd) {
   const int W = tm.warp_width(), nw = tm.nwarps();
-  for (int i = tm.rank(); i < n; i += tm.size()) invd[i] = 1.0 / A[i * ld + i];
+  for (int i = tm.rank(); i < n; i += tm.size()) invd[i] = 1.0 / A[row_off<TRI>(i, ld) + i];
   tm.sync();
   // X starts as the identity in the positions already "consumed": column k of L is read at step k only.
   for (int k = 0; k < n - 1; ++k) {
     const double ik = invd[k];
-    const double* xk = A + k * ld;            // row k of X: X[k][c], c < k (unscaled), X[k][k] = 1 implied
+    const double* xk = A + row_off<TRI>(k, ld);            // row k of X: X[k][c], c < k (unscaled), X[k][k] = 1 implied
     for (int i = k + 1 + tm.warp(); i < n; i += nw) {
-      double* row = A + i * ld;
+      double* row = A + row_off<TRI>(i, ld);
       const double f = row[k] * ik;           // L[i][k] / L[k][k]: every lane reads it before lane k % W overwrites it
       tm.sync_warp();
       for (int c = tm.lane(); c <= k; c += W) {
@@ -372,7 +270,7 @@ STP_HD void tri_inverse_rl_inplace(const Team& tm, double* A, int ld, int n, dou
     tm.sync();
   }
   for (int i = tm.warp(); i < n; i += nw) {
-    double* row = A + i * ld;
+    double* row = A + row_off<TRI>(i, ld);
     const double di = invd[i];
     for (int c = tm.lane(); c <= i; c += W) row[c] = ((c == i) ? 1.0 : row[c]) * di;
   }

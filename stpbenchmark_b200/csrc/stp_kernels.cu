@@ -217,9 +217,9 @@ __global__ void __launch_bounds__(256, STP_VAR_MINB) k_var_fit(int n_cap, int d,
                                                  const double* __restrict__ y, const int32_t* __restrict__ n_arr,
                                                  const double* __restrict__ init_noise, VarFitArgs args, int t0,
                                                  VarPtrs P, double* __restrict__ loss_hist, int32_t* __restrict__ status,
-                                                 double* __restrict__ work) {
+                                                 double* __restrict__ work, const int32_t* __restrict__ order) {
   extern __shared__ double smem[];
-  const int b = blockIdx.x;
+  const int b = order ? order[blockIdx.x] : blockIdx.x;   // longest-first scheduling (see stp_exact_bo_step)
   if (status[b] != 0) return;
   const int n = n_arr ? n_arr[b] : n_cap;
   if (n < 1 || n > n_cap) { if (threadIdx.x == 0) status[b] = 2; return; }
@@ -267,9 +267,10 @@ __global__ void __launch_bounds__(256) k_var_acq(int n_cap, int d, int N, int li
                                                  double* __restrict__ mean, double* __restrict__ var,
                                                  double* __restrict__ acq, int update, const double* __restrict__ pool_y,
                                                  double* __restrict__ X, double* __restrict__ y, int32_t* __restrict__ trace,
-                                                 int32_t* __restrict__ status, double* __restrict__ work) {
+                                                 int32_t* __restrict__ status, double* __restrict__ work,
+                                                 const int32_t* __restrict__ order) {
   extern __shared__ double smem[];
-  const int b = blockIdx.x;
+  const int b = order ? order[blockIdx.x] : blockIdx.x;
   if (status[b] != 0) { if (threadIdx.x == 0 && out_idx) out_idx[b] = -1; return; }
   const int n = n_arr ? n_arr[b] : n_cap;
   if (n < 1 || n > n_cap || (update && n >= n_cap)) { if (threadIdx.x == 0) status[b] = 2; return; }
@@ -473,7 +474,7 @@ int stp_var_fit(int B, int n_cap, int d, int lik, int epochs, double lr_ngd, dou
                 const double* X, const double* y, const int32_t* n, const double* init_noise, unsigned long long seed,
                 const double* hyp0, const double* prior, const double* gh, double* Z, double* hyp, double* nat1,
                 double* nat2, double* adam_m, double* adam_v, double* loss_hist, int32_t* status, double* work,
-                void* stream) {
+                const int32_t* order, void* stream) {
   if (check_dims(B, n_cap, d)) return -1;
   if (epochs < 0) return fail("epochs < 0");
   if (!X || !y || !Z || !hyp || !nat1 || !nat2 || !adam_m || !adam_v || !status || !work) return fail("null argument");
@@ -484,7 +485,8 @@ int stp_var_fit(int B, int n_cap, int d, int lik, int epochs, double lr_ngd, dou
   const size_t smem = var_smem_doubles(n_cap, d) * sizeof(double);
   if (set_smem(k_var_fit, smem)) return -1;
   k_var_fit<<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, init_noise, a, t0,
-                                                    VarPtrs{Z, hyp, nat1, nat2, adam_m, adam_v}, loss_hist, status, work);
+                                                    VarPtrs{Z, hyp, nat1, nat2, adam_m, adam_v}, loss_hist, status, work,
+                                                    order);
   return after_launch("stp_var_fit");
 }
 
@@ -511,7 +513,7 @@ int stp_var_acq(int B, int n_cap, int d, int N, int lik, const double* pool, con
                 const double* Z, const double* hyp, const double* nat1, const double* nat2, int32_t* n,
                 const double* best_f, int S, const double* eps, unsigned long long seed, int32_t* out_idx,
                 double* out_acq, double* mean, double* var, double* acq, int update, const double* pool_y, double* X,
-                double* y, int32_t* trace, int32_t* status, double* work, void* stream) {
+                double* y, int32_t* trace, int32_t* status, double* work, const int32_t* order, void* stream) {
   if (check_dims(B, n_cap, d)) return -1;
   if (N < 0 || S < 1) return fail("N < 0 or S < 1");
   if (lik < 0 || lik > 2) return fail("lik must be 0, 1 or 2");
@@ -525,7 +527,7 @@ int stp_var_acq(int B, int n_cap, int d, int N, int lik, const double* pool, con
       n_cap, d, N, lik, pool, pool_id, mask,
       VarPtrs{const_cast<double*>(Z), const_cast<double*>(hyp), const_cast<double*>(nat1), const_cast<double*>(nat2),
               nullptr, nullptr},
-      n, best_f, S, eps, seed, out_idx, out_acq, mean, var, acq, update, pool_y, X, y, trace, status, work);
+      n, best_f, S, eps, seed, out_idx, out_acq, mean, var, acq, update, pool_y, X, y, trace, status, work, order);
   return after_launch("stp_var_acq");
 }
 

@@ -87,15 +87,17 @@ class VarBatchState:
     def step(self) -> int:
         b = self.b
         noise = self._init_noise()
+        order = torch.argsort(b.n, descending=True, stable=True).to(torch.int32) if b.ragged else None
         _lib.var_fit(b.X, b.y, b.n, self.state, self.lik, b.epochs, b.learning_rate, ADAM_LR, self.hyp0, self.prior,
-                     self.gh, b.status, self.work, fresh=True, init_noise=noise, seed=self.philox_seed + 7919 * b.iteration)
+                     self.gh, b.status, self.work, fresh=True, init_noise=noise, seed=self.philox_seed + 7919 * b.iteration,
+                     order=order)
         eps = None
         if self.lik != 0 and self.mc_eps == "host" and self.generators is not None:
             eps = torch.stack([torch.randn(b.N, 1, b.num_samples, dtype=torch.double, generator=g).squeeze(1)
                                for g in self.generators]).to(b.device)
         out = _lib.var_acq(b.pool, self.state, b.n, self.lik, b.status, self.work, best_f=None, mask=b.mask,
                            pool_id=b.pool_id, S=b.num_samples, eps=eps, seed=self.philox_seed + 104729 * b.iteration,
-                           update={"pool_y": b.pool_y, "X": b.X, "y": b.y, "trace": b.trace})
+                           update={"pool_y": b.pool_y, "X": b.X, "y": b.y, "trace": b.trace}, order=order)
         b.acq = out["acq_best"]
         return 2
 

@@ -217,3 +217,29 @@ def test_vartgp_batched_campaigns_teacher_forced_rank():
         order = torch.where(mask)[0][torch.argsort(acq, descending=True)].tolist()
         hits += int(idx[b, 10]) in order[:3]
     assert hits >= 3
+
+
+def test_vartgp_cfg2_smoke_statistics_via_run_many_loops(tmp_path):
+    """BASELINE config #2 at SMOKE length on one dataset: VarTGP, 3 seeds, 30 trials, 200 epochs, through
+    run_many_loops (CSV written, all seeds advanced as one device batch, in-kernel Philox).  The MC stream of the
+    reference is not recoverable, so the comparison with results/VarTGP_AutoAM_*_SMOKE.csv is
+    statistical: same initial designs, comparable best-so-far value, substantial overlap of the visited points."""
+    import pandas as pd
+    from stpbenchmark_b200 import models, runners
+    X, y = dataset("AutoAM")
+    seeds = [45, 359, 6185]
+    out = tmp_path / "VarTGP_AutoAM_dataset_traces_SMOKE.csv"
+    runners.run_many_loops(X, y, model_class=models.VarTGP, seeds=seeds, n_initial=10, n_trials=30, epochs=200,
+                           learning_rate=0.01, output_path=str(out), invert_y=False)
+    df = pd.read_csv(out, header=[0, 1], index_col=0)
+    ours_best, gold_best, overlap = [], [], []
+    for s in seeds:
+        idx = df[f"seed_{s}", "x_index"].astype(int).tolist()
+        gold = trace("smoke", "VarTGP", "AutoAM", s)
+        assert len(idx) == 40 and idx[:10] == gold[:10] and len(set(idx[10:])) == 30
+        assert np.allclose(df[f"seed_{s}", "y_value"].values, y[idx].numpy())
+        ours_best.append(float(y[idx].max())); gold_best.append(float(y[gold].max()))
+        overlap.append(len(set(idx[10:]) & set(gold[10:])) / 30.0)
+    spread = float(y.max() - y.min())
+    assert np.mean(ours_best) >= np.mean(gold_best) - 0.15 * spread, (ours_best, gold_best)
+    assert np.mean(overlap) >= 0.3, overlap
