@@ -59,15 +59,25 @@ def _cpu_one_iteration(job):
 
 
 def _cpu_campaign(job):
-    """`iters` consecutive oracle BO iterations of one fresh campaign -> per-iteration seconds."""
+    """`iters` consecutive oracle BO iterations of one campaign that starts at a given age (training set = Sobol
+    initial design + `age` random pool points, then free-running) -> per-iteration seconds."""
     import torch
-    from oracle.loop import run_single_loop
+    from oracle.loop import bo_iteration
     from stpbenchmark_b200 import synthetic
-    g, seed, iters = job
+    g, seed, iters, age = job
     X, y = synthetic.cfg4_pool(g)
+    init = synthetic.initial_designs(X, y, [seed], N_INITIAL)[0].tolist()
+    gen = torch.Generator().manual_seed(seed)
+    extra = [i for i in torch.randperm(len(X), generator=gen).tolist() if i not in set(init)][:age]
+    picked = init + extra
+    mask = torch.ones(len(X), dtype=torch.bool); mask[picked] = False
     times = []
-    run_single_loop(X, y, "ExactGP", n_initial=N_INITIAL, n_trials=iters, seed=seed,
-                    on_iteration=lambda t, idx, dt, info: times.append(dt))
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        best, _acq = bo_iteration("ExactGP", X[picked], y[picked], X[mask])
+        idx = int(torch.where(mask)[0][best])
+        picked.append(idx); mask[idx] = False
+        times.append(time.perf_counter() - t0)
     return times
 
 
@@ -83,7 +93,9 @@ def run_reference_arm(args):
     W, K = args.warmup, args.steps
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_cpu_init) as pool:
-        jobs = [(c % N_POOLS, 900000 + c, W + K) for c in range(cores)]
+        span = max(N_TRIALS - (W + K), 1)          # ages spread over the campaign so that n covers 10..89 like the GPU mix
+        ages = [(c * span) // max(cores - 1, 1) if cores > 1 else 0 for c in range(cores)]
+        jobs = [(c % N_POOLS, 900000 + c, W + K, ages[c]) for c in range(cores)]
         t0 = time.perf_counter()
         per = pool.map(_cpu_campaign, jobs)
         wall = time.perf_counter() - t0
@@ -95,8 +107,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
         "warmup": W, "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(B=args.campaigns), "sample": f"{cores} campaigns (one per host core), "
-                   f"iterations {W}..{W + K - 1} of each (n = {N_INITIAL + W}..{N_INITIAL + W + K - 1})"},
+        "config": {"workload": WORKLOAD.format(B=args.campaigns), "sample": f"{cores} campaigns (one per host core) started at "
+                   f"ages 0..{max(ages)} (Sobol design + age random pool points), {W} warm-up + {K} timed consecutive "
+                   f"BO iterations each (n = {N_INITIAL}..{N_INITIAL + max(ages) + W + K - 1})"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{cores} campaigns x {K} consecutive BO iterations, oracle/ (torch fp64 + scipy "
                                    f"L-BFGS-B), 1 thread per campaign; wall {wall:.1f}s"},
