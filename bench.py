@@ -30,6 +30,7 @@ N_POOL, DIM, N_POOLS = 2048, 6, 8
 N_INITIAL, N_TRIALS = 10, 80
 CAP = N_INITIAL + N_TRIALS + 1
 METRIC, UNIT = "bo_iterations_per_sec", "it/s"
+NCU_DRAM_BYTES_PER_LAUNCH = 7.268096e6 + 0.924928e6   # measured once with ncu (see roofline.traffic_source)
 WORKLOAD = ("cfg4: synthetic pools N=2048 d=6 (Hartmann-6 + t3 noise), {B} concurrent ExactGP campaigns per GPU, "
             "n_initial=10, 80 trials, ages staggered over n=10..89 (continuous batching)")
 
@@ -372,7 +373,10 @@ def run_cuda_arm(args):
                        "l2": "inputs are L2-resident by design (0.8 MB of pools); the kernel is FP64/latency bound, "
                              "no HBM stream to flush", "threads_per_campaign": os.environ.get("STP_THREADS", "auto")},
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / fp64_peak, "traffic": None,
+                         "frac": achieved_tflops / fp64_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_exact_bo_step, ncu --set full, "
+                                           "1024 campaigns (profiles/r01_ncu_prof_r1_bostep.txt); algorithmic bytes per launch: "
+                                           f"{hbm_bytes / K:.3g}",
                          "kernel": "k_exact_bo_step",
                          "peak_source": "stp_fp64_probe (DFMA microbenchmark, this run); MEASURED_PEAKS.json has no FP64 figure",
                          "hbm": {"achieved": hbm_bytes / (float(step_ms.sum()) * 1e-3) / 1e9, "peak": hbm_peak,

@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define STP_MAX_D 8
-#define STP_MAX_N 160
+#define STP_MAX_N 144   /* (n_cap + 1)^2 doubles + the pool tile must fit in 227 KB of shared memory */
 #define STP_ABI_VERSION 1
 
 /* L-BFGS-B options; scipy.optimize.minimize(method="L-BFGS-B") defaults are

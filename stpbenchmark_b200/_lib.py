@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_PKG, "libstp_b200.so")
 _lib = None
 
 MAX_D = 8
-MAX_N = 160
+MAX_N = 144
 
 STATUS_TEXT = {
     0: "ok", 1: "matrix not positive definite", 2: "non-finite parameter or objective",
