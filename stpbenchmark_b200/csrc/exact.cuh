@@ -37,6 +37,8 @@ struct ExactSmem {
   double* y;      // cap
   double* c0;     // cap+5
   double* c1;     // cap+5
+  double* c2;     // cap+9  (pair sweep: next pivot columns)
+  double* c3;     // cap+9
   double* piv;    // cap+5 (pivots; reused as tmp by the triangular inverse)
   double* alpha;  // cap
   double* tile;   // acquisition: cap x TC cross-covariances + TC x (kMaxD) staged candidates
@@ -48,7 +50,7 @@ struct ExactSmem {
 
 STP_HD size_t exact_smem_doubles(int cap, int d, int tc, int nwarps) {
   const int ld = odd_ld(cap + 1);
-  return (size_t)(cap + 1) * ld + (size_t)d * cap + cap + 3 * (size_t)(cap + 9) + cap +
+  return (size_t)(cap + 1) * ld + (size_t)d * cap + cap + 5 * (size_t)(cap + 9) + cap +
          (size_t)cap * tc + (size_t)tc * kMaxD + 64 + 16 * kMaxWarps;  // nwarps*tc*2 <= 16*kMaxWarps
 }
 
@@ -62,6 +64,8 @@ STP_HD ExactSmem exact_smem_carve(double* base, int cap, int d, int tc, int nwar
   s.y = p;      p += cap;
   s.c0 = p;     p += cap + 9;   // (cap + 1) rounded up to a multiple of the register-block edge (<= 8)
   s.c1 = p;     p += cap + 9;
+  s.c2 = p;     p += cap + 9;
+  s.c3 = p;     p += cap + 9;
   s.piv = p;    p += cap + 9;
   s.alpha = p;  p += cap;
   s.tile = p;   p += (size_t)cap * tc + (size_t)tc * kMaxD;
@@ -130,7 +134,7 @@ STP_HD int exact_mll_fg(const Team& tm, const ExactSmem& s, int n, int d, const 
   }
   tm.sync();
   // K3+K4: bordered sweep -> -Kinv, alpha, -quad, pivots
-  const int fail = sweep_bordered(tm, s.A, ld, n + 1, n, s.c0, s.c1, s.piv);
+  const int fail = sweep_bordered4(tm, s.A, ld, n + 1, n, s.c0, s.c1, s.c2, s.c3, s.piv);
   if (fail) { *f_out = NAN; return 1; }
   const double* arow = s.A + n * ld;  // alpha
   // K5: reductions

@@ -218,27 +218,30 @@ STP_HD int lb_subsm(LbfgsbState& S) {
     rr[a] = -(S.g[i] + bz);
     for (int b = 0; b <= a; ++b) C[a][b] = S.B[i][ind[b]];
   }
+  double* idiag = S.sc_c;           // reciprocals of the Cholesky diagonal: one division per column, not per entry
   for (int j = 0; j < nf; ++j) {  // Cholesky of B_FF
     double s = C[j][j];
     for (int k = 0; k < j; ++k) s -= C[j][k] * C[j][k];
     if (!(s > 0.0)) return 1;
     const double l = sqrt(s);
+    const double il = 1.0 / l;
     C[j][j] = l;
+    idiag[j] = il;
     for (int i = j + 1; i < nf; ++i) {
       double v = C[i][j];
       for (int k = 0; k < j; ++k) v -= C[i][k] * C[j][k];
-      C[i][j] = v / l;
+      C[i][j] = v * il;
     }
   }
   for (int i = 0; i < nf; ++i) {
     double v = rr[i];
     for (int k = 0; k < i; ++k) v -= C[i][k] * dd[k];
-    dd[i] = v / C[i][i];
+    dd[i] = v * idiag[i];
   }
   for (int i = nf - 1; i >= 0; --i) {
     double v = dd[i];
     for (int k = i + 1; k < nf; ++k) v -= C[k][i] * dd[k];
-    dd[i] = v / C[i][i];
+    dd[i] = v * idiag[i];
   }
   // projection of x^cp + d onto the box
   int iword = 0;

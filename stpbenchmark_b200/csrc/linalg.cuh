@@ -123,6 +123,158 @@ STP_HD int sweep_bordered(const Team& tm, double* A, int ld, int m, int npiv, do
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Rank-2 (pivot-pair) form of the bordered symmetric sweep: pivots k and k + 1 are eliminated together,
+//     a_ij <- a_ij - [a_ik a_ik'] Pinv [a_kj a_k'j]^T ,  a_iK <- a_iK Pinv ,  A_KK <- -Pinv ,   P = A_KK (2 x 2),
+// which equals two successive single sweeps but touches every element once per PAIR: one load / two DFMA /
+// one store per element and half the barriers.  Four ping-pong vectors hold the two pivot columns of this step
+// (c0, c1: values BEFORE the step) and of the next one (published by the owners of columns k + 2, k + 3).
+// An odd last pivot is handled by a single sweep step.  CQ > 0: every lane keeps the pivot-column entries of
+// its CQ fixed columns (lane + q W) in registers; CQ == 0: generic strided loops (any m, any team).
+// Same contract as sweep_bordered (result layout, piv[], return code).  `vec`: 4 * (m rounded up) doubles.
+// ---------------------------------------------------------------------------------------
+template <int CQ, bool TRI, class Team>
+STP_HD int sweep_bordered_pair(const Team& tm, double* A, int ld, int m, int npiv, double* v0, double* v1, double* v2,
+                               double* v3, double* piv) {
+  const int W = tm.warp_width(), lane = tm.lane(), nw = tm.nwarps();
+  constexpr int NQ = CQ > 0 ? CQ : 1;
+  double* c0 = v0; double* c1 = v1; double* n0 = v2; double* n1 = v3;
+  // columns 0 and 1 of the initial matrix (symmetric fill: entry i of column c is A[max(i,c)][min(i,c)])
+  for (int i = tm.rank(); i < m; i += tm.size()) {
+    c0[i] = A[row_off<TRI>(i, ld)];
+    if (m > 1) c1[i] = (i >= 1) ? A[row_off<TRI>(i, ld) + 1] : A[row_off<TRI>(1, ld)];
+  }
+  tm.sync();
+  int k = 0;
+  for (; k + 1 < npiv; k += 2) {
+    const double p00 = c0[k], p01 = c0[k + 1], p11 = c1[k + 1];
+    if (!(p00 > 0.0) || !(p00 <= 1.79e308)) return 1 + k;
+    const double s = p11 - p01 * (p01 / p00);
+    if (!(s > 0.0) || !(s <= 1.79e308)) return 2 + k;
+    if (tm.rank() == 0) { piv[k] = p00; piv[k + 1] = s; }
+    const double idet = 1.0 / (p00 * s);
+    const double q00 = p11 * idet, q01 = -p01 * idet, q11 = p00 * idet;
+    double cj0[NQ], cj1[NQ];
+    if (CQ > 0) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int j = lane + q * W;
+        cj0[q] = (j < m) ? c0[j] : 0.0;
+        cj1[q] = (j < m) ? c1[j] : 0.0;
+      }
+    }
+    if (CQ > 0) {
+      // Register-cached columns: RU rows per iteration, all loads of the RU x CQ tile issued before the first DFMA,
+      // so that the shared-memory latency is paid once per RU rows instead of once per row (the loop is
+      // latency-bound: ~3 elements per lane per row).
+      constexpr int RU = 1;   // measured on B200: RU = 2 / 4 are slower (20.0k / 17.8k vs 20.9k it/s): register pressure, no gain
+      for (int ib = tm.warp(); ib < m; ib += nw * RU) {
+        double a[RU][NQ], t0[RU], t1[RU];
+        int ii[RU];
+        bool pr[RU];
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+          const int i = ib + r * nw;
+          ii[r] = i;
+          const int ic = (i < m) ? i : 0;
+          const double ci0 = c0[ic], ci1 = c1[ic];
+          const bool prow0 = (i == k), prow1 = (i == k + 1);
+          pr[r] = prow0 || prow1;
+          t0[r] = prow0 ? q00 : (prow1 ? q01 : ci0 * q00 + ci1 * q01);
+          t1[r] = prow0 ? q01 : (prow1 ? q11 : ci0 * q01 + ci1 * q11);
+          const double* row = A + row_off<TRI>(ic, ld);
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const int j = lane + q * W;
+            a[r][q] = (i < m && j <= i) ? row[j] : 0.0;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+          const int i = ii[r];
+          if (i < m) {
+            double* row = A + row_off<TRI>(i, ld);
+            const bool nrow0 = (i == k + 2), nrow1 = (i == k + 3);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+              const int j = lane + q * W;
+              if (j <= i) {
+                double v;
+                if (pr[r]) v = (j == k) ? -t0[r] : ((j == k + 1) ? -t1[r] : t0[r] * cj0[q] + t1[r] * cj1[q]);
+                else v = (j == k) ? t0[r] : ((j == k + 1) ? t1[r] : fma(-t1[r], cj1[q], fma(-t0[r], cj0[q], a[r][q])));
+                row[j] = v;
+                if (j == k + 2) n0[i] = v;
+                if (j == k + 3) n1[i] = v;
+                if (nrow0) n0[j] = v;
+                if (nrow1) n1[j] = v;
+              }
+            }
+          }
+        }
+      }
+    } else {
+      for (int i = tm.warp(); i < m; i += nw) {
+        double* row = A + row_off<TRI>(i, ld);
+        const double ci0 = c0[i], ci1 = c1[i];
+        const bool prow0 = (i == k), prow1 = (i == k + 1);
+        // generic rows: t = a_iK Pinv; pivot rows: the matching row of Pinv (so that t . c_j = (Pinv a_Kj)_row)
+        const double t0 = prow0 ? q00 : (prow1 ? q01 : ci0 * q00 + ci1 * q01);
+        const double t1 = prow0 ? q01 : (prow1 ? q11 : ci0 * q01 + ci1 * q11);
+        const bool pr = prow0 || prow1;
+        const bool nrow0 = (i == k + 2), nrow1 = (i == k + 3);
+        for (int j = lane; j <= i; j += W) {
+          const double a0 = c0[j], a1 = c1[j];
+          double a;
+          if (pr) a = (j == k) ? -t0 : ((j == k + 1) ? -t1 : t0 * a0 + t1 * a1);          // pivot rows
+          else a = (j == k) ? t0 : ((j == k + 1) ? t1 : fma(-t1, a1, fma(-t0, a0, row[j])));
+          row[j] = a;
+          if (j == k + 2) n0[i] = a;
+          if (j == k + 3) n1[i] = a;
+          if (nrow0) n0[j] = a;
+          if (nrow1) n1[j] = a;
+        }
+      }
+    }
+    tm.sync();
+    double* t;
+    t = c0; c0 = n0; n0 = t;
+    t = c1; c1 = n1; n1 = t;
+  }
+  if (k < npiv) {  // odd remainder: one single-pivot step on column c0
+    const double p = c0[k];
+    if (!(p > 0.0) || !(p <= 1.79e308)) return 1 + k;
+    if (tm.rank() == 0) piv[k] = p;
+    const double invp = 1.0 / p;
+    for (int i = tm.warp(); i < m; i += nw) {
+      double* row = A + row_off<TRI>(i, ld);
+      const double ti = c0[i] * invp;
+      for (int j = lane; j <= i; j += W) {
+        double a;
+        if (i == k) a = (j == k) ? -invp : c0[j] * invp;
+        else a = (j == k) ? ti : fma(-ti, c0[j], row[j]);
+        row[j] = a;
+      }
+    }
+    tm.sync();
+  }
+  return 0;
+}
+
+
+// Dispatcher used by the fit closures: pair sweep with register-cached columns when the matrix fits 3 column
+// slots per lane, generic pair sweep otherwise.
+template <bool TRI = false, class Team>
+STP_HD int sweep_bordered4(const Team& tm, double* A, int ld, int m, int npiv, double* v0, double* v1, double* v2,
+                           double* v3, double* piv) {
+  if (tm.warp_width() > 1) {
+    if (m <= 1 * tm.warp_width()) return sweep_bordered_pair<1, TRI>(tm, A, ld, m, npiv, v0, v1, v2, v3, piv);
+    if (m <= 2 * tm.warp_width()) return sweep_bordered_pair<2, TRI>(tm, A, ld, m, npiv, v0, v1, v2, v3, piv);
+    if (m <= 3 * tm.warp_width()) return sweep_bordered_pair<3, TRI>(tm, A, ld, m, npiv, v0, v1, v2, v3, piv);
+  }
+  return sweep_bordered_pair<0, TRI>(tm, A, ld, m, npiv, v0, v1, v2, v3, piv);
+}
+
 // ---------------------------------------------------------------------------------------
 // In-place Cholesky of the lower triangle: A = L L^T.  Right-looking with the column scaling
 // deferred to the end (the loop works on l_ij * l_jj), hence one barrier per column.

@@ -92,6 +92,8 @@ struct VarSmem {
   double* mu;    // cap+1
   double* c0;    // cap+1
   double* c1;    // cap+1
+  double* c2;    // cap+1  (pair sweep: next pivot columns)
+  double* c3;    // cap+1
   double* piv;   // cap+1
   double* fm;    // cap       q(f) mean at the training points
   double* fv;    // cap       q(f) variance
@@ -107,7 +109,7 @@ struct VarSmem {
 };
 
 STP_HD size_t var_smem_doubles(int cap, int d) {
-  return (size_t)(cap + 1) * odd_ld(cap + 1) + (size_t)2 * d * cap + (size_t)cap * 8 + 4 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
+  return (size_t)(cap + 1) * odd_ld(cap + 1) + (size_t)2 * d * cap + (size_t)cap * 8 + 6 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
 }
 
 STP_HD VarSmem var_smem_carve(double* base, int cap, int d) {
@@ -120,6 +122,8 @@ STP_HD VarSmem var_smem_carve(double* base, int cap, int d) {
   s.mu = p; p += cap + 1;
   s.c0 = p; p += cap + 1;
   s.c1 = p; p += cap + 1;
+  s.c2 = p; p += cap + 1;
+  s.c3 = p; p += cap + 1;
   s.piv = p; p += cap + 1;
   s.fm = p; p += cap;
   s.fv = p; p += cap;
@@ -226,7 +230,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
     else for (int j = tm.lane(); j <= n; j += W) row[j] = (j < n) ? M.nat1[j] : 0.0;
   }
   tm.sync();
-  if (sweep_bordered(tm, M0, ld, n + 1, n, s.c0, s.c1, s.piv)) { out.status = 1; return out; }
+  if (sweep_bordered4(tm, M0, ld, n + 1, n, s.c0, s.c1, s.c2, s.c3, s.piv)) { out.status = 1; return out; }
   double kl_acc[4] = {0.0, 0.0, 0.0, 0.0};   // sum log piv(P), tr S, mu.mu
   for (int i = tm.rank(); i < n; i += tm.size()) {
     const double m = M0[n * ld + i];
