@@ -208,8 +208,7 @@ STP_HD int exact_factorize(const Team& tm, const ExactSmem& s, int n, int d, con
     for (int j = tm.lane(); j <= i; j += W)
       row[j] = (j == i) ? os + noise : ard_rbf_tt(s.Xt, cap, d, invl, i, j, os);
   }
-  if (cholesky_lower(tm, s.A, ld, n, s.c0)) return 1;
-  tri_inverse_rl_inplace(tm, s.A, ld, n, s.piv);
+  if (cholesky_inverse_fused(tm, s.A, ld, n, s.c1, s.c2, s.piv, (double*)nullptr, 0)) return 1;
   // z = Linv (y - c)  -> c0 ;  alpha = Linv^T z
   for (int i = tm.rank(); i < n; i += tm.size()) {
     const double* row = s.A + i * ld;

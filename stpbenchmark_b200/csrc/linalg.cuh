@@ -25,114 +25,16 @@ STP_HD int row_off(int i, int ld) { return TRI ? (i * (i + 1)) / 2 : i * ld; }
 // logdet K = sum log piv.  One barrier per pivot; every step updates the whole triangle, so
 // the work is perfectly parallel (no shrinking trailing block, no serial substitution).
 // The strict upper triangle of A is never touched.
-// `c0`, `c1`: two scratch vectors of m doubles (ping-pong copies of the pivot column).
 // Returns 0, or 1 + k if pivot k is not positive / not finite (matrix not PD).
-// ---------------------------------------------------------------------------------------
-// Fast path: every lane owns CQ fixed columns (lane + q W, q < CQ) whose pivot-column entries stay in
-// registers for the whole step; a warp walks its rows with a running row pointer, so the body per element is
-// load / DFMA / select / store plus predicated publishes (no per-element index arithmetic or branches).
-template <int CQ, bool TRI, class Team>
-STP_HD int sweep_bordered_cf(const Team& tm, double* A, int ld, int m, int npiv, double* c0, double* c1,
-                             double* piv) {
-  const int W = tm.warp_width(), lane = tm.lane(), nw = tm.nwarps();
-  for (int i = tm.rank(); i < m; i += tm.size()) c0[i] = A[row_off<TRI>(i, ld)];
-  tm.sync();
-  double* cur = c0;
-  double* nxt = c1;
-  for (int k = 0; k < npiv; ++k) {
-    const double p = cur[k];
-    if (!(p > 0.0) || !(p <= 1.79e308)) return 1 + k;
-    if (tm.rank() == 0) piv[k] = p;
-    const double invp = 1.0 / p;
-    double cj[CQ];
-    bool own_k[CQ], own_n[CQ];
-#pragma unroll
-    for (int q = 0; q < CQ; ++q) {
-      const int j = lane + q * W;
-      cj[q] = (j < m) ? cur[j] : 0.0;
-      own_k[q] = (j == k);
-      own_n[q] = (j == k + 1);
-    }
-    for (int i = tm.warp(); i < m; i += nw) {
-      double* row = A + row_off<TRI>(i, ld);
-      if (i == k) {
-#pragma unroll
-        for (int q = 0; q < CQ; ++q) {
-          const int j = lane + q * W;
-          if (j <= i) row[j] = own_k[q] ? -invp : cj[q] * invp;
-        }
-      } else {
-        const double ti = cur[i] * invp;
-        const bool next_row = (i == k + 1);
-#pragma unroll
-        for (int q = 0; q < CQ; ++q) {
-          const int j = lane + q * W;
-          if (j <= i) {
-            double a = fma(-ti, cj[q], row[j]);
-            a = own_k[q] ? ti : a;
-            row[j] = a;
-            if (own_n[q]) nxt[i] = a;
-            if (next_row) nxt[j] = a;
-          }
-        }
-      }
-    }
-    tm.sync();
-    double* t = cur; cur = nxt; nxt = t;
-  }
-  return 0;
-}
-
-template <bool TRI = false, class Team>
-STP_HD int sweep_bordered(const Team& tm, double* A, int ld, int m, int npiv, double* c0, double* c1,
-                          double* piv) {
-  if (tm.warp_width() > 1) {
-    if (m <= 1 * tm.warp_width()) return sweep_bordered_cf<1, TRI>(tm, A, ld, m, npiv, c0, c1, piv);
-    if (m <= 2 * tm.warp_width()) return sweep_bordered_cf<2, TRI>(tm, A, ld, m, npiv, c0, c1, piv);
-    if (m <= 3 * tm.warp_width()) return sweep_bordered_cf<3, TRI>(tm, A, ld, m, npiv, c0, c1, piv);
-  }
-  for (int i = tm.rank(); i < m; i += tm.size()) c0[i] = A[row_off<TRI>(i, ld)];
-  tm.sync();
-  double* cur = c0;
-  double* nxt = c1;
-  const int W = tm.warp_width();
-  for (int k = 0; k < npiv; ++k) {
-    const double p = cur[k];
-    if (!(p > 0.0) || !(p <= 1.79e308)) return 1 + k;  // uniform: every thread reads the same p
-    if (tm.rank() == 0) piv[k] = p;
-    const double invp = 1.0 / p;
-    for (int i = tm.warp(); i < m; i += tm.nwarps()) {
-      double* row = A + row_off<TRI>(i, ld);
-      if (i == k) {  // pivot row (warp-uniform branch): a_kj / p, and -1/p on the diagonal
-        for (int j = tm.lane(); j <= i; j += W) row[j] = (j == k) ? -invp : cur[j] * invp;
-      } else {       // generic rows, branch-free body: a_ij - a_ik a_kj / p, pivot column gets a_ik / p
-        const double ti = cur[i] * invp;
-        const bool next_row = (i == k + 1);
-        for (int j = tm.lane(); j <= i; j += W) {
-          double a = fma(-ti, cur[j], row[j]);
-          a = (j == k) ? ti : a;
-          row[j] = a;
-          if (j == k + 1) nxt[i] = a;
-          if (next_row) nxt[j] = a;
-        }
-      }
-    }
-    tm.sync();
-    double* t = cur; cur = nxt; nxt = t;
-  }
-  return 0;
-}
-
-
-// ---------------------------------------------------------------------------------------
-// Rank-2 (pivot-pair) form of the bordered symmetric sweep: pivots k and k + 1 are eliminated together,
+//
+// Implemented in its rank-2 (pivot-pair) form: pivots k and k + 1 are eliminated together,
 //     a_ij <- a_ij - [a_ik a_ik'] Pinv [a_kj a_k'j]^T ,  a_iK <- a_iK Pinv ,  A_KK <- -Pinv ,   P = A_KK (2 x 2),
 // which equals two successive single sweeps but touches every element once per PAIR: one load / two DFMA /
 // one store per element and half the barriers.  Four ping-pong vectors hold the two pivot columns of this step
 // (c0, c1: values BEFORE the step) and of the next one (published by the owners of columns k + 2, k + 3).
 // An odd last pivot is handled by a single sweep step.  CQ > 0: every lane keeps the pivot-column entries of
 // its CQ fixed columns (lane + q W) in registers; CQ == 0: generic strided loops (any m, any team).
-// Same contract as sweep_bordered (result layout, piv[], return code).  `vec`: 4 * (m rounded up) doubles.
+// v0 .. v3: four scratch vectors of m doubles.
 // ---------------------------------------------------------------------------------------
 template <int CQ, bool TRI, class Team>
 STP_HD int sweep_bordered_pair(const Team& tm, double* A, int ld, int m, int npiv, double* v0, double* v1, double* v2,
@@ -140,6 +42,7 @@ STP_HD int sweep_bordered_pair(const Team& tm, double* A, int ld, int m, int npi
   const int W = tm.warp_width(), lane = tm.lane(), nw = tm.nwarps();
   constexpr int NQ = CQ > 0 ? CQ : 1;
   double* c0 = v0; double* c1 = v1; double* n0 = v2; double* n1 = v3;
+  tm.sync();   // the caller's writes to A (and the previous users of v0 .. v3) must be complete
   // columns 0 and 1 of the initial matrix (symmetric fill: entry i of column c is A[max(i,c)][min(i,c)])
   for (int i = tm.rank(); i < m; i += tm.size()) {
     c0[i] = A[row_off<TRI>(i, ld)];
@@ -276,36 +179,6 @@ STP_HD int sweep_bordered4(const Team& tm, double* A, int ld, int m, int npiv, d
 }
 
 // ---------------------------------------------------------------------------------------
-// In-place Cholesky of the lower triangle: A = L L^T.  Right-looking with the column scaling
-// deferred to the end (the loop works on l_ij * l_jj), hence one barrier per column.
-// `sd` : n doubles of scratch.  Returns 0 or 1 + j for a non-positive pivot.
-// ---------------------------------------------------------------------------------------
-template <bool TRI = false, class Team>
-STP_HD int cholesky_lower(const Team& tm, double* A, int ld, int n, double* sd) {
-  const int W = tm.warp_width();
-  for (int j = 0; j < n; ++j) {
-    tm.sync();
-    const double dj = A[row_off<TRI>(j, ld) + j];
-    if (!(dj > 0.0) || !(dj <= 1.79e308)) return 1 + j;
-    const double inv = 1.0 / dj;
-    for (int i = j + 1 + tm.warp(); i < n; i += tm.nwarps()) {
-      double* row = A + row_off<TRI>(i, ld);
-      const double lij = row[j] * inv;
-      for (int k = j + 1 + tm.lane(); k <= i; k += W) row[k] -= lij * A[row_off<TRI>(k, ld) + j];
-    }
-  }
-  tm.sync();
-  for (int j = tm.rank(); j < n; j += tm.size()) sd[j] = sqrt(A[row_off<TRI>(j, ld) + j]);
-  tm.sync();
-  for (int i = tm.warp(); i < n; i += tm.nwarps()) {
-    double* row = A + row_off<TRI>(i, ld);
-    for (int j = tm.lane(); j <= i; j += W) row[j] = (j == i) ? sd[j] : row[j] / sd[j];
-  }
-  tm.sync();
-  return 0;
-}
-
-// ---------------------------------------------------------------------------------------
 // Register-tiled contraction  out(i, k) = sum_{r = r0}^{r1 - 1} L(i, r) * [scale(r)] * R(r, k)  with
 //   L(i, r) = Lp[i * l_si + r * l_sr]   (LT = false: l_sr == 1, row-major;  LT = true: l_si == 1, read down a column)
 //   R(r, k) = Rp[r * ld_r + k]
@@ -396,37 +269,54 @@ STP_HD void contract_p(const Team& tm, int n_rows, int n_cols, const double* Lp,
 
 
 // ---------------------------------------------------------------------------------------
-// In-place right-looking inverse of a lower-triangular matrix: on exit A (lower, diagonal included) holds
-// L^-1.  Step k consumes column k of L and replaces it by column k of the (unscaled) inverse, so no second
-// buffer is needed; one barrier per step, every step parallel over (i > k, c <= k).  `invd`: n doubles.
+// Fused Cholesky + triangular inverse, in place, ONE barrier per column.  With the deferred-scaling Cholesky
+// (column k holds l_ik l_kk, d_k = l_kk^2) the multiplier f_i = a_ik / d_k = L[i][k] / L[k][k] drives both the
+// trailing update a_ij -= f_i a_jk (j > k) and the right-looking inverse update x_ic -= f_i x_kc (c < k),
+// x_ik = -f_i, so step k is one uniform pass over the whole row i > k:   a_i,: -= f_i * r_k,  r_k = row/column k
+// (symmetric fill, published by its owners during step k - 1 like the sweep's pivot column).
+// On exit A (lower) = L^-1; `Lout` (may be null; leading dimension ldo, any memory space) receives L (lower part
+// only); `sd` (n doubles) = diag(L).  `v0`, `v1`: n doubles each.  Returns 0 or 1 + k for a non-positive pivot.
 // ---------------------------------------------------------------------------------------
 template <bool TRI = false, class Team>
-STP_HD void tri_inverse_rl_inplace(const Team& tm, double* A, int ld, int n, double* invd) {
-  const int W = tm.warp_width(), nw = tm.nwarps();
-  for (int i = tm.rank(); i < n; i += tm.size()) invd[i] = 1.0 / A[row_off<TRI>(i, ld) + i];
+STP_HD int cholesky_inverse_fused(const Team& tm, double* A, int ld, int n, double* v0, double* v1, double* sd,
+                                  double* Lout, int ldo) {
+  const int W = tm.warp_width(), lane = tm.lane(), nw = tm.nwarps();
+  double* cur = v0;
+  double* nxt = v1;
+  tm.sync();   // the caller's writes to A (and the previous users of v0 / v1) must be complete
+  for (int i = tm.rank(); i < n; i += tm.size()) cur[i] = A[row_off<TRI>(i, ld)];
   tm.sync();
-  // X starts as the identity in the positions already "consumed": column k of L is read at step k only.
-  for (int k = 0; k < n - 1; ++k) {
-    const double ik = invd[k];
-    const double* xk = A + row_off<TRI>(k, ld);            // row k of X: X[k][c], c < k (unscaled), X[k][k] = 1 implied
+  for (int k = 0; k < n; ++k) {
+    const double dk = cur[k];
+    if (!(dk > 0.0) || !(dk <= 1.79e308)) return 1 + k;
+    const double inv = 1.0 / dk;
+    const double lkk = sqrt(dk);
+    const double isd = 1.0 / lkk;
+    if (tm.rank() == 0) { sd[k] = lkk; if (Lout) Lout[k * ldo + k] = lkk; }
     for (int i = k + 1 + tm.warp(); i < n; i += nw) {
       double* row = A + row_off<TRI>(i, ld);
-      const double f = row[k] * ik;           // L[i][k] / L[k][k]: every lane reads it before lane k % W overwrites it
-      tm.sync_warp();
-      for (int c = tm.lane(); c <= k; c += W) {
-        const double xkc = (c == k) ? 1.0 : xk[c];
-        const double old = (c == k) ? 0.0 : row[c];
-        row[c] = fma(-f, xkc, old);
+      const double aik = cur[i];                 // = A[i][k] before this step
+      const double f = aik * inv;
+      const bool next_row = (i == k + 1);
+      if (Lout && lane == 0) Lout[i * ldo + k] = aik * isd;
+      for (int c = lane; c <= i; c += W) {
+        double a = (c == k) ? -f : fma(-f, cur[c], row[c]);
+        row[c] = a;
+        if (c == k + 1) nxt[i] = a;
+        if (next_row) nxt[c] = a;
       }
     }
     tm.sync();
+    double* t = cur; cur = nxt; nxt = t;
   }
+  // rows hold the unscaled inverse (unit diagonal implied): scale row i by 1 / l_ii
   for (int i = tm.warp(); i < n; i += nw) {
     double* row = A + row_off<TRI>(i, ld);
-    const double di = invd[i];
-    for (int c = tm.lane(); c <= i; c += W) row[c] = ((c == i) ? 1.0 : row[c]) * di;
+    const double di = 1.0 / sd[i];
+    for (int c = lane; c <= i; c += W) row[c] = ((c == i) ? 1.0 : row[c]) * di;
   }
   tm.sync();
+  return 0;
 }
 
 }  // namespace stp

@@ -244,8 +244,8 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   for (int i = tm.warp(); i < n; i += nw)
     for (int j = tm.lane(); j < n; j += W) S[i * ld + j] = (j <= i) ? -M0[i * ld + j] : -M0[j * ld + i];
   tm.sync();
-  // (2) K_ZZ + jitter -> L_K by Cholesky in shared memory; copy L_K out (strict upper zero-filled); invert in
-  //     place (right-looking) and write Linv (lower) and Linv^T (upper), zero-filled, to global memory; Ct
+  // (2) K_ZZ + jitter: fused Cholesky + in-place inverse in shared memory (one barrier per column), L_K streamed
+  //     out (strict upper zero-filled); then Linv (lower) and Linv^T (upper), zero-filled, to global memory; Ct
   for (int i = tm.warp(); i < n; i += nw) {
     double* row = M0 + i * ld;
     for (int j = tm.lane(); j <= i; j += W)
@@ -264,10 +264,9 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
       row[j] = os * exp(-0.5 * r2);
     }
   }
-  if (cholesky_lower(tm, M0, ld, n, s.c0)) { out.status = 1; return out; }
   for (int i = tm.warp(); i < n; i += nw)
-    for (int j = tm.lane(); j < n; j += W) LK[i * ld + j] = (j <= i) ? M0[i * ld + j] : 0.0;
-  tri_inverse_rl_inplace(tm, M0, ld, n, s.c0);
+    for (int j = i + 1 + tm.lane(); j < n; j += W) LK[i * ld + j] = 0.0;
+  if (cholesky_inverse_fused(tm, M0, ld, n, s.c0, s.c1, s.c2, LK, ld)) { out.status = 1; return out; }
   for (int i = tm.warp(); i < n; i += nw)
     for (int j = tm.lane(); j < n; j += W) {
       LI[i * ld + j] = (j <= i) ? M0[i * ld + j] : 0.0;
@@ -564,8 +563,7 @@ STP_HD int var_prepare(const Team& tm, const VarSmem& s, const VarWork& w, const
         row[j] = pass == 0 ? -2.0 * M.nat2[(size_t)i * cap + j]
                            : ((j == i) ? os + kVarJitter : ard_rbf_tt(s.Zt, cap, d, invl, i, j, os));
     }
-    if (cholesky_lower(tm, M0, ld, n, s.c0)) return 1;
-    tri_inverse_rl_inplace(tm, M0, ld, n, s.c0);
+    if (cholesky_inverse_fused(tm, M0, ld, n, s.c0, s.c1, s.c2, (double*)nullptr, 0)) return 1;
     for (int i = tm.warp(); i < n; i += nw)
       for (int j = tm.lane(); j < n; j += W) dst[i * ld + j] = (j <= i) ? M0[i * ld + j] : 0.0;
     tm.sync();
