@@ -6,7 +6,8 @@ Workload (BASELINE.json configs[3], the north-star shape): synthetic pools N = 2
 n_initial = 10, 80 trials each.  Campaigns are kept at staggered ages (n = 10 ... 89 uniformly,
 "continuous batching": a campaign that finishes its 80 trials is replaced by a fresh seed), so
 that every step is one BO iteration of every campaign at the campaign-average cost, whatever
---steps is.  One step = one launch of stp_exact_bo_step over all campaigns of the rank.
+--steps is.  One step = one launch of stp_exact_bo_step per campaign group of the rank (4 groups of 256 campaigns
+on 4 CUDA streams, so that the tail of one group's launch overlaps the others).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          # CUDA arm (N > 1 under torchrun)
   python bench.py --impl reference [--steps K] [--warmup W]    # CPU arm: the oracle on host cores
@@ -212,135 +213,149 @@ def run_cuda_arm(args):
             D = synthetic.initial_designs(pools[g][0], pools[g][1], seeds, N_INITIAL)
             for i, (gen, b) in enumerate([(gen, b) for gen in range(gens) for b in slots]):
                 designs[(b, gen)] = D[i]
-    batch = CampaignBatch(PX, PY, pool_id, [designs[(b, 0)].tolist() for b in range(B)], n_cap=CAP, kind="ExactGP",
-                          device=dev)
-    batch.ragged = True                                      # ages differ: longest fits are scheduled first
-    # pre-roll (untimed): bring campaign b to age0[b]; it starts at step N_TRIALS - age0[b]
-    start_step = torch.tensor([N_TRIALS - a for a in age0], device=dev)
-    batch.status.fill_(-1)                                   # not started yet
-    for t in range(N_TRIALS):
-        batch.status[start_step == t] = 0
-        batch.step()
-    batch.status[batch.status == -1] = 0                     # age-0 campaigns start now
+    # The campaigns of a rank are split into NG contiguous groups, each with its own CampaignBatch and CUDA stream.
+    # One step of the job = one stp_exact_bo_step launch per group; the launches of different groups overlap, so the
+    # tail of one group's launch (a step cannot end before its longest fit: 38..449 closures) is filled by the others.
+    NG = max(1, min(args.groups, B // 64 if B >= 64 else 1))
+    bounds = [(g * B // NG, (g + 1) * B // NG) for g in range(NG)]
+    total_steps = W + K
+
+    class Group:
+        def __init__(self, lo, hi):
+            self.lo, self.hi, self.nb = lo, hi, hi - lo
+            self.stream = torch.cuda.Stream(device=dev)
+            self.batch = CampaignBatch(PX, PY, pool_id[lo:hi], [designs[(b, 0)].tolist() for b in range(lo, hi)],
+                                       n_cap=CAP, kind="ExactGP", device=dev)
+            self.batch.ragged = True                         # ages differ: longest fits are scheduled first
+            # the next initial designs of every slot: the kernel recycles finished campaigns itself (stp_turnover)
+            self.bank = torch.stack([torch.stack([designs[(b, g)] for g in range(1, gens)]) for b in range(lo, hi)])
+            self.host = None
+
+        def preroll(self):
+            # untimed: bring campaign b to age0[b]; it starts at step N_TRIALS - age0[b]
+            start = torch.tensor([N_TRIALS - age0[b] for b in range(self.lo, self.hi)], device=dev)
+            bt = self.batch
+            bt.status.fill_(-1)                              # not started yet
+            for t in range(N_TRIALS):
+                bt.status[start == t] = 0
+                bt.step()
+            bt.status[bt.status == -1] = 0                   # age-0 campaigns start now
+            bt.enable_turnover(self.bank, n_final=N_INITIAL + N_TRIALS, sink_capacity=self.nb * 4)
+
+        def step(self):
+            self.batch.step()                                # argsort (longest first) + ONE kernel; nothing else
+
+        def e2e_step(self):
+            bt = self.batch
+            for kname, hv in self.host.items():
+                getattr(bt, kname).copy_(hv, non_blocking=True)
+            bt.step()
+            for kname, hv in self.host.items():
+                hv.copy_(getattr(bt, kname), non_blocking=True)
+
+    groups = [Group(lo, hi) for lo, hi in bounds]
+    torch.cuda.synchronize()                                 # construction ran on the default stream
+    for gr in groups:
+        with torch.cuda.stream(gr.stream):
+            gr.preroll()
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup
-
-    # recycling schedule: slot b finishes after (N_TRIALS - age0[b]) more steps, then every N_TRIALS
-    gen_of = [0] * B
-    def schedule(step_no):
-        sl = [b for b in range(B) if (step_no + age0[b]) % N_TRIALS == 0 and step_no + age0[b] > 0]
-        if not sl:
-            return None
-        for b in sl:
-            gen_of[b] += 1
-        init = torch.stack([designs[(b, gen_of[b])] for b in sl])
-        return torch.tensor(sl, device=dev), init.to(dev)
-    total_steps = W + K
-    sched = [schedule(s) for s in range(1, 2 * total_steps + 1)]   # sched[s-1] applies AFTER step s
-    sink = torch.full((B * 4, CAP), -1, dtype=torch.int32, device=dev)
-    sink_used = 0
-    n_hist = torch.zeros(K, B, dtype=torch.int32, device=dev)
-    f_hist = torch.zeros(K, B, dtype=torch.int32, device=dev)
-    done = torch.zeros(1, dtype=torch.int64, device=dev)       # BO iterations actually completed (frozen campaigns do not count)
-
-    def one_step(step_no, k_idx=None):
-        nonlocal sink_used
-        if k_idx is not None:
-            n_hist[k_idx].copy_(batch.n)
-        batch.step()
-        if k_idx is not None:
-            f_hist[k_idx].copy_(batch.nfev)
-            done.add_((batch.status == 0).sum())
-        rc = sched[step_no - 1]
-        if rc is not None:
-            batch.recycle(rc[0], rc[1], sink, sink_used)
-            sink_used += rc[0].numel()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def all_groups(fn):
+        for gr in groups:
+            with torch.cuda.stream(gr.stream):
+                fn(gr)
+
     # ---- device-resident arm: W warm-up + K timed steps ------------------------------------
-    step_no = 0
     for _ in range(W):
-        step_no += 1
-        one_step(step_no)
+        all_groups(lambda gr: gr.step())
     barrier()
+    def totals():
+        return (float(sum(gr.batch.work_acc.sum().item() for gr in groups)),
+                int(sum(gr.batch.iters_acc.sum().item() for gr in groups)))
+    flops0, iters0 = totals()
     sampler = ClockSampler(local_rank); sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
-    launches0 = batch.launches
-    ev[0].record()
+    launches0 = sum(gr.batch.launches for gr in groups)
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev0.record()                                             # default stream, right after the synchronize
+    for gr in groups:
+        gr.stream.wait_event(ev0)
     for k in range(K):
-        step_no += 1
-        one_step(step_no, k)
-        ev[k + 1].record()
+        all_groups(lambda gr: gr.step())
+    ends = []
+    for gr in groups:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(gr.stream)
+        ends.append(e)
     barrier()
     clocks = sampler.stop()
-    gpu_launches = batch.launches - launches0
-    elapsed_ms = ev[0].elapsed_time(ev[K])
+    gpu_launches = sum(gr.batch.launches for gr in groups) - launches0
+    elapsed_ms = max(ev0.elapsed_time(e) for e in ends)
     t = torch.tensor([elapsed_ms], dtype=torch.double, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms_max = float(t.item())
-    status_bad = int((batch.status != 0).sum().item())
+    flops1, iters1 = totals()
+    status_bad = int(sum(int(((gr.batch.status != 0) & (gr.batch.status != 6)).sum().item()) for gr in groups))
+    done = torch.tensor([iters1 - iters0], dtype=torch.int64, device=dev)   # completed iterations, counted by the kernel
     if world > 1:
         dist.all_reduce(done)
     value = float(done.item()) / (elapsed_ms_max * 1e-3)
 
-    # roofline of the dominant (only) kernel: algorithmic flops per launch / launch duration
-    flops = algorithmic_flops(n_hist, f_hist, DIM, N_POOL).sum(dim=1)              # [K]
-    step_ms = torch.tensor([ev[k].elapsed_time(ev[k + 1]) for k in range(K)], dtype=torch.double)
-    achieved_tflops = float(flops.sum().item()) / (float(step_ms.sum()) * 1e-3) / 1e12
+    # roofline of the dominant (only) kernel: algorithmic flops (accumulated by the kernel itself from every
+    # campaign's n and actual closure count) / the time its launches ran in
+    achieved_tflops = (flops1 - flops0) / (elapsed_ms * 1e-3) / 1e12
     fp64_peak = _lib.fp64_probe(4096)
-    hbm_bytes = float(((N_POOL - n_hist.double()) * DIM * 8 + N_POOL + n_hist.double() * (DIM + 1) * 8 + 16 + 24).sum())
+    n_bar = N_INITIAL + (N_TRIALS - 1) / 2.0
+    bytes_per_iter = (N_POOL - n_bar) * DIM * 8 + N_POOL + n_bar * (DIM + 1) * 8 + 16 + 24
+    hbm_bytes = bytes_per_iter * (iters1 - iters0)
+    hbm_gbs = hbm_bytes / (elapsed_ms * 1e-3) / 1e9
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    mean_closures = float(torch.cat([gr.batch.nfev for gr in groups]).double().mean().item())
 
     # ---- end-to-end arm: same step through HOST buffers (pinned), H2D + launch + D2H per step --
-    host = {k: getattr(batch, k).cpu().pin_memory() for k in ("X", "y", "n", "mask", "trace", "status")}
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    for gr in groups:
+        gr.host = {k_: getattr(gr.batch, k_).cpu().pin_memory() for k_ in ("X", "y", "n", "mask", "trace", "status", "gen")}
+    h2d = sum(v.numel() * v.element_size() for gr in groups for v in gr.host.values())
     d2h = h2d
-    def e2e_step(step_no):
-        for kname, hv in host.items():
-            getattr(batch, kname).copy_(hv, non_blocking=True)
-        batch.step()
-        for kname, hv in host.items():
-            hv.copy_(getattr(batch, kname), non_blocking=True)
-        rc = sched[step_no - 1]
-        torch.cuda.synchronize()   # the host owns the state between steps: it must see the picks
-        if rc is not None:          # turnover done on the host copy
-            batch.recycle(rc[0], rc[1])
-            for kname, hv in host.items():
-                hv.copy_(getattr(batch, kname))
+
+    def e2e_step():
+        # every group's state lives in HOST buffers between its steps: before a group's next step the host waits
+        # for that group's previous device->host copy (its stream), not for the other groups
+        for gr in groups:
+            gr.stream.synchronize()
+            with torch.cuda.stream(gr.stream):
+                gr.e2e_step()
     for _ in range(min(W, 2)):
-        step_no += 1
-        e2e_step(step_no)
+        e2e_step()
     barrier()
     Ke = min(K, max(4, K // 4))
+    _, it0 = totals()
     t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    done_e2e = 0
     for _ in range(Ke):
-        step_no += 1
-        e2e_step(step_no)
-        done_e2e += int((host["status"] == 0).sum())
-    e1.record()
+        e2e_step()
     barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    e2e_ms = (time.perf_counter() - t0) * 1e3      # host-side clock: the region ends with a device synchronize
+    _, it1 = totals()
     t = torch.tensor([e2e_ms], dtype=torch.double, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    de = torch.tensor([done_e2e], dtype=torch.int64, device=dev)
+    de = torch.tensor([it1 - it0], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(de)
     e2e_value = float(de.item()) / (float(t.item()) * 1e-3)
 
+    sink = torch.cat([gr.batch.sink for gr in groups])
     # ---- the one collective of the path: gather the finished traces on rank 0 ------------------
     if world > 1:
         gathered = [torch.empty_like(sink) for _ in range(world)] if rank == 0 else None
@@ -350,7 +365,8 @@ def run_cuda_arm(args):
     cpu = None
     parity = None
     if cpu_pool is not None:
-        tr = batch.trace.cpu().long(); nn = batch.n.cpu().long(); pid = batch.pool_id.cpu().long()
+        tr = torch.cat([gr.batch.trace for gr in groups]).cpu().long(); nn = torch.cat([gr.batch.n for gr in groups]).cpu().long()
+        pid = torch.cat([gr.batch.pool_id for gr in groups]).cpu().long()
         S = min(B, max(16, min(cores, 64) * 3))
         pick = [int(i) for i in torch.linspace(0, B - 1, S).round().long().tolist()]
         # state one step back: the last pick is what the oracle must reproduce
@@ -382,13 +398,15 @@ def run_cuda_arm(args):
                        "l2": "inputs are L2-resident by design (0.8 MB of pools); the kernel is FP64/latency bound, "
                              "no HBM stream to flush", "threads_per_campaign": os.environ.get("STP_THREADS", "auto")},
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / fp64_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_exact_bo_step, ncu --set full, "
-                                           "1024 campaigns (profiles/r01_ncu_prof_r1_bostep.txt); algorithmic bytes per launch: "
-                                           f"{hbm_bytes / K:.3g}",
+                         "frac": achieved_tflops / fp64_peak,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH * (B / NG) / 1024.0,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_exact_bo_step from one ncu --set "
+                                           "full capture of a 1024-campaign launch (profiles/r01_ncu_prof_r1_bostep.txt), scaled "
+                                           f"to the {B // NG} campaigns of one launch; algorithmic bytes per launch: "
+                                           f"{hbm_bytes / max(gpu_launches, 1):.3g}",
                          "kernel": "k_exact_bo_step",
                          "peak_source": "stp_fp64_probe (DFMA microbenchmark, this run); MEASURED_PEAKS.json has no FP64 figure",
-                         "hbm": {"achieved": hbm_bytes / (float(step_ms.sum()) * 1e-3) / 1e9, "peak": hbm_peak,
+                         "hbm": {"achieved": hbm_gbs, "peak": hbm_peak,
                                  "unit": "GB/s"}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -397,7 +415,8 @@ def run_cuda_arm(args):
             "clocks": clocks,
             "parity": parity,
             "frozen_campaigns": status_bad,
-            "mean_closures_per_fit": float(f_hist.double().mean().item()),
+            "mean_closures_per_fit": mean_closures,
+            "streams": NG,
             "setup_s": setup_s,
         }
         print(json.dumps(line), flush=True)
@@ -493,6 +512,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--campaigns", type=int, default=1024, help="campaigns per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--groups", type=int, default=4, help="campaign groups per GPU, one CUDA stream each")
     ap.add_argument("--model", default="ExactGP", choices=["ExactGP", "VarGP", "VarTGP", "VarLGP"],
                     help="ExactGP = the headline workload; the others run the secondary variational workload")
     ap.add_argument("--epochs", type=int, default=600)

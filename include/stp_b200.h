@@ -20,7 +20,8 @@
  *   - return value: 0 = launched, negative = rejected (see stp_last_error_string());
  *   - status[b] (int32): 0 ok, 1 matrix not positive definite, 2 non-finite parameter or
  *     objective, 3 fit stopped on a non-finite objective, 4 iteration / evaluation cap reached,
- *     5 abnormal line-search termination.  No exception crosses the boundary.
+ *     5 abnormal line-search termination, 6 campaign finished (turnover bank exhausted).  No exception crosses
+ *     the boundary.
  *   - limits: 1 <= d <= STP_MAX_D, n_cap <= STP_MAX_N.
  */
 #ifndef STP_B200_H
@@ -47,6 +48,22 @@ typedef struct stp_lbfgsb_opts {
   double factr;
   double pgtol;
 } stp_lbfgsb_opts;
+
+/* Continuous batching for stp_exact_bo_step (all device pointers): a campaign whose training set reaches n_final
+ * rows has finished; its trace row is appended to `sink` (row index from atomicAdd(sink_count, 1), dropped beyond
+ * sink_capacity; sink may be NULL) and its slot restarts from the next initial design of its bank:
+ * bank is int32[B, generations, n_init] pool indices, gen int32[B] the next generation to use (in/out).  When the
+ * bank is exhausted the campaign stops with status 6.  n_final = 0 (or a NULL pointer) disables the feature. */
+typedef struct stp_turnover {
+  int32_t n_final;
+  int32_t n_init;
+  int32_t generations;
+  int32_t sink_capacity;
+  const int32_t* bank;
+  int32_t* gen;
+  int32_t* sink;
+  int32_t* sink_count;
+} stp_turnover;
 
 /* Likelihood of a variational model (models.py: VarGP :166, VarTGP :76, VarLGP :262). */
 enum { STP_LIK_GAUSSIAN = 0, STP_LIK_STUDENT_T = 1, STP_LIK_LAPLACE = 2 };
@@ -89,12 +106,17 @@ int stp_exact_acq(int B, int n_cap, int d, int N, const double* pool, const int3
  * try/except at runners.py:113-115); n[b] >= n_cap is rejected by status 2.
  * order: optional int32[B] permutation (NULL = identity): CTA i works on campaign order[i].  CTAs are issued in
  * index order, so passing the campaigns sorted by decreasing n (longest fits first) shortens the tail of the
- * launch when the batch mixes training-set sizes. */
+ * launch when the batch mixes training-set sizes.
+ * turnover: optional continuous batching (see stp_turnover).  work_acc: optional double[B], += the algorithmic
+ * flops of the iteration, F (n^3 + n^2 (3d+6)) + n^3/3 + (N-n)(n^2 + n(3d+8) + 60) with F the closure count;
+ * iters_acc: optional int32[B], += 1 per completed iteration (both let a caller account a run without any
+ * per-step device work of its own). */
 int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const double* pool_y,
                       const int32_t* pool_id, uint8_t* mask, double* X, double* y, int32_t* n, int32_t* trace,
                       const double* theta0, const double* lower, const double* upper, const double* prior,
                       const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
-                      int32_t* status, const int32_t* order, void* stream);
+                      int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
+                      int32_t* iters_acc, void* stream);
 
 /* ---- variational models: VarGP / VarTGP / VarLGP (models.py:114-202, 18-111, 205-297) ---------------
  * State arrays (device, caller-owned, batch-major): Z [B, n_cap, d] inducing locations, hyp [B, d+4] =

@@ -39,6 +39,14 @@ class LbfgsbOpts(ctypes.Structure):
         return LbfgsbOpts(10, 15000, 15000, 20, 2.220446049250313e-09 / eps, 1e-5)
 
 
+class Turnover(ctypes.Structure):
+    """struct stp_turnover (continuous batching of stp_exact_bo_step); pointers are device pointers."""
+
+    _fields_ = [("n_final", ctypes.c_int32), ("n_init", ctypes.c_int32), ("generations", ctypes.c_int32),
+                ("sink_capacity", ctypes.c_int32), ("bank", ctypes.c_void_p), ("gen", ctypes.c_void_p),
+                ("sink", ctypes.c_void_p), ("sink_count", ctypes.c_void_p)]
+
+
 def lib():
     """Load libstp_b200.so; raise (never fall back) when it is absent."""
     global _lib
@@ -135,16 +143,20 @@ def exact_acq(pool, X, y, theta, best_f=None, mask=None, pool_id=None, n=None, w
 
 
 def exact_bo_step(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upper, prior, status,
-                  theta_out=None, acq_out=None, nit=None, nfev=None, opts: Optional[LbfgsbOpts] = None, order=None):
+                  theta_out=None, acq_out=None, nit=None, nfev=None, opts: Optional[LbfgsbOpts] = None, order=None,
+                  turnover: Optional[Turnover] = None, work_acc=None, iters_acc=None):
     """One BO iteration for every campaign, in place (see stp_exact_bo_step)."""
-    _require_cuda(pool, pool_y, pool_id, mask, X, y, n, trace, status, theta_out, acq_out, nit, nfev, order)
+    _require_cuda(pool, pool_y, pool_id, mask, X, y, n, trace, status, theta_out, acq_out, nit, nfev, order, work_acc,
+                  iters_acc)
     B, n_cap, d = X.shape
     N = pool.shape[-2]
     lo, hi = _bounds(lower, upper, d + 3)
     o = opts or LbfgsbOpts.scipy_defaults()
     _check(lib().stp_exact_bo_step(B, n_cap, d, N, _p(pool), _p(pool_y), _p(pool_id), _p(mask), _p(X), _p(y), _p(n),
                                    _p(trace), _host(theta0), lo, hi, _host(prior), ctypes.byref(o), _p(theta_out),
-                                   _p(acq_out), _p(nit), _p(nfev), _p(status), _p(order), _stream()), "stp_exact_bo_step")
+                                   _p(acq_out), _p(nit), _p(nfev), _p(status), _p(order),
+                                   ctypes.byref(turnover) if turnover is not None else None, _p(work_acc), _p(iters_acc),
+                                   _stream()), "stp_exact_bo_step")
 
 
 def log_ei(mean: torch.Tensor, var: torch.Tensor, best_f: float) -> torch.Tensor:

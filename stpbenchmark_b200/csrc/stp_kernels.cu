@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(STP_EXACT_MAXT, STP_EXACT_MINB) k_exact_bo_ste
                                 int32_t* __restrict__ n_arr, int32_t* __restrict__ trace, BoundsArg bnd,
                                 PriorArg prior, LbfgsbOpts opts, double* __restrict__ theta_out,
                                 double* __restrict__ acq_out, int32_t* __restrict__ nit, int32_t* __restrict__ nfev,
-                                int32_t* __restrict__ status, const int32_t* __restrict__ order) {
+                                int32_t* __restrict__ status, const int32_t* __restrict__ order, stp_turnover turn,
+                                double* __restrict__ work_acc, int32_t* __restrict__ iters_acc) {
   extern __shared__ double smem[];
   const int b = order ? order[blockIdx.x] : blockIdx.x;   // longest-first scheduling: CTAs are issued in blockIdx order
   if (status[b] != 0) return;  // frozen campaign
@@ -193,6 +194,39 @@ __global__ void __launch_bounds__(STP_EXACT_MAXT, STP_EXACT_MINB) k_exact_bo_ste
     mb[bi] = 0;
     n_arr[b] = n + 1;
     if (acq_out) acq_out[b] = bv;
+    if (iters_acc) iters_acc[b] += 1;
+    if (work_acc) {   // algorithmic flops of this campaign-iteration, actual closure count
+      const double nn = n, F = r.nfev;
+      work_acc[b] += F * (nn * nn * nn + nn * nn * (3 * d + 6)) + nn * nn * nn / 3.0 +
+                     (N - nn) * (nn * nn + nn * (3 * d + 8) + 60.0);
+    }
+  }
+  // Continuous batching: a campaign that has done its last trial hands its trace to the sink and its slot to the
+  // next seed of its bank (fresh mask / trace / training set); nothing to do for the host between steps.
+  if (turn.n_final > 0 && n + 1 >= turn.n_final) {
+    __shared__ int s_slot, s_gen;
+    if (threadIdx.x == 0) {
+      s_slot = turn.sink ? atomicAdd(turn.sink_count, 1) : -1;
+      s_gen = turn.gen[b];
+    }
+    __syncthreads();
+    int32_t* tb = trace + (size_t)b * n_cap;
+    if (s_slot >= 0 && s_slot < turn.sink_capacity)
+      for (int i = threadIdx.x; i < n_cap; i += blockDim.x) turn.sink[(size_t)s_slot * n_cap + i] = tb[i];
+    __syncthreads();
+    if (s_gen >= turn.generations) { if (threadIdx.x == 0) status[b] = 6; return; }   // bank exhausted: finished
+    const int32_t* init = turn.bank + ((size_t)b * turn.generations + s_gen) * turn.n_init;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) mb[i] = 1;
+    for (int i = threadIdx.x; i < n_cap; i += blockDim.x) tb[i] = (i < turn.n_init) ? init[i] : -1;
+    for (int i = threadIdx.x; i < n_cap * d; i += blockDim.x) {
+      const int row = i / d, k = i - row * d;
+      Xb[i] = (row < turn.n_init) ? P[(size_t)init[row] * d + k] : 0.0;
+    }
+    for (int i = threadIdx.x; i < n_cap; i += blockDim.x)
+      yb[i] = (i < turn.n_init) ? pool_y[(size_t)pid * N + init[i]] : 0.0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < turn.n_init; i += blockDim.x) mb[init[i]] = 0;
+    if (threadIdx.x == 0) { n_arr[b] = turn.n_init; turn.gen[b] = s_gen + 1; }
   }
 }
 
@@ -339,12 +373,27 @@ __global__ void k_log_ei(long long count, const double* __restrict__ mean, const
     out[i] = log_ei(mean[i], var[i], best_f);
 }
 
+// Opt in to > 48 KB of dynamic shared memory.  cudaFuncSetAttribute blocks while instances of the kernel are
+// running, which would serialise launches on different streams, so it is issued only when the requested size
+// grows (cached per kernel and device).
 template <class K>
 int set_smem(K kernel, size_t bytes) {
   if (bytes > 227 * 1024) return fail("campaign does not fit in shared memory (n_cap too large)");
-  if (bytes > 48 * 1024) {
+  if (bytes <= 48 * 1024) return 0;
+  struct Grant { const void* fn; int dev; size_t bytes; };
+  static Grant table[64];
+  static int used = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const void* fn = reinterpret_cast<const void*>(kernel);
+  Grant* slot = nullptr;
+  for (int i = 0; i < used; ++i)
+    if (table[i].fn == fn && table[i].dev == dev) { slot = &table[i]; break; }
+  if (!slot && used < 64) { slot = &table[used++]; slot->fn = fn; slot->dev = dev; slot->bytes = 0; }
+  if (!slot || bytes > slot->bytes) {
     const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return fail_cuda("cudaFuncSetAttribute", e);
+    if (slot) slot->bytes = bytes;
   }
   return 0;
 }
@@ -437,9 +486,18 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
                       const int32_t* pool_id, uint8_t* mask, double* X, double* y, int32_t* n, int32_t* trace,
                       const double* theta0, const double* lower, const double* upper, const double* prior,
                       const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
-                      int32_t* status, const int32_t* order, void* stream) {
+                      int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
+                      int32_t* iters_acc, void* stream) {
   if (check_dims(B, n_cap, d)) return -1;
   if (N < 1) return fail("N < 1");
+  stp_turnover turn;
+  memset(&turn, 0, sizeof(turn));
+  if (turnover) {
+    turn = *turnover;
+    if (turn.n_final > 0 && (!turn.bank || !turn.gen || turn.n_init < 1 || turn.n_init >= n_cap || turn.generations < 0 ||
+                             turn.n_final > n_cap || (turn.sink && !turn.sink_count)))
+      return fail("inconsistent stp_turnover");
+  }
   if (!pool || !pool_y || !mask || !X || !y || !n || !trace || !theta0 || !prior || !status) return fail("null argument");
   if (B == 0) return 0;
   const int threads = threads_for(n_cap);
@@ -449,7 +507,7 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
   BoundsArg bnd; fill_bounds(bnd, d, lower, upper, theta0);
   k_exact_bo_step<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, N, pool, pool_y, pool_id, mask, X, y, n, trace,
                                                               bnd, p, to_opts(opts), theta_out, acq_out, nit, nfev,
-                                                              status, order);
+                                                              status, order, turn, work_acc, iters_acc);
   return after_launch("stp_exact_bo_step");
 }
 

@@ -77,6 +77,9 @@ class CampaignBatch:
         self.seeds = list(seeds) if seeds is not None else list(range(B))
         self.iteration = 0
         self.ragged = len({len(i) for i in init_indices}) > 1   # campaigns of different ages: schedule longest first
+        self._turnover = None
+        self.work_acc = torch.zeros(B, dtype=torch.double, device=dev)   # algorithmic flops done per campaign slot
+        self.iters_acc = torch.zeros(B, dtype=torch.int32, device=dev)   # completed BO iterations per campaign slot
         if kind == "ExactGP":
             self._theta0 = priors.exact_theta0(d)
             self._lower, self._upper = priors.exact_bounds(d)
@@ -102,7 +105,8 @@ class CampaignBatch:
             _lib.exact_bo_step(self.pool, self.pool_y, self.pool_id, self.mask, self.X, self.y, self.n, self.trace,
                                self._theta0, self._lower, self._upper, self._prior, self.status,
                                theta_out=self.theta, acq_out=self.acq, nit=self.nit, nfev=self.nfev,
-                               opts=self._opts, order=order)
+                               opts=self._opts, order=order, turnover=self._turnover, work_acc=self.work_acc,
+                               iters_acc=self.iters_acc)
             self.launches += 1
         else:
             self.launches += self._var.step()
@@ -125,6 +129,23 @@ class CampaignBatch:
         for b in range(self.B):
             out.append([float(py[pid[b], idx[b, i]]) for i in range(int(n[b]))])
         return out
+
+    # -- continuous batching inside the kernel (ExactGP): stp_turnover --------------------------------
+    def enable_turnover(self, bank: torch.Tensor, n_final: int, sink_capacity: int = 0) -> None:
+        """Let stp_exact_bo_step recycle finished campaigns itself: ``bank`` is int [B, G, n_init] (the next G initial
+        designs of every slot), a campaign is finished when its training set has ``n_final`` rows; finished traces are
+        appended to ``self.sink`` (``sink_capacity`` rows).  No host or torch work between steps."""
+        if self.kind != "ExactGP":
+            raise NotImplementedError("in-kernel turnover is provided for the ExactGP step")
+        B, G, ni = bank.shape
+        assert B == self.B and n_final <= self.cap
+        self.bank = bank.to(self.device, torch.int32).contiguous()
+        self.gen = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self.sink = torch.full((max(sink_capacity, 1), self.cap), -1, dtype=torch.int32, device=self.device)
+        self.sink_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._turnover = _lib.Turnover(int(n_final), int(ni), int(G), int(sink_capacity), self.bank.data_ptr(),
+                                       self.gen.data_ptr(), self.sink.data_ptr() if sink_capacity else None,
+                                       self.sink_count.data_ptr())
 
     # -- continuous batching: finished campaigns leave, fresh ones take their slots --------------
     def recycle(self, slots: torch.Tensor, new_init: torch.Tensor, sink: Optional[torch.Tensor] = None,

@@ -228,3 +228,35 @@ def test_synthetic_cfg4_batch_matches_oracle_step():
             pick = int(torch.where(mask)[0][oacq.first_argmax(oacq.log_ei(mean, var, y[picked].max()))])
             agree += pick == int(idx[b, t]); total += 1
     assert agree == total
+
+
+def test_in_kernel_turnover_continuous_batching():
+    """stp_turnover: finished campaigns hand their trace to the sink and their slot to the next design of the bank,
+    inside the kernel.  Every finished trace equals the trace of a stand-alone campaign from the same design."""
+    from stpbenchmark_b200.engine import CampaignBatch
+    from stpbenchmark_b200.runners import initial_design
+    X, y = dataset("AgNP")
+    seeds = [[45, 359, 6185], [102, 421, 123]]                     # slot -> generations 0, 1, 2
+    designs = [[initial_design(X, y, s, 10)[0] for s in row] for row in seeds]
+    n_trials = 5
+    batch = CampaignBatch(X, y, [0, 0], [designs[0][0], designs[1][0]], n_cap=16, kind="ExactGP")
+    bank = torch.tensor([[designs[0][1], designs[0][2]], [designs[1][1], designs[1][2]]], dtype=torch.int32)
+    batch.enable_turnover(bank, n_final=10 + n_trials, sink_capacity=8)
+    batch.run(12)                                                  # 5 + 5 + 2 iterations per slot
+    idx, n, status = batch.traces()
+    assert status.tolist() == [0, 0] and n.tolist() == [12, 12]
+    assert int(batch.sink_count.item()) == 4 and batch.gen.tolist() == [2, 2]
+    assert batch.iters_acc.tolist() == [12, 12] and (batch.work_acc > 0).all()
+    finished = {tuple(r[:10]): r[:15] for r in batch.sink[:4].cpu().tolist()}
+    for slot in range(2):
+        for g in range(2):
+            ref = CampaignBatch(X, y, [0], [designs[slot][g]], n_cap=16, kind="ExactGP")
+            ref.run(n_trials)
+            want = ref.traces()[0][0, :15].tolist()
+            assert finished[tuple(designs[slot][g])] == want
+        cur = CampaignBatch(X, y, [0], [designs[slot][2]], n_cap=16, kind="ExactGP")
+        cur.run(2)
+        assert idx[slot, :12].tolist() == cur.traces()[0][0, :12].tolist()
+    # bank exhausted -> the campaign stops with status 6 after its last trial
+    batch.run(3)
+    assert batch.traces()[2].tolist() == [6, 6] and int(batch.sink_count.item()) == 6
