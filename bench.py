@@ -452,9 +452,14 @@ def run_var_arm(args):
         age = (b * N_TRIALS // B + b) % (N_TRIALS - W - K) if N_TRIALS - W - K > 0 else 0
         rest = [i for i in torch.randperm(N_POOL, generator=gen).tolist() if i not in set(d0)][:age]
         init.append(d0 + rest)
-    batch = CampaignBatch(PX, PY, pool_id, init, n_cap=CAP, kind=args.model, device=dev, epochs=args.epochs,
-                          learning_rate=0.01, num_samples=2048)
-    n0 = batch.n.clone()
+    from stpbenchmark_b200.engine import CampaignGroups
+    batch = CampaignGroups(PX, PY, pool_id, init, n_cap=CAP, kind=args.model, groups=args.groups, device=dev,
+                           epochs=args.epochs, learning_rate=0.01, num_samples=2048)
+    for m in batch.members:
+        m.ragged = True
+    cat_n = lambda: torch.cat([m.n for m in batch.members])
+    cat_status = lambda: torch.cat([m.status for m in batch.members])
+    n0 = cat_n().clone()
     def barrier():
         if world > 1:
             dist.barrier()
@@ -463,25 +468,31 @@ def run_var_arm(args):
         batch.step()
     barrier()
     sampler = ClockSampler(local_rank); sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = batch.launches
-    n_before = batch.n.clone()
-    done = torch.zeros(1, dtype=torch.int64, device=dev)
-    e0.record()
+    n_before = cat_n().clone()
+    ok_before = int((cat_status() == 0).sum().item())
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for st in batch.streams:
+        st.wait_event(ev0)
     for _ in range(K):
         batch.step()
-        done.add_((batch.status == 0).sum())
-    e1.record()
+    ends = []
+    for st in batch.streams:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(st)
+        ends.append(e)
     barrier()
     clocks = sampler.stop()
+    done = torch.tensor([int((cat_n() - n_before).sum().item())], dtype=torch.int64, device=dev)   # completed iterations
     if world > 1:
         dist.all_reduce(done)
-    ms = e0.elapsed_time(e1)
+    ms = max(ev0.elapsed_time(e) for e in ends)
     t = torch.tensor([ms], dtype=torch.double, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    bad = int((batch.status != 0).sum().item())
+    bad = int((cat_status() != 0).sum().item())
     E, S, d = args.epochs, 2048, DIM
     nn = n_before.double() + (K - 1) / 2.0
     C = 60.0 if args.model == "VarGP" else S * 80.0
@@ -499,7 +510,7 @@ def run_var_arm(args):
             "roofline": {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                          "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None, "kernel": "k_var_fit + k_var_acq"},
             "cpu_baseline": None, "e2e": None, "gpu_launches": batch.launches - l0, "clocks": clocks,
-            "frozen_campaigns": bad}), flush=True)
+            "frozen_campaigns": bad, "streams": len(batch.streams)}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

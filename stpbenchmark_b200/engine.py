@@ -170,3 +170,50 @@ class CampaignBatch:
         self.y[slots, :ni] = self.pool_y[pid.unsqueeze(1), new_init]
         self.n[slots] = ni
         self.status[slots] = 0
+
+
+class CampaignGroups:
+    """The campaigns of one GPU split into contiguous groups, each a CampaignBatch on its own CUDA stream.
+
+    A step of an ExactGP batch cannot end before its longest fit (38...449 L-BFGS-B closures), so a single launch
+    over all campaigns leaves the SMs idle ~1/3 of the time; with independent groups the tail of one group's
+    launch is filled by the others' (campaigns never interact, so no cross-group synchronisation is needed).
+    Same ``step`` / ``run`` / ``traces`` surface as CampaignBatch."""
+
+    def __init__(self, pools: torch.Tensor, pool_ys: torch.Tensor, pool_id: Sequence[int],
+                 init_indices: Sequence[Sequence[int]], n_cap: int, kind: str = "ExactGP", groups: int = 4,
+                 device: Optional[torch.device] = None, **kwargs):
+        B = len(pool_id)
+        groups = max(1, min(int(groups), B))
+        self.bounds = [(g * B // groups, (g + 1) * B // groups) for g in range(groups)]
+        self.members: List[CampaignBatch] = []
+        self.streams: List[torch.cuda.Stream] = []
+        seeds = kwargs.pop("seeds", None)
+        for lo, hi in self.bounds:
+            self.members.append(CampaignBatch(pools, pool_ys, list(pool_id[lo:hi]), list(init_indices[lo:hi]), n_cap,
+                                              kind=kind, device=device,
+                                              seeds=None if seeds is None else list(seeds[lo:hi]), **kwargs))
+            self.streams.append(torch.cuda.Stream(device=self.members[-1].device))
+        torch.cuda.synchronize(self.members[0].device)   # construction ran on the current stream
+
+    def step(self) -> None:
+        for m, s in zip(self.members, self.streams):
+            with torch.cuda.stream(s):
+                m.step()
+
+    def run(self, n_trials: int) -> None:
+        for _ in range(int(n_trials)):
+            self.step()
+
+    def synchronize(self) -> None:
+        for s in self.streams:
+            s.synchronize()
+
+    def traces(self):
+        self.synchronize()
+        parts = [m.traces() for m in self.members]
+        return tuple(torch.cat([p[i] for p in parts]) for i in range(3))
+
+    @property
+    def launches(self) -> int:
+        return sum(m.launches for m in self.members)

@@ -65,3 +65,14 @@ def test_no_cpu_fallback():
         optim.train_exact_model_botorch(m, X, y)
     with pytest.raises(RuntimeError, match="CUDA"):
         m.posterior(X)
+
+
+def test_struct_layouts_match_the_header():
+    """ctypes mirrors of the two structs that cross the ABI: stp_lbfgsb_opts (4 x int32 + 2 x double) and
+    stp_turnover (4 x int32 + 4 pointers)."""
+    import ctypes as C
+    from stpbenchmark_b200 import _lib
+    assert C.sizeof(_lib.LbfgsbOpts) == 32 and _lib.LbfgsbOpts.factr.offset == 16
+    assert C.sizeof(_lib.Turnover) == 48 and _lib.Turnover.bank.offset == 16 and _lib.Turnover.sink_count.offset == 40
+    o = _lib.LbfgsbOpts.scipy_defaults()
+    assert (o.m, o.maxiter, o.maxfun, o.maxls) == (10, 15000, 15000, 20) and abs(o.factr - 1e7) < 1e-6 and o.pgtol == 1e-5

@@ -260,3 +260,18 @@ def test_in_kernel_turnover_continuous_batching():
     # bank exhausted -> the campaign stops with status 6 after its last trial
     batch.run(3)
     assert batch.traces()[2].tolist() == [6, 6] and int(batch.sink_count.item()) == 6
+
+
+def test_campaign_groups_on_streams_equal_single_batch():
+    """CampaignGroups (4 groups, 4 streams) produces exactly the traces of one CampaignBatch."""
+    from stpbenchmark_b200 import synthetic
+    from stpbenchmark_b200.engine import CampaignBatch, CampaignGroups
+    X, y = synthetic.cfg4_pool(3, N=512)
+    seeds = list(range(20, 32))
+    init = synthetic.initial_designs(X, y, seeds).tolist()
+    one = CampaignBatch(X, y, [0] * 12, init, n_cap=20, kind="ExactGP")
+    one.run(8)
+    many = CampaignGroups(X, y, [0] * 12, init, n_cap=20, kind="ExactGP", groups=4)
+    many.run(8)
+    a, b = one.traces(), many.traces()
+    assert all(torch.equal(p, q) for p, q in zip(a, b)) and many.launches == 32
