@@ -41,17 +41,22 @@ struct ExactSmem {
   double* c3;     // cap+9
   double* piv;    // cap+5 (pivots; reused as tmp by the triangular inverse)
   double* alpha;  // cap
-  double* tile;   // acquisition: cap x TC cross-covariances + TC x (kMaxD) staged candidates
+  double* tile;   // acquisition: cap x TC cross-covariances + TC x (kMaxD) staged candidates;
+                  // fit: the three panels of the blocked sweep (never live together)
   double* part;   // acquisition: nwarps x TC x 2 partial sums (ALIASES `red`: never live together)
   double* small;  // 64 doubles: theta (<=11), gradient (<=11), misc
   double* red;    // kRedDoubles reduction scratch
   int ld, cap;
 };
 
+STP_HD size_t exact_tile_doubles(int cap, int tc) {
+  const size_t acq = (size_t)cap * tc + (size_t)tc * kMaxD, swp = sweep_blocked_scratch_doubles(cap + 1);
+  return acq > swp ? acq : swp;
+}
 STP_HD size_t exact_smem_doubles(int cap, int d, int tc, int nwarps) {
   const int ld = odd_ld(cap + 1);
   return (size_t)(cap + 1) * ld + (size_t)d * cap + cap + 5 * (size_t)(cap + 9) + cap +
-         (size_t)cap * tc + (size_t)tc * kMaxD + 64 + 16 * kMaxWarps;  // nwarps*tc*2 <= 16*kMaxWarps
+         exact_tile_doubles(cap, tc) + 64 + 16 * kMaxWarps;  // nwarps*tc*2 <= 16*kMaxWarps
 }
 
 STP_HD ExactSmem exact_smem_carve(double* base, int cap, int d, int tc, int nwarps) {
@@ -68,7 +73,7 @@ STP_HD ExactSmem exact_smem_carve(double* base, int cap, int d, int tc, int nwar
   s.c3 = p;     p += cap + 9;
   s.piv = p;    p += cap + 9;
   s.alpha = p;  p += cap;
-  s.tile = p;   p += (size_t)cap * tc + (size_t)tc * kMaxD;
+  s.tile = p;   p += exact_tile_doubles(cap, tc);
   s.small = p;  p += 64;
   s.red = p;
   s.part = p;   // block reductions and the acquisition partials are never in flight together
@@ -97,6 +102,17 @@ STP_HD double ard_rbf_tt(const double* Xt, int cap, int d, const double* invl, i
     }
   return os * exp(-0.5 * r2);
 }
+
+// Bordered sweep of the closure: blocked tensor-core form on the device, pair sweep in the host emulation.
+template <class Team>
+STP_HD int exact_sweep(const Team& tm, const ExactSmem& s, int n) {
+  return sweep_bordered4(tm, s.A, s.ld, n + 1, n, s.c0, s.c1, s.c2, s.c3, s.piv);
+}
+#if defined(__CUDACC__) && !defined(STP_NO_BLOCKED_SWEEP)
+__device__ __forceinline__ int exact_sweep(const CtaTeam& tm, const ExactSmem& s, int n) {
+  return sweep_bordered_blocked(tm, s.A, s.ld, n + 1, n, s.tile, s.piv);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------
 // One L-BFGS-B closure call.  Every thread returns the same status and loss; the gradient
@@ -134,15 +150,19 @@ STP_HD int exact_mll_fg(const Team& tm, const ExactSmem& s, int n, int d, const 
   }
   tm.sync();
   // K3+K4: bordered sweep -> -Kinv, alpha, -quad, pivots
-  const int fail = sweep_bordered4(tm, s.A, ld, n + 1, n, s.c0, s.c1, s.c2, s.c3, s.piv);
+  const int fail = exact_sweep(tm, s, n);
   if (fail) { *f_out = NAN; return 1; }
   const double* arow = s.A + n * ld;  // alpha
   // K5: reductions
-  double acc[kMaxD + 4];
+  double acc[kMaxD + 5];
 #pragma unroll
-  for (int q = 0; q < kMaxD + 4; ++q) acc[q] = 0.0;
+  for (int q = 0; q < kMaxD + 5; ++q) acc[q] = 0.0;
   // acc[0] = sum log piv, acc[1] = sum W_ii, acc[2] = sum alpha, acc[3] = sum_{i>j} W_ij K_ij,
-  // acc[4+k] = sum_{i>j} W_ij K_ij (x_ik - x_jk)^2
+  // acc[4+k] = sum_{i>j} W_ij K_ij (x_ik - x_jk)^2, acc[4+d] = sum of the log-priors (one parameter per thread)
+  for (int k = tm.rank(); k < d + 2; k += tm.size())
+    acc[4 + d] += (k == 0)   ? lognormal_logpdf(noise, pr.noise_loc, pr.noise_scale)
+                  : (k == 1) ? lognormal_logpdf(os, pr.os_loc, pr.os_scale)
+                             : lognormal_logpdf(theta[1 + k], pr.ls_loc, pr.ls_scale);
   for (int i = tm.rank(); i < n; i += tm.size()) {
     const double ai = arow[i];
     acc[0] += log(s.piv[i]);
@@ -166,12 +186,10 @@ STP_HD int exact_mll_fg(const Team& tm, const ExactSmem& s, int n, int d, const 
         }
     }
   }
-  tm.sum_vec(acc, 4 + d);
+  tm.sum_vec(acc, 5 + d);
   const double quad = -s.A[n * ld + n];
   const double logN = -0.5 * (quad + acc[0] + n * kLog2Pi);
-  double total = logN + lognormal_logpdf(noise, pr.noise_loc, pr.noise_scale) +
-                 lognormal_logpdf(os, pr.os_loc, pr.os_scale);
-  for (int k = 0; k < d; ++k) total += lognormal_logpdf(theta[3 + k], pr.ls_loc, pr.ls_scale);
+  const double total = logN + acc[4 + d];
   const double scale = -1.0 / n;
   const double f = total * scale;
   tm.sync();

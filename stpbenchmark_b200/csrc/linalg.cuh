@@ -178,6 +178,230 @@ STP_HD int sweep_bordered4(const Team& tm, double* A, int ld, int m, int npiv, d
   return sweep_bordered_pair<0, TRI>(tm, A, ld, m, npiv, v0, v1, v2, v3, piv);
 }
 
+// fp64 tensor-core MMA, D(8x8) += A(8x4) B(4x8):  lane l holds  a = A[l / 4][l % 4],  b = B[l % 4][l / 4],
+// d0 = D[l / 4][2 (l % 4)], d1 = D[l / 4][2 (l % 4) + 1]   (DMMA in SASS; there is no fp64 tcgen05 path).
+#if defined(__CUDACC__)
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+#endif
+
+// ---------------------------------------------------------------------------------------
+// Blocked bordered sweep on the tensor cores (device only).  Same contract as sweep_bordered_pair (square storage,
+// lower triangle + diagonal of the m x m matrix updated in place, strict upper triangle untouched, pivots 0 ..
+// npiv - 1, rows >= npiv are border rows), but the pivots are taken EIGHT at a time.  With C = A[:, K] (m x 8,
+// symmetric fill), D = C[K, :] = Lu Delta Lu^T (unit lower Lu, Delta = the 8 scalar pivots) and X = Lu^-1:
+//     W = C X^T,  V = W Delta^-1,  T = V X = C D^-1,
+//     A[K, K] <- -X^T Delta^-1 X,   A[i, K] <- T[i, :] (i not in K),   A[i, j] <- A[i, j] - V[i, :] . W[j, :] otherwise.
+// (The explicit D^-1 never multiplies the trailing matrix: forming T C^T from an inverted block loses
+// cond(D) eps -- 4 to 6 digits on long-lengthscale kernels -- while the V W^T form is as accurate as the
+// pivot-by-pivot sweep; see tests/test_blocked_sweep_model.py.)
+// Per block step:
+//   (A) every warp eliminates the 8 x 8 block in registers (accumulator-fragment layout, warp shuffles only: no
+//       barrier on the critical path of 8 dependent pivots), giving X and 1 / Delta;
+//   (B) W, V, T by DMMA, 8 rows per warp; W replaces C in its panel, -V goes to a second panel, T is written
+//       straight into the pivot columns / rows of A (and into the next panel where it belongs);      -- barrier --
+//   (C) rank-8 update of the lower triangle in 16 x 16 tiles, 8 DMMA per tile; the store pass also collects the
+//       NEXT panel (columns K + 8, symmetric fill).                                                -- barrier --
+// i.e. 2 barriers per 8 pivots instead of 4, and ~8x fewer issued instructions per MAC than the pair sweep.
+// A trailing partial block is padded with identity pivots (its panel columns are zero).
+// `scratch`: sweep_blocked_scratch_doubles(m) doubles of shared memory.  Returns 0 or 1 + k for a bad pivot.
+// ---------------------------------------------------------------------------------------
+constexpr int kPanelLd = 12;   // 8 panel columns + 4 pad doubles: conflict-free fragment loads (24 g + 2 q words)
+STP_HD size_t sweep_blocked_scratch_doubles(int m) { return (size_t)3 * m * kPanelLd; }
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double* A, int ld, int m, int npiv,
+                                                      double* scratch, double* piv) {
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int PL = kPanelLd;
+  const int lane = tm.lane(), warp = tm.warp(), nw = tm.nwarps();
+  const int g = lane >> 2, q = lane & 3;
+  double* C = scratch;                           // current panel; rows outside K become W in step (B)
+  double* Cn = scratch + (size_t)m * PL;         // next panel
+  double* Vn = scratch + (size_t)2 * m * PL;     // -V
+  tm.sync();   // the caller's writes to A must be complete
+  for (int idx = tm.rank(); idx < m * 8; idx += tm.size()) {
+    const int i = idx >> 3, b = idx & 7;
+    C[i * PL + b] = (b < npiv) ? ((i >= b) ? A[i * ld + b] : A[b * ld + i]) : 0.0;
+  }
+  tm.sync();
+  const int nT = (m + 15) >> 4, n_tiles = nT * (nT + 1) / 2;
+  for (int kb = 0; kb < npiv; kb += 8) {
+    const int r = (npiv - kb < 8) ? (npiv - kb) : 8;
+    const int kn = kb + 8;
+    // ---- (A) elimination of D in registers: am = trailing block, xm = X (row g, columns 2q, 2q + 1)
+    double am0, am1;
+    if (g < r) {
+      am0 = C[(kb + g) * PL + 2 * q];
+      am1 = C[(kb + g) * PL + 2 * q + 1];
+    } else {
+      am0 = (2 * q == g) ? 1.0 : 0.0;
+      am1 = (2 * q + 1 == g) ? 1.0 : 0.0;
+    }
+    double xm0 = (2 * q == g) ? 1.0 : 0.0, xm1 = (2 * q + 1 == g) ? 1.0 : 0.0;
+    double ipa = 1.0, ipb = 1.0;     // 1 / Delta at columns 2q, 2q + 1
+    double ipq0 = 1.0, ipq1 = 1.0;   // 1 / Delta at q, q + 4
+    int fail = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double dk = (k & 1) ? am1 : am0;
+      const double p = __shfl_sync(kFull, dk, 4 * k + (k >> 1));
+      const double rk0 = __shfl_sync(kFull, am0, 4 * k + q);
+      const double rk1 = __shfl_sync(kFull, am1, 4 * k + q);
+      const double xk0 = __shfl_sync(kFull, xm0, 4 * k + q);
+      const double xk1 = __shfl_sync(kFull, xm1, 4 * k + q);
+      const double cg = __shfl_sync(kFull, dk, 4 * g + (k >> 1));
+      if (!(p > 0.0) || !(p <= 1.79e308)) { fail = 1 + kb + k; break; }
+      const double ip = 1.0 / p;
+      const double f = (g > k) ? cg * ip : 0.0;
+      am0 = fma(-f, rk0, am0);
+      am1 = fma(-f, rk1, am1);
+      xm0 = fma(-f, xk0, xm0);
+      xm1 = fma(-f, xk1, xm1);
+      if (2 * q == k) ipa = ip;
+      if (2 * q + 1 == k) ipb = ip;
+      if (q == k) ipq0 = ip;
+      if (q + 4 == k) ipq1 = ip;
+      if (warp == 0 && lane == 0 && k < r) piv[kb + k] = p;
+    }
+    if (fail) return fail;   // identical in every warp: the whole team leaves together
+    // operand fragments of X:  bw = X[g][4s + q] (B operand of C X^T),  bt = X[4s + q][g] (B operand of V X)
+    double bw0, bw1, bt0, bt1;
+    {
+      const int src = 4 * g + (q >> 1);
+      const double x0 = __shfl_sync(kFull, xm0, src), x1 = __shfl_sync(kFull, xm1, src);
+      const double y0 = __shfl_sync(kFull, xm0, src + 2), y1 = __shfl_sync(kFull, xm1, src + 2);
+      bw0 = (q & 1) ? x1 : x0;
+      bw1 = (q & 1) ? y1 : y0;
+      const int st = 4 * q + (g >> 1);
+      const double u0 = __shfl_sync(kFull, xm0, st), u1 = __shfl_sync(kFull, xm1, st);
+      const double z0 = __shfl_sync(kFull, xm0, st + 16), z1 = __shfl_sync(kFull, xm1, st + 16);
+      bt0 = (g & 1) ? u1 : u0;
+      bt1 = (g & 1) ? z1 : z0;
+    }
+    if (warp == 0) {   // A[K, K] <- -X^T Delta^-1 X
+      double s0 = 0.0, s1 = 0.0;
+      dmma884(s0, s1, bt0, bt0 * ipq0);
+      dmma884(s0, s1, bt1, bt1 * ipq1);
+      if (g < r) {
+        double* row = A + (size_t)(kb + g) * ld + kb;
+        if (2 * q <= g) row[2 * q] = -s0;
+        if (2 * q + 1 <= g) row[2 * q + 1] = -s1;
+      }
+    }
+    // ---- (B) W = C X^T, V = W / Delta, T = V X, 8 rows per warp
+    for (int rt = warp; rt * 8 < m; rt += nw) {
+      const int i = rt * 8 + g, ic = (i < m) ? i : m - 1;
+      const double a0 = C[ic * PL + q], a1 = C[ic * PL + 4 + q];
+      double w0 = 0.0, w1 = 0.0;
+      dmma884(w0, w1, a0, bw0);
+      dmma884(w0, w1, a1, bw1);
+      const double v0 = w0 * ipa, v1 = w1 * ipb;
+      const int src = 4 * g + (q >> 1);
+      const double e0 = __shfl_sync(kFull, v0, src), e1 = __shfl_sync(kFull, v1, src);
+      const double h0 = __shfl_sync(kFull, v0, src + 2), h1 = __shfl_sync(kFull, v1, src + 2);
+      const double va0 = (q & 1) ? e1 : e0, va1 = (q & 1) ? h1 : h0;
+      double t0 = 0.0, t1 = 0.0;
+      dmma884(t0, t1, va0, bt0);
+      dmma884(t0, t1, va1, bt1);
+      if (i < m && !((unsigned)(i - kb) < (unsigned)r)) {   // rows of K keep C (phase (A) of other warps reads them)
+        C[i * PL + 2 * q] = w0;
+        C[i * PL + 2 * q + 1] = w1;
+        Vn[i * PL + 2 * q] = -v0;
+        Vn[i * PL + 2 * q + 1] = -v1;
+        const bool nxt = (unsigned)(i - kn) < 8u && i < npiv;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int b = 2 * q + e, j = kb + b;
+          const double tv = e ? t1 : t0;
+          if (b < r) {
+            if (i > j) A[(size_t)i * ld + j] = tv;
+            else A[(size_t)j * ld + i] = tv;
+            if (nxt) Cn[j * PL + (i - kn)] = tv;
+          }
+        }
+      }
+    }
+    if (kn < npiv && kn + 8 > npiv) {   // the next block is partial: its unused panel columns must read as zero
+      for (int idx = tm.rank(); idx < m * 8; idx += tm.size()) {
+        const int b = idx & 7;
+        if (kn + b >= npiv) Cn[(idx >> 3) * PL + b] = 0.0;
+      }
+    }
+    tm.sync();
+    // ---- (C) A -= V W^T on the lower triangle outside K, 16 x 16 tiles
+    for (int t = warp; t < n_tiles; t += nw) {
+      int I = 0, J = t;
+      while (J > I) { J -= I + 1; ++I; }
+      const int ib = I << 4, jb = J << 4;
+      double c[2][2][2];
+      double af[2][2], bf[2][2];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int i = ib + 8 * a + g, ic = (i < m) ? i : m - 1;
+        af[a][0] = Vn[ic * PL + q];
+        af[a][1] = Vn[ic * PL + 4 + q];
+        const int j = jb + 8 * a + g, jc = (j < m) ? j : m - 1;
+        bf[a][0] = C[jc * PL + q];
+        bf[a][1] = C[jc * PL + 4 + q];
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int i = ib + 8 * a + g, j = jb + 8 * b + 2 * q;
+          const double* row = A + (size_t)((i < m) ? i : 0) * ld;
+          c[a][b][0] = (i < m && j <= i) ? row[j] : 0.0;
+          c[a][b][1] = (i < m && j + 1 <= i) ? row[j + 1] : 0.0;
+        }
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) dmma884(c[a][b][0], c[a][b][1], af[a][s], bf[b][s]);
+      const int kt = kb & ~15, nt = kn & ~15;
+      const bool edge = (ib == kt) || (jb == kt) || ((kn < npiv) && ((ib == nt) || (jb == nt)));
+      if (!edge) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int i = ib + 8 * a + g, j = jb + 8 * b + 2 * q;
+            if (i < m) {
+              double* row = A + (size_t)i * ld;
+              if (j <= i) row[j] = c[a][b][0];
+              if (j + 1 <= i) row[j + 1] = c[a][b][1];
+            }
+          }
+      } else {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = ib + 8 * a + g, j = jb + 8 * b + 2 * q + e;
+              const bool ik = (unsigned)(i - kb) < (unsigned)r, jk = (unsigned)(j - kb) < (unsigned)r;
+              if (i < m && j <= i && !ik && !jk) {
+                const double v = c[a][b][e];
+                A[(size_t)i * ld + j] = v;
+                if ((unsigned)(j - kn) < 8u && j < npiv) Cn[i * PL + (j - kn)] = v;
+                if ((unsigned)(i - kn) < 8u && i < npiv) Cn[j * PL + (i - kn)] = v;
+              }
+            }
+      }
+    }
+    tm.sync();
+    double* sw = C; C = Cn; Cn = sw;
+  }
+  return 0;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------
 // Register-tiled contraction  out(i, k) = sum_{r = r0}^{r1 - 1} L(i, r) * [scale(r)] * R(r, k)  with
 //   L(i, r) = Lp[i * l_si + r * l_sr]   (LT = false: l_sr == 1, row-major;  LT = true: l_si == 1, read down a column)
@@ -267,6 +491,118 @@ STP_HD void contract_p(const Team& tm, int n_rows, int n_cols, const double* Lp,
   }
 }
 
+
+
+// ---------------------------------------------------------------------------------------
+// Tensor-core form of the contraction (device only): out(i, k) = sum_r L(i, r) [scale(r)] R(r, k) with the legacy
+// fp64 MMA, mma.sync.aligned.m8n8k4.row.col.f64 (DMMA in SASS -- there is no fp64 tcgen05 path).  A warp owns a
+// 16 x 16 output block (2 x 2 MMA tiles, 8 accumulator registers per thread); per 4-deep reduction step it loads
+// 2 A fragments + 2 B fragments (one double per thread each) and issues 4 DMMA = 1024 MAC, i.e. ~7x fewer
+// instructions per MAC than the 4 x 2 register-tiled FMA loop.
+// Reduction ranges are widened to multiples of 4 (triangular operands are zero-filled inside the n x n square, as
+// for contract_p); the one 4-step that may cross n_red loads with clamped addresses and zeroed values.
+// Out-of-range output rows / columns are clamped on load and never stored.
+// ---------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+
+template <bool LT, bool SCALE, class RangeF, class StoreF>
+__device__ __forceinline__ void contract_mma(const CtaTeam& tm, int n_rows, int n_cols, int n_red, const double* Lp, int ld_l,
+                                             const double* Rp, int ld_r, const double* scale, RangeF range,
+                                             StoreF store) {
+  const int lane = tm.lane(), nw = tm.nwarps();
+  const int g = lane >> 2, q = lane & 3;          // fragment coordinates: row / column group and k index
+  const int TR = (n_rows + 15) >> 4, TC = (n_cols + 15) >> 4;
+  for (int wt = tm.warp(); wt < TR * TC; wt += nw) {
+    const int ib = (wt / TC) << 4, kb = (wt % TC) << 4;
+    int r0 = 0, r1 = 0;
+    range(ib, (ib + 15 < n_rows) ? ib + 15 : n_rows - 1, kb, (kb + 15 < n_cols) ? kb + 15 : n_cols - 1, r0, r1);
+    r0 &= ~3;
+    r1 = (r1 + 3) & ~3;
+    double c[2][2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) { c[a][b][0] = 0.0; c[a][b][1] = 0.0; }
+    // rows of the two A tiles and columns of the two B tiles this thread loads (clamped into the matrix)
+    int ia[2], jb[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) { const int i = ib + 8 * a + g; ia[a] = (i < n_rows) ? i : n_rows - 1; }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) { const int j = kb + 8 * b + g; jb[b] = (j < n_cols) ? j : n_cols - 1; }
+    const int r_full = (r1 < (n_red & ~3)) ? r1 : (n_red & ~3);
+    int r = r0;
+    for (; r < r_full; r += 4) {
+      const int rk = r + q;
+      double af[2], bf[2];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) af[a] = LT ? Lp[(size_t)rk * ld_l + ia[a]] : Lp[(size_t)ia[a] * ld_l + rk];
+#pragma unroll
+      for (int b = 0; b < 2; ++b) bf[b] = Rp[(size_t)rk * ld_r + jb[b]];
+      if (SCALE) {
+        const double sc = scale[rk];
+        bf[0] *= sc; bf[1] *= sc;
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) dmma884(c[a][b][0], c[a][b][1], af[a], bf[b]);
+    }
+    if (r < r1) {   // the 4-step that crosses n_red
+      const bool in = (r + q) < n_red;
+      const int rk = in ? r + q : n_red - 1;
+      double af[2], bf[2];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const double v = LT ? Lp[(size_t)rk * ld_l + ia[a]] : Lp[(size_t)ia[a] * ld_l + rk];
+        af[a] = in ? v : 0.0;
+      }
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const double v = Rp[(size_t)rk * ld_r + jb[b]];
+        bf[b] = in ? v : 0.0;
+      }
+      if (SCALE) {
+        const double sc = scale[rk];
+        bf[0] *= sc; bf[1] *= sc;
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) dmma884(c[a][b][0], c[a][b][1], af[a], bf[b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int i = ib + 8 * a + g;
+        const int j = kb + 8 * b + 2 * q;
+        if (i < n_rows) {
+          if (j < n_cols) store(i, j, c[a][b][0]);
+          if (j + 1 < n_cols) store(i, j + 1, c[a][b][1]);
+        }
+      }
+  }
+}
+#endif
+
+// Contraction dispatch: tensor cores on the device, the register-tiled FMA loop in the host emulation.
+template <bool LT, bool SCALE, class RangeF, class StoreF>
+STP_HD void contract_nn(const SoloTeam& tm, int n_rows, int n_cols, int, const double* Lp, int ld_l, const double* Rp,
+                        int ld_r, const double* scale, RangeF range, StoreF store) {
+  contract_p<4, 2, LT, SCALE>(tm, n_rows, n_cols, Lp, ld_l, Rp, ld_r, scale, range, store);
+}
+#if defined(__CUDACC__)
+template <bool LT, bool SCALE, class RangeF, class StoreF>
+__device__ __forceinline__ void contract_nn(const CtaTeam& tm, int n_rows, int n_cols, int n_red, const double* Lp, int ld_l,
+                                            const double* Rp, int ld_r, const double* scale, RangeF range,
+                                            StoreF store) {
+#if defined(STP_NO_DMMA)
+  contract_p<4, 2, LT, SCALE>(tm, n_rows, n_cols, Lp, ld_l, Rp, ld_r, scale, range, store);
+#else
+  contract_mma<LT, SCALE>(tm, n_rows, n_cols, n_red, Lp, ld_l, Rp, ld_r, scale, range, store);
+#endif
+}
+#endif
 
 // ---------------------------------------------------------------------------------------
 // Fused Cholesky + triangular inverse, in place, ONE barrier per column.  With the deferred-scaling Cholesky

@@ -274,12 +274,12 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
     }
   tm.sync();
   // (3) At[c][k] = sum_{j<=k} Ct[c][j] Linv^T[j][k]
-  contract_p<4, 2, false, false>(tm, n, n, Ct, ld, LT, ld, (const double*)nullptr,
+  contract_nn<false, false>(tm, n, n, n, Ct, ld, LT, ld, (const double*)nullptr,
                  [=](int, int, int, int k_hi, int& r0, int& r1) { r0 = 0; r1 = k_hi + 1; },
                  [=](int c, int k, double v) { At[c * ld + k] = v; });
   tm.sync();
   // (4) Tt = At S ; Dt = Tt - At ; q(f): m_c = cst + At[c].mu ; v_c = os + jitter + At[c].Dt[c]
-  contract_p<4, 2, false, false>(tm, n, n, At, ld, S, ld, (const double*)nullptr,
+  contract_nn<false, false>(tm, n, n, n, At, ld, S, ld, (const double*)nullptr,
                  [=](int, int, int, int, int& r0, int& r1) { r0 = 0; r1 = n; },
                  [=](int c, int k, double v) { Dt[c * ld + k] = v - At[c * ld + k]; });
   tm.sync();
@@ -360,7 +360,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   {
     const double* dvv = s.dv;
     const double* nat2 = M.nat2;
-    contract_p<4, 2, true, true>(tm, n, n, At, ld, At, ld, dvv,
+    contract_nn<true, true>(tm, n, n, n, At, ld, At, ld, dvv,
                    [=](int, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = 0; r1 = (k_lo > i_hi) ? 0 : n; },
                    [=](int i, int k, double v) {
                      if (k <= i) {
@@ -403,31 +403,31 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   tm.sync();
   // (8) Cbar_t[c][j] = sum_{i>=j} Abar_t[c][i] Linv[i][j]   (into R0; G_S is dead)
   double* CBt = S;
-  contract_p<4, 2, false, false>(tm, n, n, Dt, ld, LI, ld, (const double*)nullptr,
+  contract_nn<false, false>(tm, n, n, n, Dt, ld, LI, ld, (const double*)nullptr,
                  [=](int, int, int k_lo, int, int& r0, int& r1) { r0 = k_lo; r1 = n; },
                  [=](int c, int j, double v) { CBt[c * ld + j] = v; });
   tm.sync();
   // (9) Lbar[i][k] = -sum_c Cbar_t[c][i] At[c][k], i >= k, zero above   (into R5, Abar_t is dead)
   double* LB = Dt;
-  contract_p<4, 2, true, false>(tm, n, n, CBt, ld, At, ld, (const double*)nullptr,
+  contract_nn<true, false>(tm, n, n, n, CBt, ld, At, ld, (const double*)nullptr,
                  [=](int, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = 0; r1 = (k_lo > i_hi) ? 0 : n; },
                  [=](int i, int k, double v) { LB[i * ld + k] = (k <= i) ? -v : 0.0; });
   tm.sync();
   // (10) Phi[i][k] = sum_{r>=i} L[r][i] Lbar[r][k], i >= k, diagonal halved, zero above   (into R4, At is dead)
   double* PH = At;
-  contract_p<4, 2, true, false>(tm, n, n, LK, ld, LB, ld, (const double*)nullptr,
+  contract_nn<true, false>(tm, n, n, n, LK, ld, LB, ld, (const double*)nullptr,
                  [=](int i_lo, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = i_lo; r1 = (k_lo > i_hi) ? i_lo : n; },
                  [=](int i, int k, double v) { PH[i * ld + k] = (k < i) ? v : (k == i ? 0.5 * v : 0.0); });
   tm.sync();
   // (11) U[i][k] = sum_{k<=r<=i} Phi[i][r] Linv[r][k], zero above   (into R5, Lbar is dead)
   double* U = Dt;
-  contract_p<4, 2, false, false>(tm, n, n, PH, ld, LI, ld, (const double*)nullptr,
+  contract_nn<false, false>(tm, n, n, n, PH, ld, LI, ld, (const double*)nullptr,
                  [=](int, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = k_lo; r1 = (k_lo > i_hi) ? k_lo : i_hi + 1; },
                  [=](int i, int k, double v) { U[i * ld + k] = (k <= i) ? v : 0.0; });
   tm.sync();
   // (12) Kbar'[j][k] = sum_{i>=max(j,k)} Linv[i][j] U[i][k]   (into R4, Phi is dead)
   double* KB = At;
-  contract_p<4, 2, true, false>(tm, n, n, LI, ld, U, ld, (const double*)nullptr,
+  contract_nn<true, false>(tm, n, n, n, LI, ld, U, ld, (const double*)nullptr,
                  [=](int j_lo, int, int k_lo, int, int& r0, int& r1) { r0 = (j_lo > k_lo) ? j_lo : k_lo; r1 = n; },
                  [=](int j, int k, double v) { KB[j * ld + k] = v; });
   tm.sync();
@@ -587,7 +587,7 @@ STP_HD int var_prepare(const Team& tm, const VarSmem& s, const VarWork& w, const
     for (int i = j; i < n; ++i) a += LI[i * ld + j] * s.mu[i];
     s.gmu[j] = a;
   }
-  contract_p<4, 2, false, false>(tm, n, n, LPI, ld, LI, ld, (const double*)nullptr,
+  contract_nn<false, false>(tm, n, n, n, LPI, ld, LI, ld, (const double*)nullptr,
                  [=](int, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = k_lo; r1 = (k_lo > i_hi) ? k_lo : i_hi + 1; },
                  [=](int i, int k, double v) { G[i * ld + k] = (k <= i) ? v : 0.0; });
   tm.sync();

@@ -46,6 +46,7 @@ def main():
                    "failed": int(sum(1 for s in status if s != 0)),
                    "init_design_equal": int(sum(a[:10] == g[:10] for a, g in zip(idx, gold))),
                    "index_exact_90_rows": int(sum(f >= 90 for f in first)),
+                   "exact_seeds": [int(s) for s, f in zip(sd, first) if f >= 90],
                    "index_exact_40_rows": int(sum(f >= 40 for f in first)),
                    "median_first_divergence": float(np.median(first)),
                    "step_agreement_free_running": round(float(np.mean([np.mean(np.array(a[10:90]) == np.array(g[10:90]))
