@@ -22,27 +22,27 @@ STP_HD ExactFitResult exact_fit_run(const Team& tm, const ExactSmem& s, LbfgsbSt
                                     const LbfgsbOpts& opts) {
   const int np = d + 3;
   double* g = s.small + 16;
+  const typename Team::Lanes L = tm.lanes();
   tm.sync();
-  if (tm.rank() == 0) {
-    lbfgsb_init(*S, np, theta, lb, ub, opts);
-    *flag = 1;
+  if (tm.warp() == 0) {   // the optimiser is run by the first warp, lane i <-> parameter i
+    lbfgsb_init(L, *S, np, theta, lb, ub, opts);
+    if (L.lane() == 0) *flag = 1;
   }
   tm.sync();
   while (*flag) {
     double f;
     const int st = exact_closure(tm, s, n, d, S->x, pr, &f, g);
     tm.sync();
-    if (tm.rank() == 0) {
-      if (st) { f = NAN; for (int k = 0; k < np; ++k) g[k] = NAN; }
-      *flag = lbfgsb_advance_split(*S, f, g);
+    if (tm.warp() == 0) {
+      if (st) {
+        f = NAN;
+        for (int k = L.lane(); k < np; k += L.width()) g[k] = NAN;
+        L.sync();
+      }
+      const int more = lbfgsb_advance(L, *S, f, g);
+      if (L.lane() == 0) *flag = more;
     }
     tm.sync();
-    while (*flag == 3) {            // the optimiser wants the dense B: formed by warp 0, one lane per row
-      lb_build_B_team(tm, *S);
-      tm.sync();
-      if (tm.rank() == 0) *flag = lbfgsb_resume(*S);
-      tm.sync();
-    }
   }
   for (int k = tm.rank(); k < np; k += tm.size()) theta[k] = S->x[k];
   tm.sync();

@@ -13,12 +13,17 @@
 // dcsrch / dcstep) and scipy's wrapper (_minimize_lbfgsb): m = 10, factr = ftol / eps,
 // pgtol, maxls = 20, line-search ftol = 1e-3, gtol = 0.9, xtol = 0.1, maxiter checked at NEW_X.
 //
-// Ask/tell interface, serial code (run by ONE thread of the CTA; the objective between two
-// calls is evaluated by the whole CTA):
-//     lbfgsb_init(S, ...);                       // S.x holds the first point to evaluate
-//     while (lbfgsb_advance(S, f, g)) { f, g = objective(S.x); }
+// Ask/tell interface, run by ONE WARP of the CTA (the objective between two calls is evaluated by the
+// whole CTA):
+//     lbfgsb_init(L, S, ...);                       // S.x holds the first point to evaluate
+//     while (lbfgsb_advance(L, S, f, g)) { f, g = objective(S.x); }
 //     -> S.x, S.f, S.status (0 converged, 1 iteration/evaluation cap, 2 abnormal line search,
 //        3 non-finite objective), S.iter, S.nfev
+// `L` is a lane group (team.cuh): WarpLanes on the device -- lane i owns variable i / row i of the small
+// matrices, dot products are shuffle reductions, the scalar bookkeeping (line search) is done by lane 0 -- or
+// SoloLanes (one thread, every loop serial) in the host emulation and the C++ unit tests.  The state lives
+// in shared memory; every routine leaves it consistent for all lanes (ends with L.sync()) and returns a
+// lane-uniform value.  The optimiser used to run on one thread (~40 % of the CTA's time at 38k it/s).
 #pragma once
 #include "exact.cuh"
 #include "team.cuh"
@@ -57,25 +62,27 @@ struct LbfgsbState {
   int brackt, stage;
   double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1;
   int phase;                      // 0 waiting for f(x0); 1 inside a line search
-  int B_ready;                    // the dense B of the current memory has been formed (possibly by the team)
-  // scratch of the serial routines: kept in the (shared-memory) state on purpose -- with ~220 KB of the SM's
+  int lsfail;                     // lane 0 -> all lanes: the line search could not start
+  // scratch of the routines: kept in the (shared-memory) state on purpose -- with ~225 KB of the SM's
   // 228 KB carved out as shared memory there is next to no L1 left, and thread-local arrays would turn every
-  // access of the optimiser thread into an L2 round trip
-  double sc_a[kMaxP], sc_b[kMaxP], sc_c[kMaxP], sc_d[kMaxP], sc_C[kMaxP][kMaxP];
+  // access into an L2 round trip
+  double sc_a[kMaxP], sc_b[kMaxP], sc_c[kMaxP], sc_d[kMaxP], sc_e[kMaxP], sc_C[kMaxP][kMaxP];
   int sc_i[kMaxP], sc_j[kMaxP];
   int status;
 };
 
 // ------------------------------ small dense helpers -----------------------------------
-STP_HD double lb_dot(const double* a, const double* b, int n) {
+template <class LN>
+STP_HD double lb_dot(const LN& L, const double* a, const double* b, int n) {
   double s = 0.0;
-  for (int i = 0; i < n; ++i) s += a[i] * b[i];
-  return s;
+  for (int i = L.lane(); i < n; i += L.width()) s += a[i] * b[i];
+  return L.sum(s);
 }
 
-STP_HD void lb_projgr(LbfgsbState& S) {
+template <class LN>
+STP_HD void lb_projgr(const LN& L, LbfgsbState& S) {
   double m = 0.0;
-  for (int i = 0; i < S.np; ++i) {
+  for (int i = L.lane(); i < S.np; i += L.width()) {
     double gi = S.g[i];
     if (S.nbd[i] != 0) {
       if (gi < 0.0) { if (S.nbd[i] >= 2) gi = fmax(S.x[i] - S.ub[i], gi); }
@@ -83,15 +90,21 @@ STP_HD void lb_projgr(LbfgsbState& S) {
     }
     m = fmax(m, fabs(gi));
   }
-  S.sbgnrm = m;
+  m = L.max(m);
+  L.sync();
+  if (L.lane() == 0) S.sbgnrm = m;
+  L.sync();
 }
 
-STP_HD void lb_reset_memory(LbfgsbState& S) {
-  S.col = 0; S.head = 0; S.itail = -1; S.theta = 1.0; S.iupdat = 0; S.updatd = 0;
+template <class LN>
+STP_HD void lb_reset_memory(const LN& L, LbfgsbState& S) {
+  L.sync();
+  if (L.lane() == 0) { S.col = 0; S.head = 0; S.itail = -1; S.theta = 1.0; S.iupdat = 0; S.updatd = 0; }
+  L.sync();
 }
 
 // B = theta I replayed through the stored (s, y) pairs, oldest first.  Returns 1 on breakdown.
-STP_HD int lb_build_B(LbfgsbState& S) {
+STP_HD int lb_build_B(const SoloLanes&, LbfgsbState& S) {
   const int n = S.np;
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j) S.B[i][j] = (i == j) ? S.theta : 0.0;
@@ -114,54 +127,113 @@ STP_HD int lb_build_B(LbfgsbState& S) {
   }
   return 0;
 }
+#if defined(__CUDACC__)
+// Warp version: lane r keeps row r of B in registers, the pairs are replayed with shuffles.
+__device__ __forceinline__ int lb_build_B(const WarpLanes& L, LbfgsbState& S) {
+  const int n = S.np, r = L.lane();
+  const bool live = r < n;
+  double Brow[kMaxP];
+#pragma unroll
+  for (int c = 0; c < kMaxP; ++c) Brow[c] = (live && c == r) ? S.theta : 0.0;
+  int broke = 0;
+  for (int q = 0; q < S.col; ++q) {
+    const int p = (S.head + q) % S.m;
+    const double* s = S.ws[p];
+    const double* y = S.wy[p];
+    double Bs0 = 0.0, Bs1 = 0.0;   // two chains: the dot product is latency-bound
+#pragma unroll
+    for (int c = 0; c < kMaxP; c += 2) {
+      if (c < n) Bs0 += Brow[c] * s[c];
+      if (c + 1 < kMaxP && c + 1 < n) Bs1 += Brow[(c + 1 < kMaxP) ? c + 1 : c] * s[c + 1];
+    }
+    const double Bs = Bs0 + Bs1;
+    const double sr = live ? s[r] : 0.0, yr = live ? y[r] : 0.0;
+    double a = sr * Bs, b = sr * yr;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (!(a > 0.0) || !(b > 0.0)) { broke = 1; break; }
+    const double ia = 1.0 / a, ib = 1.0 / b;
+    const double ya = yr * ib, ba = Bs * ia;
+#pragma unroll
+    for (int c = 0; c < kMaxP; ++c)
+      if (c < n) {
+        const double Bsc = __shfl_sync(0xffffffffu, Bs, c);
+        Brow[c] += ya * y[c] - ba * Bsc;
+      }
+  }
+  L.sync();
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < kMaxP; ++c)
+      if (c < n) S.B[r][c] = Brow[c];
+  }
+  L.sync();
+  return broke;
+}
+#endif
 
 // ------------------------------ generalised Cauchy point -------------------------------
 // On exit S.z = x^cp and S.iwhere marks the variables fixed at a bound.
-STP_HD void lb_cauchy(LbfgsbState& S) {
-  const int n = S.np;
+template <class LN>
+STP_HD void lb_cauchy(const LN& L, LbfgsbState& S) {
+  const int n = S.np, W = L.width(), l0 = L.lane();
   double* xcp = S.z;
-  double* dvec = S.sc_a; double* tbrk = S.sc_b; double* zz = S.sc_c;
-  int* order = S.sc_i;
-  int nbreak = 0;
-  if (S.sbgnrm <= 0.0) { for (int i = 0; i < n; ++i) xcp[i] = S.x[i]; return; }
-  for (int i = 0; i < n; ++i) {
+  double* dvec = S.sc_a; double* tbrk = S.sc_b; double* tall = S.sc_c;
+  int* order = S.sc_i; int* hasb = S.sc_j;
+  if (S.sbgnrm <= 0.0) {
+    for (int i = l0; i < n; i += W) xcp[i] = S.x[i];
+    L.sync();
+    return;
+  }
+  for (int i = l0; i < n; i += W) {
     const double neggi = -S.g[i];
     double tl = 0.0, tu = 0.0;
-    if (S.iwhere[i] != 3 && S.iwhere[i] != -1) {
+    int iw = S.iwhere[i];
+    if (iw != 3 && iw != -1) {
       if (S.nbd[i] <= 2) tl = S.x[i] - S.lb[i];
       if (S.nbd[i] >= 2) tu = S.ub[i] - S.x[i];
       const int xlower = S.nbd[i] <= 2 && tl <= 0.0;
       const int xupper = S.nbd[i] >= 2 && tu <= 0.0;
-      S.iwhere[i] = 0;
-      if (xlower) { if (neggi <= 0.0) S.iwhere[i] = 1; }
-      else if (xupper) { if (neggi >= 0.0) S.iwhere[i] = 2; }
-      else { if (fabs(neggi) <= 0.0) S.iwhere[i] = -3; }
+      iw = 0;
+      if (xlower) { if (neggi <= 0.0) iw = 1; }
+      else if (xupper) { if (neggi >= 0.0) iw = 2; }
+      else { if (fabs(neggi) <= 0.0) iw = -3; }
+      S.iwhere[i] = iw;
     }
     xcp[i] = S.x[i];
-    zz[i] = 0.0;
-    if (S.iwhere[i] != 0 && S.iwhere[i] != -1) {
-      dvec[i] = 0.0;
-    } else {
-      dvec[i] = neggi;
-      if (S.nbd[i] <= 2 && S.nbd[i] != 0 && neggi < 0.0) { tbrk[nbreak] = tl / (-neggi); order[nbreak++] = i; }
-      else if (S.nbd[i] >= 2 && neggi > 0.0) { tbrk[nbreak] = tu / neggi; order[nbreak++] = i; }
+    int hb = 0;
+    double tb = 0.0, dv = 0.0;
+    if (iw == 0 || iw == -1) {
+      dv = neggi;
+      if (S.nbd[i] <= 2 && S.nbd[i] != 0 && neggi < 0.0) { tb = tl / (-neggi); hb = 1; }
+      else if (S.nbd[i] >= 2 && neggi > 0.0) { tb = tu / neggi; hb = 1; }
     }
+    dvec[i] = dv; tall[i] = tb; hasb[i] = hb;
   }
-  // sort breakpoints ascending (insertion sort on <= 11 entries)
-  for (int a = 1; a < nbreak; ++a) {
-    const double tv = tbrk[a]; const int ov = order[a];
-    int b = a - 1;
-    while (b >= 0 && tbrk[b] > tv) { tbrk[b + 1] = tbrk[b]; order[b + 1] = order[b]; --b; }
-    tbrk[b + 1] = tv; order[b + 1] = ov;
-  }
+  L.sync();
+  // breakpoints in ascending order (stable: ties keep the variable order, like the insertion sort it replaces)
+  int nbreak = 0;
+  for (int j = 0; j < n; ++j) nbreak += hasb[j];
+  for (int i = l0; i < n; i += W)
+    if (hasb[i]) {
+      const double ti = tall[i];
+      int rk = 0;
+      for (int j = 0; j < n; ++j) rk += (hasb[j] && (tall[j] < ti || (tall[j] == ti && j < i))) ? 1 : 0;
+      tbrk[rk] = ti; order[rk] = i;
+    }
   // derivatives of the quadratic model along the projected-gradient path
-  double f1 = 0.0, f2 = 0.0;
-  for (int i = 0; i < n; ++i) {
+  double f1p = 0.0, f2p = 0.0;
+  for (int i = l0; i < n; i += W) {
     double bd = 0.0;
     for (int j = 0; j < n; ++j) bd += S.B[i][j] * dvec[j];
-    f1 -= dvec[i] * dvec[i];
-    f2 += dvec[i] * bd;
+    f1p -= dvec[i] * dvec[i];
+    f2p += dvec[i] * bd;
   }
+  double f1 = L.sum(f1p), f2 = L.sum(f2p);
+  L.sync();
   const double f2_org = -S.theta * f1;  // the col = 0 value, as in the published routine
   if (!(f2 > 0.0)) return;               // d = 0: x is its own Cauchy point
   double dtm = -f1 / f2;
@@ -175,20 +247,25 @@ STP_HD void lb_cauchy(LbfgsbState& S) {
     const int ibp = order[q];
     tsum += dt;
     const double dibp = dvec[ibp];
-    dvec[ibp] = 0.0;
-    if (dibp > 0.0) { xcp[ibp] = S.ub[ibp]; S.iwhere[ibp] = 2; }
-    else { xcp[ibp] = S.lb[ibp]; S.iwhere[ibp] = 1; }
+    L.sync();   // every lane holds dvec[ibp] before lane 0 clears it
+    if (l0 == 0) {
+      dvec[ibp] = 0.0;
+      if (dibp > 0.0) { xcp[ibp] = S.ub[ibp]; S.iwhere[ibp] = 2; }
+      else { xcp[ibp] = S.lb[ibp]; S.iwhere[ibp] = 1; }
+    }
+    L.sync();
     if (q == nbreak - 1 && nbreak == n) { dtm = dt; nfixed_all = 1; break; }
     // z = x(tsum) - x : fixed variables sit on their bounds, the others moved tsum * d
-    for (int i = 0; i < n; ++i) zz[i] = (dvec[i] != 0.0 || S.iwhere[i] <= 0) ? tsum * dvec[i] : xcp[i] - S.x[i];
-    f1 = 0.0; f2 = 0.0;
-    for (int i = 0; i < n; ++i) {
+    f1p = 0.0; f2p = 0.0;
+    for (int i = l0; i < n; i += W) {
+      const double zi = (dvec[i] != 0.0 || S.iwhere[i] <= 0) ? tsum * dvec[i] : xcp[i] - S.x[i];
       double bd = 0.0;
       for (int j = 0; j < n; ++j) bd += S.B[i][j] * dvec[j];
-      f1 += dvec[i] * S.g[i];
-      f2 += dvec[i] * bd;
-      f1 += zz[i] * bd;
+      f1p += dvec[i] * S.g[i];
+      f2p += dvec[i] * bd;
+      f1p += zi * bd;
     }
+    f1 = L.sum(f1p); f2 = L.sum(f2p);
     f2 = fmax(kEpsMch * f2_org, f2);
     dtm = -f1 / f2;
   }
@@ -196,98 +273,121 @@ STP_HD void lb_cauchy(LbfgsbState& S) {
     if (dtm < 0.0) dtm = 0.0;
     tsum += dtm;
   }
-  for (int i = 0; i < n; ++i)
+  for (int i = l0; i < n; i += W)
     if (dvec[i] != 0.0) xcp[i] = S.x[i] + tsum * dvec[i];
+  L.sync();
 }
 
 // ------------------------------ subspace minimisation ----------------------------------
 // Minimise the quadratic model over the variables free at x^cp, then project (v3.0).
 // On entry S.z = x^cp; on exit S.z = the subspace minimiser.  Returns 1 if B_FF is not PD.
-STP_HD int lb_subsm(LbfgsbState& S) {
-  const int n = S.np;
+template <class LN>
+STP_HD int lb_subsm(const LN& L, LbfgsbState& S) {
+  const int n = S.np, W = L.width(), l0 = L.lane();
   int* ind = S.sc_j;
   int nf = 0;
-  for (int i = 0; i < n; ++i) if (S.iwhere[i] <= 0) ind[nf++] = i;
+  for (int i = 0; i < n; ++i) nf += (S.iwhere[i] <= 0) ? 1 : 0;
   if (nf == 0 || S.col == 0) return 0;
-  double* rr = S.sc_a; double* dd = S.sc_b;
+  L.sync();
+  for (int i = l0; i < n; i += W)
+    if (S.iwhere[i] <= 0) {
+      int pos = 0;
+      for (int j = 0; j < i; ++j) pos += (S.iwhere[j] <= 0) ? 1 : 0;
+      ind[pos] = i;
+    }
+  L.sync();
+  double* rr = S.sc_a; double* dd = S.sc_b; double* idiag = S.sc_c; double* sol = S.sc_e;
   double (*C)[kMaxP] = S.sc_C;
-  for (int a = 0; a < nf; ++a) {
+  for (int a = l0; a < nf; a += W) {
     const int i = ind[a];
     double bz = 0.0;
     for (int j = 0; j < n; ++j) bz += S.B[i][j] * (S.z[j] - S.x[j]);
     rr[a] = -(S.g[i] + bz);
     for (int b = 0; b <= a; ++b) C[a][b] = S.B[i][ind[b]];
   }
-  double* idiag = S.sc_c;           // reciprocals of the Cholesky diagonal: one division per column, not per entry
-  for (int j = 0; j < nf; ++j) {  // Cholesky of B_FF
-    double s = C[j][j];
-    for (int k = 0; k < j; ++k) s -= C[j][k] * C[j][k];
-    if (!(s > 0.0)) return 1;
-    const double l = sqrt(s);
-    const double il = 1.0 / l;
-    C[j][j] = l;
-    idiag[j] = il;
-    for (int i = j + 1; i < nf; ++i) {
+  L.sync();
+  // Cholesky of B_FF, column by column; the rows of a column in parallel (C[j][j] keeps l_jj^2, 1 / l_jj in idiag)
+  for (int j = 0; j < nf; ++j) {
+    for (int i = j + l0; i < nf; i += W) {
       double v = C[i][j];
       for (int k = 0; k < j; ++k) v -= C[i][k] * C[j][k];
-      C[i][j] = v * il;
+      C[i][j] = v;
     }
+    L.sync();
+    const double s = C[j][j];
+    if (!(s > 0.0)) return 1;
+    const double il = 1.0 / sqrt(s);
+    if (l0 == 0) idiag[j] = il;
+    for (int i = j + 1 + l0; i < nf; i += W) C[i][j] *= il;
+    L.sync();
   }
-  for (int i = 0; i < nf; ++i) {
-    double v = rr[i];
-    for (int k = 0; k < i; ++k) v -= C[i][k] * dd[k];
-    dd[i] = v * idiag[i];
+  for (int j = 0; j < nf; ++j) {          // forward substitution, column-oriented
+    const double dj = rr[j] * idiag[j];
+    if (l0 == 0) dd[j] = dj;
+    for (int i = j + 1 + l0; i < nf; i += W) rr[i] -= C[i][j] * dj;
+    L.sync();
   }
-  for (int i = nf - 1; i >= 0; --i) {
-    double v = dd[i];
-    for (int k = i + 1; k < nf; ++k) v -= C[k][i] * dd[k];
-    dd[i] = v * idiag[i];
+  for (int j = nf - 1; j >= 0; --j) {     // back substitution
+    const double dj = dd[j] * idiag[j];
+    if (l0 == 0) sol[j] = dj;
+    for (int i = l0; i < j; i += W) dd[i] -= C[j][i] * dj;
+    L.sync();
   }
   // projection of x^cp + d onto the box
-  int iword = 0;
-  for (int i = 0; i < n; ++i) S.xp[i] = S.z[i];
-  for (int a = 0; a < nf; ++a) {
+  for (int i = l0; i < n; i += W) S.xp[i] = S.z[i];
+  L.sync();
+  int iw = 0;
+  for (int a = l0; a < nf; a += W) {
     const int k = ind[a];
-    const double xk = S.z[k], dk = dd[a];
+    const double xk = S.z[k], dk = sol[a];
+    double zk;
     if (S.nbd[k] != 0) {
-      if (S.nbd[k] == 1) { S.z[k] = fmax(S.lb[k], xk + dk); if (S.z[k] == S.lb[k]) iword = 1; }
+      if (S.nbd[k] == 1) { zk = fmax(S.lb[k], xk + dk); if (zk == S.lb[k]) iw = 1; }
       else if (S.nbd[k] == 2) {
         const double v = fmax(S.lb[k], xk + dk);
-        S.z[k] = fmin(S.ub[k], v);
-        if (S.z[k] == S.lb[k] || S.z[k] == S.ub[k]) iword = 1;
-      } else { S.z[k] = fmin(S.ub[k], xk + dk); if (S.z[k] == S.ub[k]) iword = 1; }
+        zk = fmin(S.ub[k], v);
+        if (zk == S.lb[k] || zk == S.ub[k]) iw = 1;
+      } else { zk = fmin(S.ub[k], xk + dk); if (zk == S.ub[k]) iw = 1; }
     } else {
-      S.z[k] = xk + dk;
+      zk = xk + dk;
     }
+    S.z[k] = zk;
   }
+  const int iword = L.any(iw);
+  L.sync();
   if (!iword) return 0;
-  double ddp = 0.0;
-  for (int i = 0; i < n; ++i) ddp += (S.z[i] - S.x[i]) * S.g[i];
+  double ddpp = 0.0;
+  for (int i = l0; i < n; i += W) ddpp += (S.z[i] - S.x[i]) * S.g[i];
+  const double ddp = L.sum(ddpp);
+  L.sync();
   if (ddp > 0.0) {
-    for (int i = 0; i < n; ++i) S.z[i] = S.xp[i];
-    double alpha = 1.0, temp1 = 1.0;
-    int ibd = -1;
-    for (int a = 0; a < nf; ++a) {
-      const int k = ind[a];
-      const double dk = dd[a];
-      if (S.nbd[k] != 0) {
-        if (dk < 0.0 && S.nbd[k] <= 2) {
-          const double t2 = S.lb[k] - S.z[k];
-          if (t2 >= 0.0) temp1 = 0.0; else if (dk * alpha < t2) temp1 = t2 / dk;
-        } else if (dk > 0.0 && S.nbd[k] >= 2) {
-          const double t2 = S.ub[k] - S.z[k];
-          if (t2 <= 0.0) temp1 = 0.0; else if (dk * alpha > t2) temp1 = t2 / dk;
+    if (l0 == 0) {   // rare path, kept serial: the running `temp1` makes the published loop order-dependent
+      for (int i = 0; i < n; ++i) S.z[i] = S.xp[i];
+      double alpha = 1.0, temp1 = 1.0;
+      int ibd = -1;
+      for (int a = 0; a < nf; ++a) {
+        const int k = ind[a];
+        const double dk = sol[a];
+        if (S.nbd[k] != 0) {
+          if (dk < 0.0 && S.nbd[k] <= 2) {
+            const double t2 = S.lb[k] - S.z[k];
+            if (t2 >= 0.0) temp1 = 0.0; else if (dk * alpha < t2) temp1 = t2 / dk;
+          } else if (dk > 0.0 && S.nbd[k] >= 2) {
+            const double t2 = S.ub[k] - S.z[k];
+            if (t2 <= 0.0) temp1 = 0.0; else if (dk * alpha > t2) temp1 = t2 / dk;
+          }
+          if (temp1 < alpha) { alpha = temp1; ibd = a; }
         }
-        if (temp1 < alpha) { alpha = temp1; ibd = a; }
       }
+      if (alpha < 1.0 && ibd >= 0) {
+        const double dk = sol[ibd];
+        const int k = ind[ibd];
+        if (dk > 0.0) { S.z[k] = S.ub[k]; sol[ibd] = 0.0; }
+        else if (dk < 0.0) { S.z[k] = S.lb[k]; sol[ibd] = 0.0; }
+      }
+      for (int a = 0; a < nf; ++a) S.z[ind[a]] += alpha * sol[a];
     }
-    if (alpha < 1.0 && ibd >= 0) {
-      const double dk = dd[ibd];
-      const int k = ind[ibd];
-      if (dk > 0.0) { S.z[k] = S.ub[k]; dd[ibd] = 0.0; }
-      else if (dk < 0.0) { S.z[k] = S.lb[k]; dd[ibd] = 0.0; }
-    }
-    for (int a = 0; a < nf; ++a) S.z[ind[a]] += alpha * dd[a];
+    L.sync();
   }
   return 0;
 }
@@ -405,12 +505,11 @@ STP_HD void lb_dcsrch(LbfgsbState& S, double f, double g) {
 }
 
 // ------------------------------ driver ---------------------------------------------------
-STP_HD void lbfgsb_init(LbfgsbState& S, int np, const double* x0, const double* lb, const double* ub,
+template <class LN>
+STP_HD void lbfgsb_init(const LN& L, LbfgsbState& S, int np, const double* x0, const double* lb, const double* ub,
                         const LbfgsbOpts& o) {
-  S.np = np; S.m = o.m < kHist ? o.m : kHist; S.maxiter = o.maxiter; S.maxfun = o.maxfun; S.maxls = o.maxls;
-  S.factr = o.factr; S.pgtol = o.pgtol;
-  S.cnstnd = 0; S.boxed = 1;
-  for (int i = 0; i < np; ++i) {
+  int not_boxed = 0, bounded = 0;
+  for (int i = L.lane(); i < np; i += L.width()) {
     const int hl = lb[i] > -1.79e308, hu = ub[i] < 1.79e308;
     S.lb[i] = hl ? lb[i] : 0.0; S.ub[i] = hu ? ub[i] : 0.0;
     S.nbd[i] = hl ? (hu ? 2 : 1) : (hu ? 3 : 0);
@@ -418,231 +517,235 @@ STP_HD void lbfgsb_init(LbfgsbState& S, int np, const double* x0, const double* 
     if (hl && xi < lb[i]) xi = lb[i];   // scipy clips x0 into the box; `active` projects again
     if (hu && xi > ub[i]) xi = ub[i];
     S.x[i] = xi;
-    if (S.nbd[i] != 2) S.boxed = 0;
-    if (S.nbd[i] != 0) S.cnstnd = 1;
+    if (S.nbd[i] != 2) not_boxed = 1;
+    if (S.nbd[i] != 0) bounded = 1;
     S.iwhere[i] = (S.nbd[i] == 0) ? -1 : ((S.nbd[i] == 2 && S.ub[i] - S.lb[i] <= 0.0) ? 3 : 0);
   }
-  lb_reset_memory(S);
-  S.iter = 0; S.nfev = 0; S.nskip = 0; S.iback = 0; S.ifun = 0; S.info = 0;
-  S.phase = 0; S.status = -1; S.f = 0.0; S.fold = 0.0; S.sbgnrm = 0.0; S.stp = 0.0; S.B_ready = 0;
+  not_boxed = L.any(not_boxed);
+  bounded = L.any(bounded);
+  if (L.lane() == 0) {
+    S.np = np; S.m = o.m < kHist ? o.m : kHist; S.maxiter = o.maxiter; S.maxfun = o.maxfun; S.maxls = o.maxls;
+    S.factr = o.factr; S.pgtol = o.pgtol;
+    S.cnstnd = bounded; S.boxed = !not_boxed;
+    S.iter = 0; S.nfev = 0; S.nskip = 0; S.iback = 0; S.ifun = 0; S.info = 0;
+    S.phase = 0; S.status = -1; S.f = 0.0; S.fold = 0.0; S.sbgnrm = 0.0; S.stp = 0.0; S.lsfail = 0;
+  }
+  lb_reset_memory(L, S);
 }
 
 // Start (or restart) an iteration at the current x: Cauchy point, subspace step, direction,
 // first trial point of the line search.  Returns 1 when S.x holds a point to evaluate,
 // 0 when the run ended (S.status set).
-STP_HD int lb_begin_iteration(LbfgsbState& S) {
-  const int n = S.np;
+template <class LN>
+STP_HD int lb_begin_iteration(const LN& L, LbfgsbState& S) {
+  const int n = S.np, W = L.width(), l0 = L.lane();
   for (int guard = 0; guard < 4; ++guard) {
-    if (S.col > 0 && !S.B_ready) return 3;      // caller forms B (lb_build_B or its team version), then re-enters
-    if (S.col > 0 && S.B_ready == 2) { lb_reset_memory(S); S.B_ready = 0; continue; }   // breakdown while forming B
-    S.B_ready = 0;
-    if (S.col == 0)
-      for (int i = 0; i < n; ++i)
-        for (int j = 0; j < n; ++j) S.B[i][j] = (i == j) ? S.theta : 0.0;
-    if (!S.cnstnd && S.col > 0) {
-      for (int i = 0; i < n; ++i) S.z[i] = S.x[i];
+    if (S.col > 0) {
+      if (lb_build_B(L, S)) { lb_reset_memory(L, S); continue; }   // breakdown while forming B
     } else {
-      lb_cauchy(S);
+      const double th = S.theta;
+      for (int i = l0; i < n; i += W)
+        for (int j = 0; j < n; ++j) S.B[i][j] = (i == j) ? th : 0.0;
+      L.sync();
     }
-    if (S.col > 0 && lb_subsm(S)) { lb_reset_memory(S); continue; }
+    if (!S.cnstnd && S.col > 0) {
+      for (int i = l0; i < n; i += W) S.z[i] = S.x[i];
+      L.sync();
+    } else {
+      lb_cauchy(L, S);
+    }
+    if (S.col > 0 && lb_subsm(L, S)) { lb_reset_memory(L, S); continue; }
     // search direction and the line-search set-up (lnsrlb, first entry)
-    for (int i = 0; i < n; ++i) S.d[i] = S.z[i] - S.x[i];
-    S.dtd = lb_dot(S.d, S.d, n);
-    S.dnorm = sqrt(S.dtd);
-    S.stpmx = 1e10;
-    if (S.cnstnd) {
-      if (S.iter == 0) S.stpmx = 1.0;
-      else {
-        for (int i = 0; i < n; ++i) {
-          const double a1 = S.d[i];
-          if (S.nbd[i] != 0) {
-            if (a1 < 0.0 && S.nbd[i] <= 2) {
-              const double a2 = S.lb[i] - S.x[i];
-              if (a2 >= 0.0) S.stpmx = 0.0; else if (a1 * S.stpmx < a2) S.stpmx = a2 / a1;
-            } else if (a1 > 0.0 && S.nbd[i] >= 2) {
-              const double a2 = S.ub[i] - S.x[i];
-              if (a2 <= 0.0) S.stpmx = 0.0; else if (a1 * S.stpmx > a2) S.stpmx = a2 / a1;
+    for (int i = l0; i < n; i += W) { S.d[i] = S.z[i] - S.x[i]; S.t[i] = S.x[i]; S.r[i] = S.g[i]; }
+    L.sync();
+    const double dtd = lb_dot(L, S.d, S.d, n);
+    const double gd = lb_dot(L, S.g, S.d, n);
+    if (l0 == 0) {
+      S.dtd = dtd;
+      S.dnorm = sqrt(dtd);
+      double stpmx = 1e10;
+      if (S.cnstnd) {
+        if (S.iter == 0) stpmx = 1.0;
+        else {
+          for (int i = 0; i < n; ++i) {
+            const double a1 = S.d[i];
+            if (S.nbd[i] != 0) {
+              if (a1 < 0.0 && S.nbd[i] <= 2) {
+                const double a2 = S.lb[i] - S.x[i];
+                if (a2 >= 0.0) stpmx = 0.0; else if (a1 * stpmx < a2) stpmx = a2 / a1;
+              } else if (a1 > 0.0 && S.nbd[i] >= 2) {
+                const double a2 = S.ub[i] - S.x[i];
+                if (a2 <= 0.0) stpmx = 0.0; else if (a1 * stpmx > a2) stpmx = a2 / a1;
+              }
             }
           }
         }
       }
+      S.stpmx = stpmx;
+      S.stp = (S.iter == 0 && !S.boxed) ? fmin(1.0 / S.dnorm, stpmx) : 1.0;
+      S.fold = S.f;
+      S.ifun = 0; S.iback = 0; S.ls_task = 0;
+      S.gd = gd;
+      S.gdold = gd;
+      int lsfail = 0;
+      if (gd >= 0.0) lsfail = 1;               // not a descent direction: info = -4
+      if (!lsfail) {
+        lb_dcsrch(S, S.f, gd);
+        if (S.ls_task == 4) lsfail = 1;
+      }
+      S.lsfail = lsfail;
     }
-    S.stp = (S.iter == 0 && !S.boxed) ? fmin(1.0 / S.dnorm, S.stpmx) : 1.0;
-    for (int i = 0; i < n; ++i) { S.t[i] = S.x[i]; S.r[i] = S.g[i]; }
-    S.fold = S.f;
-    S.ifun = 0; S.iback = 0; S.ls_task = 0;
-    S.gd = lb_dot(S.g, S.d, n);
-    S.gdold = S.gd;
-    int lsfail = 0;
-    if (S.gd >= 0.0) lsfail = 1;               // not a descent direction: info = -4
-    if (!lsfail) {
-      lb_dcsrch(S, S.f, S.gd);
-      if (S.ls_task == 4) lsfail = 1;
-    }
-    if (lsfail) {
-      if (S.col == 0) { S.status = 2; S.iter += 1; return 0; }  // abnormal termination in lnsrch
-      lb_reset_memory(S);
+    L.sync();
+    if (S.lsfail) {
+      if (S.col == 0) {   // abnormal termination in lnsrch
+        L.sync();
+        if (l0 == 0) { S.status = 2; S.iter += 1; }
+        L.sync();
+        return 0;
+      }
+      lb_reset_memory(L, S);
       continue;
     }
-    S.ifun = 1; S.nfev += 1; S.iback = 0;
-    if (S.stp == 1.0) for (int i = 0; i < n; ++i) S.x[i] = S.z[i];
-    else for (int i = 0; i < n; ++i) S.x[i] = S.stp * S.d[i] + S.t[i];
-    S.phase = 1;
+    const double stp = S.stp;
+    if (stp == 1.0) { for (int i = l0; i < n; i += W) S.x[i] = S.z[i]; }
+    else { for (int i = l0; i < n; i += W) S.x[i] = stp * S.d[i] + S.t[i]; }
+    if (l0 == 0) { S.ifun = 1; S.nfev += 1; S.iback = 0; S.phase = 1; }
+    L.sync();
     return 1;
   }
-  S.status = 2;
+  L.sync();
+  if (l0 == 0) S.status = 2;
+  L.sync();
+  return 0;
+}
+
+// Give up the current line search: back to the iterate it started from.
+template <class LN>
+STP_HD void lb_restore_iterate(const LN& L, LbfgsbState& S) {
+  for (int i = L.lane(); i < S.np; i += L.width()) { S.x[i] = S.t[i]; S.g[i] = S.r[i]; }
+  if (L.lane() == 0) S.f = S.fold;
+  L.sync();
+}
+
+template <class LN>
+STP_HD int lb_finish(const LN& L, LbfgsbState& S, int status, int bump_iter) {
+  L.sync();
+  if (L.lane() == 0) { S.status = status; if (bump_iter) S.iter += 1; }
+  L.sync();
   return 0;
 }
 
 // One transition of the state machine.  Returns 0 finished, 1 evaluate S.x, 2 S.x is the point
 // (f, g) already belong to (the caller feeds them again without evaluating).
-STP_HD int lb_advance_once(LbfgsbState& S, double f, const double* g) {
-  const int n = S.np;
-  int finite = (f == f) && fabs(f) <= 1.79e308;
-  for (int i = 0; i < n; ++i) finite &= (g[i] == g[i]);
-  if (S.phase == 0) {
-    S.nfev = 1;
-    S.f = f;
-    for (int i = 0; i < n; ++i) S.g[i] = g[i];
-    if (!finite) { S.status = 3; return 0; }
-    lb_projgr(S);
-    if (S.sbgnrm <= S.pgtol) { S.status = 0; return 0; }
-    return lb_begin_iteration(S);
+template <class LN>
+STP_HD int lb_advance_once(const LN& L, LbfgsbState& S, double f, const double* g) {
+  const int n = S.np, W = L.width(), l0 = L.lane();
+  int badg = 0;
+  for (int i = l0; i < n; i += W) badg |= !(g[i] == g[i]);
+  const int finite = (f == f) && (fabs(f) <= 1.79e308) && !L.any(badg);
+  const int phase = S.phase;
+  L.sync();
+  for (int i = l0; i < n; i += W) S.g[i] = g[i];
+  if (l0 == 0) { S.f = f; if (phase == 0) S.nfev = 1; }
+  L.sync();
+  if (phase == 0) {
+    if (!finite) return lb_finish(L, S, 3, 0);
+    lb_projgr(L, S);
+    if (S.sbgnrm <= S.pgtol) return lb_finish(L, S, 0, 0);
+    return lb_begin_iteration(L, S);
   }
   // inside a line search: (f, g) belong to x = t + stp d
-  S.f = f;
-  for (int i = 0; i < n; ++i) S.g[i] = g[i];
   if (!finite) {
     // a non-finite objective cannot be handled by the cubic interpolation: give up on this
     // campaign (the reference's closure would raise and the trace would be NaN-padded)
-    for (int i = 0; i < n; ++i) { S.x[i] = S.t[i]; S.g[i] = S.r[i]; }
-    S.f = S.fold; S.status = 3; return 0;
+    lb_restore_iterate(L, S);
+    return lb_finish(L, S, 3, 0);
   }
-  S.gd = lb_dot(S.g, S.d, n);
-  lb_dcsrch(S, f, S.gd);
-  if (S.ls_task == 1) {
+  const double gd = lb_dot(L, S.g, S.d, n);
+  if (l0 == 0) { S.gd = gd; lb_dcsrch(S, f, gd); }
+  L.sync();
+  const int task = S.ls_task;
+  if (task == 1) {
     if (S.iback + 1 >= S.maxls) {
       // too many trial points: restore and restart from scratch (or stop if memory is empty)
-      for (int i = 0; i < n; ++i) { S.x[i] = S.t[i]; S.g[i] = S.r[i]; }
-      S.f = S.fold;
-      if (S.col == 0) { S.status = 2; S.iter += 1; return 0; }
-      lb_reset_memory(S);
-      return lb_begin_iteration(S);
+      lb_restore_iterate(L, S);
+      if (S.col == 0) return lb_finish(L, S, 2, 1);
+      lb_reset_memory(L, S);
+      return lb_begin_iteration(L, S);
     }
-    S.ifun += 1; S.iback = S.ifun - 1;
-    int moved = 0;
-    for (int i = 0; i < n; ++i) {
-      const double xi = (S.stp == 1.0) ? S.z[i] : S.stp * S.d[i] + S.t[i];
-      moved |= (xi != S.x[i]);
+    const double stp = S.stp;
+    int mv = 0;
+    for (int i = l0; i < n; i += W) {
+      const double xi = (stp == 1.0) ? S.z[i] : stp * S.d[i] + S.t[i];
+      mv |= (xi != S.x[i]);
       S.x[i] = xi;
     }
-    if (!moved) return 2;   // same point again (stp fell back to stx): reuse f, g like scipy's cache
-    S.nfev += 1;
-    return 1;
+    const int moved = L.any(mv);
+    L.sync();
+    if (l0 == 0) { S.ifun += 1; S.iback = S.ifun - 1; if (moved) S.nfev += 1; }
+    L.sync();
+    return moved ? 1 : 2;   // 2: same point again (stp fell back to stx): reuse f, g like scipy's cache
   }
-  if (S.ls_task == 4) {
-    for (int i = 0; i < n; ++i) { S.x[i] = S.t[i]; S.g[i] = S.r[i]; }
-    S.f = S.fold;
-    if (S.col == 0) { S.status = 2; S.iter += 1; return 0; }
-    lb_reset_memory(S);
-    return lb_begin_iteration(S);
+  if (task == 4) {
+    lb_restore_iterate(L, S);
+    if (S.col == 0) return lb_finish(L, S, 2, 1);
+    lb_reset_memory(L, S);
+    return lb_begin_iteration(L, S);
   }
   // line search finished (CONVERGENCE or WARNING): new iterate
-  S.iter += 1;
-  lb_projgr(S);
+  L.sync();
+  if (l0 == 0) S.iter += 1;
+  lb_projgr(L, S);
   // scipy's wrapper sees NEW_X here
-  if (S.iter >= S.maxiter) { S.status = 1; return 0; }
-  if (S.nfev > S.maxfun) { S.status = 1; return 0; }
-  if (S.sbgnrm <= S.pgtol) { S.status = 0; return 0; }
+  if (S.iter >= S.maxiter) return lb_finish(L, S, 1, 0);
+  if (S.nfev > S.maxfun) return lb_finish(L, S, 1, 0);
+  if (S.sbgnrm <= S.pgtol) return lb_finish(L, S, 0, 0);
   const double ddum = fmax(fmax(fabs(S.fold), fabs(S.f)), 1.0);
-  if (S.fold - S.f <= kEpsMch * S.factr * ddum) { S.status = 0; return 0; }
+  if (S.fold - S.f <= kEpsMch * S.factr * ddum) return lb_finish(L, S, 0, 0);
   // BFGS pair
-  double rr = 0.0, dr, dd;
-  for (int i = 0; i < n; ++i) { S.r[i] = S.g[i] - S.r[i]; rr += S.r[i] * S.r[i]; }
-  if (S.stp == 1.0) { dr = S.gd - S.gdold; dd = -S.gdold; }
-  else {
-    dr = (S.gd - S.gdold) * S.stp;
-    for (int i = 0; i < n; ++i) S.d[i] *= S.stp;
-    dd = -S.gdold * S.stp;
+  const double stp = S.stp, gdn = S.gd, gdold = S.gdold;
+  double rrp = 0.0, dr, dd;
+  for (int i = l0; i < n; i += W) {
+    const double ri = S.g[i] - S.r[i];
+    S.r[i] = ri;
+    rrp += ri * ri;
+    if (stp != 1.0) S.d[i] *= stp;
   }
+  const double rr = L.sum(rrp);
+  if (stp == 1.0) { dr = gdn - gdold; dd = -gdold; }
+  else { dr = (gdn - gdold) * stp; dd = -gdold * stp; }
+  int iupdat = S.iupdat, col = S.col, itail = S.itail, head = S.head;
+  const int m = S.m;
+  L.sync();
   if (dr <= kEpsMch * dd) {
-    S.nskip += 1; S.updatd = 0;
+    if (l0 == 0) { S.nskip += 1; S.updatd = 0; }
   } else {
-    S.updatd = 1; S.iupdat += 1;
-    if (S.iupdat <= S.m) { S.col = S.iupdat; S.itail = (S.head + S.iupdat - 1) % S.m; }
-    else { S.itail = (S.itail + 1) % S.m; S.head = (S.head + 1) % S.m; }
-    for (int i = 0; i < n; ++i) { S.ws[S.itail][i] = S.d[i]; S.wy[S.itail][i] = S.r[i]; }
-    S.theta = rr / dr;
+    iupdat += 1;
+    if (iupdat <= m) { col = iupdat; itail = (head + iupdat - 1) % m; }
+    else { itail = (itail + 1) % m; head = (head + 1) % m; }
+    for (int i = l0; i < n; i += W) { S.ws[itail][i] = S.d[i]; S.wy[itail][i] = S.r[i]; }
+    if (l0 == 0) { S.updatd = 1; S.iupdat = iupdat; S.col = col; S.itail = itail; S.head = head; S.theta = rr / dr; }
   }
-  return lb_begin_iteration(S);
+  L.sync();
+  return lb_begin_iteration(L, S);
 }
 
-// Feed the objective at S.x.  Returns 1 if S.x now holds a new point to evaluate, else 0.
+// Feed the objective at S.x.  Returns 1 if S.x now holds a new point to evaluate, else 0 (finished).
 // scipy's ScalarFunction does not re-evaluate (or count) a point equal to the previous one;
 // neither do we.
-// Return codes: 0 finished, 1 evaluate S.x, 3 form the dense B (S.B_ready = lb_build_B(S) ? 2 : 1, or the
-// team version) and call lbfgsb_resume(S).
-STP_HD int lbfgsb_advance_split(LbfgsbState& S, double f, const double* g) {
-  double* gc = S.sc_d;
-  for (int i = 0; i < S.np; ++i) gc[i] = g[i];
+template <class LN>
+STP_HD int lbfgsb_advance(const LN& L, LbfgsbState& S, double f, const double* g) {
   for (;;) {
-    const int r = lb_advance_once(S, f, gc);
+    const int r = lb_advance_once(L, S, f, g);
     if (r != 2) return r;
   }
-}
-STP_HD int lbfgsb_resume(LbfgsbState& S) {
-  for (;;) {
-    const int r = lb_begin_iteration(S);
-    if (r != 2) return r;
-  }
-}
-STP_HD int lbfgsb_advance(LbfgsbState& S, double f, const double* g) {
-  int r = lbfgsb_advance_split(S, f, g);
-  while (r == 3) {
-    S.B_ready = lb_build_B(S) ? 2 : 1;
-    r = lbfgsb_resume(S);
-  }
-  return r;
 }
 
-// Team version of lb_build_B: one lane per row of B (np <= 11 rows), pairs replayed with warp shuffles.
-STP_HD void lb_build_B_team(const SoloTeam&, LbfgsbState& S) { S.B_ready = lb_build_B(S) ? 2 : 1; }
-#if defined(__CUDACC__)
-__device__ __forceinline__ void lb_build_B_team(const CtaTeam& tm, LbfgsbState& S) {
-  if (tm.warp() != 0) return;
-  const int n = S.np, r = tm.lane();
-  const bool live = r < n;
-  double Brow[kMaxP];
-#pragma unroll
-  for (int c = 0; c < kMaxP; ++c) Brow[c] = (live && c == r) ? S.theta : 0.0;
-  int broke = 0;
-  for (int q = 0; q < S.col; ++q) {
-    const int p = (S.head + q) % S.m;
-    const double* s = S.ws[p];
-    const double* y = S.wy[p];
-    double Bs = 0.0;
-#pragma unroll
-    for (int c = 0; c < kMaxP; ++c)
-      if (c < n) Bs += Brow[c] * s[c];
-    const double sr = live ? s[r] : 0.0, yr = live ? y[r] : 0.0;
-    const double sBs = tm.warp_sum(sr * Bs), ys = tm.warp_sum(sr * yr);
-    if (!(sBs > 0.0) || !(ys > 0.0)) { broke = 1; break; }
-    const double ia = 1.0 / sBs, ib = 1.0 / ys;
-#pragma unroll
-    for (int c = 0; c < kMaxP; ++c)
-      if (c < n) {
-        const double Bsc = __shfl_sync(0xffffffffu, Bs, c);
-        Brow[c] += yr * y[c] * ib - Bs * Bsc * ia;
-      }
-  }
-  if (live) {
-#pragma unroll
-    for (int c = 0; c < kMaxP; ++c)
-      if (c < n) S.B[r][c] = Brow[c];
-  }
-  __syncwarp();
-  if (r == 0) S.B_ready = broke ? 2 : 1;
+// single-thread convenience forms (host emulation, unit tests)
+STP_HD void lbfgsb_init(LbfgsbState& S, int np, const double* x0, const double* lb, const double* ub,
+                        const LbfgsbOpts& o) {
+  lbfgsb_init(SoloLanes(), S, np, x0, lb, ub, o);
 }
-#endif
+STP_HD int lbfgsb_advance(LbfgsbState& S, double f, const double* g) { return lbfgsb_advance(SoloLanes(), S, f, g); }
 
 }  // namespace stp

@@ -24,6 +24,38 @@ namespace stp {
 constexpr int kMaxWarps = 32;
 
 // ---------------------------------------------------------------------------------------
+// Lane groups: what ONE warp of a team (or the single thread of a SoloTeam) offers to the small serial-ish
+// routines (the L-BFGS-B state machine): strided loops over lane() / width(), lane-uniform reductions, sync().
+// ---------------------------------------------------------------------------------------
+struct SoloLanes {
+  STP_HD int lane() const { return 0; }
+  STP_HD int width() const { return 1; }
+  STP_HD void sync() const {}
+  STP_HD double sum(double v) const { return v; }
+  STP_HD double max(double v) const { return v; }
+  STP_HD int any(int p) const { return p != 0; }
+};
+#if defined(__CUDACC__)
+struct WarpLanes {
+  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int width() const { return 32; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  // xor butterflies: every lane ends with the bitwise-identical result
+  __device__ __forceinline__ double sum(double v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  __device__ __forceinline__ double max(double v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  }
+  __device__ __forceinline__ int any(int p) const { return __any_sync(0xffffffffu, p); }
+};
+#endif
+
+// ---------------------------------------------------------------------------------------
 // One-thread team: host emulation (tests/hostemu) and trivially-serial device sections.
 // ---------------------------------------------------------------------------------------
 struct SoloTeam {
@@ -42,6 +74,8 @@ struct SoloTeam {
   // argmax with torch semantics (first maximal index; NaN wins, first NaN wins)
   STP_HD void argmax(double& v, int& idx) const {}
   STP_HD int any(int p) const { return p; }
+  typedef SoloLanes Lanes;
+  STP_HD SoloLanes lanes() const { return SoloLanes(); }
 };
 
 // torch.argmax ordering: NaN beats everything; ties resolved towards the smaller index.
@@ -129,6 +163,8 @@ struct CtaTeam {
       if (acq_better(red[w], ired[w], v, idx)) { v = red[w]; idx = ired[w]; }
   }
   __device__ __forceinline__ int any(int p) const { return __syncthreads_or(p); }
+  typedef WarpLanes Lanes;
+  __device__ __forceinline__ WarpLanes lanes() const { return WarpLanes(); }
 };
 constexpr int kRedDoubles = 16 * kMaxWarps;  // scratch a CtaTeam needs
 #endif
