@@ -50,7 +50,7 @@ struct ExactSmem {
 };
 
 STP_HD size_t exact_tile_doubles(int cap, int tc) {
-  const size_t acq = (size_t)cap * tc + (size_t)tc * kMaxD, swp = sweep_blocked_scratch_doubles(cap + 1);
+  const size_t acq = (size_t)((cap + 15) & ~15) * tc + (size_t)tc * kMaxD, swp = sweep_blocked_scratch_doubles(cap + 1);
   return acq > swp ? acq : swp;
 }
 STP_HD size_t exact_smem_doubles(int cap, int d, int tc, int nwarps) {
@@ -244,6 +244,96 @@ STP_HD int exact_factorize(const Team& tm, const ExactSmem& s, int n, int d, con
   return 0;
 }
 
+// Partial sums of one candidate tile (TC candidates, cross-covariances in s.tile[j * TC + c]):
+//   part[(p * TC + c) * 2 + 0], p < n_ssq : pieces of || Linv k_c ||^2      part[(p * TC + c) * 2 + 1], p < n_mu : of alpha . k_c
+// Generic form: warp w takes the rows i = w, w + nwa, ...; a lane is a candidate.
+template <class Team>
+STP_HD void acq_tile_partials(const Team& tm, const ExactSmem& s, int n, int& n_ssq, int& n_mu) {
+  const int ld = s.ld, TC = tm.warp_width(), nw = tm.nwarps();
+  const int nwa = nw < 8 ? nw : 8;   // at most 8 warps: the partials live in the 512-double reduction scratch
+  n_ssq = nwa; n_mu = nwa;
+  if (tm.warp() < nwa) {
+    const int c = tm.lane();
+    double ssq = 0.0, mu = 0.0;
+    for (int i = tm.warp(); i < n; i += nwa) {
+      const double* row = s.A + i * ld;
+      double v0 = 0.0, v1 = 0.0;
+      int j = 0;
+      for (; j + 1 <= i; j += 2) {
+        v0 += row[j] * s.tile[j * TC + c];
+        v1 += row[j + 1] * s.tile[(j + 1) * TC + c];
+      }
+      if (j <= i) v0 += row[j] * s.tile[j * TC + c];
+      const double v = v0 + v1;
+      ssq += v * v;
+      mu += s.alpha[i] * s.tile[i * TC + c];
+    }
+    s.part[(tm.warp() * TC + c) * 2 + 0] = ssq;
+    s.part[(tm.warp() * TC + c) * 2 + 1] = mu;
+  }
+}
+#if defined(__CUDACC__) && !defined(STP_NO_DMMA)
+// Tensor-core form: V = Linv K_tile in 16 x 16 DMMA tiles (heaviest row tiles first), the squares summed per row
+// tile; rows n .. 16 ceil(n / 16) - 1 of the tile are zero (exact_acquire fills them).
+__device__ __forceinline__ void acq_tile_partials(const CtaTeam& tm, const ExactSmem& s, int n, int& n_ssq, int& n_mu) {
+  const int RT = (n + 15) >> 4;
+  if (RT > 8) { acq_tile_partials<CtaTeam>(tm, s, n, n_ssq, n_mu); return; }
+  constexpr int TC = 32;
+  const int ld = s.ld, nw = tm.nwarps(), warp = tm.warp(), lane = tm.lane();
+  const int g = lane >> 2, q = lane & 3;
+  const int nwa = nw < 8 ? nw : 8;
+  n_ssq = RT; n_mu = nwa;
+  if (warp < nwa) {
+    double mu = 0.0;
+    for (int i = warp; i < n; i += nwa) mu += s.alpha[i] * s.tile[i * TC + lane];
+    s.part[(warp * TC + lane) * 2 + 1] = mu;
+  }
+  for (int t = warp; t < 2 * RT; t += nw) {
+    const int I = RT - 1 - (t >> 1), jb = (t & 1) << 4, ib = I << 4;
+    double c[2][2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) { c[a][b][0] = 0.0; c[a][b][1] = 0.0; }
+    const int i0 = ib + g, i1 = ib + 8 + g;
+    const double* r0 = s.A + (size_t)((i0 < n) ? i0 : n - 1) * ld;
+    const double* r1 = s.A + (size_t)((i1 < n) ? i1 : n - 1) * ld;
+    const double* tb = s.tile + jb + g;
+    for (int k0 = 0; k0 < ib; k0 += 4) {         // strictly below the diagonal block: no masks
+      const int kk = k0 + q;
+      const double a0 = r0[kk], a1 = r1[kk];
+      const double b0 = tb[kk * TC], b1 = tb[kk * TC + 8];
+      dmma884(c[0][0][0], c[0][0][1], a0, b0);
+      dmma884(c[0][1][0], c[0][1][1], a0, b1);
+      dmma884(c[1][0][0], c[1][0][1], a1, b0);
+      dmma884(c[1][1][0], c[1][1][1], a1, b1);
+    }
+#pragma unroll
+    for (int k0 = 0; k0 < 16; k0 += 4) {          // the diagonal block: Linv is lower triangular
+      const int kk = ib + k0 + q;
+      const double a0 = (i0 < n && kk <= i0) ? r0[kk] : 0.0, a1 = (i1 < n && kk <= i1) ? r1[kk] : 0.0;
+      const double b0 = tb[kk * TC], b1 = tb[kk * TC + 8];
+      dmma884(c[0][0][0], c[0][0][1], a0, b0);
+      dmma884(c[0][1][0], c[0][1][1], a0, b1);
+      dmma884(c[1][0][0], c[1][0][1], a1, b0);
+      dmma884(c[1][1][0], c[1][1][1], a1, b1);
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double sq = 0.0;
+        if (i0 < n) sq += c[0][b][e] * c[0][b][e];
+        if (i1 < n) sq += c[1][b][e] * c[1][b][e];
+        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+        if (g == 0) s.part[(I * TC + jb + 8 * b + 2 * q + e) * 2 + 0] = sq;
+      }
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------
 // Fused pool pass.  For every pool point c (N of them, row-major [N,d] in global memory):
 //   k_j = os exp(-1/2 ||(x_c - x_j)/l||^2),  mean = cst + k.alpha,
@@ -260,11 +350,11 @@ STP_HD void exact_acquire(const Team& tm, const ExactSmem& s, int n, int d, cons
                           const double* pool, int N, const uint8_t* mask, double best_f,
                           int* best_idx, double* best_acq, double* mean_out, double* var_out,
                           double* acq_out) {
-  const int ld = s.ld, cap = s.cap, TC = tm.warp_width(), nw = tm.nwarps();
-  const int nwa = nw < 8 ? nw : 8;
+  const int cap = s.cap, TC = tm.warp_width();
   const double noise = theta[0], cst = theta[1], os = theta[2];
   const double* invl = s.small + 32;
-  double* xc = s.tile + (size_t)cap * TC;  // [kMaxD][TC]
+  const int n16 = (n + 15) & ~15;                             // rows n .. n16 - 1 of the tile are zero-filled
+  double* xc = s.tile + (size_t)((cap + 15) & ~15) * TC;  // [kMaxD][TC]
   double run_v = -INFINITY;
   int run_i = -1;
   for (int base = 0; base < N; base += TC) {
@@ -275,10 +365,10 @@ STP_HD void exact_acquire(const Team& tm, const ExactSmem& s, int n, int d, cons
       xc[k * TC + c] = pool[(size_t)base * d + idx];
     }
     tm.sync();
-    for (int idx = tm.rank(); idx < n * TC; idx += tm.size()) {
+    for (int idx = tm.rank(); idx < n16 * TC; idx += tm.size()) {
       const int j = idx / TC, c = idx - j * TC;
       double v = 0.0;
-      if (c < cnt) {
+      if (c < cnt && j < n) {
         double r2 = 0.0;
 #pragma unroll
         for (int k = 0; k < kMaxD; ++k)
@@ -291,32 +381,13 @@ STP_HD void exact_acquire(const Team& tm, const ExactSmem& s, int n, int d, cons
       s.tile[j * TC + c] = v;
     }
     tm.sync();
-    if (tm.warp() < nwa) {   // at most 8 warps: the partials live in the 512-double reduction scratch
-      const int c = tm.lane();
-      double ssq = 0.0, mu = 0.0;
-      for (int i = tm.warp(); i < n; i += nwa) {
-        const double* row = s.A + i * ld;
-        double v0 = 0.0, v1 = 0.0;
-        int j = 0;
-        for (; j + 1 <= i; j += 2) {
-          v0 += row[j] * s.tile[j * TC + c];
-          v1 += row[j + 1] * s.tile[(j + 1) * TC + c];
-        }
-        if (j <= i) v0 += row[j] * s.tile[j * TC + c];
-        const double v = v0 + v1;
-        ssq += v * v;
-        mu += s.alpha[i] * s.tile[i * TC + c];
-      }
-      s.part[(tm.warp() * TC + c) * 2 + 0] = ssq;
-      s.part[(tm.warp() * TC + c) * 2 + 1] = mu;
-    }
+    int n_ssq, n_mu;
+    acq_tile_partials(tm, s, n, n_ssq, n_mu);
     tm.sync();
     for (int c = tm.rank(); c < cnt; c += tm.size()) {
       double ssq = 0.0, mu = 0.0;
-      for (int w = 0; w < nwa; ++w) {
-        ssq += s.part[(w * TC + c) * 2 + 0];
-        mu += s.part[(w * TC + c) * 2 + 1];
-      }
+      for (int w = 0; w < n_ssq; ++w) ssq += s.part[(w * TC + c) * 2 + 0];
+      for (int w = 0; w < n_mu; ++w) mu += s.part[(w * TC + c) * 2 + 1];
       const double mean = cst + mu;
       const double var = os - ssq + noise;
       const double a = log_ei(mean, var, best_f);

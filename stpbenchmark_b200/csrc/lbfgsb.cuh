@@ -52,6 +52,7 @@ struct LbfgsbState {
   double f, fold, sbgnrm, theta;
   double t[kMaxP], r[kMaxP], d[kMaxP], z[kMaxP], xp[kMaxP];
   double ws[kHist][kMaxP], wy[kHist][kMaxP];
+  double ys[kHist], iys[kHist];   // s.y of every stored pair and its reciprocal (fixed once the pair is stored)
   double B[kMaxP][kMaxP];
   int col, head, itail, iupdat, updatd;
   int iter, nfev, nskip, iback, ifun, info;
@@ -113,15 +114,15 @@ STP_HD int lb_build_B(const SoloLanes&, LbfgsbState& S) {
     const double* s = S.ws[p];
     const double* y = S.wy[p];
     double* Bs = S.sc_a;
-    double sBs = 0.0, ys = 0.0;
+    double sBs = 0.0;
     for (int i = 0; i < n; ++i) {
       double a = 0.0;
       for (int j = 0; j < n; ++j) a += S.B[i][j] * s[j];
       Bs[i] = a;
     }
-    for (int i = 0; i < n; ++i) { sBs += s[i] * Bs[i]; ys += s[i] * y[i]; }
-    if (!(sBs > 0.0) || !(ys > 0.0)) return 1;
-    const double ia = 1.0 / sBs, ib = 1.0 / ys;
+    for (int i = 0; i < n; ++i) sBs += s[i] * Bs[i];
+    if (!(sBs > 0.0) || !(S.ys[p] > 0.0)) return 1;
+    const double ia = 1.0 / sBs, ib = S.iys[p];
     for (int i = 0; i < n; ++i)
       for (int j = 0; j < n; ++j) S.B[i][j] += y[i] * y[j] * ib - Bs[i] * Bs[j] * ia;
   }
@@ -136,10 +137,13 @@ __device__ __forceinline__ int lb_build_B(const WarpLanes& L, LbfgsbState& S) {
 #pragma unroll
   for (int c = 0; c < kMaxP; ++c) Brow[c] = (live && c == r) ? S.theta : 0.0;
   int broke = 0;
-  for (int q = 0; q < S.col; ++q) {
-    const int p = (S.head + q) % S.m;
+  const int col = S.col, head = S.head, mm = S.m;
+  for (int q = 0; q < col; ++q) {
+    int p = head + q;
+    if (p >= mm) p -= mm;
     const double* s = S.ws[p];
     const double* y = S.wy[p];
+    const double ysp = S.ys[p], ib = S.iys[p];
     double Bs0 = 0.0, Bs1 = 0.0;   // two chains: the dot product is latency-bound
 #pragma unroll
     for (int c = 0; c < kMaxP; c += 2) {
@@ -148,14 +152,11 @@ __device__ __forceinline__ int lb_build_B(const WarpLanes& L, LbfgsbState& S) {
     }
     const double Bs = Bs0 + Bs1;
     const double sr = live ? s[r] : 0.0, yr = live ? y[r] : 0.0;
-    double a = sr * Bs, b = sr * yr;
+    double a = sr * Bs;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
-    }
-    if (!(a > 0.0) || !(b > 0.0)) { broke = 1; break; }
-    const double ia = 1.0 / a, ib = 1.0 / b;
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (!(a > 0.0) || !(ysp > 0.0)) { broke = 1; break; }
+    const double ia = 1.0 / a;
     const double ya = yr * ib, ba = Bs * ia;
 #pragma unroll
     for (int c = 0; c < kMaxP; ++c)
@@ -712,6 +713,8 @@ STP_HD int lb_advance_once(const LN& L, LbfgsbState& S, double f, const double* 
     if (stp != 1.0) S.d[i] *= stp;
   }
   const double rr = L.sum(rrp);
+  L.sync();
+  const double ysn = lb_dot(L, S.d, S.r, n);   // s.y of the new pair
   if (stp == 1.0) { dr = gdn - gdold; dd = -gdold; }
   else { dr = (gdn - gdold) * stp; dd = -gdold * stp; }
   int iupdat = S.iupdat, col = S.col, itail = S.itail, head = S.head;
@@ -724,7 +727,8 @@ STP_HD int lb_advance_once(const LN& L, LbfgsbState& S, double f, const double* 
     if (iupdat <= m) { col = iupdat; itail = (head + iupdat - 1) % m; }
     else { itail = (itail + 1) % m; head = (head + 1) % m; }
     for (int i = l0; i < n; i += W) { S.ws[itail][i] = S.d[i]; S.wy[itail][i] = S.r[i]; }
-    if (l0 == 0) { S.updatd = 1; S.iupdat = iupdat; S.col = col; S.itail = itail; S.head = head; S.theta = rr / dr; }
+    if (l0 == 0) { S.updatd = 1; S.iupdat = iupdat; S.col = col; S.itail = itail; S.head = head; S.theta = rr / dr;
+                   S.ys[itail] = ysn; S.iys[itail] = 1.0 / ysn; }
   }
   L.sync();
   return lb_begin_iteration(L, S);

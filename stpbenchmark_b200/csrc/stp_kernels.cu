@@ -308,7 +308,6 @@ __global__ void __launch_bounds__(256) k_var_acq(int n_cap, int d, int N, int li
   if (status[b] != 0) { if (threadIdx.x == 0 && out_idx) out_idx[b] = -1; return; }
   const int n = n_arr ? n_arr[b] : n_cap;
   if (n < 1 || n > n_cap || (update && n >= n_cap)) { if (threadIdx.x == 0) status[b] = 2; return; }
-  const int nw = blockDim.x >> 5;
   const VarSmem s = var_smem_carve(smem, n_cap, d);
   double* tile = smem + var_smem_doubles(n_cap, d);
   double* part = tile + (size_t)n_cap * kTC + (size_t)kMaxD * kTC;

@@ -124,27 +124,38 @@ struct CtaTeam {
     return t;
   }
   // K simultaneous block-wide sums (K <= 16), in place, every thread gets all of them.
+  // Warp stage: a halving butterfly -- at offset o the two partners split the value set, each keeps (and adds)
+  // one half -- so 16 values cost 8 + 4 + 2 + 1 + 1 = 16 exchanges instead of 16 x 5; lane l ends with the warp
+  // total of value l >> 1.  Block stage: lane q of every warp adds value q over the warps (fixed order) and the
+  // totals are handed out by shuffle.  Deterministic for a fixed block size.
   template <int KMAX>
   __device__ __forceinline__ void sum_vec(double (&v)[KMAX], int k) const {
     static_assert(KMAX <= 16, "reduction scratch holds 16 x kMaxWarps doubles");
+    const int l = lane();
+    double w[16];
 #pragma unroll
-    for (int q = 0; q < KMAX; ++q)
-      if (q < k) v[q] = warp_sum(v[q]);
+    for (int q = 0; q < 16; ++q) w[q] = (q < KMAX && q < k) ? v[q < KMAX ? q : 0] : 0.0;
+#pragma unroll
+    for (int h = 8, o = 16; h >= 1; h >>= 1, o >>= 1) {
+      const bool up = (l & o) != 0;
+#pragma unroll
+      for (int q = 0; q < h; ++q) {
+        const double send = up ? w[q] : w[q + h];
+        const double keep = up ? w[q + h] : w[q];
+        w[q] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
+    __syncthreads();   // protect `red` against the previous reduction's readers
+    if ((l & 1) == 0) red[(l >> 1) * kMaxWarps + warp()] = w[0];
     __syncthreads();
     const int nw = nwarps();
-    if (lane() == 0) {
-#pragma unroll
-      for (int q = 0; q < KMAX; ++q)
-        if (q < k) red[q * kMaxWarps + warp()] = v[q];
-    }
-    __syncthreads();
+    double t = 0.0;
+    if (l < 16)
+      for (int x = 0; x < nw; ++x) t += red[l * kMaxWarps + x];
 #pragma unroll
     for (int q = 0; q < KMAX; ++q)
-      if (q < k) {
-        double t = 0.0;
-        for (int w = 0; w < nw; ++w) t += red[q * kMaxWarps + w];
-        v[q] = t;
-      }
+      if (q < k) v[q] = __shfl_sync(0xffffffffu, t, q);
   }
   __device__ __forceinline__ void argmax(double& v, int& idx) const {
 #pragma unroll
