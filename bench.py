@@ -198,7 +198,13 @@ def run_cuda_arm(args):
     PX = torch.stack([p[0] for p in pools]); PY = torch.stack([p[1] for p in pools])
     pool_id = [b // per_pool if per_pool else 0 for b in range(B)]
     pool_id = [min(p, N_POOLS - 1) for p in pool_id]
-    age0 = [b % N_TRIALS for b in range(B)]                 # trials already done when timing starts
+    NG = max(1, min(args.groups, B // 64 if B >= 64 else 1))
+    bounds = [(g * B // NG, (g + 1) * B // NG) for g in range(NG)]
+    if args.schedule == "cohort":                             # one age per group, groups evenly staggered
+        group_of = [next(g for g, (lo, hi) in enumerate(bounds) if lo <= b < hi) for b in range(B)]
+        age0 = [(group_of[b] * N_TRIALS) // NG for b in range(B)]
+    else:
+        age0 = [b % N_TRIALS for b in range(B)]             # trials already done when timing starts
     # seeds: first generation as config #4 (1000 g + k), later generations continue per slot
     n_steps_total = W + K + K                                # device-resident region + e2e region
     gens = 1 + (n_steps_total + N_TRIALS) // N_TRIALS + 1
@@ -216,8 +222,6 @@ def run_cuda_arm(args):
     # The campaigns of a rank are split into NG contiguous groups, each with its own CampaignBatch and CUDA stream.
     # One step of the job = one stp_exact_bo_step launch per group; the launches of different groups overlap, so the
     # tail of one group's launch (a step cannot end before its longest fit: 38..449 closures) is filled by the others.
-    NG = max(1, min(args.groups, B // 64 if B >= 64 else 1))
-    bounds = [(g * B // NG, (g + 1) * B // NG) for g in range(NG)]
     total_steps = W + K
 
     class Group:
@@ -226,7 +230,7 @@ def run_cuda_arm(args):
             self.stream = torch.cuda.Stream(device=dev)
             self.batch = CampaignBatch(PX, PY, pool_id[lo:hi], [designs[(b, 0)].tolist() for b in range(lo, hi)],
                                        n_cap=CAP, kind="ExactGP", device=dev)
-            self.batch.ragged = True                         # ages differ: longest fits are scheduled first
+            self.batch.ragged = args.schedule != "cohort"    # ages differ: longest fits are scheduled first
             # the next initial designs of every slot: the kernel recycles finished campaigns itself (stp_turnover)
             self.bank = torch.stack([torch.stack([designs[(b, g)] for g in range(1, gens)]) for b in range(lo, hi)])
             self.host = None
@@ -235,11 +239,16 @@ def run_cuda_arm(args):
             # untimed: bring campaign b to age0[b]; it starts at step N_TRIALS - age0[b]
             start = torch.tensor([N_TRIALS - age0[b] for b in range(self.lo, self.hi)], device=dev)
             bt = self.batch
-            bt.status.fill_(-1)                              # not started yet
-            for t in range(N_TRIALS):
-                bt.status[start == t] = 0
-                bt.step()
-            bt.status[bt.status == -1] = 0                   # age-0 campaigns start now
+            if args.schedule == "cohort":                    # the whole group runs its common age
+                for t in range(age0[self.lo]):
+                    bt.step()
+            else:
+                bt.status.fill_(-1)                          # not started yet
+                for t in range(N_TRIALS):
+                    bt.status[start == t] = 0
+                    bt.step()
+                bt.status[bt.status == -1] = 0               # age-0 campaigns start now
+                bt.assume_ages([N_INITIAL + age0[b] for b in range(self.lo, self.hi)])
             bt.enable_turnover(self.bank, n_final=N_INITIAL + N_TRIALS, sink_capacity=self.nb * 4)
 
         def step(self):
@@ -396,7 +405,8 @@ def run_cuda_arm(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD.format(B=B), "campaigns_per_gpu": B, "pool": N_POOL, "d": DIM,
                        "l2": "inputs are L2-resident by design (0.8 MB of pools); the kernel is FP64/latency bound, "
-                             "no HBM stream to flush", "threads_per_campaign": os.environ.get("STP_THREADS", "auto")},
+                             "no HBM stream to flush", "threads_per_campaign": os.environ.get("STP_THREADS", "auto"),
+                             "groups": NG, "schedule": args.schedule},
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp64_peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH * (B / NG) / 1024.0,
@@ -523,7 +533,10 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--campaigns", type=int, default=1024, help="campaigns per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--groups", type=int, default=4, help="campaign groups per GPU, one CUDA stream each")
+    ap.add_argument("--groups", type=int, default=8, help="campaign groups per GPU, one CUDA stream each")
+    ap.add_argument("--schedule", default="cohort", choices=["mixed", "cohort"],
+                    help="mixed: every group holds campaigns of all ages; cohort: the campaigns of a group share their "
+                         "age (groups staggered over the 80 trials), so each launch is sized for its own n")
     ap.add_argument("--model", default="ExactGP", choices=["ExactGP", "VarGP", "VarTGP", "VarLGP"],
                     help="ExactGP = the headline workload; the others run the secondary variational workload")
     ap.add_argument("--epochs", type=int, default=600)

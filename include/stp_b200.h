@@ -110,13 +110,17 @@ int stp_exact_acq(int B, int n_cap, int d, int N, const double* pool, const int3
  * turnover: optional continuous batching (see stp_turnover).  work_acc: optional double[B], += the algorithmic
  * flops of the iteration, F (n^3 + n^2 (3d+6)) + n^3/3 + (N-n)(n^2 + n(3d+8) + 60) with F the closure count;
  * iters_acc: optional int32[B], += 1 per completed iteration (both let a caller account a run without any
- * per-step device work of its own). */
+ * per-step device work of its own).
+ * n_max: an upper bound of n[b] over the active campaigns of THIS launch if the caller knows one (campaigns that
+ * advance in lockstep: n_initial + steps done), else 0.  Shared memory and the thread count of the launch are sized
+ * for n_max instead of n_cap - 1, which fits 3 - 4 campaigns per SM instead of 2 while the training sets are
+ * small; a campaign with n[b] > n_max stops with status 2.  Results do not depend on n_max. */
 int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const double* pool_y,
                       const int32_t* pool_id, uint8_t* mask, double* X, double* y, int32_t* n, int32_t* trace,
                       const double* theta0, const double* lower, const double* upper, const double* prior,
                       const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
                       int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
-                      int32_t* iters_acc, void* stream);
+                      int32_t* iters_acc, int n_max, void* stream);
 
 /* ---- variational models: VarGP / VarTGP / VarLGP (models.py:114-202, 18-111, 205-297) ---------------
  * State arrays (device, caller-owned, batch-major): Z [B, n_cap, d] inducing locations, hyp [B, d+4] =

@@ -144,8 +144,9 @@ def exact_acq(pool, X, y, theta, best_f=None, mask=None, pool_id=None, n=None, w
 
 def exact_bo_step(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upper, prior, status,
                   theta_out=None, acq_out=None, nit=None, nfev=None, opts: Optional[LbfgsbOpts] = None, order=None,
-                  turnover: Optional[Turnover] = None, work_acc=None, iters_acc=None):
-    """One BO iteration for every campaign, in place (see stp_exact_bo_step)."""
+                  turnover: Optional[Turnover] = None, work_acc=None, iters_acc=None, n_max: int = 0):
+    """One BO iteration for every campaign, in place (see stp_exact_bo_step).  ``n_max``: a host-known upper bound
+    of ``n`` over the running campaigns (0 = unknown); sizes the launch's shared memory / thread count."""
     _require_cuda(pool, pool_y, pool_id, mask, X, y, n, trace, status, theta_out, acq_out, nit, nfev, order, work_acc,
                   iters_acc)
     B, n_cap, d = X.shape
@@ -156,7 +157,7 @@ def exact_bo_step(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, up
                                    _p(trace), _host(theta0), lo, hi, _host(prior), ctypes.byref(o), _p(theta_out),
                                    _p(acq_out), _p(nit), _p(nfev), _p(status), _p(order),
                                    ctypes.byref(turnover) if turnover is not None else None, _p(work_acc), _p(iters_acc),
-                                   _stream()), "stp_exact_bo_step")
+                                   ctypes.c_int(int(n_max)), _stream()), "stp_exact_bo_step")
 
 
 def log_ei(mean: torch.Tensor, var: torch.Tensor, best_f: float) -> torch.Tensor:

@@ -52,7 +52,9 @@ int threads_for(int n_cap) {
   const int blocks = reg_blocks_for(n_cap + 1);
   if (blocks <= STP_EXACT_MAXT) { const int t = (blocks + 31) / 32 * 32; return t < 128 ? 128 : t; }
 #endif
-  return n_cap <= 48 ? 128 : 256;
+  // 128 registers per thread (launch bounds): 128 threads -> 4 CTAs/SM, 160 -> 3, 256 -> 2; the shared-memory
+  // footprint of the carve-up follows the same steps (48 KB at cap 48, 74 KB at cap 66, 113 KB at cap 90)
+  return n_cap <= 48 ? 128 : (n_cap <= 66 ? 160 : 256);
 }
 
 size_t exact_smem_bytes(int n_cap, int d, int threads, bool with_optimizer) {
@@ -155,15 +157,16 @@ __global__ void __launch_bounds__(STP_EXACT_MAXT, STP_EXACT_MINB) k_exact_bo_ste
                                 PriorArg prior, LbfgsbOpts opts, double* __restrict__ theta_out,
                                 double* __restrict__ acq_out, int32_t* __restrict__ nit, int32_t* __restrict__ nfev,
                                 int32_t* __restrict__ status, const int32_t* __restrict__ order, stp_turnover turn,
-                                double* __restrict__ work_acc, int32_t* __restrict__ iters_acc) {
+                                double* __restrict__ work_acc, int32_t* __restrict__ iters_acc, int s_cap) {
   extern __shared__ double smem[];
   const int b = order ? order[blockIdx.x] : blockIdx.x;   // longest-first scheduling: CTAs are issued in blockIdx order
   if (status[b] != 0) return;  // frozen campaign
   const int n = n_arr[b];
-  if (n >= n_cap || n < 1) { if (threadIdx.x == 0) status[b] = 2; return; }
+  // n_cap: row capacity of the global arrays; s_cap <= n_cap - 1: what the shared-memory carve-up of this launch holds
+  if (n >= n_cap || n < 1 || n > s_cap) { if (threadIdx.x == 0) status[b] = 2; return; }
   const int nw = blockDim.x >> 5;
-  const ExactSmem s = exact_smem_carve(smem, n_cap, d, kTC, nw);
-  LbfgsbState* S = reinterpret_cast<LbfgsbState*>(smem + exact_smem_doubles(n_cap, d, kTC, nw));
+  const ExactSmem s = exact_smem_carve(smem, s_cap, d, kTC, nw);
+  LbfgsbState* S = reinterpret_cast<LbfgsbState*>(smem + exact_smem_doubles(s_cap, d, kTC, nw));
   int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(S) + sizeof(LbfgsbState));
   CtaTeam tm{s.red};
   const int np = d + 3;
@@ -486,9 +489,11 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
                       const double* theta0, const double* lower, const double* upper, const double* prior,
                       const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
                       int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
-                      int32_t* iters_acc, void* stream) {
+                      int32_t* iters_acc, int n_max, void* stream) {
   if (check_dims(B, n_cap, d)) return -1;
   if (N < 1) return fail("N < 1");
+  if (n_max < 0 || n_max >= n_cap) return fail("n_max must be 0 (unknown) or in [1, n_cap - 1]");
+  const int s_cap = n_max > 0 ? n_max : n_cap - 1;
   stp_turnover turn;
   memset(&turn, 0, sizeof(turn));
   if (turnover) {
@@ -499,14 +504,14 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
   }
   if (!pool || !pool_y || !mask || !X || !y || !n || !trace || !theta0 || !prior || !status) return fail("null argument");
   if (B == 0) return 0;
-  const int threads = threads_for(n_cap);
-  const size_t smem = exact_smem_bytes(n_cap, d, threads, true);
+  const int threads = threads_for(s_cap);
+  const size_t smem = exact_smem_bytes(s_cap, d, threads, true);
   if (set_smem(k_exact_bo_step, smem)) return -1;
   PriorArg p; memcpy(p.v, prior, sizeof(p.v));
   BoundsArg bnd; fill_bounds(bnd, d, lower, upper, theta0);
   k_exact_bo_step<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, N, pool, pool_y, pool_id, mask, X, y, n, trace,
                                                               bnd, p, to_opts(opts), theta_out, acq_out, nit, nfev,
-                                                              status, order, turn, work_acc, iters_acc);
+                                                              status, order, turn, work_acc, iters_acc, s_cap);
   return after_launch("stp_exact_bo_step");
 }
 

@@ -21,6 +21,7 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence
 
+import numpy as np
 import torch
 
 from . import _lib, priors
@@ -78,6 +79,9 @@ class CampaignBatch:
         self.iteration = 0
         self.ragged = len({len(i) for i in init_indices}) > 1   # campaigns of different ages: schedule longest first
         self._turnover = None
+        # host mirror of n[b] (an upper bound: frozen campaigns stop growing).  Lets a launch be sized for the current
+        # training sets instead of the row capacity (stp_exact_bo_step's n_max); None = unknown.
+        self._n_host: Optional[np.ndarray] = np.array([len(i) for i in init_indices], dtype=np.int64)
         self.work_acc = torch.zeros(B, dtype=torch.double, device=dev)   # algorithmic flops done per campaign slot
         self.iters_acc = torch.zeros(B, dtype=torch.int32, device=dev)   # completed BO iterations per campaign slot
         if kind == "ExactGP":
@@ -102,12 +106,17 @@ class CampaignBatch:
         if self.kind == "ExactGP":
             # longest-first: a fit costs ~ closures x n^3, so the biggest training sets go first (no host sync)
             order = torch.argsort(self.n, descending=True, stable=True).to(torch.int32) if self.ragged else None
+            n_max = 0 if self._n_host is None else int(min(self._n_host.max(), self.cap - 1))
             _lib.exact_bo_step(self.pool, self.pool_y, self.pool_id, self.mask, self.X, self.y, self.n, self.trace,
                                self._theta0, self._lower, self._upper, self._prior, self.status,
                                theta_out=self.theta, acq_out=self.acq, nit=self.nit, nfev=self.nfev,
                                opts=self._opts, order=order, turnover=self._turnover, work_acc=self.work_acc,
-                               iters_acc=self.iters_acc)
+                               iters_acc=self.iters_acc, n_max=n_max)
             self.launches += 1
+            if self._n_host is not None:          # what the kernel does to n: +1, and the turnover's restart
+                self._n_host += 1
+                if self._turnover is not None:
+                    self._n_host[self._n_host >= self._turnover.n_final] = self._turnover.n_init
         else:
             self.launches += self._var.step()
         self.iteration += 1
@@ -115,6 +124,11 @@ class CampaignBatch:
     def run(self, n_trials: int) -> None:
         for _ in range(int(n_trials)):
             self.step()
+
+    def assume_ages(self, n_host) -> None:
+        """Tell the engine the current training-set sizes (host array [B], or None = unknown) after state that it
+        mirrors on the host (n, status) has been changed from outside."""
+        self._n_host = None if n_host is None else np.asarray(n_host, dtype=np.int64).copy()
 
     def traces(self):
         """(indices [B, cap] int64 with -1 beyond the last pick, n [B], status [B]) on the host."""
@@ -156,6 +170,7 @@ class CampaignBatch:
         (a handful of tiny torch index kernels); no host synchronisation."""
         if slots.numel() == 0:
             return
+        self._n_host = None   # slots live on the device: the host mirror of n is no longer valid
         if sink is not None:
             sink[sink_offset: sink_offset + slots.numel()] = self.trace[slots]
         k, ni = new_init.shape
@@ -204,6 +219,11 @@ class CampaignGroups:
     def run(self, n_trials: int) -> None:
         for _ in range(int(n_trials)):
             self.step()
+
+    def assume_ages(self, n_host) -> None:
+        """Tell the engine the current training-set sizes (host array [B], or None = unknown) after state that it
+        mirrors on the host (n, status) has been changed from outside."""
+        self._n_host = None if n_host is None else np.asarray(n_host, dtype=np.int64).copy()
 
     def synchronize(self) -> None:
         for s in self.streams:

@@ -275,3 +275,23 @@ def test_campaign_groups_on_streams_equal_single_batch():
     many.run(8)
     a, b = one.traces(), many.traces()
     assert all(torch.equal(p, q) for p, q in zip(a, b)) and many.launches == 32
+
+
+def test_launch_sized_for_current_n_gives_the_same_campaigns():
+    """stp_exact_bo_step's n_max only sizes the launch (shared memory, threads): a lockstep batch run with the
+    engine's host mirror of n (n_max = 12 ... 27: 128 threads, 4 CTAs/SM) picks what it picks when every launch is
+    sized for the row capacity (256 threads)."""
+    from stpbenchmark_b200.engine import CampaignBatch
+    X, y = dataset("AgNP")
+    designs = [list(trace("gold1", "ExactGP", "AgNP", s)[:12]) for s in (45, 359, 102, 123)]
+    runs = []
+    for hint in (True, False):
+        bt = CampaignBatch(X, y, [0] * 4, designs, n_cap=80, kind="ExactGP")
+        if not hint:
+            bt.assume_ages(None)
+        bt.run(16)
+        idx, n, st = bt.traces()
+        assert st.tolist() == [0] * 4 and n.tolist() == [28] * 4
+        runs.append((idx[:, :28].tolist(), bt.theta.cpu()))
+    assert runs[0][0] == runs[1][0]
+    assert torch.allclose(runs[0][1], runs[1][1], rtol=1e-4, atol=1e-7)
