@@ -156,7 +156,7 @@ __device__ __forceinline__ int lb_build_B(const WarpLanes& L, LbfgsbState& S) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (!(a > 0.0) || !(ysp > 0.0)) { broke = 1; break; }
-    const double ia = 1.0 / a;
+    const double ia = rcp_pos(a);
     const double ya = yr * ib, ba = Bs * ia;
 #pragma unroll
     for (int c = 0; c < kMaxP; ++c)
@@ -317,7 +317,7 @@ STP_HD int lb_subsm(const LN& L, LbfgsbState& S) {
     L.sync();
     const double s = C[j][j];
     if (!(s > 0.0)) return 1;
-    const double il = 1.0 / sqrt(s);
+    const double il = rsqrt_pos(s);
     if (l0 == 0) idiag[j] = il;
     for (int i = j + 1 + l0; i < nf; i += W) C[i][j] *= il;
     L.sync();
