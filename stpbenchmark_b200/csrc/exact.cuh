@@ -110,7 +110,7 @@ STP_HD int exact_sweep(const Team& tm, const ExactSmem& s, int n) {
 }
 #if defined(__CUDACC__) && !defined(STP_NO_BLOCKED_SWEEP)
 __device__ __forceinline__ int exact_sweep(const CtaTeam& tm, const ExactSmem& s, int n) {
-  return sweep_bordered_blocked(tm, s.A, s.ld, n + 1, n, s.tile, s.piv, s.red);   // red: idle during the sweep, >= 80 doubles
+  return sweep_bordered_blocked(tm, s.A, s.ld, n + 1, n, s.tile, s.piv);
 }
 #endif
 

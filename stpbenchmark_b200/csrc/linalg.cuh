@@ -242,7 +242,7 @@ STP_HD size_t sweep_blocked_scratch_doubles(int m) { return (size_t)3 * m * kPan
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double* A, int ld, int m, int npiv,
-                                                      double* scratch, double* piv, double* xbuf) {
+                                                      double* scratch, double* piv) {
   constexpr unsigned kFull = 0xffffffffu;
   constexpr int PL = kPanelLd;
   const int lane = tm.lane(), warp = tm.warp(), nw = tm.nwarps();
@@ -272,43 +272,6 @@ __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double*
     double xm0 = (2 * q == g) ? 1.0 : 0.0, xm1 = (2 * q + 1 == g) ? 1.0 : 0.0;
     double ipa = 1.0, ipb = 1.0;     // 1 / Delta at columns 2q, 2q + 1
     double ipq0 = 1.0, ipq1 = 1.0;   // 1 / Delta at q, q + 4
-#if defined(STP_SWEEP_A_ONE_WARP)
-    // only warp 0 eliminates the block (the shuffle pipe is shared by all warps of the SM: eight redundant copies
-    // of this phase are throughput-bound on it); X and 1 / Delta reach the other warps through `xbuf` (80 doubles)
-    int fail = 0;
-    if (warp == 0) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const double dk = (k & 1) ? am1 : am0;
-        const double p = __shfl_sync(kFull, dk, 4 * k + (k >> 1));
-        const double rk0 = __shfl_sync(kFull, am0, 4 * k + q);
-        const double rk1 = __shfl_sync(kFull, am1, 4 * k + q);
-        const double xk0 = __shfl_sync(kFull, xm0, 4 * k + q);
-        const double xk1 = __shfl_sync(kFull, xm1, 4 * k + q);
-        const double cg = __shfl_sync(kFull, dk, 4 * g + (k >> 1));
-        if (!(p > 0.0) || !(p <= 1.79e308)) { fail = 1 + kb + k; break; }
-        const double ip = 1.0 / p;
-        const double f = (g > k) ? cg * ip : 0.0;
-        am0 = fma(-f, rk0, am0);
-        am1 = fma(-f, rk1, am1);
-        xm0 = fma(-f, xk0, xm0);
-        xm1 = fma(-f, xk1, xm1);
-        if (2 * q == k) ipa = ip;
-        if (2 * q + 1 == k) ipb = ip;
-        if (lane == 0 && k < r) piv[kb + k] = p;
-      }
-      xbuf[g * 8 + 2 * q] = xm0;
-      xbuf[g * 8 + 2 * q + 1] = xm1;
-      if (g == 0) { xbuf[64 + 2 * q] = ipa; xbuf[64 + 2 * q + 1] = ipb; }
-      if (lane == 0) *reinterpret_cast<int*>(xbuf + 72) = fail;
-    }
-    tm.sync();
-    fail = *reinterpret_cast<const int*>(xbuf + 72);
-    if (fail) return fail;
-    ipa = xbuf[64 + 2 * q]; ipb = xbuf[64 + 2 * q + 1]; ipq0 = xbuf[64 + q]; ipq1 = xbuf[68 + q];
-    const double bw0 = xbuf[g * 8 + q], bw1 = xbuf[g * 8 + 4 + q];        // X[g][4s + q]: B operand of C X^T
-    const double bt0 = xbuf[q * 8 + g], bt1 = xbuf[(q + 4) * 8 + g];      // X[4s + q][g]: B operand of V X
-#else
     int fail = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -348,7 +311,6 @@ __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double*
       bt0 = (g & 1) ? u1 : u0;
       bt1 = (g & 1) ? z1 : z0;
     }
-#endif
     if (warp == 0) {   // A[K, K] <- -X^T Delta^-1 X
       double s0 = 0.0, s1 = 0.0;
       dmma884(s0, s1, bt0, bt0 * ipq0);
