@@ -22,7 +22,7 @@
  *     objective, 3 fit stopped on a non-finite objective, 4 iteration / evaluation cap reached,
  *     5 abnormal line-search termination, 6 campaign finished (turnover bank exhausted).  No exception crosses
  *     the boundary.
- *   - limits: 1 <= d <= STP_MAX_D, n_cap <= STP_MAX_N.
+ *   - limits: 1 <= d <= STP_MAX_D, n_cap <= STP_MAX_N (stp_exact_*) or STP_MAX_N_VAR (stp_var_*).
  */
 #ifndef STP_B200_H
 #define STP_B200_H
@@ -35,7 +35,8 @@ extern "C" {
 #endif
 
 #define STP_MAX_D 8
-#define STP_MAX_N 144   /* (n_cap + 1)^2 doubles + the pool tile must fit in 227 KB of shared memory */
+#define STP_MAX_N 144   /* exact-GP entry points: (n_cap + 1)^2 doubles + the pool tile must fit in 227 KB of shared memory */
+#define STP_MAX_N_VAR 272   /* variational entry points: above 144 the working square moves to the global workspace */
 #define STP_ABI_VERSION 1
 
 /* L-BFGS-B options; scipy.optimize.minimize(method="L-BFGS-B") defaults are

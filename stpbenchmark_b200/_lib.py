@@ -18,7 +18,8 @@ LIB_PATH = os.path.join(_PKG, "libstp_b200.so")
 _lib = None
 
 MAX_D = 8
-MAX_N = 144
+MAX_N = 144        # STP_MAX_N: exact-GP entry points
+MAX_N_VAR = 272    # STP_MAX_N_VAR: variational entry points
 
 STATUS_TEXT = {
     0: "ok", 1: "matrix not positive definite", 2: "non-finite parameter or objective",

@@ -260,9 +260,10 @@ __global__ void __launch_bounds__(256, STP_VAR_MINB) k_var_fit(int n_cap, int d,
   if (status[b] != 0) return;
   const int n = n_arr ? n_arr[b] : n_cap;
   if (n < 1 || n > n_cap) { if (threadIdx.x == 0) status[b] = 2; return; }
-  const VarSmem s = var_smem_carve(smem, n_cap, d);
+  VarSmem s = var_smem_carve(smem, n_cap, d);
   CtaTeam tm{s.red};
   const VarWork w = var_work_carve(work + (size_t)b * var_work_doubles(n_cap), n_cap);
+  var_bind(s, w);
   const VarModel M = var_model_of(P, b, n_cap, d);
   const double* Xb = X + (size_t)b * n_cap * d;
   var_load(tm, s, n, d, Xb, y + (size_t)b * n_cap, 1);
@@ -285,9 +286,10 @@ __global__ void __launch_bounds__(256) k_var_elbo_fg(int n_cap, int d, int lik, 
   extern __shared__ double smem[];
   const int b = blockIdx.x;
   const int n = n_arr ? n_arr[b] : n_cap;
-  const VarSmem s = var_smem_carve(smem, n_cap, d);
+  VarSmem s = var_smem_carve(smem, n_cap, d);
   CtaTeam tm{s.red};
   const VarWork w = var_work_carve(work + (size_t)b * var_work_doubles(n_cap), n_cap);
+  var_bind(s, w);
   const VarModel M = var_model_of(P, b, n_cap, d);
   var_load(tm, s, n, d, X + (size_t)b * n_cap * d, y + (size_t)b * n_cap, standardise);
   const size_t G = (size_t)n_cap + (size_t)n_cap * n_cap + (size_t)n_cap * d + d + 4;
@@ -311,11 +313,12 @@ __global__ void __launch_bounds__(256) k_var_acq(int n_cap, int d, int N, int li
   if (status[b] != 0) { if (threadIdx.x == 0 && out_idx) out_idx[b] = -1; return; }
   const int n = n_arr ? n_arr[b] : n_cap;
   if (n < 1 || n > n_cap || (update && n >= n_cap)) { if (threadIdx.x == 0) status[b] = 2; return; }
-  const VarSmem s = var_smem_carve(smem, n_cap, d);
+  VarSmem s = var_smem_carve(smem, n_cap, d);
   double* tile = smem + var_smem_doubles(n_cap, d);
   double* part = tile + (size_t)n_cap * kTC + (size_t)kMaxD * kTC;
   CtaTeam tm{s.red};
   const VarWork w = var_work_carve(work + (size_t)b * var_work_doubles(n_cap), n_cap);
+  var_bind(s, w);
   const VarModel M = var_model_of(P, b, n_cap, d);
   const int st = var_prepare(tm, s, w, M, n, d);
   if (st) { if (threadIdx.x == 0) { status[b] = st; if (out_idx) out_idx[b] = -1; if (out_acq) out_acq[b] = NAN; } return; }
@@ -400,10 +403,11 @@ int set_smem(K kernel, size_t bytes) {
   return 0;
 }
 
-int check_dims(int B, int n_cap, int d) {
+int check_dims(int B, int n_cap, int d, int n_limit = STP_MAX_N) {
   if (B < 0) return fail("B < 0");
   if (d < 1 || d > STP_MAX_D) return fail("d out of range [1, STP_MAX_D]");
-  if (n_cap < 1 || n_cap > STP_MAX_N) return fail("n_cap out of range [1, STP_MAX_N]");
+  if (n_cap < 1 || n_cap > n_limit) return fail(n_limit == STP_MAX_N ? "n_cap out of range [1, STP_MAX_N]"
+                                                                      : "n_cap out of range [1, STP_MAX_N_VAR]");
   return 0;
 }
 
@@ -537,7 +541,7 @@ int stp_var_fit(int B, int n_cap, int d, int lik, int epochs, double lr_ngd, dou
                 const double* hyp0, const double* prior, const double* gh, double* Z, double* hyp, double* nat1,
                 double* nat2, double* adam_m, double* adam_v, double* loss_hist, int32_t* status, double* work,
                 const int32_t* order, void* stream) {
-  if (check_dims(B, n_cap, d)) return -1;
+  if (check_dims(B, n_cap, d, STP_MAX_N_VAR)) return -1;
   if (epochs < 0) return fail("epochs < 0");
   if (!X || !y || !Z || !hyp || !nat1 || !nat2 || !adam_m || !adam_v || !status || !work) return fail("null argument");
   if (fresh && !hyp0) return fail("fresh model needs hyp0");
@@ -556,7 +560,7 @@ int stp_var_elbo_fg(int B, int n_cap, int d, int lik, int standardise, const dou
                     const int32_t* n, const double* Z, const double* hyp, const double* nat1, const double* nat2,
                     const double* prior, const double* gh, double* loss, double* grads, int32_t* status, double* work,
                     void* stream) {
-  if (check_dims(B, n_cap, d)) return -1;
+  if (check_dims(B, n_cap, d, STP_MAX_N_VAR)) return -1;
   if (!X || !y || !Z || !hyp || !nat1 || !nat2 || !loss || !grads || !status || !work) return fail("null argument");
   if (B == 0) return 0;
   VarFitArgs a;
@@ -576,7 +580,7 @@ int stp_var_acq(int B, int n_cap, int d, int N, int lik, const double* pool, con
                 const double* best_f, int S, const double* eps, unsigned long long seed, int32_t* out_idx,
                 double* out_acq, double* mean, double* var, double* acq, int update, const double* pool_y, double* X,
                 double* y, int32_t* trace, int32_t* status, double* work, const int32_t* order, void* stream) {
-  if (check_dims(B, n_cap, d)) return -1;
+  if (check_dims(B, n_cap, d, STP_MAX_N_VAR)) return -1;
   if (N < 0 || S < 1) return fail("N < 0 or S < 1");
   if (lik < 0 || lik > 2) return fail("lik must be 0, 1 or 2");
   if (!pool || !Z || !hyp || !nat1 || !nat2 || !status || !work) return fail("null argument");

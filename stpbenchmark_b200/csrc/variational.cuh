@@ -108,8 +108,12 @@ struct VarSmem {
   int cap, ld;
 };
 
+// Above this capacity the square M0 no longer fits in shared memory next to the vectors: it then lives in the
+// campaign's global workspace (an eighth square, L2-resident); the routines are the same, only slower per step.
+constexpr int kVarSmemSquareMax = 144;
 STP_HD size_t var_smem_doubles(int cap, int d) {
-  return (size_t)(cap + 1) * odd_ld(cap + 1) + (size_t)2 * d * cap + (size_t)cap * 8 + 6 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
+  const size_t square = cap <= kVarSmemSquareMax ? (size_t)(cap + 1) * odd_ld(cap + 1) : 0;
+  return square + (size_t)2 * d * cap + (size_t)cap * 8 + 6 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
 }
 
 STP_HD VarSmem var_smem_carve(double* base, int cap, int d) {
@@ -134,24 +138,29 @@ STP_HD VarSmem var_smem_carve(double* base, int cap, int d) {
   s.gZ = p; p += (size_t)cap * d;
   s.small = p; p += 96;
   s.red = p; p += 16 * kMaxWarps;
-  s.M0 = p;
+  s.M0 = cap <= kVarSmemSquareMax ? p : nullptr;   // nullptr: bound to the workspace by var_bind()
   return s;
 }
 
-// Per-campaign global workspace: 7 squares of (cap+1) rows x ld doubles.
+// Per-campaign global workspace: 7 squares of (cap+1) rows x ld doubles (+ 1 for M0 above kVarSmemSquareMax).
 constexpr int kVarSquares = 7;
-STP_HD size_t var_work_doubles(int cap) { return (size_t)kVarSquares * (cap + 1) * odd_ld(cap + 1); }
+STP_HD size_t var_work_doubles(int cap) {
+  return (size_t)(kVarSquares + (cap > kVarSmemSquareMax ? 1 : 0)) * (cap + 1) * odd_ld(cap + 1);
+}
 
 struct VarWork {
   double* R[kVarSquares];
+  double* M0g;   // the eighth square (large capacities only)
   int ld;
 };
 STP_HD VarWork var_work_carve(double* base, int cap) {
   VarWork w;
   w.ld = odd_ld(cap + 1);
   for (int q = 0; q < kVarSquares; ++q) w.R[q] = base + (size_t)q * (cap + 1) * w.ld;
+  w.M0g = cap > kVarSmemSquareMax ? base + (size_t)kVarSquares * (cap + 1) * w.ld : nullptr;
   return w;
 }
+STP_HD void var_bind(VarSmem& s, const VarWork& w) { if (!s.M0) s.M0 = w.M0g; }
 
 // log p(y | f) and its derivatives for one quadrature node.
 struct LikConst {   // per-epoch constants of the likelihood

@@ -43,8 +43,9 @@ class CampaignBatch:
         self.G, self.N, self.d = pools.shape
         self.B = len(pool_id)
         self.cap = int(n_cap)
-        if self.cap > _lib.MAX_N or self.d > _lib.MAX_D:
-            raise ValueError(f"n_cap <= {_lib.MAX_N} and d <= {_lib.MAX_D} required")
+        max_n = _lib.MAX_N if kind == "ExactGP" else _lib.MAX_N_VAR
+        if self.cap > max_n or self.d > _lib.MAX_D:
+            raise ValueError(f"n_cap <= {max_n} and d <= {_lib.MAX_D} required for {kind}")
         dev = self.device
         self.pool = pools.to(dev, torch.double).contiguous()
         self.pool_y = pool_ys.to(dev, torch.double).contiguous()

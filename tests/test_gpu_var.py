@@ -243,3 +243,63 @@ def test_vartgp_cfg2_smoke_statistics_via_run_many_loops(tmp_path):
     spread = float(y.max() - y.min())
     assert np.mean(ours_best) >= np.mean(gold_best) - 0.15 * spread, (ours_best, gold_best)
     assert np.mean(overlap) >= 0.3, overlap
+
+
+@pytest.mark.gpu
+def test_cfg5_shape_m256_value_gradients_training_and_pool_pass():
+    """BASELINE config #5 shape (VarTGP, d = 8, M = n = 256 inducing points, pool 8192): above n_cap = 144 the
+    working square of a campaign moves from shared memory to its global workspace.  ELBO value and every gradient
+    at n = 256, then 5 NGD + Adam epochs from a fresh model and the fused pool pass with explicit eps, all against
+    the oracle."""
+    from stpbenchmark_b200 import _lib, synthetic, varops
+    kind, d, N, S, E = "VarTGP", 8, 8192, 8, 5
+    X, y = synthetic.cfg5_pool(0)
+    ns = [256, 200]
+    cap = 260
+    B = len(ns)
+    g = torch.Generator().manual_seed(5)
+    sels = [torch.randperm(N, generator=g)[:n] for n in ns]
+    Xb = torch.zeros(B, cap, d, dtype=torch.double); yb = torch.zeros(B, cap, dtype=torch.double)
+    for b, sel in enumerate(sels):
+        Xb[b, :ns[b]] = X[sel]; yb[b, :ns[b]] = y[sel]
+    Xb, yb = Xb.cuda(), yb.cuda()
+    nb = torch.tensor(ns, dtype=torch.int32, device="cuda")
+    work = _lib.var_workspace(B, cap, "cuda")
+    # (1) value + gradients at a perturbed state
+    states = [perturbed_state(X[s], kind, seed=b + 1) for b, s in enumerate(sels)]
+    dev = _dev_state([pack(st, cap) for st in states], cap, d)
+    loss, grads, status = _lib.var_elbo_fg(Xb, yb, nb, dev, LIK[kind], PRIOR, GH, work)
+    assert status.tolist() == [0] * B
+    for b, (n, sel, st) in enumerate(zip(ns, sels, states)):
+        lo, ref = ov.epoch(st, X[sel], ov.standardise(y[sel]), lr=0.0)
+        assert abs(loss[b].item() - lo) <= 1e-9 * max(1.0, abs(lo))
+        check_grads(split_grads(grads[b].cpu().numpy(), n, d, cap), ref, d, 1e-7)
+    # (2) a few epochs from a fresh model, then the pool pass
+    noise = torch.zeros(B, cap, dtype=torch.double)
+    for b, n in enumerate(ns):
+        noise[b, :n] = torch.randn(n, dtype=torch.double, generator=torch.Generator().manual_seed(10 + b))
+    st = varops.alloc_state(B, cap, d, "cuda")
+    status = torch.zeros(B, dtype=torch.int32, device="cuda")
+    hist = torch.zeros(B, E, dtype=torch.double, device="cuda")
+    _lib.var_fit(Xb, yb, nb, st, LIK[kind], E, 0.01, 0.01, varops.var_hyp0(d), PRIOR, GH, status, work, fresh=True,
+                 init_noise=noise.cuda(), loss_hist=hist)
+    assert status.tolist() == [0] * B
+    eps = torch.randn(B, N, S, dtype=torch.double, generator=torch.Generator().manual_seed(99))
+    mask = torch.ones(B, N, dtype=torch.uint8)
+    for b, sel in enumerate(sels):
+        mask[b, sel] = 0
+    best = torch.tensor([float(y[s].max()) for s in sels], dtype=torch.double)
+    out = _lib.var_acq(X.cuda().unsqueeze(0).contiguous(), st, nb, LIK[kind], status, work, best_f=best.cuda(),
+                       mask=mask.cuda(), S=S, eps=eps.cuda(), want_pointwise=True)
+    assert status.tolist() == [0] * B
+    for b, (n, sel) in enumerate(zip(ns, sels)):
+        ost = ov.train_natural(X[sel], y[sel], kind, E, 0.01, init_noise=noise[b, :n])
+        assert rel(hist[b].cpu().numpy(), ost.losses) <= 1e-7
+        assert rel(st["nat2"][b, :n, :n].cpu().numpy(), ost.nat2.numpy()) <= 1e-5
+        mo, vo = ov.latent_posterior(ost, X)
+        ao = ov.acquisition(ost, X, float(y[sel].max()), eps=eps[b])
+        assert rel(out["mean"][b].cpu().numpy(), mo.numpy()) <= 1e-5
+        assert ((out["var"][b].cpu() - vo).abs() / vo).max() <= 1e-5
+        assert ((out["acq"][b].cpu() - ao).abs() / ao.abs().clamp_min(1.0)).max() <= 1e-5
+        ref = ao.clone(); ref[mask[b] == 0] = -float("inf")
+        assert out["idx"][b].item() == int(torch.argmax(ref))

@@ -93,3 +93,22 @@ def test_digamma():
     lib.emu_digamma.argtypes = [ctypes.c_double]
     for x in (0.3, 1.0, 2.5, 3.5, 4.0, 9.99, 10.0, 57.3):
         assert abs(lib.emu_digamma(x) - digamma(x)) <= 1e-13 * max(1, abs(digamma(x)))
+
+
+def test_elbo_backward_with_the_square_in_the_workspace():
+    """n_cap above kVarSmemSquareMax (144): the working square lives in the campaign's global workspace instead of
+    shared memory (cfg #5 shapes: d = 8, M = n up to 260).  Same routines, same parity bar."""
+    from stpbenchmark_b200 import synthetic
+    lib = hostemu.load()
+    X, y = synthetic.cfg5_pool(0, N=400)
+    n, d, cap, kind = 150, 8, 152, "VarTGP"
+    Xt, yt = X[:n].contiguous(), y[:n].contiguous()
+    st = perturbed_state(Xt, kind)
+    Z, hyp, nat1, nat2 = pack(st, cap)
+    Xp = np.zeros((cap, d)); Xp[:n] = Xt.numpy(); yp = np.zeros(cap); yp[:n] = yt.numpy()
+    loss = np.zeros(1); grads = np.zeros(cap + cap * cap + cap * d + d + 4)
+    rc = lib.emu_var_elbo_fg(cap, d, LIK[kind], n, P(Xp), P(yp), 1, P(Z), P(hyp), P(nat1), P(nat2), P(np.array(PRIOR)),
+                             P(np.array(GH)), P(loss), P(grads))
+    lo, ref = ov.epoch(st, Xt, ov.standardise(yt), lr=0.0)
+    assert rc == 0 and abs(loss[0] - lo) <= 1e-11 * max(1.0, abs(lo))
+    check_grads(split_grads(grads, n, d, cap), ref, d, 1e-8)
