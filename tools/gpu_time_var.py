@@ -3,10 +3,11 @@ import sys, time, torch
 sys.path.insert(0, '/root/repo')
 from stpbenchmark_b200 import _lib, synthetic, varops
 dev = 'cuda'
-X, y = synthetic.cfg4_pool(0)
-d = 6; N = 2048
+CFG5 = len(sys.argv) > 2 and sys.argv[2] == "cfg5"     # config #5 shape: pool 8192, d = 8, M = n = 256
+X, y = synthetic.cfg5_pool(0) if CFG5 else synthetic.cfg4_pool(0)
+d = 8 if CFG5 else 6; N = 8192 if CFG5 else 2048
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 600
-for B, n in [(148, 20), (296, 20), (296, 50), (296, 89), (592, 50), (1024, 50)]:
+for B, n in ([(148, 256), (296, 256)] if CFG5 else [(148, 20), (296, 20), (296, 50), (296, 89), (592, 50), (1024, 50)]):
     cap = n + 1
     g = torch.Generator().manual_seed(n)
     Xb = torch.zeros(B, cap, d, dtype=torch.double); yb = torch.zeros(B, cap, dtype=torch.double)
