@@ -303,3 +303,18 @@ def test_cfg5_shape_m256_value_gradients_training_and_pool_pass():
         assert ((out["acq"][b].cpu() - ao).abs() / ao.abs().clamp_min(1.0)).max() <= 1e-5
         ref = ao.clone(); ref[mask[b] == 0] = -float("inf")
         assert out["idx"][b].item() == int(torch.argmax(ref))
+
+
+def test_cfg5_campaigns_through_the_batched_runner():
+    """Config #5 end to end (reduced epochs / trials): 256-point Sobol initial designs on a pool of 8192, VarTGP with
+    M = n = 256 ... 258 inducing points, two campaigns advanced together."""
+    from stpbenchmark_b200 import synthetic
+    from stpbenchmark_b200.models import VarTGP
+    from stpbenchmark_b200.runners import run_campaign_batch
+    X, y = synthetic.cfg5_pool(1)
+    idx, val, status = run_campaign_batch(X, y, VarTGP, [5120, 5121], n_initial=256, n_trials=2, epochs=10,
+                                          learning_rate=0.01, num_samples=64)
+    assert status == [0, 0]
+    for row, v in zip(idx, val):
+        assert len(row) == 258 and len(set(row[256:])) == 2 and not (set(row[256:]) & set(row[:256]))
+        assert v == [float(y[i]) for i in row]
