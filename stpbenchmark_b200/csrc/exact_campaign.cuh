@@ -3,7 +3,6 @@
 // CPU tests (tests/hostemu/hostemu.cpp).
 #pragma once
 #include "exact.cuh"
-#include "exact_regs.cuh"
 #include "lbfgsb.cuh"
 
 namespace stp {
@@ -31,7 +30,7 @@ STP_HD ExactFitResult exact_fit_run(const Team& tm, const ExactSmem& s, LbfgsbSt
   tm.sync();
   while (*flag) {
     double f;
-    const int st = exact_closure(tm, s, n, d, S->x, pr, &f, g);
+    const int st = exact_mll_fg(tm, s, n, d, S->x, pr, &f, g);
     tm.sync();
     if (tm.warp() == 0) {
       if (st) {

@@ -25,19 +25,11 @@ int fail_cuda(const char* where, cudaError_t e) {
 
 constexpr int kTC = 32;  // acquisition tile: one candidate per lane
 
-// STP_EXACT_REGS = 1 selects the register-blocked closure (exact_regs.cuh; one thread per 4 x 4 block, up to
-// 288 threads).  Measured on B200 it does not beat the shared-memory sweep yet (13.1k vs 14.5k it/s on the
-// headline workload: the 96-register cap of 2 CTAs/SM x 288 threads spills), so it is off by default.
-#ifndef STP_EXACT_REGS
-#define STP_EXACT_REGS 0
-#endif
+// launch bounds of the exact-GP kernels (overridable for A/B runs, tools/gpu_ab_exact.sh)
 #ifndef STP_EXACT_MINB
 #define STP_EXACT_MINB 2
 #endif
-#if defined(STP_EXACT_MAXT)
-#elif STP_EXACT_REGS
-#define STP_EXACT_MAXT 160      // 6 x 6 register blocks: 136 blocks at n_cap = 91; leaves ~200 registers per thread
-#else
+#ifndef STP_EXACT_MAXT
 #define STP_EXACT_MAXT 256
 #endif
 
@@ -47,11 +39,6 @@ int threads_for(int n_cap) {
     const int t = atoi(env);
     if (t >= 32 && t <= STP_EXACT_MAXT && t % 32 == 0) return t;
   }
-  // one thread per 4 x 4 block of the bordered matrix (register-blocked sweep) when that fits in 288 threads (n_cap <= 91)
-#if STP_EXACT_REGS
-  const int blocks = reg_blocks_for(n_cap + 1);
-  if (blocks <= STP_EXACT_MAXT) { const int t = (blocks + 31) / 32 * 32; return t < 128 ? 128 : t; }
-#endif
   // 128 registers per thread (launch bounds): 128 threads -> 4 CTAs/SM, 160 -> 3, 256 -> 2; the shared-memory
   // footprint of the carve-up follows the same steps (48 KB at cap 48, 74 KB at cap 66, 113 KB at cap 90)
   return n_cap <= 48 ? 128 : (n_cap <= 66 ? 160 : 256);
@@ -88,7 +75,7 @@ __global__ void k_exact_mll_fg(int n_cap, int d, const double* __restrict__ X, c
   if (threadIdx.x < np) s.small[threadIdx.x] = theta[b * np + threadIdx.x];
   __syncthreads();
   double fv;
-  const int st = exact_closure(tm, s, n, d, s.small, to_prior(prior), &fv, s.small + 16);
+  const int st = exact_mll_fg(tm, s, n, d, s.small, to_prior(prior), &fv, s.small + 16);
   if (threadIdx.x == 0) { f[b] = fv; status[b] = st; }
   if (threadIdx.x < np) g[b * np + threadIdx.x] = st ? NAN : s.small[16 + threadIdx.x];
 }
