@@ -319,7 +319,9 @@ def run_cuda_arm(args):
     # roofline of the dominant (only) kernel: algorithmic flops (accumulated by the kernel itself from every
     # campaign's n and actual closure count) / the time its launches ran in
     achieved_tflops = (flops1 - flops0) / (elapsed_ms * 1e-3) / 1e12
-    fp64_peak = _lib.fp64_probe(4096)
+    fp64_fma_peak = _lib.fp64_probe(4096)
+    fp64_mma_peak = _lib.fp64_mma_probe(4096)
+    fp64_peak = max(fp64_fma_peak, fp64_mma_peak)
     n_bar = N_INITIAL + (N_TRIALS - 1) / 2.0
     bytes_per_iter = (N_POOL - n_bar) * DIM * 8 + N_POOL + n_bar * (DIM + 1) * 8 + 16 + 24
     hbm_bytes = bytes_per_iter * (iters1 - iters0)
@@ -407,7 +409,8 @@ def run_cuda_arm(args):
                        "l2": "inputs are L2-resident by design (0.8 MB of pools); the kernel is FP64/latency bound, "
                              "no HBM stream to flush", "threads_per_campaign": os.environ.get("STP_THREADS", "auto"),
                              "groups": NG, "schedule": args.schedule},
-            "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA mma.sync.m8n8k4.f64 + DFMA; same peak on B200)",
+                         "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp64_peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH * (B / NG) / 1024.0,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_exact_bo_step from one ncu --set "
@@ -415,7 +418,9 @@ def run_cuda_arm(args):
                                            f"to the {B // NG} campaigns of one launch; algorithmic bytes per launch: "
                                            f"{hbm_bytes / max(gpu_launches, 1):.3g}",
                          "kernel": "k_exact_bo_step",
-                         "peak_source": "stp_fp64_probe (DFMA microbenchmark, this run); MEASURED_PEAKS.json has no FP64 figure",
+                         "peak_source": "max of stp_fp64_probe (DFMA) and stp_fp64_mma_probe (DMMA) microbenchmarks, this "
+                                        "run; MEASURED_PEAKS.json has no FP64 figure",
+                         "peak_dfma": fp64_fma_peak, "peak_dmma": fp64_mma_peak,
                          "hbm": {"achieved": hbm_gbs, "peak": hbm_peak,
                                  "unit": "GB/s"}},
             "cpu_baseline": cpu,
@@ -508,7 +513,7 @@ def run_var_arm(args):
     C = 60.0 if args.model == "VarGP" else S * 80.0
     flops = float((E * (9 * nn ** 3 + nn ** 2 * (14 * d + 12) + 800 * nn) + 3 * nn ** 3 +
                    (N_POOL - nn) * (nn * (3 * d + 4) + 2 * nn ** 2 + C)).sum()) * K
-    peak = _lib.fp64_probe(4096)
+    peak = max(_lib.fp64_probe(4096), _lib.fp64_mma_probe(4096))
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": float(done.item()) / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -517,7 +522,8 @@ def run_var_arm(args):
             "config": {"workload": f"{B} concurrent {args.model} campaigns per GPU, synthetic pools N=2048 d=6, n staggered over "
                                    f"{int(n0.min())}..{int(n0.max())} (+{W + K} steps), {E} epochs, S=2048 (in-kernel Philox)",
                        "campaigns_per_gpu": B},
-            "roofline": {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA + DFMA)", "achieved": flops / (ms * 1e-3) / 1e12,
+                         "peak": peak, "unit": "TFLOP/s",
                          "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None, "kernel": "k_var_fit + k_var_acq"},
             "cpu_baseline": None, "e2e": None, "gpu_launches": batch.launches - l0, "clocks": clocks,
             "frozen_campaigns": bad, "streams": len(batch.streams)}), flush=True)

@@ -182,6 +182,11 @@ int stp_log_ei(long long count, const double* mean, const double* var, double be
  * double) receives the number of floating-point operations executed. */
 int stp_fp64_probe(int iters, double* sink, void* stream);
 
+/* The same probe on the fp64 tensor-core path (mma.sync.m8n8k4.f64, DMMA): per launch 148 * 8 CTAs x 8 warps x
+ * iters x 16 x 8 instructions of 256 MAC.  The sweep, the pool-pass product and the variational contractions
+ * issue DMMA; on B200 its peak equals the DFMA peak. */
+int stp_fp64_mma_probe(int iters, double* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

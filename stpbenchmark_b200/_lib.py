@@ -188,6 +188,22 @@ def fp64_probe(iters: int = 4096) -> float:
     return flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
 
+def fp64_mma_probe(iters: int = 4096) -> float:
+    """Measured FP64 tensor-core (DMMA m8n8k4) throughput of the current device in TFLOP/s."""
+    _require_cuda()
+    sink = torch.zeros(1, dtype=torch.double, device="cuda")
+    L = lib()
+    _check(L.stp_fp64_mma_probe(64, _p(sink), _stream()), "stp_fp64_mma_probe")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _check(L.stp_fp64_mma_probe(iters, _p(sink), _stream()), "stp_fp64_mma_probe")
+    e1.record()
+    torch.cuda.synchronize()
+    flops = 148 * 8 * 8 * float(iters) * 16 * 8 * 256 * 2     # CTAs x warps x iters x 16 x 8 DMMA x 256 MAC x 2
+    return flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+
 # ---------------------------------------------------------------------------------------------
 # variational models
 # ---------------------------------------------------------------------------------------------

@@ -357,6 +357,26 @@ __global__ void k_fp64_probe(int iters, double* sink) {
   if (r == 12345.678) sink[0] = r;  // keeps the loop alive; never true in practice
 }
 
+// The same for the fp64 tensor-core path: 8 independent m8n8k4 DMMA accumulator pairs per warp
+// (256 MAC per instruction).
+__global__ void k_fp64_mma_probe(int iters, double* sink) {
+  double c[8][2];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { c[u][0] = threadIdx.x * 1e-9 + u; c[u][1] = c[u][0] + 0.5; }
+  const double a = 1.0000001, b = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dmma884(c[u][0], c[u][1], a, b);
+    }
+  }
+  double r = 0.0;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) r += c[u][0] + c[u][1];
+  if (r == 12345.678) sink[0] = r;
+}
+
 // Elementwise LogEI over `count` (mean, var) pairs; grid-stride.
 __global__ void k_log_ei(long long count, const double* __restrict__ mean, const double* __restrict__ var,
                          double best_f, double* __restrict__ out) {
@@ -607,6 +627,12 @@ int stp_fp64_probe(int iters, double* sink, void* stream) {
   if (iters < 1 || !sink) return fail("bad argument");
   k_fp64_probe<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(iters, sink);
   return after_launch("stp_fp64_probe");
+}
+
+int stp_fp64_mma_probe(int iters, double* sink, void* stream) {
+  if (iters < 1 || !sink) return fail("bad argument");
+  k_fp64_mma_probe<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+  return after_launch("stp_fp64_mma_probe");
 }
 
 }  // extern "C"

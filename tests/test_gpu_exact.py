@@ -295,3 +295,26 @@ def test_launch_sized_for_current_n_gives_the_same_campaigns():
         runs.append((idx[:, :28].tolist(), bt.theta.cpu()))
     assert runs[0][0] == runs[1][0]
     assert torch.allclose(runs[0][1], runs[1][1], rtol=1e-4, atol=1e-7)
+
+
+def test_n_max_smaller_than_a_training_set_stops_that_campaign(L):
+    """A campaign whose n exceeds the caller's n_max does not fit the launch's shared memory: status 2, nothing
+    written; the others run."""
+    from stpbenchmark_b200 import priors
+    X, y, tr, Xb, yb, nb = _batch("AgNP", 45, [12, 20], 32, "cuda")
+    d, N = X.shape[1], len(X)
+    mask = torch.ones(2, N, dtype=torch.uint8)
+    trace_t = torch.full((2, 32), -1, dtype=torch.int32)
+    for b, n in enumerate([12, 20]):
+        mask[b, tr[:n]] = 0
+        trace_t[b, :n] = torch.tensor(tr[:n], dtype=torch.int32)
+    status = torch.zeros(2, dtype=torch.int32, device="cuda")
+    lo, hi = priors.exact_bounds(d)
+    L.exact_bo_step(X.cuda().unsqueeze(0).contiguous(), y.cuda().unsqueeze(0).contiguous(),
+                    torch.zeros(2, dtype=torch.int32, device="cuda"), mask.cuda(), Xb, yb, nb, trace_t.cuda(),
+                    priors.exact_theta0(d), lo, hi, priors.exact_prior_vector(d), status, n_max=15)
+    assert status.tolist() == [0, 2] and nb.tolist() == [13, 20]
+    with pytest.raises(RuntimeError):
+        L.exact_bo_step(X.cuda().unsqueeze(0).contiguous(), y.cuda().unsqueeze(0).contiguous(),
+                        torch.zeros(2, dtype=torch.int32, device="cuda"), mask.cuda(), Xb, yb, nb, trace_t.cuda(),
+                        priors.exact_theta0(d), lo, hi, priors.exact_prior_vector(d), status, n_max=32)
