@@ -31,7 +31,7 @@ N_POOL, DIM, N_POOLS = 2048, 6, 8
 N_INITIAL, N_TRIALS = 10, 80
 CAP = N_INITIAL + N_TRIALS + 1
 METRIC, UNIT = "bo_iterations_per_sec", "it/s"
-NCU_DRAM_BYTES_PER_LAUNCH = 6.378496e6 + 0.104192e6   # measured once with ncu (see roofline.traffic_source)
+NCU_DRAM_BYTES_PER_LAUNCH = 6.717696e6 + 0.091904e6   # measured once with ncu (see roofline.traffic_source)
 WORKLOAD = ("cfg4: synthetic pools N=2048 d=6 (Hartmann-6 + t3 noise), {B} concurrent ExactGP campaigns per GPU, "
             "n_initial=10, 80 trials, ages staggered over n=10..89 (continuous batching)")
 
@@ -414,7 +414,7 @@ def run_cuda_arm(args):
                          "frac": achieved_tflops / fp64_peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH * (B / NG) / 1024.0,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of k_exact_bo_step from one ncu --set "
-                                           "full capture of a 1024-campaign launch (profiles/r01_ncu_prof_r1_bostep_v6.txt), scaled "
+                                           "full capture of a 1024-campaign launch (profiles/r01_ncu_prof_r1_bostep_v7.txt), scaled "
                                            f"to the {B // NG} campaigns of one launch; algorithmic bytes per launch: "
                                            f"{hbm_bytes / max(gpu_launches, 1):.3g}",
                          "kernel": "k_exact_bo_step",
