@@ -1,6 +1,10 @@
 """Aggregate an `ncu --page source --csv --print-source cuda,sass` export by (file, source line) and by coarse
 line ranges: which region of which header the stall samples / executed instructions of a kernel fall in.
-usage: python tools/ncu_regions.py export.csv [top_n]"""
+The export attributes a SASS instruction to EVERY source line of its inline stack (a shuffle of sum_vec shows up
+under team.cuh and under three lines of sm_30_intrinsics.hpp), so the shares are INCLUSIVE of inlined callees and can
+add up to more than 100 %.  Pass the kernel's true totals (sum over the rows of the `--print-source sass` export) as
+`--totals SAMPLES INSTRUCTIONS`; without them the sum over source lines is used (over-counts deep inline stacks).
+usage: python tools/ncu_regions.py export.csv [top_n] [--totals SAMPLES INSTRUCTIONS]"""
 import csv, sys, collections
 
 def load(path):
@@ -25,9 +29,15 @@ def load(path):
     return per_line, src
 
 if __name__ == '__main__':
-    per_line, src = load(sys.argv[1]); top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+    argv = list(sys.argv)
+    totals = None
+    if '--totals' in argv:
+        k = argv.index('--totals'); totals = (int(argv[k + 1]), int(argv[k + 2])); del argv[k:k + 3]
+    per_line, src = load(argv[1]); top = int(argv[2]) if len(argv) > 2 else 40
     ts = sum(v[0] for v in per_line.values()); ti = sum(v[1] for v in per_line.values())
-    print(f'total samples {ts}  warp instructions {ti}')
+    if totals:
+        ts, ti = totals
+    print(f'total samples {ts}  warp instructions {ti}   (shares are inclusive of inlined callees)')
     by_file = collections.defaultdict(lambda: [0, 0])
     for (f, l), v in per_line.items(): by_file[f][0] += v[0]; by_file[f][1] += v[1]
     for f, v in sorted(by_file.items(), key=lambda kv: -kv[1][0]):
