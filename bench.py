@@ -539,7 +539,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--campaigns", type=int, default=1024, help="campaigns per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--groups", type=int, default=8, help="campaign groups per GPU, one CUDA stream each")
+    ap.add_argument("--groups", type=int, default=16, help="campaign groups per GPU, one CUDA stream each (at most B / 64)")
     ap.add_argument("--schedule", default="cohort", choices=["mixed", "cohort"],
                     help="mixed: every group holds campaigns of all ages; cohort: the campaigns of a group share their "
                          "age (groups staggered over the 80 trials), so each launch is sized for its own n")
