@@ -184,6 +184,35 @@ def train_natural(X: torch.Tensor, y: torch.Tensor, kind: str, epochs: int, lr: 
     return st
 
 
+def train_adam(X: torch.Tensor, y: torch.Tensor, kind: str, epochs: int, lr: float,
+               init_noise: torch.Tensor | None = None) -> VarState:
+    """train_variational_model (optim.py:61-102) on a fresh model: ONE torch.optim.Adam(model.parameters(), lr)
+    over every parameter, the natural parameters of q(u) included.  gpytorch's natural parameterisation hands the
+    optimiser the gradient with respect to the EXPECTATION parameters as `.grad` of (natural_vec, natural_mat)
+    (that is what makes a plain SGD step a natural-gradient step), so Adam is fed the same two arrays the NGD
+    step of `epoch` uses.  Parity unpinned: no reference artefact exercises this trainer."""
+    ys = standardise(y.double())
+    st = init_state(X, kind, init_noise)
+    nat1 = st.nat1.clone().requires_grad_()
+    nat2 = st.nat2.clone().requires_grad_()
+    opt = torch.optim.Adam(st.hyper() + [nat1, nat2], lr=lr)
+    for _ in range(epochs):
+        opt.zero_grad()
+        mu, S = natural_to_moments(nat1.detach(), nat2.detach())
+        mu_ = mu.detach().requires_grad_()
+        S_ = S.detach().requires_grad_()
+        st.nat1, st.nat2 = nat1.detach(), nat2.detach()
+        loss = elbo_loss(st, X, ys, mu_, S_)
+        loss.backward()
+        gS = S_.grad
+        nat1.grad = mu_.grad - 2.0 * (gS @ mu.unsqueeze(-1)).squeeze(-1)
+        nat2.grad = gS.clone()
+        opt.step()
+        st.losses.append(float(loss.item()))
+    st.nat1, st.nat2 = nat1.detach().clone(), nat2.detach().clone()
+    return st
+
+
 def latent_posterior(st: VarState, Xc: torch.Tensor):
     """q(f) at the candidates: mean m_*, variance v_* (App. A.4 step 3), no likelihood noise."""
     with torch.no_grad():

@@ -155,10 +155,12 @@ def train_natural_variational_model(model, X, y, epochs=500, lr=0.05, verbose=Fa
     return None
 
 
-def train_variational_model(model, X, y, epochs=100, lr=0.01, verbose=False, y_standardize=True):
-    """Plain Adam on every parameter incl. the natural parameters (optim.py:61-102).  The
-    reference's only caller is the broken test_hartmann.py, and upstream rejects this scheme once
-    the natural covariance stops being positive definite; not provided."""
-    raise NotImplementedError(
-        "train_variational_model (Adam on natural parameters) is outside the BO hot path; "
-        "use train_natural_variational_model")
+def train_variational_model(model, X, y, epochs=100, lr=0.01, verbose=False, y_standardize=True, init_noise=None):
+    """Plain Adam on every parameter incl. the natural parameters of q(u) (optim.py:61-102): one CUDA
+    value-and-gradient launch (stp_var_elbo_fg) per epoch + torch.optim.Adam on the packed state.  Not on the BO hot
+    path (the loop uses train_natural_variational_model); kept so that the module surface is complete."""
+    from . import varops
+    losses = varops.train_adam(model, X, y, epochs=epochs, lr=lr, y_standardize=y_standardize, init_noise=init_noise)
+    if verbose:
+        return losses
+    return None

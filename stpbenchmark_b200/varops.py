@@ -185,6 +185,56 @@ def train_natural(model, X, y, epochs=500, lr=0.05, y_standardize=True, init_noi
     return losses
 
 
+def train_adam(model, X, y, epochs=100, lr=0.01, y_standardize=True, init_noise=None):
+    """optim.py:61-102 for one model, in place: torch.optim.Adam(lr) on EVERY parameter, the natural parameters
+    included (they receive the gradient with respect to the expectation parameters, as in gpytorch).  One
+    stp_var_elbo_fg launch per epoch gives the loss and all gradients; the Adam update itself is torch's, applied to
+    the packed state on the device.  Returns the loss history."""
+    model.train()
+    model.likelihood.train()
+    dev = model.device
+    if not y_standardize:
+        raise NotImplementedError("the reference always standardises (optim.py:80-81); y_standardize=False is not provided")
+    vs = model.variational_strategy
+    st, n, d, cap = _pack(model)
+    Xd = X.detach().to(dev).double().reshape(1, -1, d).contiguous()
+    yd = y.detach().to(dev).double().reshape(1, -1).contiguous()
+    if Xd.shape[1] != n:
+        raise NotImplementedError("train_variational_model expects as many inducing points as training points")
+    if int(vs.variational_params_initialized) == 0:
+        eps = torch.randn(n, dtype=torch.double) if init_noise is None else init_noise.double().cpu()
+        st["nat1"][0, :n] = (eps * vs._variational_distribution.mean_init_std).to(dev)
+        vs.variational_params_initialized.fill_(1)
+    ls_prior = model.lengthscale_prior
+    prior, gh = var_prior_vector(ls_prior), gauss_hermite_table()
+    lik = _LIK_OF_KIND[model.likelihood.kind]
+    work = _lib.var_workspace(1, cap, dev)
+    nn = torch.tensor([n], dtype=torch.int32, device=dev)
+    params = [st[k].requires_grad_(True) for k in ("nat1", "nat2", "Z", "hyp")]
+    opt = torch.optim.Adam(params, lr=lr)
+    o1, o2, o3 = cap, cap + cap * cap, cap + cap * cap + cap * d
+    losses = []
+    for _ in range(int(epochs)):
+        loss, grads, status = _lib.var_elbo_fg(Xd, yd, nn, {k: st[k].detach() for k in ("Z", "hyp", "nat1", "nat2")},
+                                               lik, prior, gh, work)
+        code = int(status.item())
+        if code != 0:
+            raise RuntimeError("variational fit failed: " + _lib.STATUS_TEXT.get(code, str(code)))
+        g = grads[0]
+        st["nat1"].grad = g[:o1].reshape(1, cap).clone()
+        st["nat2"].grad = g[o1:o2].reshape(1, cap, cap).clone()
+        st["Z"].grad = g[o2:o3].reshape(1, cap, d).clone()
+        st["hyp"].grad = g[o3:].reshape(1, d + 4).clone()
+        opt.step()
+        losses.append(float(loss.item()))
+    for k in ("nat1", "nat2", "Z", "hyp"):
+        st[k] = st[k].detach()
+    _unpack(model, st, n, d)
+    model._y_scaler = (float(yd.mean()), float(yd.std(unbiased=False)) + 1e-10)
+    model.fit_info = {"losses": losses}
+    return losses
+
+
 def _pointwise(model, X, best_f=float("nan"), S=1, eps=None):
     dev = model.device
     st, n, d, cap = _pack(model)

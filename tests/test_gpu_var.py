@@ -318,3 +318,25 @@ def test_cfg5_campaigns_through_the_batched_runner():
     for row, v in zip(idx, val):
         assert len(row) == 258 and len(set(row[256:])) == 2 and not (set(row[256:]) & set(row[:256]))
         assert v == [float(y[i]) for i in row]
+
+
+@pytest.mark.parametrize("cls_name", ["VarGP", "VarTGP"])
+def test_train_variational_model_plain_adam(cls_name):
+    """optim.train_variational_model (optim.py:61-102: Adam on every parameter, the natural parameters included)
+    against the oracle's restatement: loss history and the trained state after 30 epochs."""
+    from stpbenchmark_b200 import models, optim
+    X, y = dataset("AutoAM")
+    tr = trace("gold1", "ExactGP", "AutoAM", 45)
+    n, E = 16, 30
+    Xt, yt = X[tr[:n]], y[tr[:n]]
+    noise = torch.randn(n, dtype=torch.double, generator=torch.Generator().manual_seed(21))
+    model = getattr(models, cls_name)(inducing_points=Xt).double()
+    hist = optim.train_variational_model(model, Xt, yt, epochs=E, lr=0.01, verbose=True, init_noise=noise)
+    ost = ov.train_adam(Xt, yt, cls_name, E, 0.01, init_noise=noise)
+    assert len(hist) == E and rel(hist, ost.losses) <= 1e-7
+    vd = model.variational_strategy._variational_distribution
+    assert rel(vd.natural_vec.detach().cpu().numpy(), ost.nat1.numpy()) <= 1e-5
+    assert rel(vd.natural_mat.detach().cpu().numpy(), ost.nat2.numpy()) <= 1e-5
+    assert rel(model.variational_strategy.inducing_points.detach().cpu().numpy(), ost.Z.detach().numpy()) <= 1e-5
+    assert rel(model.covar_module.base_kernel.lengthscale.detach().cpu().numpy().ravel(), ost.ls.detach().numpy().ravel()) <= 1e-6
+    assert abs(float(model.likelihood.noise.detach()) - ost.noise.item()) <= 1e-6 * ost.noise.item()

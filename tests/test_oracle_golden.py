@@ -74,3 +74,16 @@ def test_posterior_includes_observation_noise():
     th = oexact.initial_theta(X.shape[1])
     mean, var = oexact.posterior_exact(th, X[sel], y[sel], X[sel])
     assert (var > th[0] * 0.999).all() and torch.allclose(mean, y[sel], atol=0.2 * float(y.std()))
+
+
+def test_oracle_plain_adam_trainer_descends():
+    """oracle.variational.train_adam (restatement of optim.py:61-102): the ELBO loss goes down and the natural
+    covariance parameter stays negative definite over a short run."""
+    from oracle import variational as ov
+    g = torch.Generator().manual_seed(3)
+    X = torch.rand(12, 3, dtype=torch.double, generator=g)
+    y = torch.sin(3 * X[:, 0]) + 0.1 * torch.randn(12, dtype=torch.double, generator=g)
+    for kind in ("VarGP", "VarTGP", "VarLGP"):
+        st = ov.train_adam(X, y, kind, 25, 0.01, init_noise=torch.randn(12, dtype=torch.double, generator=g))
+        assert len(st.losses) == 25 and st.losses[-1] < st.losses[0]
+        assert torch.linalg.eigvalsh(st.nat2).max() < 0
