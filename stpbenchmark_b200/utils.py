@@ -176,3 +176,55 @@ def EI(mean, std, best_observed, minimize: bool = False):
     z = gain / std
     unit = torch.distributions.Normal(0, 1)
     return gain * unit.cdf(z) + std * unit.log_prob(z).exp()
+
+
+# ---------------------------------------------------------------------------------------------
+# Post-processing helpers of the reference's utils.py (none of them is on the BO hot path; host only).
+# ---------------------------------------------------------------------------------------------
+def initial_points(x: torch.Tensor, y: torch.Tensor, num_initial_points: int):
+    """Random initial design away from the lowest 5 % of the targets (utils.py:136-151): a `torch.randperm` draw
+    (global generator) over the points with y above the 5 % quantile; returns (x_initial, y_initial)."""
+    keep = torch.nonzero(y > torch.quantile(y, 0.05), as_tuple=True)[0]
+    chosen = keep[torch.randperm(len(keep))[:num_initial_points]]
+    return x[chosen], y[chosen]
+
+
+def get_top_samples(train_y: torch.Tensor, top_percentage: float = 5):
+    """The ceil(top_percentage %) largest target values as a list, largest first, first occurrence first on ties
+    (utils.py:312-334; the reference also prints them)."""
+    values = train_y.detach().cpu().numpy().reshape(-1)
+    count = int(math.ceil(len(values) * (top_percentage / 100)))
+    order = np.argsort(-values, kind="stable")[:count]
+    top = values[order].tolist()
+    print(f"Number of top {top_percentage}% samples: {len(top)}")
+    print(f"Top {top_percentage}% samples: {top}")
+    return top
+
+
+def num_top_samples(y, top_samples) -> float:
+    """Fraction of the top samples that a campaign has found (utils.py:337-338)."""
+    return sum(1 for v in y if v in top_samples) / len(top_samples)
+
+
+def collect_arrays(prefix: str, num_arrays: int, namespace: dict | None = None):
+    """The arrays named f"{prefix}{i}", i < num_arrays, that exist in `namespace` (utils.py:342-349 reads its own
+    module globals; pass the caller's `globals()` to get the same effect from another module)."""
+    scope = globals() if namespace is None else namespace
+    return [scope[f"{prefix}{i}"] for i in range(num_arrays) if scope.get(f"{prefix}{i}") is not None]
+
+
+def pad_array(array, max_length: int):
+    """Right-pad a 1-D array to `max_length` by repeating its last value (utils.py:352-355)."""
+    array = np.asarray(array)
+    return np.concatenate([array, np.full(max_length - len(array), array[-1], dtype=array.dtype)])
+
+
+def find_max_length(prefix: str, num_arrays: int, namespace: dict | None = None) -> int:
+    """Length of the longest collected array (utils.py:358-360)."""
+    return max(len(a) for a in collect_arrays(prefix, num_arrays, namespace))
+
+
+def process_arrays(prefix: str, num_arrays: int, max_length: int, namespace: dict | None = None):
+    """Mean and (population) standard deviation over the collected arrays after padding (utils.py:364-370)."""
+    stack = np.stack([pad_array(a, max_length) for a in collect_arrays(prefix, num_arrays, namespace)])
+    return stack.mean(axis=0), stack.std(axis=0)

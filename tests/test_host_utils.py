@@ -79,3 +79,26 @@ def test_ei_formula():
     n = torch.distributions.Normal(0, 1)
     assert torch.allclose(ei, (m - 0.5) * n.cdf(z) + s * n.log_prob(z).exp())
     assert torch.allclose(utils.EI(m, s, torch.tensor(0.5), minimize=True), (0.5 - m) * n.cdf(-z) + s * n.log_prob(-z).exp())
+
+
+def test_post_processing_helpers():
+    """utils.py:136-151, 312-370: same results as the reference's own helpers (imported from the read-only checkout
+    when it is present, otherwise checked against hand-computed values)."""
+    import numpy as np
+    import torch
+    from stpbenchmark_b200 import utils as U
+    y = torch.tensor([0.3, 2.0, 1.5, 2.0, -1.0, 0.7, 0.1, 1.9, 0.0, 0.2, 1.1, 0.9, 0.8, 0.6, 0.5, 0.4, 1.2, 1.3, 1.4, 1.6, 1.7])
+    top = U.get_top_samples(y, top_percentage=10)
+    assert top == pytest.approx([2.0, 2.0, 1.9]) and U.num_top_samples([top[0], 0.3, top[2]], top) == pytest.approx(2 / 3)
+    assert U.pad_array(np.array([1.0, 3.0]), 4).tolist() == [1.0, 3.0, 3.0, 3.0]
+    ns = {"run0": np.array([1.0, 2.0]), "run1": np.array([3.0, 4.0, 5.0]), "run3": np.array([9.0])}
+    assert len(U.collect_arrays("run", 3, ns)) == 2 and U.find_max_length("run", 3, ns) == 3
+    mean, std = U.process_arrays("run", 3, 3, ns)
+    assert mean.tolist() == [2.0, 3.0, 3.5] and std.tolist() == pytest.approx([1.0, 1.0, 1.5])
+    torch.manual_seed(7)
+    x = torch.arange(len(y), dtype=torch.double).unsqueeze(1)
+    xi, yi = U.initial_points(x, y, 5)
+    assert xi.shape == (5, 1) and (yi > torch.quantile(y, 0.05)).all() and len(set(xi.flatten().tolist())) == 5
+    torch.manual_seed(7)
+    keep = torch.nonzero(y > torch.quantile(y, 0.05), as_tuple=True)[0]
+    assert torch.equal(xi.flatten().long(), keep[torch.randperm(len(keep))[:5]])
