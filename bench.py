@@ -315,6 +315,9 @@ def run_cuda_arm(args):
     if world > 1:
         dist.all_reduce(done)
     value = float(done.item()) / (elapsed_ms_max * 1e-3)
+    launches_all = torch.tensor([gpu_launches], dtype=torch.int64, device=dev)       # whole job, like `value`
+    if world > 1:
+        dist.all_reduce(launches_all)
 
     # roofline of the dominant (only) kernel: algorithmic flops (accumulated by the kernel itself from every
     # campaign's n and actual closure count) / the time its launches ran in
@@ -426,7 +429,7 @@ def run_cuda_arm(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke},
-            "gpu_launches": gpu_launches,
+            "gpu_launches": int(launches_all.item()),
             "clocks": clocks,
             "parity": parity,
             "frozen_campaigns": status_bad,
