@@ -237,20 +237,24 @@ __device__ __forceinline__ VarModel var_model_of(const VarPtrs& P, int b, int ca
 #ifndef STP_VAR_MINB
 #define STP_VAR_MINB 2
 #endif
+// BIG: the working square M0 of a campaign lives in its global workspace (n_cap > kVarSmemSquareMax) instead of
+// shared memory; a template parameter so that each instantiation addresses M0 in one known address space.
+template <bool BIG>
 __global__ void __launch_bounds__(256, STP_VAR_MINB) k_var_fit(int n_cap, int d, const double* __restrict__ X,
                                                  const double* __restrict__ y, const int32_t* __restrict__ n_arr,
                                                  const double* __restrict__ init_noise, VarFitArgs args, int t0,
                                                  VarPtrs P, double* __restrict__ loss_hist, int32_t* __restrict__ status,
-                                                 double* __restrict__ work, const int32_t* __restrict__ order) {
+                                                 double* __restrict__ work, const int32_t* __restrict__ order,
+                                                 int with_panels) {
   extern __shared__ double smem[];
   const int b = order ? order[blockIdx.x] : blockIdx.x;   // longest-first scheduling (see stp_exact_bo_step)
   if (status[b] != 0) return;
   const int n = n_arr ? n_arr[b] : n_cap;
   if (n < 1 || n > n_cap) { if (threadIdx.x == 0) status[b] = 2; return; }
-  VarSmem s = var_smem_carve(smem, n_cap, d);
+  VarSmem s = var_smem_carve(smem, n_cap, d, with_panels != 0, BIG ? 0 : 1);
   CtaTeam tm{s.red};
   const VarWork w = var_work_carve(work + (size_t)b * var_work_doubles(n_cap), n_cap);
-  var_bind(s, w);
+  if (BIG) s.M0 = w.M0g;
   const VarModel M = var_model_of(P, b, n_cap, d);
   const double* Xb = X + (size_t)b * n_cap * d;
   var_load(tm, s, n, d, Xb, y + (size_t)b * n_cap, 1);
@@ -265,6 +269,7 @@ __global__ void __launch_bounds__(256, STP_VAR_MINB) k_var_fit(int n_cap, int d,
   if (threadIdx.x == 0) status[b] = st;
 }
 
+template <bool BIG>
 __global__ void __launch_bounds__(256) k_var_elbo_fg(int n_cap, int d, int lik, int standardise,
                                                      const double* __restrict__ X, const double* __restrict__ y,
                                                      const int32_t* __restrict__ n_arr, VarFitArgs args, VarPtrs P,
@@ -273,10 +278,10 @@ __global__ void __launch_bounds__(256) k_var_elbo_fg(int n_cap, int d, int lik, 
   extern __shared__ double smem[];
   const int b = blockIdx.x;
   const int n = n_arr ? n_arr[b] : n_cap;
-  VarSmem s = var_smem_carve(smem, n_cap, d);
+  VarSmem s = var_smem_carve(smem, n_cap, d, false, BIG ? 0 : 1);
   CtaTeam tm{s.red};
   const VarWork w = var_work_carve(work + (size_t)b * var_work_doubles(n_cap), n_cap);
-  var_bind(s, w);
+  if (BIG) s.M0 = w.M0g;
   const VarModel M = var_model_of(P, b, n_cap, d);
   var_load(tm, s, n, d, X + (size_t)b * n_cap * d, y + (size_t)b * n_cap, standardise);
   const size_t G = (size_t)n_cap + (size_t)n_cap * n_cap + (size_t)n_cap * d + d + 4;
@@ -285,6 +290,7 @@ __global__ void __launch_bounds__(256) k_var_elbo_fg(int n_cap, int d, int lik, 
   if (threadIdx.x == 0) { loss[b] = r.loss; status[b] = r.status; }
 }
 
+template <bool BIG>
 __global__ void __launch_bounds__(256) k_var_acq(int n_cap, int d, int N, int lik, const double* __restrict__ pool,
                                                  const int32_t* __restrict__ pool_id, uint8_t* __restrict__ mask,
                                                  VarPtrs P, int32_t* __restrict__ n_arr, const double* __restrict__ best_f,
@@ -300,12 +306,12 @@ __global__ void __launch_bounds__(256) k_var_acq(int n_cap, int d, int N, int li
   if (status[b] != 0) { if (threadIdx.x == 0 && out_idx) out_idx[b] = -1; return; }
   const int n = n_arr ? n_arr[b] : n_cap;
   if (n < 1 || n > n_cap || (update && n >= n_cap)) { if (threadIdx.x == 0) status[b] = 2; return; }
-  VarSmem s = var_smem_carve(smem, n_cap, d);
+  VarSmem s = var_smem_carve(smem, n_cap, d, false, BIG ? 0 : 1);
   double* tile = smem + var_smem_doubles(n_cap, d);
   double* part = tile + (size_t)n_cap * kTC + (size_t)kMaxD * kTC;
   CtaTeam tm{s.red};
   const VarWork w = var_work_carve(work + (size_t)b * var_work_doubles(n_cap), n_cap);
-  var_bind(s, w);
+  if (BIG) s.M0 = w.M0g;
   const VarModel M = var_model_of(P, b, n_cap, d);
   const int st = var_prepare(tm, s, w, M, n, d);
   if (st) { if (threadIdx.x == 0) { status[b] = st; if (out_idx) out_idx[b] = -1; if (out_acq) out_acq[b] = NAN; } return; }
@@ -538,6 +544,15 @@ static int fill_var_args(VarFitArgs& a, int d, int lik, int epochs, int fresh, d
   return 0;
 }
 
+// The blocked sweep needs three panels next to the shared-memory square: use it while two CTAs still fit in an SM.
+static int var_use_panels(int n_cap, int d) {
+#if defined(STP_NO_DMMA)
+  return 0;
+#else
+  return n_cap <= kVarSmemSquareMax && var_smem_doubles(n_cap, d, true) * sizeof(double) <= 113u * 1024u;
+#endif
+}
+
 size_t stp_var_workspace_bytes(int B, int n_cap) {
   if (B < 0 || n_cap < 1) return 0;
   return (size_t)B * var_work_doubles(n_cap) * sizeof(double);
@@ -555,11 +570,18 @@ int stp_var_fit(int B, int n_cap, int d, int lik, int epochs, double lr_ngd, dou
   if (B == 0) return 0;
   VarFitArgs a;
   if (fill_var_args(a, d, lik, epochs, fresh, lr_ngd, lr_adam, hyp0, prior, gh, seed)) return -1;
-  const size_t smem = var_smem_doubles(n_cap, d) * sizeof(double);
-  if (set_smem(k_var_fit, smem)) return -1;
-  k_var_fit<<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, init_noise, a, t0,
-                                                    VarPtrs{Z, hyp, nat1, nat2, adam_m, adam_v}, loss_hist, status, work,
-                                                    order);
+  const int with_panels = var_use_panels(n_cap, d);
+  const size_t smem = var_smem_doubles(n_cap, d, with_panels != 0) * sizeof(double);
+  const VarPtrs ptrs{Z, hyp, nat1, nat2, adam_m, adam_v};
+  if (n_cap > kVarSmemSquareMax) {
+    if (set_smem(k_var_fit<true>, smem)) return -1;
+    k_var_fit<true><<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, init_noise, a, t0, ptrs, loss_hist, status,
+                                                            work, order, with_panels);
+  } else {
+    if (set_smem(k_var_fit<false>, smem)) return -1;
+    k_var_fit<false><<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, init_noise, a, t0, ptrs, loss_hist, status,
+                                                             work, order, with_panels);
+  }
   return after_launch("stp_var_fit");
 }
 
@@ -573,12 +595,17 @@ int stp_var_elbo_fg(int B, int n_cap, int d, int lik, int standardise, const dou
   VarFitArgs a;
   if (fill_var_args(a, d, lik, 1, 0, 0.0, 0.0, nullptr, prior, gh, 0)) return -1;
   const size_t smem = var_smem_doubles(n_cap, d) * sizeof(double);
-  if (set_smem(k_var_elbo_fg, smem)) return -1;
-  k_var_elbo_fg<<<B, 256, smem, (cudaStream_t)stream>>>(
-      n_cap, d, lik, standardise, X, y, n, a,
-      VarPtrs{const_cast<double*>(Z), const_cast<double*>(hyp), const_cast<double*>(nat1), const_cast<double*>(nat2),
-              nullptr, nullptr},
-      loss, grads, status, work);
+  const VarPtrs ptrs{const_cast<double*>(Z), const_cast<double*>(hyp), const_cast<double*>(nat1),
+                     const_cast<double*>(nat2), nullptr, nullptr};
+  if (n_cap > kVarSmemSquareMax) {
+    if (set_smem(k_var_elbo_fg<true>, smem)) return -1;
+    k_var_elbo_fg<true><<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, lik, standardise, X, y, n, a, ptrs, loss, grads,
+                                                                status, work);
+  } else {
+    if (set_smem(k_var_elbo_fg<false>, smem)) return -1;
+    k_var_elbo_fg<false><<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, lik, standardise, X, y, n, a, ptrs, loss, grads,
+                                                                 status, work);
+  }
   return after_launch("stp_var_elbo_fg");
 }
 
@@ -595,12 +622,19 @@ int stp_var_acq(int B, int n_cap, int d, int N, int lik, const double* pool, con
   if (!best_f && !y) return fail("best_f or y required");
   if (B == 0) return 0;
   const size_t smem = (var_smem_doubles(n_cap, d) + (size_t)n_cap * kTC + (size_t)kMaxD * kTC + 8 * kTC * 3) * sizeof(double);
-  if (set_smem(k_var_acq, smem)) return -1;
-  k_var_acq<<<B, 256, smem, (cudaStream_t)stream>>>(
-      n_cap, d, N, lik, pool, pool_id, mask,
-      VarPtrs{const_cast<double*>(Z), const_cast<double*>(hyp), const_cast<double*>(nat1), const_cast<double*>(nat2),
-              nullptr, nullptr},
-      n, best_f, S, eps, seed, out_idx, out_acq, mean, var, acq, update, pool_y, X, y, trace, status, work, order);
+  const VarPtrs ptrs{const_cast<double*>(Z), const_cast<double*>(hyp), const_cast<double*>(nat1),
+                     const_cast<double*>(nat2), nullptr, nullptr};
+  if (n_cap > kVarSmemSquareMax) {
+    if (set_smem(k_var_acq<true>, smem)) return -1;
+    k_var_acq<true><<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, N, lik, pool, pool_id, mask, ptrs, n, best_f, S, eps,
+                                                            seed, out_idx, out_acq, mean, var, acq, update, pool_y, X, y,
+                                                            trace, status, work, order);
+  } else {
+    if (set_smem(k_var_acq<false>, smem)) return -1;
+    k_var_acq<false><<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, N, lik, pool, pool_id, mask, ptrs, n, best_f, S, eps,
+                                                             seed, out_idx, out_acq, mean, var, acq, update, pool_y, X, y,
+                                                             trace, status, work, order);
+  }
   return after_launch("stp_var_acq");
 }
 

@@ -105,18 +105,22 @@ struct VarSmem {
   double* small; // 96
   double* red;   // 16 * kMaxWarps
   double* M0;    // (cap+1) x ld: the step-sequential routines (sweep, Cholesky, triangular inverse) run here
+  double* panels; // three panels of the blocked (DMMA) sweep, or nullptr: the pair sweep is used then
   int cap, ld;
 };
 
 // Above this capacity the square M0 no longer fits in shared memory next to the vectors: it then lives in the
 // campaign's global workspace (an eighth square, L2-resident); the routines are the same, only slower per step.
 constexpr int kVarSmemSquareMax = 144;
-STP_HD size_t var_smem_doubles(int cap, int d) {
+STP_HD size_t var_smem_doubles(int cap, int d, bool with_panels = false) {
   const size_t square = cap <= kVarSmemSquareMax ? (size_t)(cap + 1) * odd_ld(cap + 1) : 0;
-  return square + (size_t)2 * d * cap + (size_t)cap * 8 + 6 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
+  return square + (with_panels ? sweep_blocked_scratch_doubles(cap + 1) : 0) + (size_t)2 * d * cap + (size_t)cap * 8 + 6 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
 }
 
-STP_HD VarSmem var_smem_carve(double* base, int cap, int d) {
+// in_smem: where the working square lives (-1: decided by the capacity).  The kernels pass a compile-time constant
+// so that every access through M0 is compiled for ONE address space (a pointer that may be shared or global costs
+// generic loads / stores in the step-sequential routines: measured 6 % of the VarTGP bench).
+STP_HD VarSmem var_smem_carve(double* base, int cap, int d, bool with_panels = false, int in_smem = -1) {
   VarSmem s;
   s.cap = cap; s.ld = odd_ld(cap + 1);
   double* p = base;
@@ -138,7 +142,10 @@ STP_HD VarSmem var_smem_carve(double* base, int cap, int d) {
   s.gZ = p; p += (size_t)cap * d;
   s.small = p; p += 96;
   s.red = p; p += 16 * kMaxWarps;
-  s.M0 = cap <= kVarSmemSquareMax ? p : nullptr;   // nullptr: bound to the workspace by var_bind()
+  const bool square_here = in_smem < 0 ? (cap <= kVarSmemSquareMax) : (in_smem != 0);
+  s.M0 = square_here ? p : nullptr;   // nullptr: bound to the workspace by var_bind()
+  if (square_here) p += (size_t)(cap + 1) * s.ld;
+  s.panels = with_panels ? p : nullptr;
   return s;
 }
 
@@ -161,6 +168,19 @@ STP_HD VarWork var_work_carve(double* base, int cap) {
   return w;
 }
 STP_HD void var_bind(VarSmem& s, const VarWork& w) { if (!s.M0) s.M0 = w.M0g; }
+
+// Bordered sweep of P = -2 Theta_2 (in s.M0): blocked tensor-core form when the launch carved its panels (device,
+// shared-memory square, room for two CTAs per SM), pair sweep otherwise.
+template <class Team>
+STP_HD int var_sweep(const Team& tm, const VarSmem& s, int n) {
+  return sweep_bordered4(tm, s.M0, s.ld, n + 1, n, s.c0, s.c1, s.c2, s.c3, s.piv);
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ int var_sweep(const CtaTeam& tm, const VarSmem& s, int n) {
+  if (s.panels) return sweep_bordered_blocked(tm, s.M0, s.ld, n + 1, n, s.panels, s.piv);
+  return sweep_bordered4(tm, s.M0, s.ld, n + 1, n, s.c0, s.c1, s.c2, s.c3, s.piv);
+}
+#endif
 
 // log p(y | f) and its derivatives for one quadrature node.
 struct LikConst {   // per-epoch constants of the likelihood
@@ -239,7 +259,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
     else for (int j = tm.lane(); j <= n; j += W) row[j] = (j < n) ? M.nat1[j] : 0.0;
   }
   tm.sync();
-  if (sweep_bordered4(tm, M0, ld, n + 1, n, s.c0, s.c1, s.c2, s.c3, s.piv)) { out.status = 1; return out; }
+  if (var_sweep(tm, s, n)) { out.status = 1; return out; }
   double kl_acc[4] = {0.0, 0.0, 0.0, 0.0};   // sum log piv(P), tr S, mu.mu
   for (int i = tm.rank(); i < n; i += tm.size()) {
     const double m = M0[n * ld + i];
