@@ -35,7 +35,9 @@ extern "C" {
 #endif
 
 #define STP_MAX_D 8
-#define STP_MAX_N 144   /* exact-GP entry points: (n_cap + 1)^2 doubles + the pool tile must fit in 227 KB of shared memory */
+#define STP_MAX_N 144   /* exact-GP entry points: (n_cap + 1)^2 doubles + the pool tile must fit in 227 KB of shared memory;
+                           stp_exact_fit / stp_exact_bo_step also hold the optimiser state there: n_cap <= 142, beyond
+                           that they return an error ("campaign does not fit in shared memory") */
 #define STP_MAX_N_VAR 272   /* variational entry points: above 144 the working square moves to the global workspace */
 #define STP_ABI_VERSION 1
 

@@ -318,3 +318,44 @@ def test_n_max_smaller_than_a_training_set_stops_that_campaign(L):
         L.exact_bo_step(X.cuda().unsqueeze(0).contiguous(), y.cuda().unsqueeze(0).contiguous(),
                         torch.zeros(2, dtype=torch.int32, device="cuda"), mask.cuda(), Xb, yb, nb, trace_t.cuda(),
                         priors.exact_theta0(d), lo, hi, priors.exact_prior_vector(d), status, n_max=32)
+
+
+def test_largest_supported_exact_campaigns(L):
+    """n_cap = 142 is the largest capacity whose shared-memory carve-up with the optimiser state fits in 227 KB
+    (144 without it).  Closure parity at n = 96 ... 141 (7 - 9 tile rows in the blocked sweep, partial last blocks),
+    then fit + fused acquisition of the n = 141 campaign against the oracle."""
+    from stpbenchmark_b200 import priors, synthetic
+    X, y = synthetic.cfg4_pool(1)
+    d, cap, ns = X.shape[1], 142, [96, 97, 120, 141]
+    g = torch.Generator().manual_seed(11)
+    sels = [torch.randperm(len(X), generator=g)[:n] for n in ns]
+    Xb = torch.zeros(len(ns), cap, d, dtype=torch.double); yb = torch.zeros(len(ns), cap, dtype=torch.double)
+    for b, sel in enumerate(sels):
+        Xb[b, :ns[b]] = X[sel]; yb[b, :ns[b]] = y[sel]
+    Xb, yb = Xb.cuda(), yb.cuda()
+    nb = torch.tensor(ns, dtype=torch.int32, device="cuda")
+    rng = np.random.default_rng(5)
+    th = np.stack([np.array(priors.exact_theta0(d)) * rng.uniform(0.7, 1.5, d + 3) for _ in ns])
+    f, gr, st = L.exact_mll_fg(Xb, yb, torch.tensor(th, device="cuda"), priors.exact_prior_vector(d), n=nb)
+    assert st.tolist() == [0] * len(ns)
+    for b, (n, sel) in enumerate(zip(ns, sels)):
+        fo, go = oexact.mll_value_and_grad(th[b], X[sel], y[sel])
+        assert abs(f[b].item() - fo) <= 1e-8 * max(1.0, abs(fo))
+        assert np.abs(gr[b].cpu().numpy() - go).max() <= 1e-8 * max(1.0, np.abs(go).max())
+    # device fit of the largest one, then the fused pool pass at the device optimum
+    lo, hi = priors.exact_bounds(d)
+    theta = torch.tensor([priors.exact_theta0(d)], dtype=torch.double, device="cuda")
+    fit = L.exact_fit(Xb[3:4].contiguous(), yb[3:4].contiguous(), theta, lo, hi, priors.exact_prior_vector(d), n=nb[3:4].contiguous())
+    assert int(fit[3].item()) == 0
+    sel = sels[3]
+    mask = torch.ones(1, len(X), dtype=torch.uint8); mask[0, sel] = 0
+    best = torch.tensor([float(y[sel].max())], dtype=torch.double)
+    out = L.exact_acq(X.cuda().unsqueeze(0).contiguous(), Xb[3:4].contiguous(), yb[3:4].contiguous(), theta, best_f=best.cuda(),
+                      mask=mask.cuda(), n=nb[3:4].contiguous(), want_pointwise=True)
+    assert out["status"].tolist() == [0]
+    mean, var = oexact.posterior_exact(theta[0].cpu().numpy(), X[sel], y[sel], X)
+    acq = oacq.log_ei(mean, var, y[sel].max())
+    assert (out["mean"][0].cpu() - mean).abs().max() <= 1e-8 * mean.abs().max()
+    assert ((out["var"][0].cpu() - var).abs() / var.abs()).max() <= 1e-7
+    ref = acq.clone(); ref[mask[0] == 0] = -float("inf")
+    assert out["idx"][0].item() == int(torch.argmax(ref))
