@@ -198,7 +198,10 @@ def run_cuda_arm(args):
     PX = torch.stack([p[0] for p in pools]); PY = torch.stack([p[1] for p in pools])
     pool_id = [b // per_pool if per_pool else 0 for b in range(B)]
     pool_id = [min(p, N_POOLS - 1) for p in pool_id]
-    NG = max(1, min(args.groups, B // 64 if B >= 64 else 1))
+    NG = max(1, min(args.groups, B // 16 if B >= 16 else 1))
+    queue = args.schedule == "queue"           # persistent work-queue kernel: K iterations per campaign in ONE launch
+    if queue and args.groups == 16:
+        NG = 1
     bounds = [(g * B // NG, (g + 1) * B // NG) for g in range(NG)]
     if args.schedule == "cohort":                             # one age per group, groups evenly staggered
         group_of = [next(g for g, (lo, hi) in enumerate(bounds) if lo <= b < hi) for b in range(B)]
@@ -242,6 +245,8 @@ def run_cuda_arm(args):
             if args.schedule == "cohort":                    # the whole group runs its common age
                 for t in range(age0[self.lo]):
                     bt.step()
+            elif queue:                                      # one persistent launch: campaign b does age0[b] iterations
+                bt.run_queue([age0[b] for b in range(self.lo, self.hi)])
             else:
                 bt.status.fill_(-1)                          # not started yet
                 for t in range(N_TRIALS):
@@ -281,8 +286,11 @@ def run_cuda_arm(args):
                 fn(gr)
 
     # ---- device-resident arm: W warm-up + K timed steps ------------------------------------
-    for _ in range(W):
-        all_groups(lambda gr: gr.step())
+    if queue:
+        all_groups(lambda gr: gr.batch.run_queue(W))
+    else:
+        for _ in range(W):
+            all_groups(lambda gr: gr.step())
     barrier()
     def totals():
         return (float(sum(gr.batch.work_acc.sum().item() for gr in groups)),
@@ -294,8 +302,11 @@ def run_cuda_arm(args):
     ev0.record()                                             # default stream, right after the synchronize
     for gr in groups:
         gr.stream.wait_event(ev0)
-    for k in range(K):
-        all_groups(lambda gr: gr.step())
+    if queue:
+        all_groups(lambda gr: gr.batch.run_queue(K))
+    else:
+        for k in range(K):
+            all_groups(lambda gr: gr.step())
     ends = []
     for gr in groups:
         e = torch.cuda.Event(enable_timing=True)
@@ -543,13 +554,17 @@ def main():
     ap.add_argument("--campaigns", type=int, default=1024, help="campaigns per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--groups", type=int, default=16, help="campaign groups per GPU, one CUDA stream each (at most B / 64)")
-    ap.add_argument("--schedule", default="cohort", choices=["mixed", "cohort"],
+    ap.add_argument("--schedule", default="cohort", choices=["mixed", "cohort", "queue"],
                     help="mixed: every group holds campaigns of all ages; cohort: the campaigns of a group share their "
                          "age (groups staggered over the 80 trials), so each launch is sized for its own n")
     ap.add_argument("--model", default="ExactGP", choices=["ExactGP", "VarGP", "VarTGP", "VarLGP"],
                     help="ExactGP = the headline workload; the others run the secondary variational workload")
     ap.add_argument("--epochs", type=int, default=600)
+    ap.add_argument("--trials", type=int, default=N_TRIALS,
+                    help="trials per campaign (diagnostic: 80 is the workload; smaller keeps n = 10..9+trials)")
     args = ap.parse_args()
+    if args.trials != N_TRIALS:
+        globals().update(N_TRIALS=args.trials, CAP=N_INITIAL + args.trials + 1)
     if args.impl == "reference":
         args.steps = max(1, min(args.steps, N_TRIALS - args.warmup))  # one campaign per core has 80 trials
         run_reference_arm(args)

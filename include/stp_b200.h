@@ -125,6 +125,22 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
                       int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
                       int32_t* iters_acc, int n_max, void* stream);
 
+/* The same loop body as a PERSISTENT launch over a work queue: one CTA per SM slot (as many as are resident at the
+ * launch's shared-memory footprint, at most max_ctas if max_ctas > 0) serves the B campaigns from a ticket ring; a
+ * work item is one BO iteration of one campaign, and campaign b is advanced until iters_left[b] (int32[B], in/out,
+ * decremented per completed iteration) reaches 0 or its status becomes non-zero.  Campaigns advance independently
+ * -- nobody waits for the slowest fit of a lock-step batch -- so one call replaces iters x stp_exact_bo_step
+ * (runners.py:64-109 inside `for trial in range(n_trials)`, runners.py:64) with identical per-campaign results.
+ * sched: int32[B + 1] scratch (busy flags + ticket counter), zero it once after allocation.
+ * n_max: upper bound of n[b] + iters_left[b] over the campaigns (what a training set can grow to in this launch),
+ * 0 = n_cap - 1; other arguments as for stp_exact_bo_step (order = ring order of the campaigns). */
+int stp_exact_bo_run(int B, int n_cap, int d, int N, const double* pool, const double* pool_y,
+                     const int32_t* pool_id, uint8_t* mask, double* X, double* y, int32_t* n, int32_t* trace,
+                     const double* theta0, const double* lower, const double* upper, const double* prior,
+                     const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
+                     int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
+                     int32_t* iters_acc, int n_max, int32_t* iters_left, int32_t* sched, int max_ctas, void* stream);
+
 /* ---- variational models: VarGP / VarTGP / VarLGP (models.py:114-202, 18-111, 205-297) ---------------
  * State arrays (device, caller-owned, batch-major): Z [B, n_cap, d] inducing locations, hyp [B, d+4] =
  * (constant, lengthscale_1..d, outputscale, noise, raw_deg_free), nat1 [B, n_cap], nat2 [B, n_cap, n_cap]
@@ -180,14 +196,21 @@ int stp_philox_normal(unsigned long long seed, unsigned long long stream_id, uns
 int stp_log_ei(long long count, const double* mean, const double* var, double best_f, double* out, void* stream);
 
 /* Sustained FP64 FMA throughput probe (roofline denominator; MEASURED_PEAKS.json has no FP64
- * figure).  Runs `iters` dependent-chain-free DFMA batches on every SM; *flops_out (device,
- * double) receives the number of floating-point operations executed. */
+ * figure).  Launches 148 * 8 CTAs x 256 threads, each running iters x 16 x 8 independent DFMAs
+ * (= 2 flop each; the caller times the launch with CUDA events and divides).  `sink` (device,
+ * one double) only keeps the loop alive: nothing meaningful is written to it. */
 int stp_fp64_probe(int iters, double* sink, void* stream);
 
 /* The same probe on the fp64 tensor-core path (mma.sync.m8n8k4.f64, DMMA): per launch 148 * 8 CTAs x 8 warps x
  * iters x 16 x 8 instructions of 256 MAC.  The sweep, the pool-pass product and the variational contractions
  * issue DMMA; on B200 its peak equals the DFMA peak. */
 int stp_fp64_mma_probe(int iters, double* sink, void* stream);
+
+/* Diagnostic: per-phase cycle counters of stp_exact_bo_step (clock64 of thread 0 of every CTA, summed over CTAs;
+ * ids in csrc/team.cuh).  Only in libraries built with -DSTP_PHASE_TIMERS (tools/gpu_phase_timers.py builds one
+ * beside the shipped library); the shipped build returns an error.  out32: HOST array of 32 counters (may be
+ * NULL); reset != 0 zeroes them.  Synchronises the device. */
+int stp_phase_timers(unsigned long long* out32, int reset);
 
 #ifdef __cplusplus
 }

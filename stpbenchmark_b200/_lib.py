@@ -14,7 +14,8 @@ from typing import Optional
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libstp_b200.so")
+# STP_LIB: load another build of the same library (diagnostic variants, e.g. tools/gpu_phase_timers.py)
+LIB_PATH = os.environ.get("STP_LIB") or os.path.join(_PKG, "libstp_b200.so")
 _lib = None
 
 MAX_D = 8
@@ -161,6 +162,27 @@ def exact_bo_step(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, up
                                    ctypes.c_int(int(n_max)), _stream()), "stp_exact_bo_step")
 
 
+def exact_bo_run(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upper, prior, status, iters_left, sched,
+                 theta_out=None, acq_out=None, nit=None, nfev=None, opts: Optional[LbfgsbOpts] = None, order=None,
+                 turnover: Optional[Turnover] = None, work_acc=None, iters_acc=None, n_max: int = 0, max_ctas: int = 0):
+    """Persistent work-queue form of exact_bo_step: every campaign b is advanced ``iters_left[b]`` iterations in ONE
+    launch (see stp_exact_bo_run).  ``sched``: int32 [B + 1] scratch, zeroed once by the caller."""
+    _require_cuda(pool, pool_y, pool_id, mask, X, y, n, trace, status, iters_left, sched, theta_out, acq_out, nit, nfev,
+                  order, work_acc, iters_acc)
+    B, n_cap, d = X.shape
+    N = pool.shape[-2]
+    if sched.numel() < B + 1 or sched.dtype != torch.int32 or iters_left.dtype != torch.int32:
+        raise ValueError("sched must be int32 [B + 1] and iters_left int32 [B]")
+    lo, hi = _bounds(lower, upper, d + 3)
+    o = opts or LbfgsbOpts.scipy_defaults()
+    _check(lib().stp_exact_bo_run(B, n_cap, d, N, _p(pool), _p(pool_y), _p(pool_id), _p(mask), _p(X), _p(y), _p(n),
+                                  _p(trace), _host(theta0), lo, hi, _host(prior), ctypes.byref(o), _p(theta_out),
+                                  _p(acq_out), _p(nit), _p(nfev), _p(status), _p(order),
+                                  ctypes.byref(turnover) if turnover is not None else None, _p(work_acc), _p(iters_acc),
+                                  ctypes.c_int(int(n_max)), _p(iters_left), _p(sched), ctypes.c_int(int(max_ctas)),
+                                  _stream()), "stp_exact_bo_run")
+
+
 def log_ei(mean: torch.Tensor, var: torch.Tensor, best_f: float) -> torch.Tensor:
     """Elementwise analytic LogEI on the device; output has the shape of ``mean``."""
     _require_cuda(mean, var)
@@ -170,6 +192,18 @@ def log_ei(mean: torch.Tensor, var: torch.Tensor, best_f: float) -> torch.Tensor
     _check(lib().stp_log_ei(ctypes.c_longlong(mean.numel()), _p(mean), _p(var), ctypes.c_double(best_f), _p(out),
                             _stream()), "stp_log_ei")
     return out
+
+
+PHASE_NAMES = {0: "load", 1: "gram", 2: "sweep_A", 3: "sweep_B", 4: "sweep_C", 5: "gradient", 6: "reduce", 7: "advance",
+               8: "factorise", 9: "pool_pass", 10: "update", 11: "adv_build_B", 12: "adv_cauchy", 13: "adv_subsm",
+               14: "adv_ls_start", 15: "adv_ls_step", 16: "closures", 17: "sweep_blocks", 18: "campaigns"}
+
+
+def phase_timers(reset: bool = False) -> dict:
+    """Per-phase cycle counters of stp_exact_bo_step (only in a -DSTP_PHASE_TIMERS build, see stp_phase_timers)."""
+    out = (ctypes.c_ulonglong * 32)()
+    _check(lib().stp_phase_timers(out, int(bool(reset))), "stp_phase_timers")
+    return {name: int(out[i]) for i, name in PHASE_NAMES.items()}
 
 
 def fp64_probe(iters: int = 4096) -> float:

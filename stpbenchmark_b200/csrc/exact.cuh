@@ -21,12 +21,12 @@ struct ExactPrior {               // LogNormal(loc, scale) on noise, outputscale
   double noise_loc, noise_scale, os_loc, os_scale, ls_loc, ls_scale;
 };
 
-STP_HD double lognormal_logpdf(double x, double loc, double scale) {
+STP_HD_NOINLINE double lognormal_logpdf(double x, double loc, double scale) {
   const double lx = log(x);
   const double z = lx - loc;
   return -lx - log(scale) - 0.5 * kLog2Pi - z * z / (2.0 * scale * scale);
 }
-STP_HD double lognormal_dlogpdf(double x, double loc, double scale) {
+STP_HD_NOINLINE double lognormal_dlogpdf(double x, double loc, double scale) {
   return -(1.0 + (log(x) - loc) / (scale * scale)) / x;
 }
 
@@ -91,6 +91,16 @@ STP_HD void exact_load(const Team& tm, const ExactSmem& s, int n, int d, const d
   tm.sync();
 }
 
+// Availability byte of pool point i.  Read through the L2 on the device: in the persistent campaign kernel the mask
+// row may have been written by another SM earlier in the same launch (this SM's L1 could hold a stale line).
+STP_HD uint8_t mask_byte(const uint8_t* mask, int i) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(mask + i);
+#else
+  return mask[i];
+#endif
+}
+
 // noise-free kernel value between training points i and j (direct differences, App. A.1)
 STP_HD double ard_rbf_tt(const double* Xt, int cap, int d, const double* invl, int i, int j, double os) {
   double r2 = 0.0;
@@ -127,11 +137,12 @@ STP_HD int exact_mll_fg(const Team& tm, const ExactSmem& s, int n, int d, const 
   const double noise = theta[0], cst = theta[1], os = theta[2];
   double* invl = s.small + 32;  // d doubles
   tm.sync();
-  for (int k = tm.rank(); k < d; k += tm.size()) invl[k] = 1.0 / theta[3 + k];
+  STP_OWNED(tm, k, d) invl[k] = 1.0 / theta[3 + k];
   int bad = !(noise > 0.0) || !(os > 0.0) || !(cst == cst);
-  for (int k = 0; k < d; ++k) bad |= !(theta[3 + k] > 0.0);
+  STP_ROLLED for (int k = 0; k < d; ++k) bad |= !(theta[3 + k] > 0.0);
   if (bad) { *f_out = NAN; return 2; }
   tm.sync();
+  STP_PHASE(-1); STP_COUNT(16);
   // K1: lower = K + noise I (to be swept), strict upper = K (kept for the gradient), border = y - c
   for (int i = tm.warp(); i <= n; i += tm.nwarps()) {
     double* row = s.A + i * ld;
@@ -149,9 +160,11 @@ STP_HD int exact_mll_fg(const Team& tm, const ExactSmem& s, int n, int d, const 
     }
   }
   tm.sync();
+  STP_PHASE(1);
   // K3+K4: bordered sweep -> -Kinv, alpha, -quad, pivots
   const int fail = exact_sweep(tm, s, n);
   if (fail) { *f_out = NAN; return 1; }
+  STP_PHASE(-1);
   const double* arow = s.A + n * ld;  // alpha
   // K5: reductions
   double acc[kMaxD + 5];
@@ -159,11 +172,13 @@ STP_HD int exact_mll_fg(const Team& tm, const ExactSmem& s, int n, int d, const 
   for (int q = 0; q < kMaxD + 5; ++q) acc[q] = 0.0;
   // acc[0] = sum log piv, acc[1] = sum W_ii, acc[2] = sum alpha, acc[3] = sum_{i>j} W_ij K_ij,
   // acc[4+k] = sum_{i>j} W_ij K_ij (x_ik - x_jk)^2, acc[4+d] = sum of the log-priors (one parameter per thread)
-  for (int k = tm.rank(); k < d + 2; k += tm.size())
-    acc[4 + d] += (k == 0)   ? lognormal_logpdf(noise, pr.noise_loc, pr.noise_scale)
-                  : (k == 1) ? lognormal_logpdf(os, pr.os_loc, pr.os_scale)
-                             : lognormal_logpdf(theta[1 + k], pr.ls_loc, pr.ls_scale);
-  for (int i = tm.rank(); i < n; i += tm.size()) {
+  STP_OWNED(tm, k, d + 2) {   // one call site: the inlined log() sequences are what made this part large
+    const double x = (k == 0) ? noise : ((k == 1) ? os : theta[1 + k]);
+    const double loc = (k == 0) ? pr.noise_loc : ((k == 1) ? pr.os_loc : pr.ls_loc);
+    const double sc = (k == 0) ? pr.noise_scale : ((k == 1) ? pr.os_scale : pr.ls_scale);
+    acc[4 + d] += lognormal_logpdf(x, loc, sc);
+  }
+  STP_ROLLED for (int i = tm.rank(); i < n; i += tm.size()) {
     const double ai = arow[i];
     acc[0] += log(s.piv[i]);
     acc[1] += ai * ai + s.A[i * ld + i];
@@ -186,6 +201,7 @@ STP_HD int exact_mll_fg(const Team& tm, const ExactSmem& s, int n, int d, const 
         }
     }
   }
+  STP_PHASE(5);
   tm.sum_vec(acc, 5 + d);
   const double quad = -s.A[n * ld + n];
   const double logN = -0.5 * (quad + acc[0] + n * kLog2Pi);
@@ -193,19 +209,28 @@ STP_HD int exact_mll_fg(const Team& tm, const ExactSmem& s, int n, int d, const 
   const double scale = -1.0 / n;
   const double f = total * scale;
   tm.sync();
-  if (tm.rank() == 0) {
-    g[0] = scale * (0.5 * acc[1] + lognormal_dlogpdf(noise, pr.noise_loc, pr.noise_scale));
-    g[1] = scale * acc[2];
-    g[2] = scale * (acc[3] / os + 0.5 * acc[1] + lognormal_dlogpdf(os, pr.os_loc, pr.os_scale));
-  }
-  for (int k = tm.rank(); k < d; k += tm.size()) {
-    const double l = theta[3 + k];
-    g[3 + k] = scale * (acc[4 + k] / (l * l * l) + lognormal_dlogpdf(l, pr.ls_loc, pr.ls_scale));
+  // parameter p of (noise, constant, outputscale, lengthscale_1..d) by thread p; one division / one prior call site:
+  //   g0 = scale (tr W / 2 + dlogp(noise)), g1 = scale sum alpha, g2 = scale (S_K / os + tr W / 2 + dlogp(os)),
+  //   g_{3+k} = scale (S_k / l_k^3 + dlogp(l_k))
+  STP_OWNED(tm, p, d + 3) {
+    if (p == 1) g[1] = scale * acc[2];
+    else {
+      const double x = (p == 0) ? noise : ((p == 2) ? os : theta[p]);
+      const double loc = (p == 0) ? pr.noise_loc : ((p == 2) ? pr.os_loc : pr.ls_loc);
+      const double sc = (p == 0) ? pr.noise_scale : ((p == 2) ? pr.os_scale : pr.ls_scale);
+      double data = 0.5 * acc[1];
+      if (p >= 2) {
+        const double q = acc[1 + p] / ((p == 2) ? os : x * x * x);
+        data = (p == 2) ? q + data : q;
+      }
+      g[p] = scale * (data + lognormal_dlogpdf(x, loc, sc));
+    }
   }
   tm.sync();
+  STP_PHASE(6);
   *f_out = f;
   int st = !(f == f) || !(fabs(f) <= 1.79e308);
-  for (int k = 0; k < d + 3; ++k) st |= !(g[k] == g[k]);
+  STP_ROLLED for (int k = 0; k < d + 3; ++k) st |= !(g[k] == g[k]);
   return st ? 2 : 0;
 }
 
@@ -219,7 +244,7 @@ STP_HD int exact_factorize(const Team& tm, const ExactSmem& s, int n, int d, con
   const double noise = theta[0], cst = theta[1], os = theta[2];
   double* invl = s.small + 32;
   tm.sync();
-  for (int k = tm.rank(); k < d; k += tm.size()) invl[k] = 1.0 / theta[3 + k];
+  STP_OWNED(tm, k, d) invl[k] = 1.0 / theta[3 + k];
   tm.sync();
   for (int i = tm.warp(); i < n; i += tm.nwarps()) {
     double* row = s.A + i * ld;
@@ -395,7 +420,7 @@ STP_HD void exact_acquire(const Team& tm, const ExactSmem& s, int n, int d, cons
       if (mean_out) mean_out[gi] = mean;
       if (var_out) var_out[gi] = var;
       if (acq_out) acq_out[gi] = a;
-      if ((!mask || mask[gi]) && acq_better(a, gi, run_v, run_i)) { run_v = a; run_i = gi; }
+      if ((!mask || mask_byte(mask, gi)) && acq_better(a, gi, run_v, run_i)) { run_v = a; run_i = gi; }
     }
   }
   tm.argmax(run_v, run_i);

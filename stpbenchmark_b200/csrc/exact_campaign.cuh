@@ -32,18 +32,20 @@ STP_HD ExactFitResult exact_fit_run(const Team& tm, const ExactSmem& s, LbfgsbSt
     double f;
     const int st = exact_mll_fg(tm, s, n, d, S->x, pr, &f, g);
     tm.sync();
+    STP_PHASE(-1);
     if (tm.warp() == 0) {
       if (st) {
         f = NAN;
-        for (int k = L.lane(); k < np; k += L.width()) g[k] = NAN;
+        STP_OWNED(L, k, np) g[k] = NAN;
         L.sync();
       }
       const int more = lbfgsb_advance(L, *S, f, g);
       if (L.lane() == 0) *flag = more;
     }
     tm.sync();
+    STP_PHASE(7);
   }
-  for (int k = tm.rank(); k < np; k += tm.size()) theta[k] = S->x[k];
+  STP_OWNED(tm, k, np) theta[k] = S->x[k];
   tm.sync();
   ExactFitResult r;
   r.f = S->f; r.nit = S->iter; r.nfev = S->nfev; r.status = S->status;

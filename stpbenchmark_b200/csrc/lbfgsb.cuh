@@ -23,7 +23,16 @@
 // matrices, dot products are shuffle reductions, the scalar bookkeeping (line search) is done by lane 0 -- or
 // SoloLanes (one thread, every loop serial) in the host emulation and the C++ unit tests.  The state lives
 // in shared memory; every routine leaves it consistent for all lanes (ends with L.sync()) and returns a
-// lane-uniform value.  The optimiser used to run on one thread (~40 % of the CTA's time at 38k it/s).
+// lane-uniform value.
+//
+// Code size is a first-class constraint here.  One warp runs this branchy state machine between two closures while
+// the other warps of the CTA wait, and the SM's instruction caches are small (L0 ~6 KB, L1.5 32 KB per SM, shared
+// GPC-level cache behind them): with every routine force-inlined at each call site and every `for (i = lane; i < n;
+// i += 32)` unrolled, the optimiser was 270 KB of SASS inside a 505 KB kernel, ran at ~32 cycles per instruction
+// (117 k cycles per step, 50 - 75 % of a CTA's time) and the GPC instruction cache sat at 40 % of its peak request
+// rate (profiles/r02_summary.md).  Hence: every routine exists ONCE (STP_HD_NOINLINE), lane-owned loops are
+// STP_OWNED (at most one trip per lane), serial loops are STP_ROLLED, divisions / square roots off the dependent
+// chains go through one out-of-line helper, reductions through warp_sum16 / warp_max16.
 #pragma once
 #include "exact.cuh"
 #include "team.cuh"
@@ -73,21 +82,26 @@ struct LbfgsbState {
 };
 
 // ------------------------------ small dense helpers -----------------------------------
+// IEEE division / square root, one copy (the inlined sequences are ~30 instructions each plus a slow path).
+STP_HD_NOINLINE double lb_div(double a, double b) { return a / b; }
+STP_HD_NOINLINE double lb_sqrt(double a) { return sqrt(a); }
+
 template <class LN>
 STP_HD double lb_dot(const LN& L, const double* a, const double* b, int n) {
   double s = 0.0;
-  for (int i = L.lane(); i < n; i += L.width()) s += a[i] * b[i];
+  STP_OWNED(L, i, n) s += a[i] * b[i];
   return L.sum(s);
 }
 
 template <class LN>
 STP_HD void lb_projgr(const LN& L, LbfgsbState& S) {
   double m = 0.0;
-  for (int i = L.lane(); i < S.np; i += L.width()) {
+  STP_OWNED(L, i, S.np) {
     double gi = S.g[i];
-    if (S.nbd[i] != 0) {
-      if (gi < 0.0) { if (S.nbd[i] >= 2) gi = fmax(S.x[i] - S.ub[i], gi); }
-      else { if (S.nbd[i] <= 2) gi = fmin(S.x[i] - S.lb[i], gi); }
+    const int nb = S.nbd[i];
+    if (nb != 0) {
+      if (gi < 0.0) { if (nb >= 2) gi = fmax(S.x[i] - S.ub[i], gi); }
+      else { if (nb <= 2) gi = fmin(S.x[i] - S.lb[i], gi); }
     }
     m = fmax(m, fabs(gi));
   }
@@ -105,7 +119,7 @@ STP_HD void lb_reset_memory(const LN& L, LbfgsbState& S) {
 }
 
 // B = theta I replayed through the stored (s, y) pairs, oldest first.  Returns 1 on breakdown.
-STP_HD int lb_build_B(const SoloLanes&, LbfgsbState& S) {
+STP_HD_NOINLINE int lb_build_B(const SoloLanes&, LbfgsbState& S) {
   const int n = S.np;
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < n; ++j) S.B[i][j] = (i == j) ? S.theta : 0.0;
@@ -130,7 +144,7 @@ STP_HD int lb_build_B(const SoloLanes&, LbfgsbState& S) {
 }
 #if defined(__CUDACC__)
 // Warp version: lane r keeps row r of B in registers, the pairs are replayed with shuffles.
-__device__ __forceinline__ int lb_build_B(const WarpLanes& L, LbfgsbState& S) {
+static __device__ __noinline__ int lb_build_B(const WarpLanes& L, LbfgsbState& S) {
   const int n = S.np, r = L.lane();
   const bool live = r < n;
   double Brow[kMaxP];
@@ -138,7 +152,7 @@ __device__ __forceinline__ int lb_build_B(const WarpLanes& L, LbfgsbState& S) {
   for (int c = 0; c < kMaxP; ++c) Brow[c] = (live && c == r) ? S.theta : 0.0;
   int broke = 0;
   const int col = S.col, head = S.head, mm = S.m;
-  for (int q = 0; q < col; ++q) {
+  STP_ROLLED for (int q = 0; q < col; ++q) {
     int p = head + q;
     if (p >= mm) p -= mm;
     const double* s = S.ws[p];
@@ -152,9 +166,7 @@ __device__ __forceinline__ int lb_build_B(const WarpLanes& L, LbfgsbState& S) {
     }
     const double Bs = Bs0 + Bs1;
     const double sr = live ? s[r] : 0.0, yr = live ? y[r] : 0.0;
-    double a = sr * Bs;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    const double a = warp_sum16(sr * Bs);
     if (!(a > 0.0) || !(ysp > 0.0)) { broke = 1; break; }
     const double ia = rcp_pos(a);
     const double ya = yr * ib, ba = Bs * ia;
@@ -176,28 +188,37 @@ __device__ __forceinline__ int lb_build_B(const WarpLanes& L, LbfgsbState& S) {
 }
 #endif
 
+// row i of B times a vector (serial over the <= 11 columns)
+STP_HD double lb_Brow_dot(const LbfgsbState& S, int i, const double* v, int n) {
+  double a = 0.0;
+  STP_ROLLED for (int j = 0; j < n; ++j) a += S.B[i][j] * v[j];
+  return a;
+}
+
 // ------------------------------ generalised Cauchy point -------------------------------
 // On exit S.z = x^cp and S.iwhere marks the variables fixed at a bound.
 template <class LN>
-STP_HD void lb_cauchy(const LN& L, LbfgsbState& S) {
-  const int n = S.np, W = L.width(), l0 = L.lane();
+STP_HD_NOINLINE void lb_cauchy(const LN& L, LbfgsbState& S) {
+  const int n = S.np, l0 = L.lane();
   double* xcp = S.z;
   double* dvec = S.sc_a; double* tbrk = S.sc_b; double* tall = S.sc_c;
   int* order = S.sc_i; int* hasb = S.sc_j;
   if (S.sbgnrm <= 0.0) {
-    for (int i = l0; i < n; i += W) xcp[i] = S.x[i];
+    STP_OWNED(L, i, n) xcp[i] = S.x[i];
     L.sync();
     return;
   }
-  for (int i = l0; i < n; i += W) {
+  int nb_own = 0;
+  STP_OWNED(L, i, n) {
     const double neggi = -S.g[i];
+    const int nbd = S.nbd[i];
     double tl = 0.0, tu = 0.0;
     int iw = S.iwhere[i];
     if (iw != 3 && iw != -1) {
-      if (S.nbd[i] <= 2) tl = S.x[i] - S.lb[i];
-      if (S.nbd[i] >= 2) tu = S.ub[i] - S.x[i];
-      const int xlower = S.nbd[i] <= 2 && tl <= 0.0;
-      const int xupper = S.nbd[i] >= 2 && tu <= 0.0;
+      if (nbd <= 2) tl = S.x[i] - S.lb[i];
+      if (nbd >= 2) tu = S.ub[i] - S.x[i];
+      const int xlower = nbd <= 2 && tl <= 0.0;
+      const int xupper = nbd >= 2 && tu <= 0.0;
       iw = 0;
       if (xlower) { if (neggi <= 0.0) iw = 1; }
       else if (xupper) { if (neggi >= 0.0) iw = 2; }
@@ -209,38 +230,39 @@ STP_HD void lb_cauchy(const LN& L, LbfgsbState& S) {
     double tb = 0.0, dv = 0.0;
     if (iw == 0 || iw == -1) {
       dv = neggi;
-      if (S.nbd[i] <= 2 && S.nbd[i] != 0 && neggi < 0.0) { tb = tl / (-neggi); hb = 1; }
-      else if (S.nbd[i] >= 2 && neggi > 0.0) { tb = tu / neggi; hb = 1; }
+      if (nbd <= 2 && nbd != 0 && neggi < 0.0) { tb = lb_div(tl, -neggi); hb = 1; }
+      else if (nbd >= 2 && neggi > 0.0) { tb = lb_div(tu, neggi); hb = 1; }
     }
     dvec[i] = dv; tall[i] = tb; hasb[i] = hb;
+    nb_own += hb;
   }
+  const int nbreak = L.isum(nb_own);
   L.sync();
   // breakpoints in ascending order (stable: ties keep the variable order, like the insertion sort it replaces)
-  int nbreak = 0;
-  for (int j = 0; j < n; ++j) nbreak += hasb[j];
-  for (int i = l0; i < n; i += W)
-    if (hasb[i]) {
-      const double ti = tall[i];
-      int rk = 0;
-      for (int j = 0; j < n; ++j) rk += (hasb[j] && (tall[j] < ti || (tall[j] == ti && j < i))) ? 1 : 0;
-      tbrk[rk] = ti; order[rk] = i;
-    }
+  if (nbreak > 0) {
+    STP_OWNED(L, i, n)
+      if (hasb[i]) {
+        const double ti = tall[i];
+        int rk = 0;
+        STP_ROLLED for (int j = 0; j < n; ++j) rk += (hasb[j] && (tall[j] < ti || (tall[j] == ti && j < i))) ? 1 : 0;
+        tbrk[rk] = ti; order[rk] = i;
+      }
+  }
   // derivatives of the quadratic model along the projected-gradient path
   double f1p = 0.0, f2p = 0.0;
-  for (int i = l0; i < n; i += W) {
-    double bd = 0.0;
-    for (int j = 0; j < n; ++j) bd += S.B[i][j] * dvec[j];
-    f1p -= dvec[i] * dvec[i];
-    f2p += dvec[i] * bd;
+  STP_OWNED(L, i, n) {
+    const double di = dvec[i], bd = lb_Brow_dot(S, i, dvec, n);
+    f1p -= di * di;
+    f2p += di * bd;
   }
   double f1 = L.sum(f1p), f2 = L.sum(f2p);
   L.sync();
   const double f2_org = -S.theta * f1;  // the col = 0 value, as in the published routine
   if (!(f2 > 0.0)) return;               // d = 0: x is its own Cauchy point
-  double dtm = -f1 / f2;
+  double dtm = lb_div(-f1, f2);
   double tsum = 0.0, tj = 0.0;
   int nfixed_all = 0;
-  for (int q = 0; q < nbreak; ++q) {
+  STP_ROLLED for (int q = 0; q < nbreak; ++q) {
     const double tj0 = tj;
     tj = tbrk[q];
     const double dt = tj - tj0;
@@ -258,23 +280,23 @@ STP_HD void lb_cauchy(const LN& L, LbfgsbState& S) {
     if (q == nbreak - 1 && nbreak == n) { dtm = dt; nfixed_all = 1; break; }
     // z = x(tsum) - x : fixed variables sit on their bounds, the others moved tsum * d
     f1p = 0.0; f2p = 0.0;
-    for (int i = l0; i < n; i += W) {
-      const double zi = (dvec[i] != 0.0 || S.iwhere[i] <= 0) ? tsum * dvec[i] : xcp[i] - S.x[i];
-      double bd = 0.0;
-      for (int j = 0; j < n; ++j) bd += S.B[i][j] * dvec[j];
-      f1p += dvec[i] * S.g[i];
-      f2p += dvec[i] * bd;
+    STP_OWNED(L, i, n) {
+      const double di = dvec[i];
+      const double zi = (di != 0.0 || S.iwhere[i] <= 0) ? tsum * di : xcp[i] - S.x[i];
+      const double bd = lb_Brow_dot(S, i, dvec, n);
+      f1p += di * S.g[i];
+      f2p += di * bd;
       f1p += zi * bd;
     }
     f1 = L.sum(f1p); f2 = L.sum(f2p);
     f2 = fmax(kEpsMch * f2_org, f2);
-    dtm = -f1 / f2;
+    dtm = lb_div(-f1, f2);
   }
   if (!nfixed_all) {
     if (dtm < 0.0) dtm = 0.0;
     tsum += dtm;
   }
-  for (int i = l0; i < n; i += W)
+  STP_OWNED(L, i, n)
     if (dvec[i] != 0.0) xcp[i] = S.x[i] + tsum * dvec[i];
   L.sync();
 }
@@ -283,74 +305,76 @@ STP_HD void lb_cauchy(const LN& L, LbfgsbState& S) {
 // Minimise the quadratic model over the variables free at x^cp, then project (v3.0).
 // On entry S.z = x^cp; on exit S.z = the subspace minimiser.  Returns 1 if B_FF is not PD.
 template <class LN>
-STP_HD int lb_subsm(const LN& L, LbfgsbState& S) {
-  const int n = S.np, W = L.width(), l0 = L.lane();
+STP_HD_NOINLINE int lb_subsm(const LN& L, LbfgsbState& S) {
+  const int n = S.np, l0 = L.lane();
   int* ind = S.sc_j;
-  int nf = 0;
-  for (int i = 0; i < n; ++i) nf += (S.iwhere[i] <= 0) ? 1 : 0;
+  int nf_own = 0;
+  STP_OWNED(L, i, n) nf_own += (S.iwhere[i] <= 0) ? 1 : 0;
+  const int nf = L.isum(nf_own);
   if (nf == 0 || S.col == 0) return 0;
   L.sync();
-  for (int i = l0; i < n; i += W)
+  STP_OWNED(L, i, n)
     if (S.iwhere[i] <= 0) {
       int pos = 0;
-      for (int j = 0; j < i; ++j) pos += (S.iwhere[j] <= 0) ? 1 : 0;
+      STP_ROLLED for (int j = 0; j < i; ++j) pos += (S.iwhere[j] <= 0) ? 1 : 0;
       ind[pos] = i;
     }
+  // z - x, once (the rows of B_FF need it nf times)
+  double* dz = S.sc_d;
+  STP_OWNED(L, i, n) dz[i] = S.z[i] - S.x[i];
   L.sync();
   double* rr = S.sc_a; double* dd = S.sc_b; double* idiag = S.sc_c; double* sol = S.sc_e;
   double (*C)[kMaxP] = S.sc_C;
-  for (int a = l0; a < nf; a += W) {
+  STP_OWNED(L, a, nf) {
     const int i = ind[a];
-    double bz = 0.0;
-    for (int j = 0; j < n; ++j) bz += S.B[i][j] * (S.z[j] - S.x[j]);
-    rr[a] = -(S.g[i] + bz);
-    for (int b = 0; b <= a; ++b) C[a][b] = S.B[i][ind[b]];
+    rr[a] = -(S.g[i] + lb_Brow_dot(S, i, dz, n));
+    STP_ROLLED for (int b = 0; b <= a; ++b) C[a][b] = S.B[i][ind[b]];
   }
   L.sync();
   // Cholesky of B_FF, column by column; the rows of a column in parallel (C[j][j] keeps l_jj^2, 1 / l_jj in idiag)
-  for (int j = 0; j < nf; ++j) {
-    for (int i = j + l0; i < nf; i += W) {
-      double v = C[i][j];
-      for (int k = 0; k < j; ++k) v -= C[i][k] * C[j][k];
-      C[i][j] = v;
-    }
+  STP_ROLLED for (int j = 0; j < nf; ++j) {
+    STP_OWNED(L, i, nf)
+      if (i >= j) {
+        double v = C[i][j];
+        STP_ROLLED for (int k = 0; k < j; ++k) v -= C[i][k] * C[j][k];
+        C[i][j] = v;
+      }
     L.sync();
     const double s = C[j][j];
     if (!(s > 0.0)) return 1;
     const double il = rsqrt_pos(s);
     if (l0 == 0) idiag[j] = il;
-    for (int i = j + 1 + l0; i < nf; i += W) C[i][j] *= il;
+    STP_OWNED(L, i, nf)
+      if (i > j) C[i][j] *= il;
     L.sync();
   }
-  for (int j = 0; j < nf; ++j) {          // forward substitution, column-oriented
+  STP_ROLLED for (int j = 0; j < nf; ++j) {          // forward substitution, column-oriented
     const double dj = rr[j] * idiag[j];
     if (l0 == 0) dd[j] = dj;
-    for (int i = j + 1 + l0; i < nf; i += W) rr[i] -= C[i][j] * dj;
+    STP_OWNED(L, i, nf)
+      if (i > j) rr[i] -= C[i][j] * dj;
     L.sync();
   }
-  for (int j = nf - 1; j >= 0; --j) {     // back substitution
+  STP_ROLLED for (int j = nf - 1; j >= 0; --j) {     // back substitution
     const double dj = dd[j] * idiag[j];
     if (l0 == 0) sol[j] = dj;
-    for (int i = l0; i < j; i += W) dd[i] -= C[j][i] * dj;
+    STP_OWNED(L, i, j) dd[i] -= C[j][i] * dj;
     L.sync();
   }
   // projection of x^cp + d onto the box
-  for (int i = l0; i < n; i += W) S.xp[i] = S.z[i];
+  STP_OWNED(L, i, n) S.xp[i] = S.z[i];
   L.sync();
   int iw = 0;
-  for (int a = l0; a < nf; a += W) {
+  STP_OWNED(L, a, nf) {
     const int k = ind[a];
-    const double xk = S.z[k], dk = sol[a];
-    double zk;
-    if (S.nbd[k] != 0) {
-      if (S.nbd[k] == 1) { zk = fmax(S.lb[k], xk + dk); if (zk == S.lb[k]) iw = 1; }
-      else if (S.nbd[k] == 2) {
-        const double v = fmax(S.lb[k], xk + dk);
-        zk = fmin(S.ub[k], v);
-        if (zk == S.lb[k] || zk == S.ub[k]) iw = 1;
-      } else { zk = fmin(S.ub[k], xk + dk); if (zk == S.ub[k]) iw = 1; }
-    } else {
-      zk = xk + dk;
+    const int nbd = S.nbd[k];
+    const double zk0 = S.z[k] + sol[a];
+    double zk = zk0;
+    if (nbd != 0) {
+      const double lo = S.lb[k], hi = S.ub[k];
+      if (nbd <= 2) zk = fmax(lo, zk);
+      if (nbd >= 2) zk = fmin(hi, zk);
+      if ((nbd <= 2 && zk == lo) || (nbd >= 2 && zk == hi)) iw = 1;
     }
     S.z[k] = zk;
   }
@@ -358,24 +382,24 @@ STP_HD int lb_subsm(const LN& L, LbfgsbState& S) {
   L.sync();
   if (!iword) return 0;
   double ddpp = 0.0;
-  for (int i = l0; i < n; i += W) ddpp += (S.z[i] - S.x[i]) * S.g[i];
+  STP_OWNED(L, i, n) ddpp += (S.z[i] - S.x[i]) * S.g[i];
   const double ddp = L.sum(ddpp);
   L.sync();
   if (ddp > 0.0) {
     if (l0 == 0) {   // rare path, kept serial: the running `temp1` makes the published loop order-dependent
-      for (int i = 0; i < n; ++i) S.z[i] = S.xp[i];
+      STP_ROLLED for (int i = 0; i < n; ++i) S.z[i] = S.xp[i];
       double alpha = 1.0, temp1 = 1.0;
       int ibd = -1;
-      for (int a = 0; a < nf; ++a) {
+      STP_ROLLED for (int a = 0; a < nf; ++a) {
         const int k = ind[a];
         const double dk = sol[a];
         if (S.nbd[k] != 0) {
           if (dk < 0.0 && S.nbd[k] <= 2) {
             const double t2 = S.lb[k] - S.z[k];
-            if (t2 >= 0.0) temp1 = 0.0; else if (dk * alpha < t2) temp1 = t2 / dk;
+            if (t2 >= 0.0) temp1 = 0.0; else if (dk * alpha < t2) temp1 = lb_div(t2, dk);
           } else if (dk > 0.0 && S.nbd[k] >= 2) {
             const double t2 = S.ub[k] - S.z[k];
-            if (t2 <= 0.0) temp1 = 0.0; else if (dk * alpha > t2) temp1 = t2 / dk;
+            if (t2 <= 0.0) temp1 = 0.0; else if (dk * alpha > t2) temp1 = lb_div(t2, dk);
           }
           if (temp1 < alpha) { alpha = temp1; ibd = a; }
         }
@@ -386,7 +410,7 @@ STP_HD int lb_subsm(const LN& L, LbfgsbState& S) {
         if (dk > 0.0) { S.z[k] = S.ub[k]; sol[ibd] = 0.0; }
         else if (dk < 0.0) { S.z[k] = S.lb[k]; sol[ibd] = 0.0; }
       }
-      for (int a = 0; a < nf; ++a) S.z[ind[a]] += alpha * sol[a];
+      STP_ROLLED for (int a = 0; a < nf; ++a) S.z[ind[a]] += alpha * sol[a];
     }
     L.sync();
   }
@@ -394,40 +418,46 @@ STP_HD int lb_subsm(const LN& L, LbfgsbState& S) {
 }
 
 // ------------------------------ More-Thuente line search -------------------------------
-STP_HD void lb_dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy, double& stp,
-                      double fp, double dp, int& brackt, double stpmin, double stpmax) {
-  const double sgnd = dp * (dx / fabs(dx));
-  double stpf, stpc, stpq, th, s, gamma, p, q, r;
+// cubic-interpolation helper shared by the four cases of dcstep: gamma = s sqrt(max(0, (th/s)^2 - (a/s)(b/s)))
+STP_HD_NOINLINE double lb_gamma(double th, double a, double b, int clamp) {
+  const double s = fmax(fabs(th), fmax(fabs(a), fabs(b)));
+  const double ts = lb_div(th, s);
+  double r = ts * ts - lb_div(a, s) * lb_div(b, s);
+  if (clamp) r = fmax(0.0, r);
+  return s * lb_sqrt(r);
+}
+
+STP_HD_NOINLINE void lb_dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy, double& stp,
+                               double fp, double dp, int& brackt, double stpmin, double stpmax) {
+  const double sgnd = dp * lb_div(dx, fabs(dx));
+  double stpf, stpc, stpq, th, gamma, p, q, r;
   if (fp > fx) {
-    th = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    s = fmax(fabs(th), fmax(fabs(dx), fabs(dp)));
-    gamma = s * sqrt((th / s) * (th / s) - (dx / s) * (dp / s));
+    th = lb_div(3.0 * (fx - fp), stp - stx) + dx + dp;
+    gamma = lb_gamma(th, dx, dp, 0);
     if (stp < stx) gamma = -gamma;
-    p = (gamma - dx) + th; q = ((gamma - dx) + gamma) + dp; r = p / q;
+    p = (gamma - dx) + th; q = ((gamma - dx) + gamma) + dp; r = lb_div(p, q);
     stpc = stx + r * (stp - stx);
-    stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
+    stpq = stx + (lb_div(dx, lb_div(fx - fp, stp - stx) + dx) / 2.0) * (stp - stx);
     stpf = (fabs(stpc - stx) < fabs(stpq - stx)) ? stpc : stpc + (stpq - stpc) / 2.0;
     brackt = 1;
   } else if (sgnd < 0.0) {
-    th = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    s = fmax(fabs(th), fmax(fabs(dx), fabs(dp)));
-    gamma = s * sqrt((th / s) * (th / s) - (dx / s) * (dp / s));
+    th = lb_div(3.0 * (fx - fp), stp - stx) + dx + dp;
+    gamma = lb_gamma(th, dx, dp, 0);
     if (stp > stx) gamma = -gamma;
-    p = (gamma - dp) + th; q = ((gamma - dp) + gamma) + dx; r = p / q;
+    p = (gamma - dp) + th; q = ((gamma - dp) + gamma) + dx; r = lb_div(p, q);
     stpc = stp + r * (stx - stp);
-    stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    stpq = stp + lb_div(dp, dp - dx) * (stx - stp);
     stpf = (fabs(stpc - stp) > fabs(stpq - stp)) ? stpc : stpq;
     brackt = 1;
   } else if (fabs(dp) < fabs(dx)) {
-    th = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
-    s = fmax(fabs(th), fmax(fabs(dx), fabs(dp)));
-    gamma = s * sqrt(fmax(0.0, (th / s) * (th / s) - (dx / s) * (dp / s)));
+    th = lb_div(3.0 * (fx - fp), stp - stx) + dx + dp;
+    gamma = lb_gamma(th, dx, dp, 1);
     if (stp > stx) gamma = -gamma;
-    p = (gamma - dp) + th; q = (gamma + (dx - dp)) + gamma; r = p / q;
+    p = (gamma - dp) + th; q = (gamma + (dx - dp)) + gamma; r = lb_div(p, q);
     if (r < 0.0 && gamma != 0.0) stpc = stp + r * (stx - stp);
     else if (stp > stx) stpc = stpmax;
     else stpc = stpmin;
-    stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    stpq = stp + lb_div(dp, dp - dx) * (stx - stp);
     if (brackt) {
       stpf = (fabs(stpc - stp) < fabs(stpq - stp)) ? stpc : stpq;
       if (stp > stx) stpf = fmin(stp + 0.66 * (sty - stp), stpf);
@@ -439,11 +469,10 @@ STP_HD void lb_dcstep(double& stx, double& fx, double& dx, double& sty, double& 
     }
   } else {
     if (brackt) {
-      th = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
-      s = fmax(fabs(th), fmax(fabs(dy), fabs(dp)));
-      gamma = s * sqrt((th / s) * (th / s) - (dy / s) * (dp / s));
+      th = lb_div(3.0 * (fp - fy), sty - stp) + dy + dp;
+      gamma = lb_gamma(th, dy, dp, 0);
       if (stp > sty) gamma = -gamma;
-      p = (gamma - dp) + th; q = ((gamma - dp) + gamma) + dy; r = p / q;
+      p = (gamma - dp) + th; q = ((gamma - dp) + gamma) + dy; r = lb_div(p, q);
       stpc = stp + r * (sty - stp);
       stpf = stpc;
     } else if (stp > stx) stpf = stpmax;
@@ -458,7 +487,7 @@ STP_HD void lb_dcstep(double& stx, double& fx, double& dx, double& sty, double& 
 }
 
 // One call of dcsrch with (f, g) at S.stp; updates S.stp and S.ls_task.
-STP_HD void lb_dcsrch(LbfgsbState& S, double f, double g) {
+STP_HD_NOINLINE void lb_dcsrch(LbfgsbState& S, double f, double g) {
   const double ftol = 1e-3, gtol = 0.9, xtol = 0.1, stpmin = 0.0, stpmax = S.stpmx;
   const double xtrapl = 1.1, xtrapu = 4.0;
   if (S.ls_task == 0) {
@@ -510,7 +539,7 @@ template <class LN>
 STP_HD void lbfgsb_init(const LN& L, LbfgsbState& S, int np, const double* x0, const double* lb, const double* ub,
                         const LbfgsbOpts& o) {
   int not_boxed = 0, bounded = 0;
-  for (int i = L.lane(); i < np; i += L.width()) {
+  STP_OWNED(L, i, np) {
     const int hl = lb[i] > -1.79e308, hu = ub[i] < 1.79e308;
     S.lb[i] = hl ? lb[i] : 0.0; S.ub[i] = hu ? ub[i] : 0.0;
     S.nbd[i] = hl ? (hu ? 2 : 1) : (hu ? 3 : 0);
@@ -538,52 +567,58 @@ STP_HD void lbfgsb_init(const LN& L, LbfgsbState& S, int np, const double* x0, c
 // first trial point of the line search.  Returns 1 when S.x holds a point to evaluate,
 // 0 when the run ended (S.status set).
 template <class LN>
-STP_HD int lb_begin_iteration(const LN& L, LbfgsbState& S) {
-  const int n = S.np, W = L.width(), l0 = L.lane();
-  for (int guard = 0; guard < 4; ++guard) {
+STP_HD_NOINLINE int lb_begin_iteration(const LN& L, LbfgsbState& S) {
+  const int n = S.np, l0 = L.lane();
+  STP_ROLLED for (int guard = 0; guard < 4; ++guard) {
+    STP_PHASE(15);
     if (S.col > 0) {
       if (lb_build_B(L, S)) { lb_reset_memory(L, S); continue; }   // breakdown while forming B
     } else {
       const double th = S.theta;
-      for (int i = l0; i < n; i += W)
-        for (int j = 0; j < n; ++j) S.B[i][j] = (i == j) ? th : 0.0;
+      STP_OWNED(L, i, n) {
+        STP_ROLLED for (int j = 0; j < n; ++j) S.B[i][j] = (i == j) ? th : 0.0;
+      }
       L.sync();
     }
+    STP_PHASE(11);
     if (!S.cnstnd && S.col > 0) {
-      for (int i = l0; i < n; i += W) S.z[i] = S.x[i];
+      STP_OWNED(L, i, n) S.z[i] = S.x[i];
       L.sync();
     } else {
       lb_cauchy(L, S);
     }
+    STP_PHASE(12);
     if (S.col > 0 && lb_subsm(L, S)) { lb_reset_memory(L, S); continue; }
+    STP_PHASE(13);
     // search direction and the line-search set-up (lnsrlb, first entry)
-    for (int i = l0; i < n; i += W) { S.d[i] = S.z[i] - S.x[i]; S.t[i] = S.x[i]; S.r[i] = S.g[i]; }
+    STP_OWNED(L, i, n) { S.d[i] = S.z[i] - S.x[i]; S.t[i] = S.x[i]; S.r[i] = S.g[i]; }
     L.sync();
     const double dtd = lb_dot(L, S.d, S.d, n);
     const double gd = lb_dot(L, S.g, S.d, n);
     if (l0 == 0) {
       S.dtd = dtd;
-      S.dnorm = sqrt(dtd);
+      S.dnorm = lb_sqrt(dtd);
       double stpmx = 1e10;
       if (S.cnstnd) {
         if (S.iter == 0) stpmx = 1.0;
         else {
-          for (int i = 0; i < n; ++i) {
+          STP_ROLLED for (int i = 0; i < n; ++i) {
             const double a1 = S.d[i];
-            if (S.nbd[i] != 0) {
-              if (a1 < 0.0 && S.nbd[i] <= 2) {
+            const int nbd = S.nbd[i];
+            if (nbd != 0) {
+              if (a1 < 0.0 && nbd <= 2) {
                 const double a2 = S.lb[i] - S.x[i];
-                if (a2 >= 0.0) stpmx = 0.0; else if (a1 * stpmx < a2) stpmx = a2 / a1;
-              } else if (a1 > 0.0 && S.nbd[i] >= 2) {
+                if (a2 >= 0.0) stpmx = 0.0; else if (a1 * stpmx < a2) stpmx = lb_div(a2, a1);
+              } else if (a1 > 0.0 && nbd >= 2) {
                 const double a2 = S.ub[i] - S.x[i];
-                if (a2 <= 0.0) stpmx = 0.0; else if (a1 * stpmx > a2) stpmx = a2 / a1;
+                if (a2 <= 0.0) stpmx = 0.0; else if (a1 * stpmx > a2) stpmx = lb_div(a2, a1);
               }
             }
           }
         }
       }
       S.stpmx = stpmx;
-      S.stp = (S.iter == 0 && !S.boxed) ? fmin(1.0 / S.dnorm, stpmx) : 1.0;
+      S.stp = (S.iter == 0 && !S.boxed) ? fmin(lb_div(1.0, S.dnorm), stpmx) : 1.0;
       S.fold = S.f;
       S.ifun = 0; S.iback = 0; S.ls_task = 0;
       S.gd = gd;
@@ -608,10 +643,10 @@ STP_HD int lb_begin_iteration(const LN& L, LbfgsbState& S) {
       continue;
     }
     const double stp = S.stp;
-    if (stp == 1.0) { for (int i = l0; i < n; i += W) S.x[i] = S.z[i]; }
-    else { for (int i = l0; i < n; i += W) S.x[i] = stp * S.d[i] + S.t[i]; }
+    STP_OWNED(L, i, n) S.x[i] = (stp == 1.0) ? S.z[i] : stp * S.d[i] + S.t[i];
     if (l0 == 0) { S.ifun = 1; S.nfev += 1; S.iback = 0; S.phase = 1; }
     L.sync();
+    STP_PHASE(14);
     return 1;
   }
   L.sync();
@@ -623,7 +658,7 @@ STP_HD int lb_begin_iteration(const LN& L, LbfgsbState& S) {
 // Give up the current line search: back to the iterate it started from.
 template <class LN>
 STP_HD void lb_restore_iterate(const LN& L, LbfgsbState& S) {
-  for (int i = L.lane(); i < S.np; i += L.width()) { S.x[i] = S.t[i]; S.g[i] = S.r[i]; }
+  STP_OWNED(L, i, S.np) { S.x[i] = S.t[i]; S.g[i] = S.r[i]; }
   if (L.lane() == 0) S.f = S.fold;
   L.sync();
 }
@@ -639,14 +674,14 @@ STP_HD int lb_finish(const LN& L, LbfgsbState& S, int status, int bump_iter) {
 // One transition of the state machine.  Returns 0 finished, 1 evaluate S.x, 2 S.x is the point
 // (f, g) already belong to (the caller feeds them again without evaluating).
 template <class LN>
-STP_HD int lb_advance_once(const LN& L, LbfgsbState& S, double f, const double* g) {
-  const int n = S.np, W = L.width(), l0 = L.lane();
+STP_HD_NOINLINE int lb_advance_once(const LN& L, LbfgsbState& S, double f, const double* g) {
+  const int n = S.np, l0 = L.lane();
   int badg = 0;
-  for (int i = l0; i < n; i += W) badg |= !(g[i] == g[i]);
+  STP_OWNED(L, i, n) badg |= !(g[i] == g[i]);
   const int finite = (f == f) && (fabs(f) <= 1.79e308) && !L.any(badg);
   const int phase = S.phase;
   L.sync();
-  for (int i = l0; i < n; i += W) S.g[i] = g[i];
+  STP_OWNED(L, i, n) S.g[i] = g[i];
   if (l0 == 0) { S.f = f; if (phase == 0) S.nfev = 1; }
   L.sync();
   if (phase == 0) {
@@ -676,7 +711,7 @@ STP_HD int lb_advance_once(const LN& L, LbfgsbState& S, double f, const double* 
     }
     const double stp = S.stp;
     int mv = 0;
-    for (int i = l0; i < n; i += W) {
+    STP_OWNED(L, i, n) {
       const double xi = (stp == 1.0) ? S.z[i] : stp * S.d[i] + S.t[i];
       mv |= (xi != S.x[i]);
       S.x[i] = xi;
@@ -706,7 +741,7 @@ STP_HD int lb_advance_once(const LN& L, LbfgsbState& S, double f, const double* 
   // BFGS pair
   const double stp = S.stp, gdn = S.gd, gdold = S.gdold;
   double rrp = 0.0, dr, dd;
-  for (int i = l0; i < n; i += W) {
+  STP_OWNED(L, i, n) {
     const double ri = S.g[i] - S.r[i];
     S.r[i] = ri;
     rrp += ri * ri;
@@ -726,9 +761,9 @@ STP_HD int lb_advance_once(const LN& L, LbfgsbState& S, double f, const double* 
     iupdat += 1;
     if (iupdat <= m) { col = iupdat; itail = (head + iupdat - 1) % m; }
     else { itail = (itail + 1) % m; head = (head + 1) % m; }
-    for (int i = l0; i < n; i += W) { S.ws[itail][i] = S.d[i]; S.wy[itail][i] = S.r[i]; }
-    if (l0 == 0) { S.updatd = 1; S.iupdat = iupdat; S.col = col; S.itail = itail; S.head = head; S.theta = rr / dr;
-                   S.ys[itail] = ysn; S.iys[itail] = 1.0 / ysn; }
+    STP_OWNED(L, i, n) { S.ws[itail][i] = S.d[i]; S.wy[itail][i] = S.r[i]; }
+    if (l0 == 0) { S.updatd = 1; S.iupdat = iupdat; S.col = col; S.itail = itail; S.head = head; S.theta = lb_div(rr, dr);
+                   S.ys[itail] = ysn; S.iys[itail] = lb_div(1.0, ysn); }
   }
   L.sync();
   return lb_begin_iteration(L, S);

@@ -260,6 +260,7 @@ __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double*
   for (int kb = 0; kb < npiv; kb += 8) {
     const int r = (npiv - kb < 8) ? (npiv - kb) : 8;
     const int kn = kb + 8;
+    STP_PHASE(-1); STP_COUNT(17);
     // ---- (A) elimination of D in registers: am = trailing block, xm = X (row g, columns 2q, 2q + 1)
     double am0, am1;
     if (g < r) {
@@ -297,6 +298,7 @@ __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double*
       if (warp == 0 && lane == 0 && k < r) piv[kb + k] = p;
     }
     if (fail) return fail;   // identical in every warp: the whole team leaves together
+    STP_PHASE(2);
     // operand fragments of X:  bw = X[g][4s + q] (B operand of C X^T),  bt = X[4s + q][g] (B operand of V X)
     double bw0, bw1, bt0, bt1;
     {
@@ -361,6 +363,7 @@ __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double*
       }
     }
     tm.sync();
+    STP_PHASE(3);
     // ---- (C) A -= V W^T on the lower triangle outside K, 16 x 16 tiles
     for (int t = warp; t < n_tiles; t += nw) {
       int I = 0, J = t;
@@ -425,6 +428,7 @@ __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double*
       }
     }
     tm.sync();
+    STP_PHASE(4);
     double* sw = C; C = Cn; Cn = sw;
   }
   return 0;

@@ -25,6 +25,12 @@ int fail_cuda(const char* where, cudaError_t e) {
 
 constexpr int kTC = 32;  // acquisition tile: one candidate per lane
 
+// extra dynamic shared memory per CTA (bytes; diagnostic: lowers the number of resident campaigns per SM)
+size_t smem_pad() {
+  const char* env = getenv("STP_SMEM_PAD");
+  return env ? (size_t)atol(env) : 0;
+}
+
 // launch bounds of the exact-GP kernels (overridable for A/B runs, tools/gpu_ab_exact.sh)
 #ifndef STP_EXACT_MINB
 #define STP_EXACT_MINB 2
@@ -136,75 +142,98 @@ __global__ void k_exact_acq(int n_cap, int d, int N, const double* __restrict__ 
   if (threadIdx.x == 0) { status[b] = 0; if (out_idx) out_idx[b] = bi; if (out_acq) out_acq[b] = bv; }
 }
 
-// The whole loop body runners.py:64-109 for one campaign.
-__global__ void __launch_bounds__(STP_EXACT_MAXT, STP_EXACT_MINB) k_exact_bo_step(int n_cap, int d, int N, const double* __restrict__ pool,
-                                const double* __restrict__ pool_y, const int32_t* __restrict__ pool_id,
-                                uint8_t* __restrict__ mask, double* __restrict__ X, double* __restrict__ y,
-                                int32_t* __restrict__ n_arr, int32_t* __restrict__ trace, BoundsArg bnd,
-                                PriorArg prior, LbfgsbOpts opts, double* __restrict__ theta_out,
-                                double* __restrict__ acq_out, int32_t* __restrict__ nit, int32_t* __restrict__ nfev,
-                                int32_t* __restrict__ status, const int32_t* __restrict__ order, stp_turnover turn,
-                                double* __restrict__ work_acc, int32_t* __restrict__ iters_acc, int s_cap) {
-  extern __shared__ double smem[];
-  const int b = order ? order[blockIdx.x] : blockIdx.x;   // longest-first scheduling: CTAs are issued in blockIdx order
-  if (status[b] != 0) return;  // frozen campaign
-  const int n = n_arr[b];
+// Arguments of one BO iteration (the whole loop body runners.py:64-109) shared by the two exact-GP campaign kernels.
+struct BoArgs {
+  int n_cap, d, N, s_cap;
+  const double* pool; const double* pool_y; const int32_t* pool_id;
+  uint8_t* mask; double* X; double* y; int32_t* n_arr; int32_t* trace;
+  BoundsArg bnd; PriorArg prior; LbfgsbOpts opts;
+  double* theta_out; double* acq_out; int32_t* nit; int32_t* nfev; int32_t* status;
+  stp_turnover turn; double* work_acc; int32_t* iters_acc;
+};
+
+// One BO iteration of campaign b by the whole CTA.  CG: the campaign state may have been written by another SM
+// during this launch (persistent kernel), so it is read through the L2 (ld.global.cg), never through this SM's L1.
+// Returns 0 when the iteration completed, non-zero when the campaign stopped (status[b] set).
+template <bool CG>
+__device__ __forceinline__ int exact_bo_iteration(const BoArgs& a, double* smem, int b) {
+  const int n_cap = a.n_cap, d = a.d, N = a.N, s_cap = a.s_cap;
+  const int n = CG ? __ldcg(a.n_arr + b) : a.n_arr[b];
   // n_cap: row capacity of the global arrays; s_cap <= n_cap - 1: what the shared-memory carve-up of this launch holds
-  if (n >= n_cap || n < 1 || n > s_cap) { if (threadIdx.x == 0) status[b] = 2; return; }
+  if (n >= n_cap || n < 1 || n > s_cap) { if (threadIdx.x == 0) a.status[b] = 2; return 2; }
   const int nw = blockDim.x >> 5;
   const ExactSmem s = exact_smem_carve(smem, s_cap, d, kTC, nw);
   LbfgsbState* S = reinterpret_cast<LbfgsbState*>(smem + exact_smem_doubles(s_cap, d, kTC, nw));
   int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(S) + sizeof(LbfgsbState));
   CtaTeam tm{s.red};
   const int np = d + 3;
-  double* Xb = X + (size_t)b * n_cap * d;
-  double* yb = y + (size_t)b * n_cap;
-  exact_load(tm, s, n, d, Xb, yb);
+  double* Xb = a.X + (size_t)b * n_cap * d;
+  double* yb = a.y + (size_t)b * n_cap;
+  STP_PHASE(-1); STP_COUNT(18);
+  __syncthreads();   // the previous work item of this CTA is done with the shared memory
+  if (CG) {
+    for (int idx = threadIdx.x; idx < n * d; idx += blockDim.x) {
+      const int i = idx / d, k = idx - i * d;
+      s.Xt[k * s.cap + i] = __ldcg(Xb + idx);
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s.y[i] = __ldcg(yb + i);
+    __syncthreads();
+  } else {
+    exact_load(tm, s, n, d, Xb, yb);
+  }
   double* th = s.small;
-  if (threadIdx.x < np) th[threadIdx.x] = bnd.theta0[threadIdx.x];  // no warm start (App. D-7)
+  if (threadIdx.x < np) th[threadIdx.x] = a.bnd.theta0[threadIdx.x];  // no warm start (App. D-7)
   __syncthreads();
-  const ExactFitResult r = exact_fit_run(tm, s, S, flag, n, d, th, bnd.lb, bnd.ub, to_prior(prior), opts);
-  if (threadIdx.x < np && theta_out) theta_out[b * np + threadIdx.x] = th[threadIdx.x];
-  if (threadIdx.x == 0) { if (nit) nit[b] = r.nit; if (nfev) nfev[b] = r.nfev; }
-  if (r.status == 3) { if (threadIdx.x == 0) status[b] = 3; return; }
-  if (exact_factorize(tm, s, n, d, th)) { if (threadIdx.x == 0) status[b] = 1; return; }
+  STP_PHASE(0);
+  const ExactFitResult r = exact_fit_run(tm, s, S, flag, n, d, th, a.bnd.lb, a.bnd.ub, to_prior(a.prior), a.opts);
+  if (threadIdx.x < np && a.theta_out) a.theta_out[b * np + threadIdx.x] = th[threadIdx.x];
+  if (threadIdx.x == 0) { if (a.nit) a.nit[b] = r.nit; if (a.nfev) a.nfev[b] = r.nfev; }
+  if (r.status == 3) { if (threadIdx.x == 0) a.status[b] = 3; return 3; }
+  STP_PHASE(-1);
+  if (exact_factorize(tm, s, n, d, th)) { if (threadIdx.x == 0) a.status[b] = 1; return 1; }
+  STP_PHASE(8);
   double best = -INFINITY;                      // best_f = y_train.max(), raw (runners.py:89)
-  for (int i = 0; i < n; ++i) best = fmax(best, s.y[i]);
+  STP_ROLLED for (int i = 0; i < n; ++i) best = fmax(best, s.y[i]);
   int bi; double bv;
-  const int pid = pool_id ? pool_id[b] : 0;
-  const double* P = pool + (size_t)pid * N * d;
-  uint8_t* mb = mask + (size_t)b * N;
+  const int pid = a.pool_id ? a.pool_id[b] : 0;
+  const double* P = a.pool + (size_t)pid * N * d;
+  uint8_t* mb = a.mask + (size_t)b * N;
   exact_acquire(tm, s, n, d, th, P, N, mb, best, &bi, &bv, nullptr, nullptr, nullptr);
-  if (bi < 0) { if (threadIdx.x == 0) status[b] = 2; return; }
+  STP_PHASE(9);
+  if (bi < 0) { if (threadIdx.x == 0) a.status[b] = 2; return 2; }
   // runners.py:98-109: record the pick, append it to the training set, drop it from the pool
   if (threadIdx.x < d) Xb[(size_t)n * d + threadIdx.x] = P[(size_t)bi * d + threadIdx.x];
   if (threadIdx.x == 0) {
-    yb[n] = pool_y[(size_t)pid * N + bi];
-    trace[(size_t)b * n_cap + n] = bi;
+    yb[n] = a.pool_y[(size_t)pid * N + bi];
+    a.trace[(size_t)b * n_cap + n] = bi;
     mb[bi] = 0;
-    n_arr[b] = n + 1;
-    if (acq_out) acq_out[b] = bv;
-    if (iters_acc) iters_acc[b] += 1;
-    if (work_acc) {   // algorithmic flops of this campaign-iteration, actual closure count
+    a.n_arr[b] = n + 1;
+    if (a.acq_out) a.acq_out[b] = bv;
+    if (a.iters_acc) a.iters_acc[b] = (CG ? __ldcg(a.iters_acc + b) : a.iters_acc[b]) + 1;
+    if (a.work_acc) {   // algorithmic flops of this campaign-iteration, actual closure count
       const double nn = n, F = r.nfev;
-      work_acc[b] += F * (nn * nn * nn + nn * nn * (3 * d + 6)) + nn * nn * nn / 3.0 +
-                     (N - nn) * (nn * nn + nn * (3 * d + 8) + 60.0);
+      a.work_acc[b] = (CG ? __ldcg(a.work_acc + b) : a.work_acc[b]) +
+                      F * (nn * nn * nn + nn * nn * (3 * d + 6)) + nn * nn * nn / 3.0 +
+                      (N - nn) * (nn * nn + nn * (3 * d + 8) + 60.0);
     }
   }
   // Continuous batching: a campaign that has done its last trial hands its trace to the sink and its slot to the
   // next seed of its bank (fresh mask / trace / training set); nothing to do for the host between steps.
+  const stp_turnover& turn = a.turn;
   if (turn.n_final > 0 && n + 1 >= turn.n_final) {
     __shared__ int s_slot, s_gen;
+    __syncthreads();                               // the pick has been recorded in the trace row
     if (threadIdx.x == 0) {
       s_slot = turn.sink ? atomicAdd(turn.sink_count, 1) : -1;
-      s_gen = turn.gen[b];
+      s_gen = CG ? __ldcg(turn.gen + b) : turn.gen[b];
     }
     __syncthreads();
-    int32_t* tb = trace + (size_t)b * n_cap;
+    int32_t* tb = a.trace + (size_t)b * n_cap;
     if (s_slot >= 0 && s_slot < turn.sink_capacity)
-      for (int i = threadIdx.x; i < n_cap; i += blockDim.x) turn.sink[(size_t)s_slot * n_cap + i] = tb[i];
+      for (int i = threadIdx.x; i < n_cap; i += blockDim.x)
+        turn.sink[(size_t)s_slot * n_cap + i] = CG ? __ldcg(tb + i) : tb[i];
     __syncthreads();
-    if (s_gen >= turn.generations) { if (threadIdx.x == 0) status[b] = 6; return; }   // bank exhausted: finished
+    if (s_gen >= turn.generations) { if (threadIdx.x == 0) a.status[b] = 6; return 6; }   // bank exhausted: finished
     const int32_t* init = turn.bank + ((size_t)b * turn.generations + s_gen) * turn.n_init;
     for (int i = threadIdx.x; i < N; i += blockDim.x) mb[i] = 1;
     for (int i = threadIdx.x; i < n_cap; i += blockDim.x) tb[i] = (i < turn.n_init) ? init[i] : -1;
@@ -213,10 +242,59 @@ __global__ void __launch_bounds__(STP_EXACT_MAXT, STP_EXACT_MINB) k_exact_bo_ste
       Xb[i] = (row < turn.n_init) ? P[(size_t)init[row] * d + k] : 0.0;
     }
     for (int i = threadIdx.x; i < n_cap; i += blockDim.x)
-      yb[i] = (i < turn.n_init) ? pool_y[(size_t)pid * N + init[i]] : 0.0;
+      yb[i] = (i < turn.n_init) ? a.pool_y[(size_t)pid * N + init[i]] : 0.0;
     __syncthreads();
     for (int i = threadIdx.x; i < turn.n_init; i += blockDim.x) mb[init[i]] = 0;
-    if (threadIdx.x == 0) { n_arr[b] = turn.n_init; turn.gen[b] = s_gen + 1; }
+    if (threadIdx.x == 0) { a.n_arr[b] = turn.n_init; turn.gen[b] = s_gen + 1; }
+  }
+  return 0;
+}
+
+// One BO iteration per campaign, one CTA per campaign (lock-step batch).
+__global__ void __launch_bounds__(STP_EXACT_MAXT, STP_EXACT_MINB) k_exact_bo_step(BoArgs a, const int32_t* __restrict__ order) {
+  extern __shared__ double smem[];
+  const int b = order ? order[blockIdx.x] : blockIdx.x;   // longest-first scheduling: CTAs are issued in blockIdx order
+  if (a.status[b] != 0) return;  // frozen campaign
+  exact_bo_iteration<false>(a, smem, b);
+}
+
+// Persistent form: gridDim.x resident CTAs serve B campaigns from a ticket ring until every campaign has done its
+// `iters_left[b]` iterations (or stopped).  A work item is ONE BO iteration of one campaign: campaigns advance
+// independently, so no CTA ever waits for the slowest fit of a lock-step batch (the tail that limits
+// k_exact_bo_step) -- the SM slots stay full until the whole job is done.  busy[b] serialises the iterations of a
+// campaign; the release/acquire pair (threadfence + atomic) orders its state between SMs.
+__global__ void __launch_bounds__(STP_EXACT_MAXT, STP_EXACT_MINB) k_exact_bo_run(BoArgs a, int B, const int32_t* __restrict__ order,
+                                                                               int32_t* iters_left, int32_t* busy,
+                                                                               unsigned int* ticket) {
+  extern __shared__ double smem[];
+  __shared__ int s_b;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      int found = -1;
+      for (int tries = 0; tries < B; ++tries) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        const int slot = (int)(t % (unsigned int)B);
+        const int b = order ? order[slot] : slot;
+        if (__ldcg(a.status + b) != 0 || __ldcg(iters_left + b) <= 0) continue;
+        if (atomicCAS(busy + b, 0, 1) != 0) continue;                 // another CTA is advancing this campaign
+        __threadfence();                                               // acquire: see that CTA's writes
+        if (__ldcg(a.status + b) != 0 || __ldcg(iters_left + b) <= 0) { atomicExch(busy + b, 0); continue; }
+        found = b;
+        break;
+      }
+      s_b = found;
+    }
+    __syncthreads();
+    const int b = s_b;
+    if (b < 0) return;              // a whole ring of tickets without work: the job is done (or in other hands)
+    exact_bo_iteration<true>(a, smem, b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();              // release: the campaign state is visible before the slot is handed back
+      iters_left[b] = __ldcg(iters_left + b) - 1;
+      __threadfence();
+      atomicExch(busy + b, 0);
+    }
   }
 }
 
@@ -501,35 +579,77 @@ int stp_exact_acq(int B, int n_cap, int d, int N, const double* pool, const int3
   return after_launch("stp_exact_acq");
 }
 
+static int fill_bo_args(BoArgs& a, int B, int n_cap, int d, int N, const double* pool, const double* pool_y,
+                        const int32_t* pool_id, uint8_t* mask, double* X, double* y, int32_t* n, int32_t* trace,
+                        const double* theta0, const double* lower, const double* upper, const double* prior,
+                        const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
+                        int32_t* status, const stp_turnover* turnover, double* work_acc, int32_t* iters_acc, int n_max) {
+  if (check_dims(B, n_cap, d)) return -1;
+  if (N < 1) return fail("N < 1");
+  if (n_max < 0 || n_max >= n_cap) return fail("n_max must be 0 (unknown) or in [1, n_cap - 1]");
+  memset(&a.turn, 0, sizeof(a.turn));
+  if (turnover) {
+    a.turn = *turnover;
+    const stp_turnover& turn = a.turn;
+    if (turn.n_final > 0 && (!turn.bank || !turn.gen || turn.n_init < 1 || turn.n_init >= n_cap || turn.generations < 0 ||
+                             turn.n_final > n_cap || (turn.sink && !turn.sink_count)))
+      return fail("inconsistent stp_turnover");
+  }
+  if (!pool || !pool_y || !mask || !X || !y || !n || !trace || !theta0 || !prior || !status) return fail("null argument");
+  a.n_cap = n_cap; a.d = d; a.N = N; a.s_cap = n_max > 0 ? n_max : n_cap - 1;
+  a.pool = pool; a.pool_y = pool_y; a.pool_id = pool_id; a.mask = mask; a.X = X; a.y = y; a.n_arr = n; a.trace = trace;
+  fill_bounds(a.bnd, d, lower, upper, theta0);
+  memcpy(a.prior.v, prior, sizeof(a.prior.v));
+  a.opts = to_opts(opts);
+  a.theta_out = theta_out; a.acq_out = acq_out; a.nit = nit; a.nfev = nfev; a.status = status;
+  a.work_acc = work_acc; a.iters_acc = iters_acc;
+  return 0;
+}
+
 int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const double* pool_y,
                       const int32_t* pool_id, uint8_t* mask, double* X, double* y, int32_t* n, int32_t* trace,
                       const double* theta0, const double* lower, const double* upper, const double* prior,
                       const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
                       int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
                       int32_t* iters_acc, int n_max, void* stream) {
-  if (check_dims(B, n_cap, d)) return -1;
-  if (N < 1) return fail("N < 1");
-  if (n_max < 0 || n_max >= n_cap) return fail("n_max must be 0 (unknown) or in [1, n_cap - 1]");
-  const int s_cap = n_max > 0 ? n_max : n_cap - 1;
-  stp_turnover turn;
-  memset(&turn, 0, sizeof(turn));
-  if (turnover) {
-    turn = *turnover;
-    if (turn.n_final > 0 && (!turn.bank || !turn.gen || turn.n_init < 1 || turn.n_init >= n_cap || turn.generations < 0 ||
-                             turn.n_final > n_cap || (turn.sink && !turn.sink_count)))
-      return fail("inconsistent stp_turnover");
-  }
-  if (!pool || !pool_y || !mask || !X || !y || !n || !trace || !theta0 || !prior || !status) return fail("null argument");
+  BoArgs a;
+  if (fill_bo_args(a, B, n_cap, d, N, pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upper, prior, opts,
+                   theta_out, acq_out, nit, nfev, status, turnover, work_acc, iters_acc, n_max)) return -1;
   if (B == 0) return 0;
-  const int threads = threads_for(s_cap);
-  const size_t smem = exact_smem_bytes(s_cap, d, threads, true);
+  const int threads = threads_for(a.s_cap);
+  const size_t smem = exact_smem_bytes(a.s_cap, d, threads, true) + smem_pad();
   if (set_smem(k_exact_bo_step, smem)) return -1;
-  PriorArg p; memcpy(p.v, prior, sizeof(p.v));
-  BoundsArg bnd; fill_bounds(bnd, d, lower, upper, theta0);
-  k_exact_bo_step<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, N, pool, pool_y, pool_id, mask, X, y, n, trace,
-                                                              bnd, p, to_opts(opts), theta_out, acq_out, nit, nfev,
-                                                              status, order, turn, work_acc, iters_acc, s_cap);
+  k_exact_bo_step<<<B, threads, smem, (cudaStream_t)stream>>>(a, order);
   return after_launch("stp_exact_bo_step");
+}
+
+int stp_exact_bo_run(int B, int n_cap, int d, int N, const double* pool, const double* pool_y,
+                     const int32_t* pool_id, uint8_t* mask, double* X, double* y, int32_t* n, int32_t* trace,
+                     const double* theta0, const double* lower, const double* upper, const double* prior,
+                     const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
+                     int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
+                     int32_t* iters_acc, int n_max, int32_t* iters_left, int32_t* sched, int max_ctas, void* stream) {
+  BoArgs a;
+  if (fill_bo_args(a, B, n_cap, d, N, pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upper, prior, opts,
+                   theta_out, acq_out, nit, nfev, status, turnover, work_acc, iters_acc, n_max)) return -1;
+  if (!iters_left || !sched) return fail("null argument");
+  if (B == 0) return 0;
+  const int threads = threads_for(a.s_cap);
+  const size_t smem = exact_smem_bytes(a.s_cap, d, threads, true) + smem_pad();
+  if (set_smem(k_exact_bo_run, smem)) return -1;
+  // one CTA per SM slot: as many as can be resident at this footprint (cached per device / footprint)
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_exact_bo_run, threads, smem);
+  if (e != cudaSuccess || per_sm < 1 || sms < 1) return fail_cuda("cudaOccupancyMaxActiveBlocksPerMultiprocessor", e);
+  int grid = sms * per_sm;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  if (grid > B) grid = B;
+  // sched: int32[B + 1], zeroed by the caller before the FIRST launch: busy flags, then the ticket counter
+  k_exact_bo_run<<<grid, threads, smem, (cudaStream_t)stream>>>(a, B, order, iters_left, sched,
+                                                                reinterpret_cast<unsigned int*>(sched + B));
+  return after_launch("stp_exact_bo_run");
 }
 
 
@@ -655,6 +775,24 @@ int stp_log_ei(long long count, const double* mean, const double* var, double be
   if (blocks > 148 * 16) blocks = 148 * 16;
   k_log_ei<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(count, mean, var, best_f, out);
   return after_launch("stp_log_ei");
+}
+
+int stp_phase_timers(unsigned long long* out32, int reset) {
+#if defined(STP_PHASE_TIMERS)
+  if (out32) {
+    const cudaError_t e = cudaMemcpyFromSymbol(out32, g_stp_phase, 32 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return fail_cuda("stp_phase_timers", e);
+  }
+  if (reset) {
+    unsigned long long zero[32] = {0};
+    const cudaError_t e = cudaMemcpyToSymbol(g_stp_phase, zero, sizeof(zero));
+    if (e != cudaSuccess) return fail_cuda("stp_phase_timers", e);
+  }
+  return 0;
+#else
+  (void)out32; (void)reset;
+  return fail("library built without -DSTP_PHASE_TIMERS");
+#endif
 }
 
 int stp_fp64_probe(int iters, double* sink, void* stream) {

@@ -11,9 +11,14 @@
 #if defined(__CUDACC__)
 #define STP_HD __host__ __device__ __forceinline__
 #define STP_D __device__ __forceinline__
+// Out-of-line on purpose: routines run by ONE warp through a lot of branchy code (the L-BFGS-B state machine) are
+// instruction-fetch bound once their inlined copies exceed the SM's instruction caches (L0 ~6 KB, L1.5 32 KB);
+// one shared copy per routine keeps the optimiser's footprint small (tools/sass_footprint.py).
+#define STP_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define STP_HD inline
 #define STP_D inline
+#define STP_HD_NOINLINE inline
 #endif
 
 #include <math.h>
@@ -23,34 +28,82 @@ namespace stp {
 
 constexpr int kMaxWarps = 32;
 
+// Phase timers (diagnostic builds only, -DSTP_PHASE_TIMERS; tools/gpu_phase_timers.py): thread 0 of the CTA charges the
+// cycles since its previous mark to phase `id` (marks sit right after the barrier that ends a phase).
+// ids: 0 load, 1 Gram build, 2 sweep (A) 8-pivot elimination, 3 sweep (B) panel products, 4 sweep (C) rank-8 update,
+// 5 gradient contraction, 6 block reduction + gradient, 7 L-BFGS-B advance (what ids 11 - 15 do not cover),
+// 8 factorise, 9 pool pass, 10 update, 11 BFGS matrix, 12 Cauchy point, 13 subspace step, 14 line-search start,
+// 15 line-search step + BFGS pair (from the closure's end to the start of the next iteration),
+// 16 closures (count), 17 sweep block steps (count), 18 campaigns (count).
+#if defined(__CUDACC__) && defined(STP_PHASE_TIMERS)
+__device__ unsigned long long g_stp_phase[32];
+__device__ __forceinline__ void phase_mark(int id) {
+  __shared__ long long last;
+  if (threadIdx.x == 0) {
+    const long long t = clock64();
+    if (id >= 0) atomicAdd(&g_stp_phase[id], (unsigned long long)(t - last));
+    last = t;
+  }
+}
+__device__ __forceinline__ void phase_count(int id) { if (threadIdx.x == 0) atomicAdd(&g_stp_phase[id], 1ull); }
+#if defined(__CUDA_ARCH__)
+#define STP_PHASE(id) ::stp::phase_mark(id)
+#define STP_COUNT(id) ::stp::phase_count(id)
+#else
+#define STP_PHASE(id) ((void)0)
+#define STP_COUNT(id) ((void)0)
+#endif
+#else
+#define STP_PHASE(id) ((void)0)
+#define STP_COUNT(id) ((void)0)
+#endif
+
 // ---------------------------------------------------------------------------------------
 // Lane groups: what ONE warp of a team (or the single thread of a SoloTeam) offers to the small serial-ish
 // routines (the L-BFGS-B state machine): strided loops over lane() / width(), lane-uniform reductions, sync().
 // ---------------------------------------------------------------------------------------
+// Loops over the n <= 32 entries of a small vector are written  STP_OWNED(L, i, n) { ... }:  a warp gives entry i
+// to lane i (the body runs at most once per lane -- written so that the compiler sees that and emits no unrolled
+// strided loop: the optimiser's code footprint is what limits it, see STP_HD_NOINLINE), one thread walks all n.
+#define STP_PRAGMA(x) _Pragma(#x)
+#define STP_OWNED(L, i, n) STP_PRAGMA(unroll 1) for (int i = (L).first(), i##_end = (L).last(n); i < i##_end; ++i)
+#define STP_ROLLED STP_PRAGMA(unroll 1)
+
 struct SoloLanes {
   STP_HD int lane() const { return 0; }
   STP_HD int width() const { return 1; }
+  STP_HD int first() const { return 0; }
+  STP_HD int last(int n) const { return n; }
   STP_HD void sync() const {}
   STP_HD double sum(double v) const { return v; }
   STP_HD double max(double v) const { return v; }
+  STP_HD int isum(int v) const { return v; }
   STP_HD int any(int p) const { return p != 0; }
 };
 #if defined(__CUDACC__)
+// xor butterflies over the 16 low lanes (the small vectors have <= 16 entries; higher lanes contribute the neutral
+// element through the first exchange): every lane ends with the bitwise-identical result.  Out of line: ~40 call sites.
+static __device__ __noinline__ double warp_sum16(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+static __device__ __noinline__ double warp_max16(double v) {
+  v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 16));
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
 struct WarpLanes {
   __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
   __device__ __forceinline__ int width() const { return 32; }
+  __device__ __forceinline__ int first() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int last(int n) const { const int l = (threadIdx.x & 31) + 1; return n < l ? n : l; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
-  // xor butterflies: every lane ends with the bitwise-identical result
-  __device__ __forceinline__ double sum(double v) const {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-  }
-  __device__ __forceinline__ double max(double v) const {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-  }
+  __device__ __forceinline__ double sum(double v) const { return warp_sum16(v); }
+  __device__ __forceinline__ double max(double v) const { return warp_max16(v); }
+  __device__ __forceinline__ int isum(int v) const { return __reduce_add_sync(0xffffffffu, v); }
   __device__ __forceinline__ int any(int p) const { return __any_sync(0xffffffffu, p); }
 };
 #endif
@@ -61,6 +114,8 @@ struct WarpLanes {
 struct SoloTeam {
   STP_HD int rank() const { return 0; }
   STP_HD int size() const { return 1; }
+  STP_HD int first() const { return 0; }           // STP_OWNED(tm, i, n): n <= size() of the device teams
+  STP_HD int last(int n) const { return n; }
   STP_HD int lane() const { return 0; }
   STP_HD int warp() const { return 0; }
   STP_HD int nwarps() const { return 1; }
@@ -100,6 +155,8 @@ struct CtaTeam {
   double* red;
   __device__ __forceinline__ int rank() const { return threadIdx.x; }
   __device__ __forceinline__ int size() const { return blockDim.x; }
+  __device__ __forceinline__ int first() const { return threadIdx.x; }
+  __device__ __forceinline__ int last(int n) const { const int l = threadIdx.x + 1; return n < l ? n : l; }
   __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
   __device__ __forceinline__ int warp() const { return threadIdx.x >> 5; }
   __device__ __forceinline__ int nwarps() const { return blockDim.x >> 5; }

@@ -122,9 +122,58 @@ class CampaignBatch:
             self.launches += self._var.step()
         self.iteration += 1
 
-    def run(self, n_trials: int) -> None:
-        for _ in range(int(n_trials)):
-            self.step()
+    def run(self, n_trials: int, chunk: Optional[int] = None) -> None:
+        """``n_trials`` BO iterations of every campaign.  ExactGP: persistent work-queue launches (stp_exact_bo_run)
+        of ``chunk`` iterations each (default 16; each launch is sized for the training sets it can reach, so young
+        campaigns run 3 - 4 per SM); campaigns advance independently inside a launch.  Variational kinds: lock-step
+        steps (two launches per iteration)."""
+        n_trials = int(n_trials)
+        if self.kind != "ExactGP":
+            for _ in range(n_trials):
+                self.step()
+            return
+        chunk = int(chunk) if chunk else 16
+        done = 0
+        while done < n_trials:
+            k = min(chunk, n_trials - done)
+            self.run_queue(k)
+            done += k
+
+    def run_queue(self, iters, max_ctas: int = 0) -> None:
+        """ONE persistent launch that advances every running campaign by ``iters`` BO iterations (ExactGP); ``iters``
+        is an int or one count per campaign."""
+        if self.kind != "ExactGP":
+            raise NotImplementedError("the persistent work-queue launch is provided for the ExactGP step")
+        if not hasattr(self, "_sched"):
+            self._sched = torch.zeros(self.B + 1, dtype=torch.int32, device=self.device)
+            self._iters_left = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        if isinstance(iters, int):
+            self._iters_left.fill_(iters)
+            per = None
+        else:                                  # per-campaign iteration counts
+            per = np.asarray(list(iters), dtype=np.int64)
+            self._iters_left.copy_(torch.as_tensor(per, dtype=torch.int32))
+            iters = int(per.max()) if per.size else 0
+        if self._n_host is None:
+            n_max = 0
+        elif self._turnover is not None:      # restarted campaigns are young again: the oldest one bounds the launch
+            n_max = int(min(max(self._n_host.max() + iters, self._turnover.n_init + iters), self._turnover.n_final - 1,
+                            self.cap - 1))
+        else:
+            n_max = int(min(self._n_host.max() + iters - 1, self.cap - 1))
+        _lib.exact_bo_run(self.pool, self.pool_y, self.pool_id, self.mask, self.X, self.y, self.n, self.trace,
+                          self._theta0, self._lower, self._upper, self._prior, self.status, self._iters_left, self._sched,
+                          theta_out=self.theta, acq_out=self.acq, nit=self.nit, nfev=self.nfev, opts=self._opts,
+                          turnover=self._turnover, work_acc=self.work_acc, iters_acc=self.iters_acc, n_max=n_max,
+                          max_ctas=max_ctas)
+        self.launches += 1
+        self.iteration += int(iters)
+        if self._n_host is not None:
+            self._n_host += int(iters) if per is None else per
+            if self._turnover is not None:
+                span = self._turnover.n_final - self._turnover.n_init
+                over = self._n_host >= self._turnover.n_final
+                self._n_host[over] = self._turnover.n_init + (self._n_host[over] - self._turnover.n_final) % span
 
     def assume_ages(self, n_host) -> None:
         """Tell the engine the current training-set sizes (host array [B], or None = unknown) after state that it
@@ -220,11 +269,6 @@ class CampaignGroups:
     def run(self, n_trials: int) -> None:
         for _ in range(int(n_trials)):
             self.step()
-
-    def assume_ages(self, n_host) -> None:
-        """Tell the engine the current training-set sizes (host array [B], or None = unknown) after state that it
-        mirrors on the host (n, status) has been changed from outside."""
-        self._n_host = None if n_host is None else np.asarray(n_host, dtype=np.int64).copy()
 
     def synchronize(self) -> None:
         for s in self.streams:

@@ -277,6 +277,56 @@ def test_campaign_groups_on_streams_equal_single_batch():
     assert all(torch.equal(p, q) for p, q in zip(a, b)) and many.launches == 32
 
 
+def test_persistent_work_queue_matches_lockstep_steps():
+    """stp_exact_bo_run (persistent CTAs serving campaign-iterations from a ticket ring) advances every campaign
+    exactly like iters x stp_exact_bo_step: same picks, same fitted theta -- with as many CTAs as fit, with 3 CTAs
+    for 12 campaigns (every CTA serves several campaigns, iterations of a campaign hop between SMs), with
+    per-campaign iteration counts, and with in-kernel turnover."""
+    from stpbenchmark_b200 import synthetic
+    from stpbenchmark_b200.engine import CampaignBatch
+    X, y = dataset("AgNP")
+    seeds = list(range(40, 52))
+    init = synthetic.initial_designs(X, y, seeds).tolist()
+    ref = CampaignBatch(X, y, [0] * 12, init, n_cap=24, kind="ExactGP")
+    for _ in range(9):
+        ref.step()
+    a = ref.traces()
+    for max_ctas in (0, 3):
+        q = CampaignBatch(X, y, [0] * 12, init, n_cap=24, kind="ExactGP")
+        q.run_queue(9, max_ctas=max_ctas)
+        b = q.traces()
+        assert all(torch.equal(u, v) for u, v in zip(a, b)), max_ctas
+        assert torch.equal(ref.theta, q.theta) and torch.equal(ref.nfev, q.nfev)
+        assert q.launches == 1 and int(q._iters_left.sum()) == 0 and int(q._sched[:12].sum()) == 0
+    # chunked run() and ragged iteration counts
+    q = CampaignBatch(X, y, [0] * 12, init, n_cap=24, kind="ExactGP")
+    q.run(9, chunk=4)
+    assert all(torch.equal(u, v) for u, v in zip(a, q.traces())) and q.launches == 3
+    per = [b % 5 for b in range(12)]
+    q = CampaignBatch(X, y, [0] * 12, init, n_cap=24, kind="ExactGP")
+    q.run_queue(per, max_ctas=5)
+    idx, n, st = q.traces()
+    assert n.tolist() == [len(init[b]) + per[b] for b in range(12)] and st.tolist() == [0] * 12
+    for b in range(12):
+        assert idx[b, : int(n[b])].tolist() == a[0][b, : int(n[b])].tolist()
+    # turnover inside the persistent launch: 3 generations of 4-trial campaigns, finished traces land in the sink
+    bank = synthetic.initial_designs(X, y, list(range(100, 124))).reshape(12, 2, -1)
+    outs = []
+    for mode in ("step", "queue"):
+        t = CampaignBatch(X, y, [0] * 12, init, n_cap=24, kind="ExactGP")
+        t.enable_turnover(bank, n_final=len(init[0]) + 4, sink_capacity=40)
+        if mode == "step":
+            for _ in range(10):
+                t.step()
+        else:
+            t.run_queue(10, max_ctas=4)
+        torch.cuda.synchronize()
+        sink = t.sink[: int(t.sink_count)].cpu()
+        outs.append((sorted(map(tuple, sink.tolist())), t.traces()))
+    assert outs[0][0] == outs[1][0] and len(outs[0][0]) == 24
+    assert all(torch.equal(u, v) for u, v in zip(outs[0][1], outs[1][1]))
+
+
 def test_launch_sized_for_current_n_gives_the_same_campaigns():
     """stp_exact_bo_step's n_max only sizes the launch (shared memory, threads): a lockstep batch run with the
     engine's host mirror of n (n_max = 12 ... 27: 128 threads, 4 CTAs/SM) picks what it picks when every launch is
