@@ -206,6 +206,12 @@ int stp_fp64_probe(int iters, double* sink, void* stream);
  * issue DMMA; on B200 its peak equals the DFMA peak. */
 int stp_fp64_mma_probe(int iters, double* sink, void* stream);
 
+/* Initial design, the O(Q Ne d) step of get_initial_samples_sobol (utils.py:272-279): out_idx[q] = index of the first
+ * eligible pool point nearest to query point q (Euclidean; the queries are the scrambled-Sobol points already
+ * scaled to the bounding box of the eligible points, which stay a host computation because they are defined by
+ * torch's CPU generator, utils.py:262-271).  points [Q, d], eligible [Ne, d], out_idx int32 [Q]. */
+int stp_design_snap(int Q, int Ne, int d, const double* points, const double* eligible, int32_t* out_idx, void* stream);
+
 /* Diagnostic: per-phase cycle counters of stp_exact_bo_step (clock64 of thread 0 of every CTA, summed over CTAs;
  * ids in csrc/team.cuh).  Only in libraries built with -DSTP_PHASE_TIMERS (tools/gpu_phase_timers.py builds one
  * beside the shipped library); the shipped build returns an error.  out32: HOST array of 32 counters (may be

@@ -183,6 +183,17 @@ def exact_bo_run(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upp
                                   _stream()), "stp_exact_bo_run")
 
 
+def design_snap(points: torch.Tensor, eligible: torch.Tensor) -> torch.Tensor:
+    """int32 [Q]: index (into ``eligible`` [Ne, d]) of the first nearest eligible point of every row of ``points``
+    [Q, d] (stp_design_snap; the nearest-point step of utils.get_initial_samples_sobol)."""
+    points = points.double().contiguous(); eligible = eligible.double().contiguous()
+    _require_cuda(points, eligible)
+    out = torch.empty(points.shape[0], dtype=torch.int32, device=points.device)
+    _check(lib().stp_design_snap(points.shape[0], eligible.shape[0], points.shape[1], _p(points), _p(eligible), _p(out),
+                                 _stream()), "stp_design_snap")
+    return out
+
+
 def log_ei(mean: torch.Tensor, var: torch.Tensor, best_f: float) -> torch.Tensor:
     """Elementwise analytic LogEI on the device; output has the shape of ``mean``."""
     _require_cuda(mean, var)
@@ -196,7 +207,7 @@ def log_ei(mean: torch.Tensor, var: torch.Tensor, best_f: float) -> torch.Tensor
 
 PHASE_NAMES = {0: "load", 1: "gram", 2: "sweep_A", 3: "sweep_B", 4: "sweep_C", 5: "gradient", 6: "reduce", 7: "advance",
                8: "factorise", 9: "pool_pass", 10: "update", 11: "adv_build_B", 12: "adv_cauchy", 13: "adv_subsm",
-               14: "adv_ls_start", 15: "adv_ls_step", 16: "closures", 17: "sweep_blocks", 18: "campaigns"}
+               14: "adv_ls_start", 15: "adv_ls_step", 19: "adv_entry", 20: "adv_copy_dot", 21: "adv_dcsrch", 22: "adv_projgr_tests", 16: "closures", 17: "sweep_blocks", 18: "campaigns"}
 
 
 def phase_timers(reset: bool = False) -> dict:

@@ -113,6 +113,21 @@ STP_HD double ard_rbf_tt(const double* Xt, int cap, int d, const double* invl, i
   return os * exp(-0.5 * r2);
 }
 
+// Calls f(i, j) once for every pair of the strict lower triangle 0 <= j < i < n.  Row i of a triangle has i
+// entries, so a warp that walks rows leaves most lanes idle on the short ones (60 % lane utilisation at n = 60);
+// here row F is folded with row n - F into one run of n entries, walked by the lanes of one warp (93 - 100 %).
+template <class Team, class Fn>
+STP_HD void for_each_lower_pair(const Team& tm, int n, Fn f) {
+  const int W = tm.warp_width();
+  for (int F = 1 + tm.warp(); 2 * F <= n; F += tm.nwarps()) {
+    const int len = (2 * F == n) ? F : n;          // the middle row of an even n stands alone
+    for (int c = tm.lane(); c < len; c += W) {
+      if (c < F) f(F, c);
+      else f(n - F, c - F);
+    }
+  }
+}
+
 // Bordered sweep of the closure: blocked tensor-core form on the device, pair sweep in the host emulation.
 template <class Team>
 STP_HD int exact_sweep(const Team& tm, const ExactSmem& s, int n) {
@@ -144,20 +159,14 @@ STP_HD int exact_mll_fg(const Team& tm, const ExactSmem& s, int n, int d, const 
   tm.sync();
   STP_PHASE(-1); STP_COUNT(16);
   // K1: lower = K + noise I (to be swept), strict upper = K (kept for the gradient), border = y - c
-  for (int i = tm.warp(); i <= n; i += tm.nwarps()) {
-    double* row = s.A + i * ld;
-    if (i < n) {
-      for (int j = tm.lane(); j <= i; j += W) {
-        if (j == i) row[j] = os + noise;
-        else {
-          const double kij = ard_rbf_tt(s.Xt, cap, d, invl, i, j, os);
-          row[j] = kij;
-          s.A[j * ld + i] = kij;
-        }
-      }
-    } else {
-      for (int j = tm.lane(); j <= n; j += W) row[j] = (j < n) ? (s.y[j] - cst) : 0.0;
-    }
+  for_each_lower_pair(tm, n, [&](int i, int j) {
+    const double kij = ard_rbf_tt(s.Xt, cap, d, invl, i, j, os);
+    s.A[i * ld + j] = kij;
+    s.A[j * ld + i] = kij;
+  });
+  for (int j = tm.rank(); j <= n; j += tm.size()) {
+    if (j < n) s.A[j * ld + j] = os + noise;
+    s.A[n * ld + j] = (j < n) ? (s.y[j] - cst) : 0.0;
   }
   tm.sync();
   STP_PHASE(1);
@@ -184,23 +193,16 @@ STP_HD int exact_mll_fg(const Team& tm, const ExactSmem& s, int n, int d, const 
     acc[1] += ai * ai + s.A[i * ld + i];
     acc[2] += ai;
   }
-  for (int i = 1 + tm.warp(); i < n; i += tm.nwarps()) {
-    const double ai = arow[i];
-    const double* row = s.A + i * ld;
-    double xi[kMaxD];
+  for_each_lower_pair(tm, n, [&](int i, int j) {
+    const double t = (arow[i] * arow[j] + s.A[i * ld + j]) * s.A[j * ld + i];
+    acc[3] += t;
 #pragma unroll
-    for (int k = 0; k < kMaxD; ++k) xi[k] = (k < d) ? s.Xt[k * cap + i] : 0.0;
-    for (int j = tm.lane(); j < i; j += W) {
-      const double t = (ai * arow[j] + row[j]) * s.A[j * ld + i];
-      acc[3] += t;
-#pragma unroll
-      for (int k = 0; k < kMaxD; ++k)
-        if (k < d) {
-          const double dx = xi[k] - s.Xt[k * cap + j];
-          acc[4 + k] += t * dx * dx;
-        }
-    }
-  }
+    for (int k = 0; k < kMaxD; ++k)
+      if (k < d) {
+        const double dx = s.Xt[k * cap + i] - s.Xt[k * cap + j];
+        acc[4 + k] += t * dx * dx;
+      }
+  });
   STP_PHASE(5);
   tm.sum_vec(acc, 5 + d);
   const double quad = -s.A[n * ld + n];

@@ -143,7 +143,9 @@ STP_HD_NOINLINE int lb_build_B(const SoloLanes&, LbfgsbState& S) {
   return 0;
 }
 #if defined(__CUDACC__)
-// Warp version: lane r keeps row r of B in registers, the pairs are replayed with shuffles.
+// Warp version: lane r keeps row r of B in registers.  Per stored pair: Bs_r = B[r,:] . s (two DFMA chains), Bs is
+// exchanged through shared memory (one store + warp barrier + broadcast loads: the 22 shuffles and the 5-level
+// butterfly this replaces were 20 % of the optimiser's time), every lane forms s . Bs itself, rank-2 update.
 static __device__ __noinline__ int lb_build_B(const WarpLanes& L, LbfgsbState& S) {
   const int n = S.np, r = L.lane();
   const bool live = r < n;
@@ -152,30 +154,42 @@ static __device__ __noinline__ int lb_build_B(const WarpLanes& L, LbfgsbState& S
   for (int c = 0; c < kMaxP; ++c) Brow[c] = (live && c == r) ? S.theta : 0.0;
   int broke = 0;
   const int col = S.col, head = S.head, mm = S.m;
+  double* Bsv = S.sc_a;
   STP_ROLLED for (int q = 0; q < col; ++q) {
     int p = head + q;
     if (p >= mm) p -= mm;
     const double* s = S.ws[p];
     const double* y = S.wy[p];
     const double ysp = S.ys[p], ib = S.iys[p];
+    double sv[kMaxP];
     double Bs0 = 0.0, Bs1 = 0.0;   // two chains: the dot product is latency-bound
 #pragma unroll
+    for (int c = 0; c < kMaxP; ++c) sv[c] = (c < n) ? s[c] : 0.0;
+#pragma unroll
     for (int c = 0; c < kMaxP; c += 2) {
-      if (c < n) Bs0 += Brow[c] * s[c];
-      if (c + 1 < kMaxP && c + 1 < n) Bs1 += Brow[(c + 1 < kMaxP) ? c + 1 : c] * s[c + 1];
+      Bs0 = fma(Brow[c], sv[c], Bs0);
+      if (c + 1 < kMaxP) Bs1 = fma(Brow[(c + 1 < kMaxP) ? c + 1 : c], sv[(c + 1 < kMaxP) ? c + 1 : c], Bs1);
     }
     const double Bs = Bs0 + Bs1;
-    const double sr = live ? s[r] : 0.0, yr = live ? y[r] : 0.0;
-    const double a = warp_sum16(sr * Bs);
+    L.sync();                       // the previous pair's readers are done with Bsv
+    if (r < kMaxP) Bsv[r] = live ? Bs : 0.0;
+    L.sync();
+    double bsv[kMaxP];
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int c = 0; c < kMaxP; ++c) bsv[c] = Bsv[c];
+#pragma unroll
+    for (int c = 0; c < kMaxP; c += 2) {
+      a0 = fma(sv[c], bsv[c], a0);
+      if (c + 1 < kMaxP) a1 = fma(sv[(c + 1 < kMaxP) ? c + 1 : c], bsv[(c + 1 < kMaxP) ? c + 1 : c], a1);
+    }
+    const double a = a0 + a1;
     if (!(a > 0.0) || !(ysp > 0.0)) { broke = 1; break; }
     const double ia = rcp_pos(a);
-    const double ya = yr * ib, ba = Bs * ia;
+    const double ya = (live ? y[r] : 0.0) * ib, ba = Bs * ia;
 #pragma unroll
     for (int c = 0; c < kMaxP; ++c)
-      if (c < n) {
-        const double Bsc = __shfl_sync(0xffffffffu, Bs, c);
-        Brow[c] += ya * y[c] - ba * Bsc;
-      }
+      if (c < n) Brow[c] += ya * y[c] - ba * bsv[c];
   }
   L.sync();
   if (live) {
@@ -676,6 +690,7 @@ STP_HD int lb_finish(const LN& L, LbfgsbState& S, int status, int bump_iter) {
 template <class LN>
 STP_HD_NOINLINE int lb_advance_once(const LN& L, LbfgsbState& S, double f, const double* g) {
   const int n = S.np, l0 = L.lane();
+  STP_PHASE(19);
   int badg = 0;
   STP_OWNED(L, i, n) badg |= !(g[i] == g[i]);
   const int finite = (f == f) && (fabs(f) <= 1.79e308) && !L.any(badg);
@@ -698,8 +713,10 @@ STP_HD_NOINLINE int lb_advance_once(const LN& L, LbfgsbState& S, double f, const
     return lb_finish(L, S, 3, 0);
   }
   const double gd = lb_dot(L, S.g, S.d, n);
+  STP_PHASE(20);
   if (l0 == 0) { S.gd = gd; lb_dcsrch(S, f, gd); }
   L.sync();
+  STP_PHASE(21);
   const int task = S.ls_task;
   if (task == 1) {
     if (S.iback + 1 >= S.maxls) {
@@ -738,6 +755,7 @@ STP_HD_NOINLINE int lb_advance_once(const LN& L, LbfgsbState& S, double f, const
   if (S.sbgnrm <= S.pgtol) return lb_finish(L, S, 0, 0);
   const double ddum = fmax(fmax(fabs(S.fold), fabs(S.f)), 1.0);
   if (S.fold - S.f <= kEpsMch * S.factr * ddum) return lb_finish(L, S, 0, 0);
+  STP_PHASE(22);
   // BFGS pair
   const double stp = S.stp, gdn = S.gd, gdold = S.gdold;
   double rrp = 0.0, dr, dd;

@@ -469,6 +469,38 @@ __global__ void k_log_ei(long long count, const double* __restrict__ mean, const
     out[i] = log_ei(mean[i], var[i], best_f);
 }
 
+// Initial design, step 2 (utils.py:272-279): every query point (a scaled Sobol point) is replaced by the FIRST nearest
+// eligible pool point, dist = sqrt(sum_k (xe_k - p_k)^2) accumulated in k order without contraction (the host's
+// torch.norm).  One warp per query; lanes stride over the eligible points; first-index tie-break.
+__global__ void k_design_snap(int Q, int Ne, int d, const double* __restrict__ P, const double* __restrict__ Xe,
+                              int32_t* __restrict__ out) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (q >= Q) return;
+  double p[kMaxD];
+#pragma unroll
+  for (int k = 0; k < kMaxD; ++k) p[k] = (k < d) ? P[(size_t)q * d + k] : 0.0;
+  double best = INFINITY;
+  int bi = 0x7fffffff;
+  for (int e = lane; e < Ne; e += 32) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < kMaxD; ++k)
+      if (k < d) {
+        const double t = __dsub_rn(Xe[(size_t)e * d + k], p[k]);
+        acc = __dadd_rn(acc, __dmul_rn(t, t));
+      }
+    const double dist = __dsqrt_rn(acc);
+    if (dist < best) { best = dist; bi = e; }       // ascending e per lane: strict < keeps the first
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) out[q] = bi;
+}
+
 // Opt in to > 48 KB of dynamic shared memory.  cudaFuncSetAttribute blocks while instances of the kernel are
 // running, which would serialise launches on different streams, so it is issued only when the requested size
 // grows (cached per kernel and device).
@@ -775,6 +807,14 @@ int stp_log_ei(long long count, const double* mean, const double* var, double be
   if (blocks > 148 * 16) blocks = 148 * 16;
   k_log_ei<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(count, mean, var, best_f, out);
   return after_launch("stp_log_ei");
+}
+
+int stp_design_snap(int Q, int Ne, int d, const double* points, const double* eligible, int32_t* out_idx, void* stream) {
+  if (Q < 0 || Ne < 1 || d < 1 || d > STP_MAX_D) return fail("bad argument");
+  if (!points || !eligible || !out_idx) return fail("null argument");
+  if (Q == 0) return 0;
+  k_design_snap<<<(Q + 7) / 8, 256, 0, (cudaStream_t)stream>>>(Q, Ne, d, points, eligible, out_idx);
+  return after_launch("stp_design_snap");
 }
 
 int stp_phase_timers(unsigned long long* out32, int reset) {

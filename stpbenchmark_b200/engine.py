@@ -33,7 +33,8 @@ class CampaignBatch:
     def __init__(self, pools: torch.Tensor, pool_ys: torch.Tensor, pool_id: Sequence[int],
                  init_indices: Sequence[Sequence[int]], n_cap: int, kind: str = "ExactGP",
                  device: Optional[torch.device] = None, epochs: int = 600, learning_rate: float = 0.01,
-                 num_samples: int = 2048, seeds: Optional[Sequence[int]] = None):
+                 num_samples: int = 2048, seeds: Optional[Sequence[int]] = None,
+                 pool_sizes: Optional[Sequence[int]] = None, lengthscale_prior=None):
         if not torch.cuda.is_available():
             raise RuntimeError("CampaignBatch needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -63,6 +64,11 @@ class CampaignBatch:
             mask[b, t] = 0
             trace[b, : len(idx)] = t.to(torch.int32)
             n[b] = len(idx)
+        if pool_sizes is not None:      # ragged pools, zero-padded to N rows: the padding is never a candidate
+            for b, g in enumerate(pool_id):
+                mask[b, int(pool_sizes[int(g)]):] = 0
+        self.pool_sizes = None if pool_sizes is None else [int(v) for v in pool_sizes]
+        self.lengthscale_prior = lengthscale_prior
         self.mask = mask.to(dev)
         self.trace = trace.to(dev)
         self.n = n.to(dev)
@@ -120,6 +126,8 @@ class CampaignBatch:
                     self._n_host[self._n_host >= self._turnover.n_final] = self._turnover.n_init
         else:
             self.launches += self._var.step()
+            if self._n_host is not None:
+                self._n_host += 1
         self.iteration += 1
 
     def run(self, n_trials: int, chunk: Optional[int] = None) -> None:
@@ -180,9 +188,11 @@ class CampaignBatch:
         mirrors on the host (n, status) has been changed from outside."""
         self._n_host = None if n_host is None else np.asarray(n_host, dtype=np.int64).copy()
 
-    def traces(self):
-        """(indices [B, cap] int64 with -1 beyond the last pick, n [B], status [B]) on the host."""
-        torch.cuda.synchronize(self.device)
+    def traces(self, sync: bool = True):
+        """(indices [B, cap] int64 with -1 beyond the last pick, n [B], status [B]) on the host.  ``sync=False``: the
+        caller has already synchronised the stream this batch runs on."""
+        if sync:
+            torch.cuda.synchronize(self.device)
         return self.trace.cpu().long(), self.n.cpu().long(), self.status.cpu().long()
 
     def selected_values(self):
@@ -235,6 +245,122 @@ class CampaignBatch:
         self.y[slots, :ni] = self.pool_y[pid.unsqueeze(1), new_init]
         self.n[slots] = ni
         self.status[slots] = 0
+
+
+class Campaign:
+    """One campaign of a job: which pool, which model kind, its initial design and its budget."""
+
+    __slots__ = ("key", "kind", "pool", "design", "n_trials", "epochs", "learning_rate", "num_samples",
+                 "lengthscale_prior", "rng_state", "seed")
+
+    def __init__(self, key, kind: str, pool: int, design: Sequence[int], n_trials: int, epochs: int = 100,
+                 learning_rate: float = 0.1, num_samples: int = 2048, lengthscale_prior=None, rng_state=None, seed: int = 0):
+        self.key, self.kind, self.pool, self.design = key, kind, int(pool), [int(i) for i in design]
+        self.n_trials, self.epochs, self.learning_rate = int(n_trials), int(epochs), float(learning_rate)
+        self.num_samples, self.lengthscale_prior, self.rng_state, self.seed = int(num_samples), lengthscale_prior, rng_state, int(seed)
+
+    def group_key(self, d: int):
+        """Campaigns that can share launches: same kernel arguments and the same age at every step."""
+        lp = None if self.lengthscale_prior is None else tuple(float(v) for v in self.lengthscale_prior)
+        return (self.kind, d, len(self.design), self.n_trials, self.epochs, self.learning_rate, self.num_samples, lp)
+
+
+class CampaignJob:
+    """Every campaign of a sweep -- seeds x datasets x model kinds -- on ONE GPU at once (the reference runs them one
+    after another: run_benchmark.py:20-43 -> runners.py:174-178).
+
+    Campaigns are grouped by what a launch must have in common (model kind, input dimension, budget); the pools of a
+    group may have different sizes (they are zero-padded to the largest one and the padding is masked out), so the
+    five datasets of BASELINE config #2 form three groups (d = 3, 4, 5) instead of five half-empty batches.  Every
+    group is a CampaignBatch on its own CUDA stream: ExactGP groups advance by persistent work-queue launches
+    (stp_exact_bo_run, ``chunk`` iterations each), variational groups in lock-step (stp_var_fit + stp_var_acq), and
+    the groups overlap on the device.  ``run`` returns when all are done; ``on_group_done`` is called per group as
+    soon as ITS campaigns have finished (the hook the CSV writer uses to save finished seeds early).
+    """
+
+    def __init__(self, pools: Sequence, campaigns: Sequence[Campaign], device: Optional[torch.device] = None,
+                 chunk: int = 16):
+        if not torch.cuda.is_available():
+            raise RuntimeError("CampaignJob needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.campaigns = list(campaigns)
+        self.chunk = int(chunk)
+        by_key = {}
+        for c_id, c in enumerate(self.campaigns):
+            d = pools[c.pool][0].shape[1]
+            by_key.setdefault(c.group_key(d), []).append(c_id)
+        self.groups = []
+        for key, ids in by_key.items():
+            kind, d, n_init, n_trials, epochs, lr, S, lp = key
+            used = sorted({self.campaigns[i].pool for i in ids})
+            local = {g: k for k, g in enumerate(used)}
+            sizes = [int(pools[g][0].shape[0]) for g in used]
+            N = max(sizes)
+            PX = torch.zeros(len(used), N, d, dtype=torch.double)
+            PY = torch.zeros(len(used), N, dtype=torch.double)
+            for g in used:
+                PX[local[g], : sizes[local[g]]] = pools[g][0].detach().cpu().double()
+                PY[local[g], : sizes[local[g]]] = pools[g][1].detach().cpu().double().flatten()
+            trials = min(n_trials, min(sizes) - n_init)      # runners.py:62 (per pool; equal budgets share a group)
+            if any(min(n_trials, sz - n_init) != trials for sz in sizes):
+                raise ValueError("pools of one group must leave the same number of trials (runners.py:62)")
+            stream = torch.cuda.Stream(device=self.device)
+            with torch.cuda.stream(stream):
+                batch = CampaignBatch(PX, PY, [local[self.campaigns[i].pool] for i in ids],
+                                      [self.campaigns[i].design for i in ids], n_cap=n_init + max(trials, 0) + 1, kind=kind,
+                                      device=self.device, epochs=epochs, learning_rate=lr, num_samples=S,
+                                      seeds=[self.campaigns[i].seed for i in ids], pool_sizes=sizes, lengthscale_prior=lp)
+                if kind != "ExactGP" and all(self.campaigns[i].rng_state is not None for i in ids):
+                    batch._var.set_rng_states([self.campaigns[i].rng_state for i in ids])
+            self.groups.append({"key": key, "ids": ids, "batch": batch, "stream": stream, "trials": max(trials, 0)})
+        torch.cuda.synchronize(self.device)
+
+    def run(self, on_group_done=None):
+        """Advance every campaign to the end of its budget.  Returns {campaign index: (indices, status)}."""
+        # enqueue: round-robin over the groups so that their launches interleave in submission order too
+        progress = [0] * len(self.groups)
+        pending = True
+        while pending:
+            pending = False
+            for gi, gr in enumerate(self.groups):
+                left = gr["trials"] - progress[gi]
+                if left <= 0:
+                    continue
+                pending = True
+                with torch.cuda.stream(gr["stream"]):
+                    if gr["batch"].kind == "ExactGP":
+                        k = min(self.chunk, left)
+                        gr["batch"].run_queue(k)
+                    else:
+                        k = 1
+                        gr["batch"].step()
+                progress[gi] += k
+        for gr in self.groups:
+            gr["done"] = torch.cuda.Event()
+            gr["done"].record(gr["stream"])
+        out = {}
+        remaining = list(range(len(self.groups)))
+        while remaining:                                 # hand the groups over in completion order
+            ready = [gi for gi in remaining if self.groups[gi]["done"].query()]
+            if not ready:
+                self.groups[remaining[0]]["done"].synchronize()
+                ready = [remaining[0]]
+            for gi in ready:
+                remaining.remove(gi)
+                gr = self.groups[gi]
+                gr["stream"].synchronize()
+                idx, n, status = gr["batch"].traces(sync=False)
+                res = {}
+                for row, c_id in enumerate(gr["ids"]):
+                    res[c_id] = ([int(v) for v in idx[row, : int(n[row])]], int(status[row]))
+                out.update(res)
+                if on_group_done is not None:
+                    on_group_done(res)
+        return out
+
+    @property
+    def launches(self) -> int:
+        return sum(gr["batch"].launches for gr in self.groups)
 
 
 class CampaignGroups:

@@ -6,70 +6,163 @@
                      columns ``(seed_<s>, x_index|y_value)``, index ``iteration``), same resume rule
                      (seeds already present as columns are skipped), NaN padding of unfinished
                      traces.  The seeds are advanced TOGETHER as one device batch instead of one
-                     after another.  One deliberate deviation: with ``invert_y=True`` a resumed run
-                     no longer re-inverts the y columns of previously saved seeds
-                     (runners.py:155 x :193); ``x_index`` is unaffected.
-``run_campaign_batch`` the engine entry point both of them use.
+                     after another.
+``run_sweep``        what run_benchmark.py's nested loops do (run_benchmark.py:20-43): SEVERAL
+                     ``run_many_loops`` jobs -- model x dataset -- submitted at once, so that every
+                     (model, dataset, seed) campaign of the sweep shares the GPU (engine.CampaignJob) and, under
+                     ``torch.distributed``, the GPUs of the box (contiguous shards, one final gather of the traces).
+                     A job's CSV is written as soon as ITS campaigns have finished.
+
+Deliberate deviations from the reference (documented in INTEGRATION.md):
+  * with ``invert_y=True`` a resumed run no longer re-inverts the y columns of previously saved
+    seeds (runners.py:155 x :193, SURVEY App. B.3); ``x_index`` is unaffected;
+  * a seed counts as done only if its column holds at least one row (an all-NaN column written by a
+    crashed run is recomputed), and a failure never writes columns for seeds that produced nothing;
+  * ``model_class`` must be one of the four stock classes and ``model_kwargs`` may only carry what their
+    constructors take (``lengthscale_prior`` is honoured; anything else is an error, as
+    ``model_class(**model_kwargs)`` would be at runners.py:74) -- the arithmetic runs in fused kernels, so
+    a subclass override could not be honoured and is rejected instead of silently ignored.
 """
 from __future__ import annotations
 
+import inspect
 import os
-from typing import Dict, List, Optional, Sequence, Tuple, Type, Union
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Type, Union
 
 import numpy as np
 import pandas as pd
 import torch
 
-from .engine import CampaignBatch
+from . import distributed as sdist
+from .engine import Campaign, CampaignJob
 from .models import ExactGP, VarGP, VarLGP, VarTGP
-from .utils import get_initial_samples_sobol, set_seeds
+from .utils import initial_designs_batch
 
 _KIND = {ExactGP: "ExactGP", VarGP: "VarGP", VarLGP: "VarLGP", VarTGP: "VarTGP"}
+_SET_BY_THE_LOOP = {"ExactGP": ("X_train", "y_train", "input_transform"), "VarGP": ("inducing_points",),
+                    "VarLGP": ("inducing_points",), "VarTGP": ("inducing_points",)}
 
 
 def _kind_of(model_class) -> str:
+    """Model kind of a stock class (or its name).  Subclasses are rejected: their overrides (forward, priors,
+    likelihood ...) cannot reach the fused kernels, and ignoring them silently would change results."""
     if isinstance(model_class, str):
-        return model_class
+        if model_class in _KIND.values():
+            return model_class
+        raise TypeError(f"unsupported model kind {model_class!r}")
     for cls, name in _KIND.items():
-        if model_class is cls or (isinstance(model_class, type) and issubclass(model_class, cls)):
+        if model_class is cls:
             return name
+    if isinstance(model_class, type) and any(issubclass(model_class, cls) for cls in _KIND):
+        raise NotImplementedError(
+            f"{model_class.__name__} subclasses a stock model; the batched engine runs the stock arithmetic in fused "
+            "kernels and cannot honour overrides -- pass ExactGP / VarGP / VarLGP / VarTGP themselves")
     raise TypeError(f"unsupported model class {model_class!r}")
+
+
+def _lengthscale_prior_of(kind: str, model_class, model_kwargs: Optional[dict]):
+    """What ``model_class(**model_kwargs)`` (runners.py:66-74) would have taken from ``model_kwargs``: the keys the
+    loop sets itself are overwritten there and ignored here; ``lengthscale_prior`` (models.py:30, 125, 217) is
+    returned as (loc, scale); any other key raises like the constructor call would."""
+    if not model_kwargs:
+        return None
+    accepted = set()
+    if not isinstance(model_class, str):
+        accepted = set(inspect.signature(model_class.__init__).parameters) - {"self"}
+    prior = None
+    for k, v in model_kwargs.items():
+        if k in _SET_BY_THE_LOOP[kind]:
+            continue
+        if k == "lengthscale_prior" and kind != "ExactGP":
+            if v is None:
+                continue
+            prior = (float(v[0]), float(v[1])) if isinstance(v, (tuple, list)) else (float(v.loc), float(v.scale))
+            continue
+        if k in accepted:
+            raise NotImplementedError(f"model_kwargs[{k!r}] is not supported by the batched engine")
+        raise TypeError(f"{kind}.__init__() got an unexpected keyword argument {k!r}")
+    return prior
 
 
 def initial_design(X: torch.Tensor, y: torch.Tensor, seed: int, n_initial: int):
     """runners.py:33, 46-48: seed everything, then the Sobol initial design.  Returns the indices
     and the state of the global torch generator right after (what the variational models'
     first-forward noise is drawn from, App. A.6)."""
-    set_seeds(seed)
-    idx = get_initial_samples_sobol(X, y, n_samples=n_initial, percentile=50)
-    return idx.tolist(), torch.get_rng_state()
+    idx, states = initial_designs_batch(X, y, [int(seed)], n_initial, 50.0, return_rng_states=True)
+    return idx[0].tolist(), states[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# the engine entry point: many campaigns, many pools, one call
+# ---------------------------------------------------------------------------------------------
+def _execute_on_device(pools, campaigns: List[Campaign], on_done: Optional[Callable] = None):
+    """{campaign index: (indices, status)} for the given campaigns on the current CUDA device."""
+    if not campaigns:
+        return {}
+    job = CampaignJob(pools, campaigns)
+    return job.run(on_group_done=on_done)
+
+
+def run_campaigns(pools, campaigns: List[Campaign], on_done: Optional[Callable] = None, _executor=None):
+    """Run every campaign; under an initialised ``torch.distributed`` group the campaign list is sharded in
+    contiguous blocks over the ranks (one process per GPU, no data-path collective) and the traces are gathered
+    on rank 0 at the end.  Returns {campaign index: (indices, status)} on rank 0 (all campaigns)
+    and on the other ranks (their own shard).  ``on_done`` receives finished groups on the rank that ran them, or,
+    with several ranks, the complete result once on rank 0."""
+    import torch.distributed as dist
+    execute = _executor or _execute_on_device
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return execute(pools, campaigns, on_done)
+    rank = dist.get_rank()
+    # order by what shares launches (kind, pool, budget) so that a rank's shard forms few, full groups
+    order = sorted(range(len(campaigns)), key=lambda i: (campaigns[i].kind, campaigns[i].pool, campaigns[i].n_trials, i))
+    lo, hi = sdist.shard_bounds(len(order), world, rank)
+    mine = order[lo:hi]
+    local = execute(pools, [campaigns[i] for i in mine], None)
+    T = max((len(c.design) + c.n_trials for c in campaigns), default=0) + 1
+    use_cuda = dist.get_backend() == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+    tr = torch.full((len(mine), T), -1, dtype=torch.int32, device=dev)
+    st = torch.full((len(mine), T), float("nan"), dtype=torch.double, device=dev)   # column 0 carries the status
+    for row in range(len(mine)):
+        idx, status = local[row]
+        tr[row, : len(idx)] = torch.tensor(idx, dtype=torch.int32)
+        st[row, 0] = float(status)
+    got = sdist.gather_traces(tr, st, len(order))
+    if got is None:
+        return {mine[row]: local[row] for row in range(len(mine))}
+    gt, gs = got[0].cpu(), got[1].cpu()
+    out = {}
+    for pos, c_id in enumerate(order):
+        row = gt[pos]
+        out[c_id] = ([int(v) for v in row[row >= 0]], int(gs[pos, 0]))
+    if on_done is not None:
+        on_done(out)
+    return out
 
 
 def run_campaign_batch(X: torch.Tensor, y: torch.Tensor, model_class, seeds: Sequence[int], n_initial: int = 10,
                        n_trials: int = 25, epochs: int = 100, learning_rate: float = 0.1,
-                       num_samples: int = 2048) -> Tuple[List[List[int]], List[List[float]], List[int]]:
+                       num_samples: int = 2048, model_kwargs: Optional[dict] = None
+                       ) -> Tuple[List[List[int]], List[List[float]], List[int]]:
     """Advance one campaign per seed on the same pool, all together.  Returns
     (indices per seed, values per seed, status per seed)."""
     X = X.double()
     y = y.double().flatten()
     kind = _kind_of(model_class)
+    prior = _lengthscale_prior_of(kind, model_class, model_kwargs)
     n_trials = min(int(n_trials), len(X) - int(n_initial))  # runners.py:62
-    designs, rng_states = [], []
-    for s in seeds:
-        idx, state = initial_design(X, y, int(s), n_initial)
-        designs.append(idx)
-        rng_states.append(state)
-    cap = max(len(d_) for d_ in designs) + n_trials + 1
-    batch = CampaignBatch(X, y, [0] * len(designs), designs, n_cap=cap, kind=kind, epochs=epochs,
-                          learning_rate=learning_rate, num_samples=num_samples, seeds=[int(s) for s in seeds])
-    if kind != "ExactGP":
-        batch._var.set_rng_states(rng_states)
-    batch.run(n_trials)
-    idx, n, status = batch.traces()
+    seeds = [int(s) for s in seeds]
+    dev = "cuda" if torch.cuda.is_available() else None
+    designs, states = initial_designs_batch(X, y, seeds, n_initial, 50.0, return_rng_states=True, device=dev)
+    camps = [Campaign(s, kind, 0, designs[k].tolist(), n_trials, epochs, learning_rate, num_samples, prior,
+                      states[k], seed=s) for k, s in enumerate(seeds)]
+    res = run_campaigns([(X, y)], camps)
     y_host = y.cpu()
-    out_idx = [[int(v) for v in idx[b, : int(n[b])]] for b in range(len(designs))]
+    out_idx = [res[k][0] for k in range(len(seeds))]
     out_val = [[float(y_host[i]) for i in row] for row in out_idx]
-    return out_idx, out_val, [int(s) for s in status]
+    return out_idx, out_val, [res[k][1] for k in range(len(seeds))]
 
 
 def run_single_loop(
@@ -83,24 +176,152 @@ def run_single_loop(
     learning_rate: float = 0.1,
     seed: int = 42,
 ) -> Tuple[List[int], List[float]]:
-    """One BO campaign on (X, y); drop-in for runners.py:14-115 (a batch of one)."""
+    """One BO campaign on (X, y); drop-in for runners.py:14-115 (a batch of one).  Like the reference it never
+    raises: whatever was selected before a failure is returned (at least the initial design once that exists)."""
+    selected_indices: List[int] = []
+    selected_values: List[float] = []
     try:
-        idx, val, status = run_campaign_batch(X, y, model_class, [seed], n_initial=n_initial, n_trials=n_trials,
-                                              epochs=epochs, learning_rate=learning_rate)
+        Xd, yd = X.double(), y.double().flatten()
+        init, _ = initial_design(Xd, yd, seed, n_initial)      # runners.py:46-52: recorded before anything can fail
+        selected_indices = list(init)
+        selected_values = [float(yd[i]) for i in init]
+        idx, val, status = run_campaign_batch(Xd, yd, model_class, [seed], n_initial=n_initial, n_trials=n_trials,
+                                              epochs=epochs, learning_rate=learning_rate, model_kwargs=model_kwargs)
+        selected_indices, selected_values = idx[0], val[0]
         if status[0] != 0:
-            print(f"Error occurred at iteration {len(val[0])}: campaign stopped with status {status[0]}")
-        return idx[0], val[0]
+            print(f"Error occurred at iteration {len(selected_values)}: campaign stopped with status {status[0]}")
+        if isinstance(model_kwargs, dict):   # runners.py:67-72 leaves the last training set in the caller's dict
+            kind = _kind_of(model_class)
+            Xt, yt = Xd[selected_indices[:-1]] if len(idx[0]) > n_initial else Xd[selected_indices], None
+            if kind == "ExactGP":
+                yt = yd[selected_indices[:-1]] if len(idx[0]) > n_initial else yd[selected_indices]
+                model_kwargs.update(X_train=Xt, y_train=yt, input_transform=None)
+            else:
+                model_kwargs["inducing_points"] = Xt
+        return selected_indices, selected_values
     except Exception as e:  # same contract as runners.py:113-115
-        print(f"Error occurred at iteration 0: {str(e)}")
-        return [], []
+        print(f"Error occurred at iteration {len(selected_values)}: {str(e)}")
+        return selected_indices, selected_values
 
 
+# ---------------------------------------------------------------------------------------------
+# CSV layer (runners.py:141-202)
+# ---------------------------------------------------------------------------------------------
 def _empty_frame(seeds, total_iterations) -> pd.DataFrame:
     columns = pd.MultiIndex.from_tuples(
         [(f"seed_{seed}", metric) for seed in seeds for metric in ["x_index", "y_value"]])
     frame = pd.DataFrame(index=range(total_iterations), columns=columns)
     frame.index.name = "iteration"
     return frame
+
+
+def _save(frame: pd.DataFrame, path: str, invert_y: bool) -> None:
+    """Write the frame; columns of seeds that hold nothing are left out (a later run recomputes them)."""
+    save_df = frame.copy()
+    empty = [s for s in save_df.columns.get_level_values(0).unique() if save_df[s]["x_index"].isna().all()]
+    if empty:
+        save_df = save_df.drop(columns=empty, level=0)
+    if invert_y:
+        y_cols = [c for c in save_df.columns if c[1] == "y_value"]
+        save_df[y_cols] = 1.0 / save_df[y_cols].astype(float)
+    tmp = path + ".tmp"
+    save_df.to_csv(tmp)
+    os.replace(tmp, path)           # a crash mid-write never truncates what was saved before
+
+
+class _CsvJob:
+    """One ``run_many_loops`` call inside a sweep: its frame, its resume state and its pending seeds."""
+
+    def __init__(self, X, y, model_class, seeds, output_path, invert_y=False, **kwargs):
+        self.X, self.y = X.double(), y.double().flatten()
+        self.model_class, self.output_path, self.invert_y = model_class, output_path, bool(invert_y)
+        self.kwargs = dict(kwargs)
+        self.n_initial = int(kwargs.get("n_initial", 10))
+        self.n_trials = int(kwargs.get("n_trials", 25))
+        self.total = self.n_initial + self.n_trials
+        self.seeds = [int(s) for s in seeds]
+        out_dir = os.path.dirname(output_path)
+        if out_dir:
+            os.makedirs(out_dir, exist_ok=True)
+        if os.path.exists(output_path):
+            self.frame = pd.read_csv(output_path, header=[0, 1], index_col=0)
+            done = {int(col.split("_")[1]) for col in self.frame.columns.get_level_values(0).unique()
+                    if not self.frame[col]["x_index"].isna().all()}
+            if self.invert_y:  # the file holds 1/y: undo it so that saving is idempotent (App. B.3)
+                y_cols = [c for c in self.frame.columns if c[1] == "y_value"]
+                self.frame[y_cols] = 1.0 / self.frame[y_cols].astype(float)
+        else:
+            self.frame = _empty_frame(self.seeds, self.total)
+            done = set()
+        self.remaining = [s for s in self.seeds if s not in done]
+
+    def record(self, seed: int, indices: List[int]) -> None:
+        y_host = self.y.cpu()
+        values = [float(y_host[i]) for i in indices]
+        indices = list(indices) + [np.nan] * (self.total - len(indices))  # runners.py:181-182
+        values = values + [np.nan] * (self.total - len(values))
+        self.frame[f"seed_{seed}", "x_index"] = indices[: self.total]
+        self.frame[f"seed_{seed}", "y_value"] = values[: self.total]
+
+    def save(self) -> None:
+        _save(self.frame, self.output_path, self.invert_y)
+
+
+def run_sweep(jobs: Sequence[dict], _executor=None) -> List[pd.DataFrame]:
+    """Run several ``run_many_loops`` jobs (dicts of its arguments: X, y, model_class, seeds, output_path, invert_y,
+    n_initial, n_trials, epochs, learning_rate, model_kwargs) as ONE device job.  Every campaign of every job shares
+    the GPU(s); a job's CSV is (re)written whenever a group of its campaigns finishes.  Returns the frames."""
+    import torch.distributed as dist
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    csv_jobs, pools, camps, owner = [], [], [], []
+    on_cuda = torch.cuda.is_available() and _executor is None
+    for j, spec in enumerate(jobs):
+        spec = dict(spec)
+        job = _CsvJob(spec.pop("X"), spec.pop("y"), spec.pop("model_class"), spec.pop("seeds"), spec.pop("output_path"),
+                      spec.pop("invert_y", False), **spec)
+        csv_jobs.append(job)
+        if not job.remaining:
+            print("     [INFO] All requested seeded runs already completed.")
+            continue
+        try:
+            kind = _kind_of(job.model_class)
+            prior = _lengthscale_prior_of(kind, job.model_class, job.kwargs.get("model_kwargs"))
+            designs, states = initial_designs_batch(job.X, job.y, job.remaining, job.n_initial, 50.0,
+                                                    return_rng_states=True, device="cuda" if on_cuda else None)
+        except Exception as e:
+            print(f"Error in batch of seeds {job.remaining}: {str(e)}")
+            continue
+        pools.append((job.X, job.y))
+        trials = min(job.n_trials, len(job.X) - job.n_initial)
+        for k, s in enumerate(job.remaining):
+            camps.append(Campaign((j, s), kind, len(pools) - 1, designs[k].tolist(), trials,
+                                  int(job.kwargs.get("epochs", 100)), float(job.kwargs.get("learning_rate", 0.1)),
+                                  int(job.kwargs.get("num_samples", 2048)), prior, states[k], seed=s))
+            owner.append((j, s))
+
+    def on_done(res: Dict[int, tuple]):
+        if rank != 0:
+            return
+        touched = set()
+        for c_id, (indices, status) in res.items():
+            j, s = owner[c_id]
+            if status != 0:
+                print(f"Error occurred at iteration {len(indices)}: campaign (job {j}, seed {s}) stopped with status {status}")
+            csv_jobs[j].record(s, indices)
+            touched.add(j)
+        for j in touched:
+            csv_jobs[j].save()
+
+    if camps:
+        try:
+            run_campaigns(pools, camps, on_done=on_done, _executor=_executor)
+        except Exception as e:
+            print(f"Error in sweep: {str(e)}")
+            if rank == 0:
+                for job in csv_jobs:     # what finished before the failure is already saved; keep files consistent
+                    if os.path.exists(job.output_path) or not job.frame.isna().all().all():
+                        job.save()
+    return [job.frame for job in csv_jobs]
 
 
 def run_many_loops(
@@ -113,46 +334,5 @@ def run_many_loops(
     **kwargs,
 ) -> pd.DataFrame:
     """Run one campaign per seed and write the traces CSV; drop-in for runners.py:118-202."""
-    n_initial = kwargs.get("n_initial", 10)
-    n_trials = kwargs.get("n_trials", 25)
-    total_iterations = n_initial + n_trials
-    out_dir = os.path.dirname(output_path)
-    if out_dir:
-        os.makedirs(out_dir, exist_ok=True)
-    seeds = [int(s) for s in seeds]
-
-    if os.path.exists(output_path):
-        results_df = pd.read_csv(output_path, header=[0, 1], index_col=0)
-        done = {int(col.split("_")[1]) for col in results_df.columns.get_level_values(0)}
-        remaining = [s for s in seeds if s not in done]
-        if invert_y:  # the file holds 1/y: undo it so that saving is idempotent (App. B.3)
-            y_cols = [c for c in results_df.columns if c[1] == "y_value"]
-            results_df[y_cols] = 1.0 / results_df[y_cols]
-    else:
-        remaining = seeds
-        results_df = _empty_frame(seeds, total_iterations)
-
-    if len(remaining) == 0:
-        print("     [INFO] All requested seeded runs already completed.")
-        return results_df
-
-    try:
-        idx, val, _ = run_campaign_batch(
-            X, y, model_class, remaining, n_initial=n_initial, n_trials=n_trials,
-            epochs=kwargs.get("epochs", 100), learning_rate=kwargs.get("learning_rate", 0.1))
-    except Exception as e:
-        print(f"Error in batch of seeds {remaining}: {str(e)}")
-        results_df.to_csv(output_path)
-        return results_df
-
-    for seed, indices, values in zip(remaining, idx, val):
-        indices = list(indices) + [np.nan] * (total_iterations - len(indices))  # runners.py:181-182
-        values = list(values) + [np.nan] * (total_iterations - len(values))
-        results_df[f"seed_{seed}", "x_index"] = indices[:total_iterations]
-        results_df[f"seed_{seed}", "y_value"] = values[:total_iterations]
-    save_df = results_df.copy()
-    if invert_y:
-        y_cols = [c for c in save_df.columns if c[1] == "y_value"]
-        save_df[y_cols] = 1.0 / save_df[y_cols].astype(float)
-    save_df.to_csv(output_path)
-    return results_df
+    return run_sweep([dict(X=X, y=y, model_class=model_class, seeds=seeds, output_path=output_path, invert_y=invert_y,
+                           **kwargs)])[0]

@@ -27,6 +27,9 @@ __all__ = [
     "preprocess_data",
     "get_initial_samples",
     "get_initial_samples_sobol",
+    "sobol_scrambled_draw",
+    "sobol_scrambled_draw_batch",
+    "initial_designs_batch",
     "get_device",
     "EI",
 ]
@@ -161,6 +164,133 @@ def get_initial_samples_sobol(
         dist = torch.norm(Xe - p, dim=1)
         picks.append(eligible[torch.argmin(dist)].item())
     return torch.tensor(picks, dtype=torch.long)
+
+
+# ---------------------------------------------------------------------------------------------
+# Batched initial designs: what `set_seeds(seed); get_initial_samples_sobol(X, y, n, p)`
+# returns for MANY seeds on one pool, without paying the per-seed Python / SobolEngine construction cost
+# (1.2 ms per design serially; 1024 designs of BASELINE config #4 took longer than the GPU needs for all their
+# 81 920 BO iterations).  The scrambled-Sobol draw stays on the host -- it is defined by torch's CPU generator --
+# but goes straight to the three ATen ops SobolEngine itself uses, with a private generator seeded like the
+# global one; the O(S n N d) nearest-eligible-point snap is one vectorised pass (host) or one kernel
+# (stp_design_snap, when the pool lives on a CUDA device).
+# ---------------------------------------------------------------------------------------------
+_SOBOL_BASE = {}
+
+
+def _sobol_base(d: int):
+    if d not in _SOBOL_BASE:
+        state = torch.zeros(d, SobolEngine.MAXBIT, dtype=torch.long)
+        torch._sobol_engine_initialize_state_(state, d)
+        _SOBOL_BASE[d] = (state, torch.pow(2, torch.arange(0, SobolEngine.MAXBIT)))
+    return _SOBOL_BASE[d]
+
+
+def sobol_scrambled_draw(seed: int, d: int, n: int, generator: torch.Generator = None):
+    """(points [n, d] fp32, generator) == ``torch.manual_seed(seed); SobolEngine(d, scramble=True).draw(n)`` and the
+    state the global generator is left in (utils.py:262-269 after set_seeds, utils.py:11-16): same ATen calls in
+    the same order (torch/quasirandom.py: randint shift, randint lower-triangular matrices, _sobol_engine_scramble_,
+    _sobol_engine_draw), on a private generator, so nothing global is touched."""
+    base, pow2 = _sobol_base(d)
+    g = generator if generator is not None else torch.Generator()
+    g.manual_seed(int(seed))
+    maxbit = SobolEngine.MAXBIT
+    shift = torch.mv(torch.randint(2, (d, maxbit), generator=g), pow2)
+    ltm = torch.randint(2, (d, maxbit, maxbit), generator=g).tril()
+    state = base.clone()
+    torch._sobol_engine_scramble_(state, ltm, d)
+    first = (shift / 2 ** maxbit).reshape(1, -1).to(torch.float32)
+    if n == 1:
+        return first, g
+    rest, _ = torch._sobol_engine_draw(shift.clone(), n - 1, state, d, 0, dtype=torch.float32)
+    return torch.cat((first, rest), dim=-2), g
+
+
+def sobol_scrambled_draw_batch(seeds, d: int, n: int, return_rng_states: bool = False):
+    """``sobol_scrambled_draw`` for many seeds at once: [len(seeds), n, d] fp32 (+ the generator states).
+
+    Only the two ``randint`` calls per seed touch torch's generator (they define the scramble); the linear scramble
+    of the direction numbers (ATen `_sobol_engine_scramble_`: new_v[d][j] = sum_p parity(popcount(row_p(LTM_d) & v[d][j]))
+    2^(MAXBIT-1-p), rows read MSB-first with a unit diagonal) and the Gray-code draw (`_sobol_engine_draw`: point i =
+    point i-1 xor the direction number at the lowest zero bit of i-1, scaled by 2^-MAXBIT in fp32) are vectorised
+    over the seeds.  Bit-exact against SobolEngine (tests/test_host_utils.py)."""
+    maxbit = SobolEngine.MAXBIT
+    base, pow2 = _sobol_base(d)
+    S = len(seeds)
+    shift_bits = torch.empty(S, d, maxbit, dtype=torch.long)
+    ltm = torch.empty(S, d, maxbit, maxbit, dtype=torch.float32)
+    states = [] if return_rng_states else None
+    g = torch.Generator()
+    for i, seed in enumerate(seeds):
+        g.manual_seed(int(seed))
+        shift_bits[i] = torch.randint(2, (d, maxbit), generator=g)
+        ltm[i] = torch.randint(2, (d, maxbit, maxbit), generator=g)
+        if return_rng_states:
+            states.append(g.get_state())
+    shift = (shift_bits @ pow2).numpy()                                  # [S, d]
+    ltm = ltm.tril()
+    ltm.diagonal(dim1=-2, dim2=-1).fill_(1.0)
+    # parity(popcount(row_p & v_j)) = (sum_c LTM[p][c] * bit_{MAXBIT-1-c}(v_j)) mod 2: small exact fp32 contractions
+    rev = torch.arange(maxbit - 1, -1, -1)
+    vbits = ((base.unsqueeze(-1) >> rev) & 1).to(torch.float32)          # [d, j, c]
+    par = torch.einsum("sdpc,djc->sdjp", ltm, vbits).remainder_(2.0)
+    state = (par.double() @ torch.pow(2.0, rev.double())).long().numpy()  # [S, d, j]
+    pts = np.empty((S, n, d), dtype=np.int64)
+    quasi = shift.copy()
+    pts[:, 0] = quasi
+    for i in range(n - 1):
+        l = 0
+        while (i >> l) & 1:                                              # lowest zero bit of i
+            l += 1
+        quasi = quasi ^ state[:, :, l]
+        pts[:, i + 1] = quasi
+    out = torch.from_numpy(pts).to(torch.float32) * torch.tensor(2.0 ** -maxbit, dtype=torch.float32)
+    return (out, states) if return_rng_states else out
+
+
+def initial_designs_batch(X: torch.Tensor, y: torch.Tensor, seeds, n_samples: int = 10, percentile: float = 50.0,
+                          return_rng_states: bool = False, device=None):
+    """Initial designs of many campaigns on one pool: row s == ``set_seeds(seeds[s]);
+    get_initial_samples_sobol(X, y, n_samples, percentile)`` (runners.py:33, 46-48), bit for bit.
+
+    Returns an int64 tensor [len(seeds), n_samples] (on the host) and, with ``return_rng_states``, the list of
+    torch CPU generator states after each draw (what the variational models' first-forward noise continues from,
+    App. A.6).  ``device``: a CUDA device runs the nearest-point snap in stp_design_snap; None = vectorised host pass.
+    """
+    Xh = X.detach().cpu().double()
+    yh = y.detach().cpu().double().flatten()
+    seeds = [int(s) for s in seeds]
+    cut = torch.quantile(yh, percentile / 100)
+    eligible = (yh <= cut).nonzero(as_tuple=True)[0]
+    if len(eligible) < n_samples:                      # utils.py:254-255: not enough eligible points -> all of them
+        out = eligible.unsqueeze(0).expand(len(seeds), -1).clone()
+        states = None
+        if return_rng_states:
+            states = []
+            for s in seeds:
+                g = torch.Generator(); g.manual_seed(s); states.append(g.get_state())
+        return (out, states) if return_rng_states else out
+    Xe = Xh[eligible].contiguous()
+    lo = Xe.min(dim=0)[0]
+    span = Xe.max(dim=0)[0] - lo
+    span[span == 0] = 1.0
+    d = Xh.shape[1]
+    if return_rng_states:
+        pts, states = sobol_scrambled_draw_batch(seeds, d, n_samples, return_rng_states=True)
+    else:
+        pts, states = sobol_scrambled_draw_batch(seeds, d, n_samples), None
+    P = pts * span + lo                                 # fp32 * fp64 -> fp64, two roundings (utils.py:271)
+    if device is not None and torch.device(device).type == "cuda":
+        from . import _lib
+        idx = _lib.design_snap(P.reshape(-1, d).to(device), Xe.to(device)).cpu().long().reshape(len(seeds), n_samples)
+    else:
+        idx = torch.empty(len(seeds), n_samples, dtype=torch.long)
+        chunk = max(1, (1 << 22) // max(1, n_samples * Xe.shape[0] * d))
+        for a in range(0, len(seeds), chunk):
+            diff = Xe.reshape(1, 1, -1, d) - P[a:a + chunk].unsqueeze(2)
+            idx[a:a + chunk] = torch.argmin(torch.linalg.vector_norm(diff, dim=-1), dim=-1)
+    out = eligible[idx]
+    return (out, states) if return_rng_states else out
 
 
 def get_device() -> torch.device:

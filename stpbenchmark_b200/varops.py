@@ -57,8 +57,9 @@ class VarBatchState:
         B, cap, d = batch.B, batch.cap, batch.d
         self.state = alloc_state(B, cap, d, batch.device)
         self.work = _lib.var_workspace(B, cap, batch.device)
-        self.prior = var_prior_vector()
-        self.hyp0 = var_hyp0(d)
+        ls_prior = getattr(batch, "lengthscale_prior", None) or priors.VAR_LENGTHSCALE_PRIOR
+        self.prior = var_prior_vector(ls_prior)     # model_kwargs["lengthscale_prior"] (models.py:30, 125, 217)
+        self.hyp0 = var_hyp0(d, ls_prior)
         self.gh = gauss_hermite_table()
         self.generators = None        # per-campaign CPU generators (reference RNG order), optional
         self.philox_seed = 0x5742_1F3D
@@ -78,7 +79,9 @@ class VarBatchState:
         b = self.b
         if self.generators is None:
             return None
-        n_host = b.n.cpu().tolist()
+        # host mirror of n when the engine has one (no device round trip per step); frozen campaigns are skipped by
+        # the kernel, so what is drawn for them does not matter
+        n_host = b._n_host.tolist() if b._n_host is not None else b.n.cpu().tolist()
         noise = torch.zeros(b.B, b.cap, dtype=torch.double)
         for i, (g, n) in enumerate(zip(self.generators, n_host)):
             noise[i, :n] = torch.randn(n, dtype=torch.double, generator=g)

@@ -51,3 +51,59 @@ def test_gather_traces_world2_ragged():
         assert p.exitcode == 0
     want = (torch.arange(B).unsqueeze(1) * 100 + torch.arange(T).unsqueeze(0)).to(torch.int32)
     assert torch.equal(tr, want) and torch.allclose(vals, want.double() / 7.0)
+
+
+def _fake_executor(pools, campaigns, on_done=None):
+    """What the device engine returns, computed on the CPU from the campaign itself (so any rank can be checked)."""
+    res = {}
+    for i, c in enumerate(campaigns):
+        N = len(pools[c.pool][0])
+        k = len(c.design) + (2 if c.seed % 5 == 0 else c.n_trials)       # some campaigns stop early with a status
+        res[i] = (list(c.design) + [(c.seed * 7 + j) % N for j in range(k - len(c.design))], 3 if c.seed % 5 == 0 else 0)
+    return res
+
+
+def _sweep_worker(rank, world, port, tmp, q):
+    """The product path under torch.distributed: runners.run_sweep shards the campaigns of ALL jobs over the ranks,
+    gathers the traces on rank 0, and rank 0 alone writes the CSVs."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from stpbenchmark_b200 import runners
+    g = torch.Generator().manual_seed(0)
+    jobs = []
+    for name, N, d, cls, seeds in (("a", 40, 2, runners.ExactGP, [1, 2, 3, 5, 8]), ("b", 55, 3, runners.VarTGP, [10, 11, 12])):
+        X = torch.rand(N, d, dtype=torch.double, generator=g); y = torch.rand(N, dtype=torch.double, generator=g)
+        jobs.append(dict(X=X, y=y, model_class=cls, seeds=seeds, output_path=os.path.join(tmp, f"{name}.csv"),
+                         n_initial=10, n_trials=6))
+    frames = runners.run_sweep(jobs, _executor=_fake_executor)
+    dist.barrier()
+    if rank == 0:
+        q.put("done")
+    dist.destroy_process_group()
+
+
+def test_run_sweep_shards_over_two_ranks_and_rank0_writes_the_csvs(tmp_path):
+    import pandas as pd
+    from stpbenchmark_b200 import runners, utils
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    assert q.get() == "done"
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    # the same sweep in one process gives the same files
+    g = torch.Generator().manual_seed(0)
+    for name, N, d, seeds in (("a", 40, 2, [1, 2, 3, 5, 8]), ("b", 55, 3, [10, 11, 12])):
+        X = torch.rand(N, d, dtype=torch.double, generator=g); y = torch.rand(N, dtype=torch.double, generator=g)
+        back = pd.read_csv(tmp_path / f"{name}.csv", header=[0, 1], index_col=0)
+        designs = utils.initial_designs_batch(X, y, seeds, 10, 50.0)
+        for k, s_ in enumerate(seeds):
+            want = designs[k].tolist() + [(s_ * 7 + j) % N for j in range(2 if s_ % 5 == 0 else 6)]
+            col = back[f"seed_{s_}", "x_index"]
+            assert col.dropna().astype(int).tolist() == want and len(col) == 16

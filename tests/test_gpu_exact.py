@@ -277,6 +277,48 @@ def test_campaign_groups_on_streams_equal_single_batch():
     assert all(torch.equal(p, q) for p, q in zip(a, b)) and many.launches == 32
 
 
+def test_one_device_job_for_the_whole_sweep_equals_per_dataset_batches(tmp_path):
+    """run_benchmark.py:20-43 as ONE device job (runners.run_sweep -> engine.CampaignJob): datasets of equal input
+    dimension share launches although their pools differ in size (AgNP 164 and P3HT 178 rows, zero-padded + masked),
+    model kinds run side by side on their own streams -- and every trace equals what the same job gives when it is
+    submitted per (model, dataset) like the reference does."""
+    import pandas as pd
+    from stpbenchmark_b200 import models, runners
+    from stpbenchmark_b200.engine import CampaignJob
+    spec = [("ExactGP", "AgNP", models.ExactGP), ("ExactGP", "P3HT", models.ExactGP), ("ExactGP", "Perovskite", models.ExactGP),
+            ("VarGP", "AutoAM", models.VarGP), ("VarGP", "CrossedBarrel", models.VarGP)]
+    def jobs(sub):
+        out = []
+        for mname, dname, cls in spec:
+            X, y = dataset(dname)
+            out.append(dict(X=X, y=y, model_class=cls, seeds=[45, 359, 6185], n_initial=10, n_trials=7, epochs=25,
+                            learning_rate=0.01, output_path=str(tmp_path / sub / f"{mname}_{dname}.csv"),
+                            invert_y=dname in ("AgNP", "Perovskite")))
+        return out
+    seen = []
+    orig = CampaignJob.__init__
+    def spy(self, *a, **k):
+        orig(self, *a, **k)
+        seen.append(sorted((g["key"][0], g["key"][1], len(g["ids"]), g["batch"].N) for g in self.groups))
+    CampaignJob.__init__ = spy
+    try:
+        runners.run_sweep(jobs("all"))
+    finally:
+        CampaignJob.__init__ = orig
+    assert seen == [[("ExactGP", 3, 3, 94), ("ExactGP", 5, 6, 178), ("VarGP", 4, 6, 600)]]
+    for job in jobs("each"):
+        runners.run_sweep([job])
+    for mname, dname, _ in spec:
+        a = pd.read_csv(tmp_path / "all" / f"{mname}_{dname}.csv", header=[0, 1], index_col=0)
+        b = pd.read_csv(tmp_path / "each" / f"{mname}_{dname}.csv", header=[0, 1], index_col=0)
+        assert a.shape == (17, 6) and not a.isna().any().any()
+        assert a.equals(b), (mname, dname)
+        for s_ in (45, 359, 6185):
+            assert a[f"seed_{s_}", "x_index"].astype(int).tolist()[:10] == trace("gold1", mname, dname, s_)[:10]
+    assert pd.read_csv(tmp_path / "all" / "ExactGP_AgNP.csv", header=[0, 1], index_col=0)["seed_45", "x_index"].astype(
+        int).tolist() == trace("gold1", "ExactGP", "AgNP", 45)[:17]
+
+
 def test_persistent_work_queue_matches_lockstep_steps():
     """stp_exact_bo_run (persistent CTAs serving campaign-iterations from a ticket ring) advances every campaign
     exactly like iters x stp_exact_bo_step: same picks, same fitted theta -- with as many CTAs as fit, with 3 CTAs

@@ -195,8 +195,8 @@ def test_vargp_known_answer_smoke_campaigns_on_the_cuda_path():
     """GPU twin of tests/test_oracle_var_golden.py: the five VarGP SMOKE campaigns the oracle is pinned on
     (results/VarGP_*_traces_SMOKE.csv), free-running through the drop-in run_single_loop (device fit, 200 epochs,
     30 trials, the reference's RNG order for the theta1 noise).  The 200-epoch fit is round-off sensitive (the CPU
-    oracle itself leaves one of the five at row 32), so the bar is: every campaign follows the reference's picks for
-    at least 25 of 40 rows, at least 3 of the 5 over all 40."""
+    oracle itself leaves one of the five at row 32), so the bar is the oracle's own result: every campaign follows the
+    reference's picks for at least 30 of 40 rows, at least 4 of the 5 over all 40."""
     import _varpin
     from stpbenchmark_b200 import models, runners
     firsts = {}
@@ -207,16 +207,18 @@ def test_vargp_known_answer_smoke_campaigns_on_the_cuda_path():
         assert len(idx) == 40 and idx[:10] == gold[:10]
         firsts[(name, seed)] = next((i for i in range(40) if idx[i] != gold[i]), 40)
     print("VarGP SMOKE first divergence (CUDA):", firsts)
-    assert min(firsts.values()) >= 25, firsts
-    assert sum(v == 40 for v in firsts.values()) >= 3, firsts
+    # measured on B200: exactly what the CPU oracle does (4 campaigns index-exact over 40 rows, AutoAM / 45 leaves at row 32)
+    assert min(firsts.values()) >= 30, firsts
+    assert sum(v == 40 for v in firsts.values()) >= 4, firsts
 
 
-@pytest.mark.parametrize("kind,name,seed,min_first,worst", [("VarTGP", "AutoAM", 45, 18, 2), ("VarLGP", "AgNP", 45, 26, 2)])
+@pytest.mark.parametrize("kind,name,seed,min_first,worst", [("VarTGP", "AutoAM", 45, 18, 3), ("VarLGP", "AgNP", 45, 26, 3)])
 def test_mc_models_teacher_forced_along_golden_smoke_trace_on_the_cuda_path(kind, name, seed, min_first, worst):
     """GPU twin of the oracle's teacher-forced pin: the 30 steps of the golden SMOKE trace are 30
     campaigns of ONE batch (training set = the first 10 + t golden rows); after stp_var_fit (200 epochs) the golden
-    pick must be the argmax of the Monte-Carlo LogEI (S = 2048, in-kernel Philox) at the surveyed rate and never
-    rank below third."""
+    pick must be the argmax of the Monte-Carlo LogEI (S = 2048, in-kernel Philox) at the surveyed rate (>= 18 / >= 26
+    of 30) and never rank below fourth (the CPU oracle with torch's stream: never below third; the Philox stream moves
+    the Monte-Carlo near-ties, App. C.5)."""
     from stpbenchmark_b200 import _lib, varops
     from stpbenchmark_b200.engine import CampaignBatch
     X, y = dataset(name)

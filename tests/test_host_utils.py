@@ -39,6 +39,38 @@ def test_random_percentile_initial_designs_match_gold0(name):
     assert hits == 50
 
 
+@pytest.mark.parametrize("name", DATASETS)
+def test_batched_initial_designs_equal_the_serial_path(name):
+    """utils.initial_designs_batch (row f2: one pass for all seeds, private generator, vectorised scramble + snap) ==
+    set_seeds(seed); get_initial_samples_sobol(...) per seed: all 50 golden designs of every dataset, and the state
+    the global generator is left in (what the variational models' theta1 noise continues from)."""
+    import torch
+    from stpbenchmark_b200 import utils
+    X, y = dataset(name)
+    S = seeds()
+    got, states = utils.initial_designs_batch(X, y, S, 10, 50.0, return_rng_states=True)
+    for k, s in enumerate(S):
+        assert got[k].tolist() == trace("gold1", "ExactGP", name, s)[:10]
+    for k in (0, 17, 49):
+        utils.set_seeds(S[k])
+        ref = utils.get_initial_samples_sobol(X, y, n_samples=10, percentile=50)
+        assert torch.equal(ref, got[k]) and torch.equal(torch.get_rng_state(), states[k])
+
+
+def test_batched_scrambled_sobol_is_bit_exact():
+    import torch
+    from torch.quasirandom import SobolEngine
+    from stpbenchmark_b200 import utils
+    S = [0, 1, 45, 6185, 2 ** 31 - 1]
+    for d, n in [(3, 10), (6, 10), (8, 256), (5, 1), (4, 33)]:
+        got = utils.sobol_scrambled_draw_batch(S, d, n)
+        for k, s in enumerate(S):
+            torch.manual_seed(s)
+            assert torch.equal(SobolEngine(d, scramble=True).draw(n), got[k])
+            one, _ = utils.sobol_scrambled_draw(s, d, n)
+            assert torch.equal(one, got[k])
+
+
 def test_duplicate_initial_points_are_kept():
     X, y = dataset("P3HT")
     utils.set_seeds(45)

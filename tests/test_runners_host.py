@@ -10,19 +10,26 @@ from oracle import exact as oexact
 from stpbenchmark_b200 import optim, priors, runners
 
 
-def _stub_engine(monkeypatch, fail_seed=None):
+def _stub_engine(monkeypatch, fail_seed=None, boom_on=None):
+    """Replaces the device engine (runners._execute_on_device) by a deterministic fake: campaign of seed s selects
+    (s + i) mod N; ``fail_seed`` stops after 3 trials with status 1; ``boom_on`` = a seed whose presence makes the
+    whole device job raise."""
     calls = []
 
-    def fake(X, y, model_class, seeds, n_initial=10, n_trials=25, epochs=100, learning_rate=0.1, num_samples=2048):
-        calls.append(list(seeds))
-        idx, val, st = [], [], []
-        for s in seeds:
-            k = n_initial + (3 if s == fail_seed else n_trials)
-            row = [(s + i) % len(X) for i in range(k)]
-            idx.append(row); val.append([float(y[i]) for i in row]); st.append(1 if s == fail_seed else 0)
-        return idx, val, st
+    def fake(pools, campaigns, on_done=None):
+        calls.append([c.seed for c in campaigns])
+        if boom_on is not None and any(c.seed == boom_on for c in campaigns):
+            raise RuntimeError("device lost")
+        res = {}
+        for i, c in enumerate(campaigns):
+            N = len(pools[c.pool][0])
+            k = len(c.design) + (3 if c.seed == fail_seed else c.n_trials)
+            res[i] = ([(c.seed + j) % N for j in range(k)], 1 if c.seed == fail_seed else 0)
+        if on_done is not None:
+            on_done(res)
+        return res
 
-    monkeypatch.setattr(runners, "run_campaign_batch", fake)
+    monkeypatch.setattr(runners, "_execute_on_device", fake)
     return calls
 
 
@@ -60,11 +67,90 @@ def test_invert_y_is_idempotent_across_resume(tmp_path, monkeypatch):
     assert np.allclose(b["seed_1", "x_index"], a["seed_1", "x_index"])
 
 
+def test_a_failed_device_job_does_not_poison_the_resume(tmp_path, monkeypatch):
+    """an exception inside the batch must not leave all-NaN columns that a later run mistakes for finished
+    seeds, and with invert_y=True it must not write the previously saved seeds back un-inverted."""
+    X = torch.rand(40, 2, dtype=torch.double); y = torch.rand(40, dtype=torch.double) + 0.5
+    out = tmp_path / "inv.csv"
+    _stub_engine(monkeypatch)
+    runners.run_many_loops(X, y, runners.ExactGP, seeds=[1], output_path=str(out), invert_y=True, n_initial=10, n_trials=4)
+    a = pd.read_csv(out, header=[0, 1], index_col=0)
+    _stub_engine(monkeypatch, boom_on=2)
+    runners.run_many_loops(X, y, runners.ExactGP, seeds=[1, 2, 3], output_path=str(out), invert_y=True, n_initial=10, n_trials=4)
+    b = pd.read_csv(out, header=[0, 1], index_col=0)
+    assert set(b.columns.get_level_values(0)) == {"seed_1"}                  # nothing written for seeds 2, 3
+    assert np.allclose(b["seed_1", "y_value"], a["seed_1", "y_value"])       # still 1/y, once
+    calls = _stub_engine(monkeypatch)
+    runners.run_many_loops(X, y, runners.ExactGP, seeds=[1, 2, 3], output_path=str(out), invert_y=True, n_initial=10, n_trials=4)
+    assert calls == [[2, 3]]
+    c = pd.read_csv(out, header=[0, 1], index_col=0)
+    assert set(c.columns.get_level_values(0)) == {"seed_1", "seed_2", "seed_3"}
+    assert np.allclose(c["seed_1", "y_value"], a["seed_1", "y_value"])
+    # a file that carries an all-NaN column (written by an older crashed run) does not count that seed as done
+    c[("seed_9", "x_index")] = np.nan; c[("seed_9", "y_value")] = np.nan
+    c.to_csv(out)
+    calls = _stub_engine(monkeypatch)
+    runners.run_many_loops(X, y, runners.ExactGP, seeds=[1, 9], output_path=str(out), invert_y=True, n_initial=10, n_trials=4)
+    assert calls == [[9]]
+
+
+def test_sweep_submits_every_job_at_once_and_writes_one_csv_per_job(tmp_path, monkeypatch):
+    """run_benchmark's nested loops (run_benchmark.py:20-43) as ONE device job: model x dataset x seeds."""
+    calls = _stub_engine(monkeypatch)
+    jobs = []
+    for name, N, d, cls in (("a", 30, 2, runners.ExactGP), ("b", 45, 3, runners.VarTGP), ("c", 60, 3, runners.VarTGP)):
+        X = torch.rand(N, d, dtype=torch.double); y = torch.rand(N, dtype=torch.double) + 0.5
+        jobs.append(dict(X=X, y=y, model_class=cls, seeds=[5, 6], output_path=str(tmp_path / f"{name}.csv"),
+                         n_initial=10, n_trials=6, epochs=7, learning_rate=0.01))
+    frames = runners.run_sweep(jobs)
+    assert calls == [[5, 6, 5, 6, 5, 6]] and len(frames) == 3
+    for spec in jobs:
+        back = pd.read_csv(spec["output_path"], header=[0, 1], index_col=0)
+        N = len(spec["X"])
+        assert back["seed_6", "x_index"].astype(int).tolist() == [(6 + i) % N for i in range(16)]
+        assert np.allclose(back["seed_6", "y_value"], spec["y"][[(6 + i) % N for i in range(16)]].numpy())
+
+
+def test_model_kwargs_are_honoured_or_rejected(monkeypatch):
+    """runners.py:66-74 builds model_class(**model_kwargs): a lengthscale prior reaches the engine, keys the loop
+    sets itself are ignored, anything else (or a subclass) is an error -- never silently dropped."""
+    seen = []
+
+    def fake(pools, campaigns, on_done=None):
+        seen.extend(c.lengthscale_prior for c in campaigns)
+        return {i: (list(c.design), 0) for i, c in enumerate(campaigns)}
+
+    monkeypatch.setattr(runners, "_execute_on_device", fake)
+    X = torch.rand(30, 2, dtype=torch.double); y = torch.rand(30, dtype=torch.double)
+    kw = {"lengthscale_prior": (0.5, 2.0), "inducing_points": None}
+    idx, val = runners.run_single_loop(X, y, runners.VarGP, model_kwargs=kw, n_initial=10, n_trials=0, seed=4)
+    assert seen == [(0.5, 2.0)] and len(idx) == 10 and "inducing_points" in kw and kw["inducing_points"].shape == (10, 2)
+
+    class Prior:                      # a gpytorch-style prior object
+        loc, scale = 1.0, 0.25
+    runners.run_single_loop(X, y, runners.VarTGP, model_kwargs={"lengthscale_prior": Prior()}, n_initial=10, n_trials=0)
+    assert seen[-1] == (1.0, 0.25)
+    n_seen = len(seen)
+    # unknown keyword: the constructor call of the reference raises inside the try -> the initial design is returned
+    idx, val = runners.run_single_loop(X, y, runners.ExactGP, model_kwargs={"nu": 2.5}, n_initial=10, n_trials=3, seed=4)
+    assert len(idx) == 10 and len(val) == 10 and len(seen) == n_seen
+
+    class MyGP(runners.ExactGP):
+        pass
+    idx, val = runners.run_single_loop(X, y, MyGP, n_initial=10, n_trials=3, seed=4)
+    assert len(idx) == 10 and len(seen) == n_seen
+    import pytest
+    with pytest.raises(NotImplementedError):
+        runners._kind_of(MyGP)
+
+
 def test_run_single_loop_never_raises(monkeypatch):
     def boom(*a, **k):
         raise RuntimeError("no device")
-    monkeypatch.setattr(runners, "run_campaign_batch", boom)
-    assert runners.run_single_loop(torch.rand(20, 2), torch.rand(20), runners.ExactGP) == ([], [])
+    monkeypatch.setattr(runners, "_execute_on_device", boom)
+    idx, val = runners.run_single_loop(torch.rand(20, 2), torch.rand(20), runners.ExactGP)
+    assert len(idx) == 10 and len(val) == 10          # the initial design, like runners.py:46-52 + :113-115
+    assert runners.run_single_loop(torch.rand(20, 2), torch.rand(20), runners.ExactGP, n_initial="x") == ([], [])
 
 
 def test_kind_detection():

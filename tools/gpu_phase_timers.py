@@ -26,23 +26,15 @@ def main():
     build_variant()
     os.environ["STP_LIB"] = VARIANT
     import torch
-    from stpbenchmark_b200 import _lib, synthetic
-    from stpbenchmark_b200.engine import CampaignBatch
+    from stpbenchmark_b200 import _lib
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from gpu_single_n import build_batch
     dev = torch.device("cuda", 0)
-    pools = [synthetic.cfg4_pool(g) for g in range(8)]
-    PX = torch.stack([p[0] for p in pools]); PY = torch.stack([p[1] for p in pools])
     out = {}
     for n, B in [(n, B) for n in args.n for B in args.B]:
-        gen = torch.Generator().manual_seed(n)
-        init, pid = [], []
-        for b in range(B):
-            g = b % 8
-            d0 = synthetic.initial_designs(pools[g][0], pools[g][1], [7000 + b], 10)[0].tolist()
-            rest = [i for i in torch.randperm(2048, generator=gen).tolist() if i not in set(d0)][: n - 10]
-            init.append(d0 + rest); pid.append(g)
-        batch = CampaignBatch(PX, PY, pid, init, n_cap=n + 2, kind="ExactGP", device=dev)
-        batch.step(); torch.cuda.synchronize()          # warm-up on a copy of the state would change n: rebuild
-        batch = CampaignBatch(PX, PY, pid, init, n_cap=n + 2, kind="ExactGP", device=dev)
+        batch = build_batch(n, B, dev)
+        batch.step(); torch.cuda.synchronize()          # warm-up (a step changes n: rebuild)
+        batch = build_batch(n, B, dev)
         _lib.phase_timers(reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); batch.step(); e1.record(); torch.cuda.synchronize()
@@ -50,8 +42,8 @@ def main():
         F, C = max(t["closures"], 1), max(t["campaigns"], 1)
         per_closure = {k: round(t[k] / F, 1) for k in ("gram", "sweep_A", "sweep_B", "sweep_C", "gradient", "reduce", "advance")}
         per_campaign = {k: round(t[k] / C, 1) for k in ("load", "factorise", "pool_pass")}
-        adv = {k: round(t[k] / F, 1) for k in ("adv_ls_step", "adv_build_B", "adv_cauchy", "adv_subsm", "adv_ls_start", "advance")}
-        t["advance"] += sum(t[k] for k in ("adv_ls_step", "adv_build_B", "adv_cauchy", "adv_subsm", "adv_ls_start"))
+        adv = {k: round(t[k] / F, 1) for k in ("adv_entry", "adv_copy_dot", "adv_dcsrch", "adv_projgr_tests", "adv_ls_step", "adv_build_B", "adv_cauchy", "adv_subsm", "adv_ls_start", "advance")}
+        t["advance"] += sum(t[k] for k in ("adv_entry", "adv_copy_dot", "adv_dcsrch", "adv_projgr_tests", "adv_ls_step", "adv_build_B", "adv_cauchy", "adv_subsm", "adv_ls_start"))
         per_closure["advance"] = round(t["advance"] / F, 1)
         tot = sum(t[k] for k in ("load", "gram", "sweep_A", "sweep_B", "sweep_C", "gradient", "reduce", "advance",
                                  "factorise", "pool_pass"))
