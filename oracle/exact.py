@@ -89,13 +89,27 @@ def rbf(x1: torch.Tensor, x2: torch.Tensor, ls: torch.Tensor, os: torch.Tensor) 
     return os * torch.exp(-0.5 * sq_dist(x1 / ls, x2 / ls))
 
 
+PSD_SAFE_JITTERS = (0.0, 1e-8, 1e-7, 1e-6)   # linear_operator.utils.cholesky.psd_safe_cholesky in fp64: 3 tries, x10
+
+
+def psd_safe_cholesky(K: torch.Tensor) -> torch.Tensor:
+    """[UPSTREAM] what gpytorch factorises with (every Cholesky of the path goes through it): a plain Cholesky; if
+    that fails, the same matrix with 1e-8, then 1e-7, then 1e-6 added to its diagonal; then NotPSDError."""
+    eye = torch.eye(K.shape[-1], dtype=K.dtype)
+    for k, jit in enumerate(PSD_SAFE_JITTERS):
+        L, info = torch.linalg.cholesky_ex(K if jit == 0.0 else K + jit * eye)
+        if int(info) == 0:
+            return L
+    raise torch.linalg.LinAlgError("matrix not positive definite after jitter 1e-6")
+
+
 def neg_mll(theta: torch.Tensor, X: torch.Tensor, y: torch.Tensor, pri: ExactPriors | None = None) -> torch.Tensor:
     """-(log N(y | c, K + noise I) + sum log-priors) / n, y RAW (App. A.3, App. D-1)."""
     n, d = X.shape
     pri = pri or ExactPriors.for_dim(d)
     noise, c, os, ls = theta[0], theta[1], theta[2], theta[3:]
     K = rbf(X, X, ls, os) + noise * torch.eye(n, dtype=X.dtype)
-    L = torch.linalg.cholesky(K)
+    L = psd_safe_cholesky(K)
     r = (y - c).unsqueeze(-1)
     a = torch.cholesky_solve(r, L)
     quad = (r * a).sum()

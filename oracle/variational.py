@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from .acq import log_ei_helper
-from .exact import LOG_2PI, _f32, _lognormal_mode_f32, lognormal_logpdf, rbf
+from .exact import LOG_2PI, _f32, _lognormal_mode_f32, lognormal_logpdf, psd_safe_cholesky, rbf
 
 JITTER = 1e-6  # gpytorch's variational Cholesky jitter in fp64 (App. A.4 step 2)
 KINDS = ("VarGP", "VarTGP", "VarLGP")
@@ -95,7 +95,7 @@ def _interp(st: VarState, X: torch.Tensor) -> torch.Tensor:
     """A = L_K^-1 K_ZX with K_ZZ + 1e-6 I = L_K L_K^T (App. A.4 step 2)."""
     m = st.Z.shape[0]
     Kzz = rbf(st.Z, st.Z, st.ls, st.os) + JITTER * torch.eye(m, dtype=X.dtype)
-    Lk = torch.linalg.cholesky(Kzz)
+    Lk = psd_safe_cholesky(Kzz)          # optim.py:153-154 -> variational strategy -> psd_safe_cholesky (jitter retry)
     Kzx = rbf(st.Z, X, st.ls, st.os)
     return torch.linalg.solve_triangular(Lk, Kzx, upper=False)
 

@@ -159,19 +159,26 @@ STP_HD int exact_mll_fg(const Team& tm, const ExactSmem& s, int n, int d, const 
   tm.sync();
   STP_PHASE(-1); STP_COUNT(16);
   // K1: lower = K + noise I (to be swept), strict upper = K (kept for the gradient), border = y - c
-  for_each_lower_pair(tm, n, [&](int i, int j) {
-    const double kij = ard_rbf_tt(s.Xt, cap, d, invl, i, j, os);
-    s.A[i * ld + j] = kij;
-    s.A[j * ld + i] = kij;
-  });
-  for (int j = tm.rank(); j <= n; j += tm.size()) {
-    if (j < n) s.A[j * ld + j] = os + noise;
-    s.A[n * ld + j] = (j < n) ? (s.y[j] - cst) : 0.0;
+  // The sweep works in place, so a retry with more jitter (psd_safe_cholesky) rebuilds the matrix; it never happens
+  // on a healthy fit and costs one extra Gram build when it does.
+  int fail = 1;
+  STP_ROLLED for (int attempt = 0; attempt < kPsdSafeTries && fail; ++attempt) {
+    const double diag = os + noise + psd_safe_jitter(attempt);
+    for_each_lower_pair(tm, n, [&](int i, int j) {
+      const double kij = ard_rbf_tt(s.Xt, cap, d, invl, i, j, os);
+      s.A[i * ld + j] = kij;
+      s.A[j * ld + i] = kij;
+    });
+    for (int j = tm.rank(); j <= n; j += tm.size()) {
+      if (j < n) s.A[j * ld + j] = diag;
+      s.A[n * ld + j] = (j < n) ? (s.y[j] - cst) : 0.0;
+    }
+    tm.sync();
+    STP_PHASE(1);
+    // K3+K4: bordered sweep -> -Kinv, alpha, -quad, pivots
+    fail = exact_sweep(tm, s, n);
+    if (fail) tm.sync();      // every thread has left the sweep before the matrix is rebuilt
   }
-  tm.sync();
-  STP_PHASE(1);
-  // K3+K4: bordered sweep -> -Kinv, alpha, -quad, pivots
-  const int fail = exact_sweep(tm, s, n);
   if (fail) { *f_out = NAN; return 1; }
   STP_PHASE(-1);
   const double* arow = s.A + n * ld;  // alpha
@@ -248,12 +255,18 @@ STP_HD int exact_factorize(const Team& tm, const ExactSmem& s, int n, int d, con
   tm.sync();
   STP_OWNED(tm, k, d) invl[k] = 1.0 / theta[3 + k];
   tm.sync();
-  for (int i = tm.warp(); i < n; i += tm.nwarps()) {
-    double* row = s.A + i * ld;
-    for (int j = tm.lane(); j <= i; j += W)
-      row[j] = (j == i) ? os + noise : ard_rbf_tt(s.Xt, cap, d, invl, i, j, os);
+  int fail = 1;
+  STP_ROLLED for (int attempt = 0; attempt < kPsdSafeTries && fail; ++attempt) {   // psd_safe_cholesky
+    const double diag = os + noise + psd_safe_jitter(attempt);
+    for (int i = tm.warp(); i < n; i += tm.nwarps()) {
+      double* row = s.A + i * ld;
+      for (int j = tm.lane(); j <= i; j += W)
+        row[j] = (j == i) ? diag : ard_rbf_tt(s.Xt, cap, d, invl, i, j, os);
+    }
+    fail = cholesky_inverse_fused(tm, s.A, ld, n, s.c1, s.c2, s.piv, (double*)nullptr, 0);
+    if (fail) tm.sync();
   }
-  if (cholesky_inverse_fused(tm, s.A, ld, n, s.c1, s.c2, s.piv, (double*)nullptr, 0)) return 1;
+  if (fail) return 1;
   // z = Linv (y - c)  -> c0 ;  alpha = Linv^T z
   for (int i = tm.rank(); i < n; i += tm.size()) {
     const double* row = s.A + i * ld;

@@ -38,6 +38,11 @@ STP_HD double rsqrt_pos(double p) {
 
 STP_HD int odd_ld(int n) { return n | 1; }
 
+// Extra diagonal jitter of attempt k of a Cholesky: what the reference's factorisations do through
+// linear_operator's psd_safe_cholesky in fp64 (plain, then +1e-8, +1e-7, +1e-6 on the diagonal, then NotPSDError).
+constexpr int kPsdSafeTries = 4;
+STP_HD double psd_safe_jitter(int attempt) { return attempt == 0 ? 0.0 : (attempt == 1 ? 1e-8 : (attempt == 2 ? 1e-7 : 1e-6)); }
+
 // Row offset of a lower-triangular matrix: square storage (row i at i * ld) or packed rows (row i at i (i + 1) / 2,
 // half the shared memory; rows stay contiguous, which is all the sweep / Cholesky / inverse / pool pass need).
 template <bool TRI>

@@ -386,12 +386,12 @@ __global__ void __launch_bounds__(256) k_var_acq(int n_cap, int d, int N, int li
   if (n < 1 || n > n_cap || (update && n >= n_cap)) { if (threadIdx.x == 0) status[b] = 2; return; }
   VarSmem s = var_smem_carve(smem, n_cap, d, false, BIG ? 0 : 1);
   double* tile = smem + var_smem_doubles(n_cap, d);
-  double* part = tile + (size_t)n_cap * kTC + (size_t)kMaxD * kTC;
+  double* part = tile + (size_t)(((n_cap + 15) & ~15) + kMaxD) * kTC;
   CtaTeam tm{s.red};
   const VarWork w = var_work_carve(work + (size_t)b * var_work_doubles(n_cap), n_cap);
   if (BIG) s.M0 = w.M0g;
   const VarModel M = var_model_of(P, b, n_cap, d);
-  const int st = var_prepare(tm, s, w, M, n, d);
+  const int st = var_prepare(tm, s, w, M, n, d, !BIG);
   if (st) { if (threadIdx.x == 0) { status[b] = st; if (out_idx) out_idx[b] = -1; if (out_acq) out_acq[b] = NAN; } return; }
   double best;
   if (best_f) best = best_f[b];
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(256) k_var_acq(int n_cap, int d, int N, int li
   int bi; double bv;
   var_acquire(tm, s, w, n, d, lik, tile, part, Pl, N, mb, best, S, eps ? eps + (size_t)b * N * S : nullptr, seed,
               (unsigned long long)b, &bi, &bv, mean ? mean + (size_t)b * N : nullptr,
-              var ? var + (size_t)b * N : nullptr, acq ? acq + (size_t)b * N : nullptr);
+              var ? var + (size_t)b * N : nullptr, acq ? acq + (size_t)b * N : nullptr, !BIG);
   if (threadIdx.x == 0) { if (out_idx) out_idx[b] = bi; if (out_acq) out_acq[b] = bv; }
   if (!update) return;
   if (bi < 0) { if (threadIdx.x == 0) status[b] = 2; return; }
@@ -773,7 +773,7 @@ int stp_var_acq(int B, int n_cap, int d, int N, int lik, const double* pool, con
   if (update && (!pool_y || !X || !y || !trace || !mask || !n)) return fail("update needs pool_y, X, y, n, trace and mask");
   if (!best_f && !y) return fail("best_f or y required");
   if (B == 0) return 0;
-  const size_t smem = (var_smem_doubles(n_cap, d) + (size_t)n_cap * kTC + (size_t)kMaxD * kTC + 8 * kTC * 3) * sizeof(double);
+  const size_t smem = (var_smem_doubles(n_cap, d) + var_acq_smem_doubles(n_cap, kTC)) * sizeof(double);
   const VarPtrs ptrs{const_cast<double*>(Z), const_cast<double*>(hyp), const_cast<double*>(nat1),
                      const_cast<double*>(nat2), nullptr, nullptr};
   if (n_cap > kVarSmemSquareMax) {

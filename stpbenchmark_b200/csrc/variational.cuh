@@ -275,11 +275,6 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   tm.sync();
   // (2) K_ZZ + jitter: fused Cholesky + in-place inverse in shared memory (one barrier per column), L_K streamed
   //     out (strict upper zero-filled); then Linv (lower) and Linv^T (upper), zero-filled, to global memory; Ct
-  for (int i = tm.warp(); i < n; i += nw) {
-    double* row = M0 + i * ld;
-    for (int j = tm.lane(); j <= i; j += W)
-      row[j] = (j < i) ? ard_rbf_tt(s.Zt, cap, d, invl, i, j, os) : os + kVarJitter;
-  }
   for (int c = tm.warp(); c < n; c += nw) {
     double* row = Ct + c * ld;
     for (int j = tm.lane(); j < n; j += W) {
@@ -295,7 +290,20 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   }
   for (int i = tm.warp(); i < n; i += nw)
     for (int j = i + 1 + tm.lane(); j < n; j += W) LK[i * ld + j] = 0.0;
-  if (cholesky_inverse_fused(tm, M0, ld, n, s.c0, s.c1, s.c2, LK, ld)) { out.status = 1; return out; }
+  {
+    int chol_fail = 1;
+    STP_ROLLED for (int attempt = 0; attempt < kPsdSafeTries && chol_fail; ++attempt) {   // psd_safe_cholesky (jitter retry)
+      const double diag = os + kVarJitter + psd_safe_jitter(attempt);
+      for (int i = tm.warp(); i < n; i += nw) {
+        double* row = M0 + i * ld;
+        for (int j = tm.lane(); j <= i; j += W)
+          row[j] = (j < i) ? ard_rbf_tt(s.Zt, cap, d, invl, i, j, os) : diag;
+      }
+      chol_fail = cholesky_inverse_fused(tm, M0, ld, n, s.c0, s.c1, s.c2, LK, ld);
+      if (chol_fail) tm.sync();
+    }
+    if (chol_fail) { out.status = 1; return out; }
+  }
   for (int i = tm.warp(); i < n; i += nw)
     for (int j = tm.lane(); j < n; j += W) {
       LI[i * ld + j] = (j <= i) ? M0[i * ld + j] : 0.0;
@@ -561,7 +569,8 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
 // Returns 0, 1 (not PD) or 2 (non-finite hyper-parameter).
 // ------------------------------------------------------------------------------------------
 template <class Team>
-STP_HD int var_prepare(const Team& tm, const VarSmem& s, const VarWork& w, const VarModel& M, int n, int d) {
+STP_HD int var_prepare(const Team& tm, const VarSmem& s, const VarWork& w, const VarModel& M, int n, int d,
+                       bool pack_in_smem = false) {
   const int ld = w.ld, cap = s.cap, W = tm.warp_width(), nw = tm.nwarps();
   double* LI = w.R[1];    // Linv_K mirrored
   double* G = w.R[2];
@@ -586,13 +595,19 @@ STP_HD int var_prepare(const Team& tm, const VarSmem& s, const VarWork& w, const
   double* M0 = s.M0;
   for (int pass = 0; pass < 2; ++pass) {
     double* dst = pass == 0 ? LPI : LI;
-    for (int i = tm.warp(); i < n; i += nw) {
-      double* row = M0 + i * ld;
-      for (int j = tm.lane(); j <= i; j += W)
-        row[j] = pass == 0 ? -2.0 * M.nat2[(size_t)i * cap + j]
-                           : ((j == i) ? os + kVarJitter : ard_rbf_tt(s.Zt, cap, d, invl, i, j, os));
+    int chol_fail = 1;
+    STP_ROLLED for (int attempt = 0; attempt < kPsdSafeTries && chol_fail; ++attempt) {   // psd_safe_cholesky (jitter retry)
+      const double extra = psd_safe_jitter(attempt);
+      for (int i = tm.warp(); i < n; i += nw) {
+        double* row = M0 + i * ld;
+        for (int j = tm.lane(); j <= i; j += W)
+          row[j] = pass == 0 ? -2.0 * M.nat2[(size_t)i * cap + j] + ((j == i) ? extra : 0.0)
+                             : ((j == i) ? os + kVarJitter + extra : ard_rbf_tt(s.Zt, cap, d, invl, i, j, os));
+      }
+      chol_fail = cholesky_inverse_fused(tm, M0, ld, n, s.c0, s.c1, s.c2, (double*)nullptr, 0);
+      if (chol_fail) tm.sync();
     }
-    if (cholesky_inverse_fused(tm, M0, ld, n, s.c0, s.c1, s.c2, (double*)nullptr, 0)) return 1;
+    if (chol_fail) return 1;
     for (int i = tm.warp(); i < n; i += nw)
       for (int j = tm.lane(); j < n; j += W) dst[i * ld + j] = (j <= i) ? M0[i * ld + j] : 0.0;
     tm.sync();
@@ -620,6 +635,18 @@ STP_HD int var_prepare(const Team& tm, const VarSmem& s, const VarWork& w, const
                  [=](int, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = k_lo; r1 = (k_lo > i_hi) ? k_lo : i_hi + 1; },
                  [=](int i, int k, double v) { G[i * ld + k] = (k <= i) ? v : 0.0; });
   tm.sync();
+  if (pack_in_smem) {
+    // The pool pass multiplies every candidate tile by Linv_K and by G: keep BOTH triangles in the shared-memory
+    // square (free after the factorisations) -- Linv_K in the lower triangle, G transposed in the upper one, shifted
+    // by one column so that the two diagonals do not collide (ld >= n + 1):  M0[i][k] = Linv_K[i][k],
+    // M0[k][i + 1] = G[i][k]  (k <= i).  No global load is left in the pool pass.
+    for (int i = tm.warp(); i < n; i += nw)
+      for (int k = tm.lane(); k <= i; k += W) {
+        M0[i * ld + k] = LI[i * ld + k];
+        M0[k * ld + i + 1] = G[i * ld + k];
+      }
+    tm.sync();
+  }
   return 0;
 }
 
@@ -630,9 +657,124 @@ STP_HD double var_lik_variance(int lik, double noise, double rho) {
   return noise;
 }
 
+// Partial-sum slots per candidate of the pool pass: one per 16-row tile of the triangular factors (tensor-core form)
+// or per warp (generic form), whichever is larger.  Shared-memory need of var_acquire, in doubles: tile
+// (cap16 + kMaxD) x TC, partial sums (2 slots + 8) x TC.
+STP_HD int var_acq_slots(int cap) { const int rt = (cap + 15) >> 4; return rt > 8 ? rt : 8; }
+STP_HD size_t var_acq_smem_doubles(int cap, int tc) {
+  return (size_t)(((cap + 15) & ~15) + kMaxD) * tc + (size_t)(2 * var_acq_slots(cap) + 8) * tc;
+}
+
+// Partial sums of one candidate tile (TC candidates, cross-covariances in tile[j * TC + c]):
+//   part[p * TC + c], p < n_slots: pieces of ||Linv_K k_c||^2;  part[(slots + p) * TC + c]: of ||G k_c||^2;
+//   part[(2 slots + w) * TC + c], w < min(nwarps, 8): of gmu . k_c.
+// Generic form: warp w takes the rows i = w, w + nw, ...; a lane is a candidate.
+template <class Team>
+STP_HD void var_tile_partials(const Team& tm, const VarSmem& s, const VarWork& w, int n, const double* tile, double* part,
+                              int slots, bool packed, int& n_slots) {
+  const int ld = w.ld, TC = tm.warp_width(), nw = tm.nwarps();
+  const int nwa = nw < 8 ? nw : 8;
+  const double* LI = w.R[1];
+  const double* G = w.R[2];
+  const double* M0 = s.M0;
+  n_slots = nwa;
+  if (tm.warp() < nwa) {
+    const int c = tm.lane();
+    double sa = 0.0, sb = 0.0, mu = 0.0;
+    for (int i = tm.warp(); i < n; i += nwa) {
+      double a = 0.0, b = 0.0;
+      for (int j = 0; j <= i; ++j) {
+        const double kj = tile[j * TC + c];
+        a += (packed ? M0[i * ld + j] : LI[i * ld + j]) * kj;
+        b += (packed ? M0[j * ld + i + 1] : G[i * ld + j]) * kj;
+      }
+      sa += a * a;
+      sb += b * b;
+      mu += s.gmu[i] * tile[i * TC + c];
+    }
+    part[tm.warp() * TC + c] = sa;
+    part[(slots + tm.warp()) * TC + c] = sb;
+    part[(2 * slots + tm.warp()) * TC + c] = mu;
+  }
+}
+#if defined(__CUDACC__) && !defined(STP_NO_DMMA)
+// Tensor-core form: V = [Linv_K; G] K_tile in 16 x 16 DMMA tiles (both factors are lower triangular: the reduction of
+// row tile I stops at its diagonal block, which is masked), squares summed per row tile.  PACKED: both factors come
+// from the shared-memory square (see var_prepare); otherwise from their global (L2-resident) copies (M = 256).
+template <bool PACKED>
+__device__ __forceinline__ void var_tile_partials_mma(const CtaTeam& tm, const VarSmem& s, const VarWork& w, int n,
+                                                      const double* tile, double* part, int slots, int& n_slots) {
+  constexpr int TC = 32;
+  const int ld = w.ld, nw = tm.nwarps(), warp = tm.warp(), lane = tm.lane();
+  const int g = lane >> 2, q = lane & 3;
+  const int RT = (n + 15) >> 4;
+  const int nwa = nw < 8 ? nw : 8;
+  const double* LI = PACKED ? s.M0 : w.R[1];
+  const double* G = PACKED ? s.M0 : w.R[2];
+  n_slots = RT;
+  if (warp < nwa) {
+    double mu = 0.0;
+    for (int i = warp; i < n; i += nwa) mu += s.gmu[i] * tile[i * TC + lane];
+    part[(2 * slots + warp) * TC + lane] = mu;
+  }
+  for (int t = warp; t < 4 * RT; t += nw) {
+    const int mat = t & 1, jb = ((t >> 1) & 1) << 4, I = RT - 1 - (t >> 2), ib = I << 4;   // heaviest row tiles first
+    double c[2][2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) { c[a][b][0] = 0.0; c[a][b][1] = 0.0; }
+    const int i0 = ib + g, i1 = ib + 8 + g;
+    const int r0 = (i0 < n) ? i0 : n - 1, r1 = (i1 < n) ? i1 : n - 1;
+    // element (i, k) of the factor: row-major lower triangle, or (PACKED, G) the shifted transposed upper triangle
+    const double* p0 = (PACKED && mat) ? G + r0 + 1 : (mat ? G : LI) + (size_t)r0 * ld;
+    const double* p1 = (PACKED && mat) ? G + r1 + 1 : (mat ? G : LI) + (size_t)r1 * ld;
+    const int ks = (PACKED && mat) ? ld : 1;
+    const double* tb = tile + jb + g;
+    for (int k0 = 0; k0 < ib; k0 += 4) {           // strictly below the diagonal block: no masks
+      const int kk = k0 + q;
+      const double a0 = p0[(size_t)kk * ks], a1 = p1[(size_t)kk * ks];
+      const double b0 = tb[kk * TC], b1 = tb[kk * TC + 8];
+      dmma884(c[0][0][0], c[0][0][1], a0, b0);
+      dmma884(c[0][1][0], c[0][1][1], a0, b1);
+      dmma884(c[1][0][0], c[1][0][1], a1, b0);
+      dmma884(c[1][1][0], c[1][1][1], a1, b1);
+    }
+#pragma unroll
+    for (int k0 = 0; k0 < 16; k0 += 4) {            // the diagonal block
+      const int kk = ib + k0 + q;
+      const int kc = (kk < n) ? kk : n - 1;
+      const double a0 = (i0 < n && kk <= i0) ? p0[(size_t)kc * ks] : 0.0, a1 = (i1 < n && kk <= i1) ? p1[(size_t)kc * ks] : 0.0;
+      const double b0 = tb[kk * TC], b1 = tb[kk * TC + 8];
+      dmma884(c[0][0][0], c[0][0][1], a0, b0);
+      dmma884(c[0][1][0], c[0][1][1], a0, b1);
+      dmma884(c[1][0][0], c[1][0][1], a1, b0);
+      dmma884(c[1][1][0], c[1][1][1], a1, b1);
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double sq = 0.0;
+        if (i0 < n) sq += c[0][b][e] * c[0][b][e];
+        if (i1 < n) sq += c[1][b][e] * c[1][b][e];
+        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+        if (g == 0) part[(mat * slots + I) * TC + jb + 8 * b + 2 * q + e] = sq;
+      }
+  }
+}
+__device__ __forceinline__ void var_tile_partials(const CtaTeam& tm, const VarSmem& s, const VarWork& w, int n,
+                                                  const double* tile, double* part, int slots, bool packed, int& n_slots) {
+  if (packed) var_tile_partials_mma<true>(tm, s, w, n, tile, part, slots, n_slots);
+  else var_tile_partials_mma<false>(tm, s, w, n, tile, part, slots, n_slots);
+}
+#endif
+
 // ------------------------------------------------------------------------------------------
-// Fused pool pass of a variational model (after var_prepare).  `tile`: cap x TC + kMaxD x TC doubles
-// and `part`: nwarps x TC x 3 doubles of shared memory.  MC models: `eps` (global, [N, S]) if non-null,
+// Fused pool pass of a variational model (after var_prepare).  `tile` and `part`: var_acq_smem_doubles(cap, TC)
+// doubles of shared memory in all (part = tile + (cap16 + kMaxD) x TC).  MC models: `eps` (global, [N, S]) if non-null,
 // else Philox(seed, stream = campaign id, counter = candidate * (S/2) + pair).
 // Optional outputs (may be null): mean_out / var_out = q(f) moments (no likelihood noise), acq_out.
 // ------------------------------------------------------------------------------------------
@@ -640,14 +782,14 @@ template <class Team>
 STP_HD void var_acquire(const Team& tm, const VarSmem& s, const VarWork& w, int n, int d, int lik, double* tile,
                         double* part, const double* pool, int N, const uint8_t* mask, double best_f, int S,
                         const double* eps, uint64_t seed, uint64_t stream, int* best_idx, double* best_acq,
-                        double* mean_out, double* var_out, double* acq_out) {
-  const int ld = w.ld, cap = s.cap, TC = tm.warp_width(), nw = tm.nwarps();
-  const double* LI = w.R[1];
-  const double* G = w.R[2];
+                        double* mean_out, double* var_out, double* acq_out, bool packed = false) {
+  const int cap = s.cap, TC = tm.warp_width(), nw = tm.nwarps();
+  const int n16 = (n + 15) & ~15;                 // rows n .. n16 - 1 of the tile are zero (DMMA row tiles)
+  const int slots = var_acq_slots(cap);           // partial-sum slots per candidate and quantity
   const double* hyp = s.small;
   const double* invl = s.small + 16;
   const double cst = hyp[0], os = hyp[1 + d], noise = hyp[2 + d], rho = hyp[3 + d];
-  double* xc = tile + (size_t)cap * TC;
+  double* xc = tile + (size_t)((cap + 15) & ~15) * TC;
   const double lik_var = var_lik_variance(lik, noise, rho);
   const double sig_l = sqrt(lik_var > 1e-12 ? lik_var : 1e-12);
   const double log_sig_l = log(sig_l);
@@ -661,10 +803,10 @@ STP_HD void var_acquire(const Team& tm, const VarSmem& s, const VarWork& w, int 
       xc[k * TC + c] = pool[(size_t)base * d + idx];
     }
     tm.sync();
-    for (int idx = tm.rank(); idx < n * TC; idx += tm.size()) {
+    for (int idx = tm.rank(); idx < n16 * TC; idx += tm.size()) {
       const int j = idx / TC, c = idx - j * TC;
       double v = 0.0;
-      if (c < cnt) {
+      if (c < cnt && j < n) {
         double r2 = 0.0;
 #pragma unroll
         for (int k = 0; k < kMaxD; ++k)
@@ -677,47 +819,30 @@ STP_HD void var_acquire(const Team& tm, const VarSmem& s, const VarWork& w, int 
       tile[j * TC + c] = v;
     }
     tm.sync();
-    {
-      const int c = tm.lane();
-      double sa = 0.0, sb = 0.0, mu = 0.0;
-      for (int i = tm.warp(); i < n; i += nw) {
-        const double* r1 = LI + i * ld;
-        const double* r2 = G + i * ld;
-        double a = 0.0, b = 0.0;
-        for (int j = 0; j <= i; ++j) {
-          const double kj = tile[j * TC + c];
-          a += r1[j] * kj;
-          b += r2[j] * kj;
-        }
-        sa += a * a;
-        sb += b * b;
-        mu += s.gmu[i] * tile[i * TC + c];
-      }
-      part[(tm.warp() * TC + c) * 3 + 0] = sa;
-      part[(tm.warp() * TC + c) * 3 + 1] = sb;
-      part[(tm.warp() * TC + c) * 3 + 2] = mu;
-    }
+    int n_slots;
+    var_tile_partials(tm, s, w, n, tile, part, slots, packed, n_slots);
     tm.sync();
     for (int c = tm.rank(); c < cnt; c += tm.size()) {
       double sa = 0.0, sb = 0.0, mu = 0.0;
-      for (int ww = 0; ww < nw; ++ww) {
-        sa += part[(ww * TC + c) * 3 + 0];
-        sb += part[(ww * TC + c) * 3 + 1];
-        mu += part[(ww * TC + c) * 3 + 2];
+      for (int ww = 0; ww < n_slots; ++ww) {
+        sa += part[ww * TC + c];
+        sb += part[(slots + ww) * TC + c];
       }
+      const int nmu = nw < 8 ? nw : 8;
+      for (int ww = 0; ww < nmu; ++ww) mu += part[(2 * slots + ww) * TC + c];
       const int gi = base + c;
       const double mean = cst + mu;
       const double var = os + kVarJitter + (sb - sa);
       if (mean_out) mean_out[gi] = mean;
       if (var_out) var_out[gi] = var;
-      part[c * 3 + 0] = mean;   // warp 0's slots are dead now; reuse them to hand (mean, var) over
-      part[c * 3 + 1] = var;
+      part[c] = mean;              // slot 0 of this column is dead now (only this thread read it): hand (mean, var) over
+      part[slots * TC + c] = var;
     }
     tm.sync();
     if (lik == kLikGaussian) {
       for (int c = tm.rank(); c < cnt; c += tm.size()) {
         const int gi = base + c;
-        const double a = log_ei(part[c * 3 + 0], part[c * 3 + 1] + noise, best_f);
+        const double a = log_ei(part[c], part[slots * TC + c] + noise, best_f);
         if (acq_out) acq_out[gi] = a;
         if ((!mask || mask[gi]) && acq_better(a, gi, run_v, run_i)) { run_v = a; run_i = gi; }
       }
@@ -726,7 +851,7 @@ STP_HD void var_acquire(const Team& tm, const VarSmem& s, const VarWork& w, int 
       for (int c = tm.warp(); c < cnt; c += nw) {
         const int gi = base + c;
         if (mask && !mask[gi] && !acq_out) continue;
-        const double mean = part[c * 3 + 0], sd = sqrt(part[c * 3 + 1]);
+        const double mean = part[c], sd = sqrt(part[slots * TC + c]);
         double a = 0.0;
         if (eps) {
           const double* e = eps + (size_t)gi * S;

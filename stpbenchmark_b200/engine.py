@@ -251,11 +251,16 @@ class Campaign:
     """One campaign of a job: which pool, which model kind, its initial design and its budget."""
 
     __slots__ = ("key", "kind", "pool", "design", "n_trials", "epochs", "learning_rate", "num_samples",
-                 "lengthscale_prior", "rng_state", "seed")
+                 "lengthscale_prior", "rng_state", "seed", "n_initial")
 
-    def __init__(self, key, kind: str, pool: int, design: Sequence[int], n_trials: int, epochs: int = 100,
-                 learning_rate: float = 0.1, num_samples: int = 2048, lengthscale_prior=None, rng_state=None, seed: int = 0):
-        self.key, self.kind, self.pool, self.design = key, kind, int(pool), [int(i) for i in design]
+    def __init__(self, key, kind: str, pool: int, design: Optional[Sequence[int]], n_trials: int, epochs: int = 100,
+                 learning_rate: float = 0.1, num_samples: int = 2048, lengthscale_prior=None, rng_state=None, seed: int = 0,
+                 n_initial: Optional[int] = None):
+        """``design`` may be None until the rank that owns the campaign fills it in (``n_initial`` then says how long
+        it will be)."""
+        self.key, self.kind, self.pool = key, kind, int(pool)
+        self.design = None if design is None else [int(i) for i in design]
+        self.n_initial = int(n_initial) if n_initial is not None else len(self.design)
         self.n_trials, self.epochs, self.learning_rate = int(n_trials), int(epochs), float(learning_rate)
         self.num_samples, self.lengthscale_prior, self.rng_state, self.seed = int(num_samples), lengthscale_prior, rng_state, int(seed)
 

@@ -103,33 +103,44 @@ def _execute_on_device(pools, campaigns: List[Campaign], on_done: Optional[Calla
     return job.run(on_group_done=on_done)
 
 
-def run_campaigns(pools, campaigns: List[Campaign], on_done: Optional[Callable] = None, _executor=None):
+def _shard_order(campaigns: List[Campaign]) -> List[int]:
+    """Campaign order used for sharding: what shares launches (kind, pool, budget) stays together, so that a rank's
+    contiguous block forms few, full groups."""
+    return sorted(range(len(campaigns)), key=lambda i: (campaigns[i].kind, campaigns[i].pool, campaigns[i].n_trials, i))
+
+
+def run_campaigns(pools, campaigns: List[Campaign], on_done: Optional[Callable] = None, _executor=None,
+                  prepare: Optional[Callable] = None):
     """Run every campaign; under an initialised ``torch.distributed`` group the campaign list is sharded in
     contiguous blocks over the ranks (one process per GPU, no data-path collective) and the traces are gathered
     on rank 0 at the end.  Returns {campaign index: (indices, status)} on rank 0 (all campaigns)
     and on the other ranks (their own shard).  ``on_done`` receives finished groups on the rank that ran them, or,
-    with several ranks, the complete result once on rank 0."""
+    with several ranks, the complete result once on rank 0.  ``prepare(ids)`` is called with the indices this rank
+    owns before they run (run_sweep computes the initial designs of its own shard only)."""
     import torch.distributed as dist
     execute = _executor or _execute_on_device
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     if world == 1:
+        if prepare is not None:
+            prepare(list(range(len(campaigns))))
         return execute(pools, campaigns, on_done)
     rank = dist.get_rank()
-    # order by what shares launches (kind, pool, budget) so that a rank's shard forms few, full groups
-    order = sorted(range(len(campaigns)), key=lambda i: (campaigns[i].kind, campaigns[i].pool, campaigns[i].n_trials, i))
+    order = _shard_order(campaigns)
     lo, hi = sdist.shard_bounds(len(order), world, rank)
     mine = order[lo:hi]
+    if prepare is not None:
+        prepare(mine)
     local = execute(pools, [campaigns[i] for i in mine], None)
-    T = max((len(c.design) + c.n_trials for c in campaigns), default=0) + 1
+    T = max((c.n_initial + c.n_trials for c in campaigns), default=0) + 1
     use_cuda = dist.get_backend() == "nccl"
     dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
-    tr = torch.full((len(mine), T), -1, dtype=torch.int32, device=dev)
-    st = torch.full((len(mine), T), float("nan"), dtype=torch.double, device=dev)   # column 0 carries the status
+    tr = torch.full((len(mine), T), -1, dtype=torch.int32)
+    st = torch.full((len(mine), T), float("nan"), dtype=torch.double)   # column 0 carries the status
     for row in range(len(mine)):
         idx, status = local[row]
         tr[row, : len(idx)] = torch.tensor(idx, dtype=torch.int32)
         st[row, 0] = float(status)
-    got = sdist.gather_traces(tr, st, len(order))
+    got = sdist.gather_traces(tr.to(dev), st.to(dev), len(order))
     if got is None:
         return {mine[row]: local[row] for row in range(len(mine))}
     gt, gs = got[0].cpu(), got[1].cpu()
@@ -218,7 +229,8 @@ def _empty_frame(seeds, total_iterations) -> pd.DataFrame:
 def _save(frame: pd.DataFrame, path: str, invert_y: bool) -> None:
     """Write the frame; columns of seeds that hold nothing are left out (a later run recomputes them)."""
     save_df = frame.copy()
-    empty = [s for s in save_df.columns.get_level_values(0).unique() if save_df[s]["x_index"].isna().all()]
+    x = save_df.xs("x_index", axis=1, level=1)
+    empty = list(x.columns[x.isna().all().values])
     if empty:
         save_df = save_df.drop(columns=empty, level=0)
     if invert_y:
@@ -245,8 +257,8 @@ class _CsvJob:
             os.makedirs(out_dir, exist_ok=True)
         if os.path.exists(output_path):
             self.frame = pd.read_csv(output_path, header=[0, 1], index_col=0)
-            done = {int(col.split("_")[1]) for col in self.frame.columns.get_level_values(0).unique()
-                    if not self.frame[col]["x_index"].isna().all()}
+            x = self.frame.xs("x_index", axis=1, level=1)
+            done = {int(col.split("_")[1]) for col in x.columns[~x.isna().all().values]}
             if self.invert_y:  # the file holds 1/y: undo it so that saving is idempotent (App. B.3)
                 y_cols = [c for c in self.frame.columns if c[1] == "y_value"]
                 self.frame[y_cols] = 1.0 / self.frame[y_cols].astype(float)
@@ -255,13 +267,39 @@ class _CsvJob:
             done = set()
         self.remaining = [s for s in self.seeds if s not in done]
 
+    def record_many(self, items: Sequence[Tuple[int, List[int]]]) -> None:
+        """Traces of several finished seeds at once (runners.py:181-186, NaN-padded to n_initial + n_trials rows)."""
+        y_host = self.y.cpu().numpy()
+        cols = {}
+        for seed, indices in items:
+            k = min(len(indices), self.total)
+            picked = np.asarray(indices[:k], dtype=np.int64)
+            if k == self.total:
+                idx = picked
+            else:
+                idx = np.full(self.total, np.nan)
+                idx[:k] = picked
+            val = np.full(self.total, np.nan)
+            val[:k] = y_host[picked]
+            cols[(f"seed_{seed}", "x_index")] = idx
+            cols[(f"seed_{seed}", "y_value")] = val
+        new = pd.DataFrame(cols, index=self.frame.index)
+        new.columns = pd.MultiIndex.from_tuples(list(cols))
+        old = set(self.frame.columns)
+        present = [c for c in new.columns if c in old]
+        if len(present) == len(old):                 # every column of the frame is replaced (a fresh run finishing at once)
+            self.frame = new[list(self.frame.columns)]
+        elif present:
+            keep = [c for c in self.frame.columns if c not in set(present)]
+            order = list(self.frame.columns)
+            self.frame = pd.concat([self.frame[keep], new[present]], axis=1)[order]
+        extra = [c for c in new.columns if c not in old]
+        if extra:
+            self.frame = pd.concat([self.frame, new[extra]], axis=1)
+        self.frame.index.name = "iteration"
+
     def record(self, seed: int, indices: List[int]) -> None:
-        y_host = self.y.cpu()
-        values = [float(y_host[i]) for i in indices]
-        indices = list(indices) + [np.nan] * (self.total - len(indices))  # runners.py:181-182
-        values = values + [np.nan] * (self.total - len(values))
-        self.frame[f"seed_{seed}", "x_index"] = indices[: self.total]
-        self.frame[f"seed_{seed}", "y_value"] = values[: self.total]
+        self.record_many([(seed, indices)])
 
     def save(self) -> None:
         _save(self.frame, self.output_path, self.invert_y)
@@ -273,7 +311,7 @@ def run_sweep(jobs: Sequence[dict], _executor=None) -> List[pd.DataFrame]:
     the GPU(s); a job's CSV is (re)written whenever a group of its campaigns finishes.  Returns the frames."""
     import torch.distributed as dist
     rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
-    csv_jobs, pools, camps, owner = [], [], [], []
+    csv_jobs, pools, camps, owner, job_of_pool = [], [], [], [], []
     on_cuda = torch.cuda.is_available() and _executor is None
     for j, spec in enumerate(jobs):
         spec = dict(spec)
@@ -286,35 +324,47 @@ def run_sweep(jobs: Sequence[dict], _executor=None) -> List[pd.DataFrame]:
         try:
             kind = _kind_of(job.model_class)
             prior = _lengthscale_prior_of(kind, job.model_class, job.kwargs.get("model_kwargs"))
-            designs, states = initial_designs_batch(job.X, job.y, job.remaining, job.n_initial, 50.0,
-                                                    return_rng_states=True, device="cuda" if on_cuda else None)
         except Exception as e:
             print(f"Error in batch of seeds {job.remaining}: {str(e)}")
             continue
         pools.append((job.X, job.y))
+        job_of_pool.append(j)
         trials = min(job.n_trials, len(job.X) - job.n_initial)
-        for k, s in enumerate(job.remaining):
-            camps.append(Campaign((j, s), kind, len(pools) - 1, designs[k].tolist(), trials,
+        for s in job.remaining:   # the initial design is filled in by the rank that owns the campaign (`prepare`)
+            camps.append(Campaign((j, s), kind, len(pools) - 1, None, trials,
                                   int(job.kwargs.get("epochs", 100)), float(job.kwargs.get("learning_rate", 0.1)),
-                                  int(job.kwargs.get("num_samples", 2048)), prior, states[k], seed=s))
+                                  int(job.kwargs.get("num_samples", 2048)), prior, None, seed=s,
+                                  n_initial=min(job.n_initial, len(job.X))))
             owner.append((j, s))
+
+    def prepare(ids: List[int]):
+        by_pool: Dict[int, List[int]] = {}
+        for i in ids:
+            by_pool.setdefault(camps[i].pool, []).append(i)
+        for pool_id, members in by_pool.items():
+            job = csv_jobs[job_of_pool[pool_id]]
+            designs, states = initial_designs_batch(job.X, job.y, [camps[i].seed for i in members], job.n_initial, 50.0,
+                                                    return_rng_states=True, device="cuda" if on_cuda else None)
+            for k, i in enumerate(members):
+                camps[i].design = designs[k].tolist()
+                camps[i].rng_state = states[k]
 
     def on_done(res: Dict[int, tuple]):
         if rank != 0:
             return
-        touched = set()
+        per_job: Dict[int, list] = {}
         for c_id, (indices, status) in res.items():
             j, s = owner[c_id]
             if status != 0:
                 print(f"Error occurred at iteration {len(indices)}: campaign (job {j}, seed {s}) stopped with status {status}")
-            csv_jobs[j].record(s, indices)
-            touched.add(j)
-        for j in touched:
+            per_job.setdefault(j, []).append((s, indices))
+        for j, items in per_job.items():
+            csv_jobs[j].record_many(items)
             csv_jobs[j].save()
 
     if camps:
         try:
-            run_campaigns(pools, camps, on_done=on_done, _executor=_executor)
+            run_campaigns(pools, camps, on_done=on_done, _executor=_executor, prepare=prepare)
         except Exception as e:
             print(f"Error in sweep: {str(e)}")
             if rank == 0:
