@@ -39,7 +39,7 @@ extern "C" {
                            stp_exact_fit / stp_exact_bo_step also hold the optimiser state there: n_cap <= 142, beyond
                            that they return an error ("campaign does not fit in shared memory") */
 #define STP_MAX_N_VAR 272   /* variational entry points: above 144 the working square moves to the global workspace */
-#define STP_ABI_VERSION 1
+#define STP_ABI_VERSION 2
 
 /* L-BFGS-B options; scipy.optimize.minimize(method="L-BFGS-B") defaults are
  * {10, 15000, 15000, 20, ftol / DBL_EPSILON with ftol = 2.220446049250313e-09, 1e-5}. */
@@ -68,6 +68,21 @@ typedef struct stp_turnover {
   int32_t* sink_count;
 } stp_turnover;
 
+/* Model / acquisition variants beyond what the reference instantiates (north_star names a
+ * Matern kernel and UCB / EI acquisitions; the reference itself has RBF only (models.py:12) and LogEI in its loop).
+ * Every entry point that takes a `const stp_model_opts* model` accepts NULL = {RBF, LogEI}: the reference's path.
+ *   kernel       STP_KERNEL_RBF | STP_KERNEL_MATERN52 (gpytorch MaternKernel(nu=2.5), ARD): exact-GP entry points only
+ *   acquisition  STP_ACQ_LOGEI (botorch LogExpectedImprovement, runners.py:88-90) | STP_ACQ_UCB (botorch
+ *                UpperConfidenceBound: mean + sqrt(beta) sigma) | STP_ACQ_EI (botorch ExpectedImprovement = utils.EI,
+ *                utils.py:299-309); sigma = sqrt(max(var, 1e-12)); for the Monte-Carlo models the mean over the samples. */
+enum { STP_KERNEL_RBF = 0, STP_KERNEL_MATERN52 = 1 };
+enum { STP_ACQ_LOGEI = 0, STP_ACQ_UCB = 1, STP_ACQ_EI = 2 };
+typedef struct stp_model_opts {
+  int32_t kernel;
+  int32_t acquisition;
+  double beta;
+} stp_model_opts;
+
 /* Likelihood of a variational model (models.py: VarGP :166, VarTGP :76, VarLGP :262). */
 enum { STP_LIK_GAUSSIAN = 0, STP_LIK_STUDENT_T = 1, STP_LIK_LAPLACE = 2 };
 
@@ -80,14 +95,14 @@ const char* stp_last_error_string(void);
  * os_loc, os_scale, ls_loc, ls_scale} of the LogNormal priors.  f: [B], g: [B, d+3]. */
 int stp_exact_mll_fg(int B, int n_cap, int d, const double* X, const double* y, const int32_t* n,
                      const double* theta, const double* prior, double* f, double* g, int32_t* status,
-                     void* stream);
+                     const stp_model_opts* model, void* stream);
 
 /* Device-resident L-BFGS-B fit of theta (in/out) for B campaigns: train_exact_model_botorch
  * (optim.py:11-32).  lower/upper: host arrays [d+3], +-HUGE_VAL = unbounded.
  * f_out [B], nit [B], nfev [B] may be NULL. */
 int stp_exact_fit(int B, int n_cap, int d, const double* X, const double* y, const int32_t* n, double* theta,
                   const double* lower, const double* upper, const double* prior, const stp_lbfgsb_opts* opts,
-                  double* f_out, int32_t* nit, int32_t* nfev, int32_t* status, void* stream);
+                  double* f_out, int32_t* nit, int32_t* nfev, int32_t* status, const stp_model_opts* model, void* stream);
 
 /* Fused predictive + LogEI + argmax over the pool at fixed theta: ExactGP.posterior
  * (models.py:387-395) + botorch LogExpectedImprovement.forward + argmax (runners.py:88-95).
@@ -98,7 +113,7 @@ int stp_exact_fit(int B, int n_cap, int d, const double* X, const double* y, con
 int stp_exact_acq(int B, int n_cap, int d, int N, const double* pool, const int32_t* pool_id, const uint8_t* mask,
                   const double* X, const double* y, const int32_t* n, const double* theta, const double* best_f,
                   int32_t* out_idx, double* out_acq, double* mean, double* var, double* acq, int32_t* status,
-                  void* stream);
+                  const stp_model_opts* model, void* stream);
 
 /* One whole BO iteration (the loop body runners.py:64-109) for B campaigns in ONE launch:
  * fresh theta0 -> L-BFGS-B fit -> factorise -> pool pass -> argmax -> append the pick to
@@ -123,7 +138,7 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
                       const double* theta0, const double* lower, const double* upper, const double* prior,
                       const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
                       int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
-                      int32_t* iters_acc, int n_max, void* stream);
+                      int32_t* iters_acc, int n_max, const stp_model_opts* model, void* stream);
 
 /* The same loop body as a PERSISTENT launch over a work queue: one CTA per SM slot (as many as are resident at the
  * launch's shared-memory footprint, at most max_ctas if max_ctas > 0) serves the B campaigns from a ticket ring; a
@@ -139,7 +154,8 @@ int stp_exact_bo_run(int B, int n_cap, int d, int N, const double* pool, const d
                      const double* theta0, const double* lower, const double* upper, const double* prior,
                      const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
                      int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
-                     int32_t* iters_acc, int n_max, int32_t* iters_left, int32_t* sched, int max_ctas, void* stream);
+                     int32_t* iters_acc, int n_max, int32_t* iters_left, int32_t* sched, int max_ctas,
+                     const stp_model_opts* model, void* stream);
 
 /* ---- variational models: VarGP / VarTGP / VarLGP (models.py:114-202, 18-111, 205-297) ---------------
  * State arrays (device, caller-owned, batch-major): Z [B, n_cap, d] inducing locations, hyp [B, d+4] =
@@ -184,7 +200,8 @@ int stp_var_acq(int B, int n_cap, int d, int N, int lik, const double* pool, con
                 const double* Z, const double* hyp, const double* nat1, const double* nat2, int32_t* n,
                 const double* best_f, int S, const double* eps, unsigned long long seed, int32_t* out_idx,
                 double* out_acq, double* mean, double* var, double* acq, int update, const double* pool_y, double* X,
-                double* y, int32_t* trace, int32_t* status, double* work, const int32_t* order, void* stream);
+                double* y, int32_t* trace, int32_t* status, double* work, const int32_t* order,
+                const stp_model_opts* model, void* stream);
 
 /* 2 * pairs standard normals of the in-kernel generator: out[2q], out[2q+1] for counters counter0 + q. */
 int stp_philox_normal(unsigned long long seed, unsigned long long stream_id, unsigned long long counter0,
@@ -194,6 +211,16 @@ int stp_philox_normal(unsigned long long seed, unsigned long long stream_id, uns
  * `count` (mean, var) pairs against one best_f: out[i] = log_h((mean - best_f)/sigma) + log sigma,
  * sigma = sqrt(max(var, 1e-12)). */
 int stp_log_ei(long long count, const double* mean, const double* var, double best_f, double* out, void* stream);
+
+/* The same elementwise pass for any acquisition of stp_model_opts (kernel ignored): UCB and EI next to LogEI. */
+int stp_acq_values(long long count, const double* mean, const double* var, double best_f, const stp_model_opts* model,
+                   double* out, void* stream);
+
+/* Elementwise Student-t LogEI, the device form of acqf.log_expected_improvement_t (acqf.py:7-52, scipy.stats.t on the
+ * host in the reference): Z = (mean - best_f) / sd; log(mean - best_f) + log T_df(Z) where the improvement is positive,
+ * log t_df(Z) + log sd elsewhere, -inf where sd <= 1e-9.  mean, sd, df: [count]. */
+int stp_log_ei_t(long long count, const double* mean, const double* sd, const double* df, double best_f, double* out,
+                 void* stream);
 
 /* Sustained FP64 FMA throughput probe (roofline denominator; MEASURED_PEAKS.json has no FP64
  * figure).  Launches 148 * 8 CTAs x 256 threads, each running iters x 16 x 8 independent DFMAs

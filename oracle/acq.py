@@ -55,6 +55,36 @@ def log_ei(mean: torch.Tensor, var: torch.Tensor, best_f) -> torch.Tensor:
     return log_ei_helper(u) + sigma.log()
 
 
+def ucb(mean: torch.Tensor, var: torch.Tensor, beta: float) -> torch.Tensor:
+    """[UPSTREAM] botorch UpperConfidenceBound(maximize=True): mean + sqrt(beta) sigma, sigma = sqrt(max(var, 1e-12))
+    (botorch's AnalyticAcquisitionFunction._mean_and_sigma clamps the variance at 1e-12).  north_star names UCB; the
+    reference's loop itself uses LogEI only (runners.py:88-90)."""
+    return mean + math.sqrt(beta) * var.clamp_min(1e-12).sqrt()
+
+
+def ei(mean: torch.Tensor, var: torch.Tensor, best_f) -> torch.Tensor:
+    """utils.EI (utils.py:299-309) = botorch ExpectedImprovement: improvement Phi(z) + sigma phi(z), z = improvement /
+    sigma, with botorch's sigma clamp so that it is defined on the whole pool."""
+    sigma = var.clamp_min(1e-12).sqrt()
+    gain = mean - best_f
+    z = gain / sigma
+    return gain * _Phi(z) + sigma * _phi(z)
+
+
+def log_ei_t(mean, sd, df, best_f):
+    """acqf.log_expected_improvement_t's elementwise formula (acqf.py:34-50) with scipy.stats.t, as the reference
+    evaluates it on the host: log(gain) + logcdf(Z) where gain > 0, logpdf(Z) + log(sd) elsewhere, -inf at sd <= 1e-9."""
+    import numpy as np
+    from scipy.stats import t as student_t
+    mean, sd, df = (np.asarray(a, dtype=np.float64) for a in (mean, sd, df))
+    gain = mean - float(best_f)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        z = gain / sd
+        dist = student_t(df=df)
+        out = np.where(gain > 0, np.log(gain) + dist.logcdf(z), dist.logpdf(z) + np.log(sd))
+    return np.where(sd > 1e-9, out, -np.inf)
+
+
 def first_argmax(acq: torch.Tensor) -> int:
     """torch.argmax semantics: first maximal index, NaN wins (runners.py:95)."""
     return int(torch.argmax(acq).item())

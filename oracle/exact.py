@@ -89,6 +89,17 @@ def rbf(x1: torch.Tensor, x2: torch.Tensor, ls: torch.Tensor, os: torch.Tensor) 
     return os * torch.exp(-0.5 * sq_dist(x1 / ls, x2 / ls))
 
 
+def matern52(x1: torch.Tensor, x2: torch.Tensor, ls: torch.Tensor, os: torch.Tensor) -> torch.Tensor:
+    """[UPSTREAM] ScaleKernel(MaternKernel(nu=2.5, ard)) as gpytorch evaluates it: r = sqrt(max(sq_dist, 1e-30)) of
+    the lengthscale-scaled inputs, os (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r).  The reference instantiates RBF only
+    (models.py:342-358); Matern is the alternative BASELINE.json's north_star names."""
+    r = sq_dist(x1 / ls, x2 / ls).clamp_min(1e-30).sqrt()
+    s5 = math.sqrt(5.0) * r
+    return os * (1.0 + s5 + (5.0 / 3.0) * r * r) * torch.exp(-s5)
+
+
+KERNELS = {"rbf": rbf, "matern52": matern52}
+
 PSD_SAFE_JITTERS = (0.0, 1e-8, 1e-7, 1e-6)   # linear_operator.utils.cholesky.psd_safe_cholesky in fp64: 3 tries, x10
 
 
@@ -103,12 +114,13 @@ def psd_safe_cholesky(K: torch.Tensor) -> torch.Tensor:
     raise torch.linalg.LinAlgError("matrix not positive definite after jitter 1e-6")
 
 
-def neg_mll(theta: torch.Tensor, X: torch.Tensor, y: torch.Tensor, pri: ExactPriors | None = None) -> torch.Tensor:
+def neg_mll(theta: torch.Tensor, X: torch.Tensor, y: torch.Tensor, pri: ExactPriors | None = None,
+            kernel: str = "rbf") -> torch.Tensor:
     """-(log N(y | c, K + noise I) + sum log-priors) / n, y RAW (App. A.3, App. D-1)."""
     n, d = X.shape
     pri = pri or ExactPriors.for_dim(d)
     noise, c, os, ls = theta[0], theta[1], theta[2], theta[3:]
-    K = rbf(X, X, ls, os) + noise * torch.eye(n, dtype=X.dtype)
+    K = KERNELS[kernel](X, X, ls, os) + noise * torch.eye(n, dtype=X.dtype)
     L = psd_safe_cholesky(K)
     r = (y - c).unsqueeze(-1)
     a = torch.cholesky_solve(r, L)
@@ -121,11 +133,11 @@ def neg_mll(theta: torch.Tensor, X: torch.Tensor, y: torch.Tensor, pri: ExactPri
     return -(total / n)
 
 
-def mll_value_and_grad(theta_np: np.ndarray, X: torch.Tensor, y: torch.Tensor):
+def mll_value_and_grad(theta_np: np.ndarray, X: torch.Tensor, y: torch.Tensor, kernel: str = "rbf"):
     """One L-BFGS-B closure call: loss and autograd gradient (optim.py:32 via botorch)."""
     t = torch.tensor(np.asarray(theta_np, dtype=np.float64), dtype=torch.double, requires_grad=True)
     try:
-        loss = neg_mll(t, X, y)
+        loss = neg_mll(t, X, y, kernel=kernel)
         loss.backward()
         return float(loss.item()), t.grad.numpy().astype(np.float64)
     except Exception:  # non-PD matrix: report NaN like a failed closure
@@ -169,26 +181,27 @@ def mll_value_and_grad_analytic(theta_np: np.ndarray, X: torch.Tensor, y: torch.
     return -total / n, -g / n
 
 
-def fit_exact(X: torch.Tensor, y: torch.Tensor, theta0: np.ndarray | None = None):
+def fit_exact(X: torch.Tensor, y: torch.Tensor, theta0: np.ndarray | None = None, kernel: str = "rbf"):
     """scipy L-BFGS-B with scipy's defaults over (noise, c, os, ls) (App. A.3).  Returns
     (theta*, OptimizeResult)."""
     d = X.shape[1]
     x0 = initial_theta(d) if theta0 is None else np.asarray(theta0, dtype=np.float64)
-    res = minimize(lambda t: mll_value_and_grad(t, X, y), x0, jac=True, method="L-BFGS-B",
+    res = minimize(lambda t: mll_value_and_grad(t, X, y, kernel), x0, jac=True, method="L-BFGS-B",
                    bounds=theta_bounds(d))
     return res.x.copy(), res
 
 
-def posterior_exact(theta: np.ndarray, X: torch.Tensor, y: torch.Tensor, Xc: torch.Tensor):
+def posterior_exact(theta: np.ndarray, X: torch.Tensor, y: torch.Tensor, Xc: torch.Tensor, kernel: str = "rbf"):
     """Noisy predictive at every candidate (models.py:387-395, App. A.5):
     mean = c + k^T alpha, var = os - ||L^-1 k||^2 + noise."""
     t = torch.as_tensor(theta, dtype=torch.double)
     noise, c, os, ls = t[0], t[1], t[2], t[3:]
     n = X.shape[0]
-    K = rbf(X, X, ls, os) + noise * torch.eye(n, dtype=X.dtype)
+    kfn = KERNELS[kernel]
+    K = kfn(X, X, ls, os) + noise * torch.eye(n, dtype=X.dtype)
     L = torch.linalg.cholesky(K)
     alpha = torch.cholesky_solve((y - c).unsqueeze(-1), L).squeeze(-1)
-    Kc = rbf(Xc, X, ls, os)
+    Kc = kfn(Xc, X, ls, os)
     mean = c + Kc @ alpha
     V = torch.linalg.solve_triangular(L, Kc.T, upper=False)
     var = os - (V * V).sum(0) + noise

@@ -41,6 +41,25 @@ class LbfgsbOpts(ctypes.Structure):
         return LbfgsbOpts(10, 15000, 15000, 20, 2.220446049250313e-09 / eps, 1e-5)
 
 
+class ModelOpts(ctypes.Structure):
+    """struct stp_model_opts: kernel / acquisition variants (None everywhere = RBF + LogEI, the reference's path)."""
+
+    _fields_ = [("kernel", ctypes.c_int32), ("acquisition", ctypes.c_int32), ("beta", ctypes.c_double)]
+    KERNELS = {"rbf": 0, "matern52": 1}
+    ACQUISITIONS = {"logei": 0, "ucb": 1, "ei": 2}
+
+    @staticmethod
+    def make(kernel: str = "rbf", acquisition: str = "logei", beta: float = 0.0) -> Optional["ModelOpts"]:
+        k, a = ModelOpts.KERNELS[str(kernel).lower()], ModelOpts.ACQUISITIONS[str(acquisition).lower()]
+        if k == 0 and a == 0:
+            return None
+        return ModelOpts(k, a, float(beta))
+
+
+def _m(model):
+    return ctypes.byref(model) if model is not None else None
+
+
 class Turnover(ctypes.Structure):
     """struct stp_turnover (continuous batching of stp_exact_bo_step); pointers are device pointers."""
 
@@ -96,7 +115,7 @@ def _bounds(lower, upper, np_):
     return _host(lo), _host(hi)
 
 
-def exact_mll_fg(X, y, theta, prior, n=None):
+def exact_mll_fg(X, y, theta, prior, n=None, model: Optional[ModelOpts] = None):
     """f [B], g [B, d+3], status [B] for X [B, n_cap, d], y [B, n_cap], theta [B, d+3]."""
     _require_cuda(X, y, theta, n)
     B, n_cap, d = X.shape
@@ -104,11 +123,12 @@ def exact_mll_fg(X, y, theta, prior, n=None):
     g = torch.empty(B, d + 3, dtype=torch.double, device=X.device)
     status = torch.zeros(B, dtype=torch.int32, device=X.device)
     _check(lib().stp_exact_mll_fg(B, n_cap, d, _p(X), _p(y), _p(n), _p(theta), _host(prior), _p(f), _p(g),
-                                  _p(status), _stream()), "stp_exact_mll_fg")
+                                  _p(status), _m(model), _stream()), "stp_exact_mll_fg")
     return f, g, status
 
 
-def exact_fit(X, y, theta, lower, upper, prior, n=None, opts: Optional[LbfgsbOpts] = None):
+def exact_fit(X, y, theta, lower, upper, prior, n=None, opts: Optional[LbfgsbOpts] = None,
+              model: Optional[ModelOpts] = None):
     """In-place device L-BFGS-B fit of theta [B, d+3]; returns (f, nit, nfev, status)."""
     _require_cuda(X, y, theta, n)
     B, n_cap, d = X.shape
@@ -119,11 +139,12 @@ def exact_fit(X, y, theta, lower, upper, prior, n=None, opts: Optional[LbfgsbOpt
     lo, hi = _bounds(lower, upper, d + 3)
     o = opts or LbfgsbOpts.scipy_defaults()
     _check(lib().stp_exact_fit(B, n_cap, d, _p(X), _p(y), _p(n), _p(theta), lo, hi, _host(prior), ctypes.byref(o),
-                               _p(f), _p(nit), _p(nfev), _p(status), _stream()), "stp_exact_fit")
+                               _p(f), _p(nit), _p(nfev), _p(status), _m(model), _stream()), "stp_exact_fit")
     return f, nit, nfev, status
 
 
-def exact_acq(pool, X, y, theta, best_f=None, mask=None, pool_id=None, n=None, want_pointwise=False):
+def exact_acq(pool, X, y, theta, best_f=None, mask=None, pool_id=None, n=None, want_pointwise=False,
+              model: Optional[ModelOpts] = None):
     """Fused predictive + LogEI + argmax.  pool [G, N, d].  Returns dict(idx, acq_best, status
     [, mean, var, acq])."""
     _require_cuda(pool, X, y, theta, best_f, mask, pool_id, n)
@@ -139,14 +160,15 @@ def exact_acq(pool, X, y, theta, best_f=None, mask=None, pool_id=None, n=None, w
         var = torch.empty(B, N, dtype=torch.double, device=dev)
         acq = torch.empty(B, N, dtype=torch.double, device=dev)
     _check(lib().stp_exact_acq(B, n_cap, d, N, _p(pool), _p(pool_id), _p(mask), _p(X), _p(y), _p(n), _p(theta),
-                               _p(best_f), _p(idx), _p(best), _p(mean), _p(var), _p(acq), _p(status), _stream()),
+                               _p(best_f), _p(idx), _p(best), _p(mean), _p(var), _p(acq), _p(status), _m(model), _stream()),
            "stp_exact_acq")
     return {"idx": idx, "acq_best": best, "status": status, "mean": mean, "var": var, "acq": acq}
 
 
 def exact_bo_step(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upper, prior, status,
                   theta_out=None, acq_out=None, nit=None, nfev=None, opts: Optional[LbfgsbOpts] = None, order=None,
-                  turnover: Optional[Turnover] = None, work_acc=None, iters_acc=None, n_max: int = 0):
+                  turnover: Optional[Turnover] = None, work_acc=None, iters_acc=None, n_max: int = 0,
+                  model: Optional[ModelOpts] = None):
     """One BO iteration for every campaign, in place (see stp_exact_bo_step).  ``n_max``: a host-known upper bound
     of ``n`` over the running campaigns (0 = unknown); sizes the launch's shared memory / thread count."""
     _require_cuda(pool, pool_y, pool_id, mask, X, y, n, trace, status, theta_out, acq_out, nit, nfev, order, work_acc,
@@ -159,12 +181,13 @@ def exact_bo_step(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, up
                                    _p(trace), _host(theta0), lo, hi, _host(prior), ctypes.byref(o), _p(theta_out),
                                    _p(acq_out), _p(nit), _p(nfev), _p(status), _p(order),
                                    ctypes.byref(turnover) if turnover is not None else None, _p(work_acc), _p(iters_acc),
-                                   ctypes.c_int(int(n_max)), _stream()), "stp_exact_bo_step")
+                                   ctypes.c_int(int(n_max)), _m(model), _stream()), "stp_exact_bo_step")
 
 
 def exact_bo_run(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upper, prior, status, iters_left, sched,
                  theta_out=None, acq_out=None, nit=None, nfev=None, opts: Optional[LbfgsbOpts] = None, order=None,
-                 turnover: Optional[Turnover] = None, work_acc=None, iters_acc=None, n_max: int = 0, max_ctas: int = 0):
+                 turnover: Optional[Turnover] = None, work_acc=None, iters_acc=None, n_max: int = 0, max_ctas: int = 0,
+                 model: Optional[ModelOpts] = None):
     """Persistent work-queue form of exact_bo_step: every campaign b is advanced ``iters_left[b]`` iterations in ONE
     launch (see stp_exact_bo_run).  ``sched``: int32 [B + 1] scratch, zeroed once by the caller."""
     _require_cuda(pool, pool_y, pool_id, mask, X, y, n, trace, status, iters_left, sched, theta_out, acq_out, nit, nfev,
@@ -180,7 +203,7 @@ def exact_bo_run(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upp
                                   _p(acq_out), _p(nit), _p(nfev), _p(status), _p(order),
                                   ctypes.byref(turnover) if turnover is not None else None, _p(work_acc), _p(iters_acc),
                                   ctypes.c_int(int(n_max)), _p(iters_left), _p(sched), ctypes.c_int(int(max_ctas)),
-                                  _stream()), "stp_exact_bo_run")
+                                  _m(model), _stream()), "stp_exact_bo_run")
 
 
 def design_snap(points: torch.Tensor, eligible: torch.Tensor) -> torch.Tensor:
@@ -215,6 +238,27 @@ def phase_timers(reset: bool = False) -> dict:
     out = (ctypes.c_ulonglong * 32)()
     _check(lib().stp_phase_timers(out, int(bool(reset))), "stp_phase_timers")
     return {name: int(out[i]) for i, name in PHASE_NAMES.items()}
+
+
+def acq_values(mean: torch.Tensor, var: torch.Tensor, best_f: float, acquisition: str = "logei", beta: float = 0.0):
+    """Elementwise LogEI / UCB / EI on the device (stp_acq_values); output has the shape of ``mean``."""
+    _require_cuda(mean, var)
+    if mean.shape != var.shape:
+        raise ValueError("mean and var must have the same shape")
+    out = torch.empty_like(mean)
+    m = ModelOpts(0, ModelOpts.ACQUISITIONS[acquisition.lower()], float(beta))
+    _check(lib().stp_acq_values(ctypes.c_longlong(mean.numel()), _p(mean), _p(var), ctypes.c_double(best_f), ctypes.byref(m),
+                                _p(out), _stream()), "stp_acq_values")
+    return out
+
+
+def log_ei_t(mean: torch.Tensor, sd: torch.Tensor, df: torch.Tensor, best_f: float) -> torch.Tensor:
+    """Elementwise Student-t LogEI on the device (stp_log_ei_t, acqf.py:7-52)."""
+    _require_cuda(mean, sd, df)
+    out = torch.empty_like(mean)
+    _check(lib().stp_log_ei_t(ctypes.c_longlong(mean.numel()), _p(mean), _p(sd), _p(df), ctypes.c_double(best_f), _p(out),
+                              _stream()), "stp_log_ei_t")
+    return out
 
 
 def fp64_probe(iters: int = 4096) -> float:
@@ -293,7 +337,7 @@ def var_elbo_fg(X, y, n, state: dict, lik: int, prior, gh, work, standardise: bo
 
 
 def var_acq(pool, state: dict, n, lik: int, status, work, best_f=None, mask=None, pool_id=None, S: int = 2048, eps=None,
-            seed: int = 0, want_pointwise: bool = False, update=None, order=None):
+            seed: int = 0, want_pointwise: bool = False, update=None, order=None, model: Optional[ModelOpts] = None):
     """stp_var_acq.  ``update`` = dict(pool_y, X, y, trace) performs the append of runners.py:98-109."""
     _require_cuda(pool, n, status, work, best_f, mask, pool_id, eps, *[state[k] for k in ("Z", "hyp", "nat1", "nat2")])
     B, n_cap, d = state["Z"].shape
@@ -311,8 +355,8 @@ def var_acq(pool, state: dict, n, lik: int, status, work, best_f=None, mask=None
     _check(lib().stp_var_acq(B, n_cap, d, N, int(lik), _p(pool), _p(pool_id), _p(mask), _p(state["Z"]), _p(state["hyp"]),
                              _p(state["nat1"]), _p(state["nat2"]), _p(n), _p(best_f), int(S), _p(eps), _u64(seed),
                              _p(idx), _p(best), _p(mean), _p(var), _p(acq), int(update is not None), _p(u.get("pool_y")),
-                             _p(u.get("X")), _p(u.get("y")), _p(u.get("trace")), _p(status), _p(work), _p(order), _stream()),
-           "stp_var_acq")
+                             _p(u.get("X")), _p(u.get("y")), _p(u.get("trace")), _p(status), _p(work), _p(order), _m(model),
+                             _stream()), "stp_var_acq")
     return {"idx": idx, "acq_best": best, "mean": mean, "var": var, "acq": acq}
 
 

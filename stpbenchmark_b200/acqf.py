@@ -16,7 +16,8 @@ import math
 import numpy as np
 import torch
 
-__all__ = ["LogExpectedImprovement", "log_expected_improvement", "log_expected_improvement_t"]
+__all__ = ["LogExpectedImprovement", "UpperConfidenceBound", "ExpectedImprovement", "log_expected_improvement",
+           "log_expected_improvement_t"]
 
 
 class LogExpectedImprovement:
@@ -33,6 +34,8 @@ class LogExpectedImprovement:
         self.best_f = torch.as_tensor(best_f, dtype=torch.double)
         self.maximize = maximize
 
+    _kind, _beta = "logei", 0.0
+
     def forward(self, X: torch.Tensor) -> torch.Tensor:
         from . import _lib
         post = self.model.posterior(X=X, posterior_transform=None)
@@ -46,9 +49,29 @@ class LogExpectedImprovement:
         best = self.best_f.to(mean.device)
         if not self.maximize:
             mean, best = -mean, -best
-        return _lib.log_ei(mean.contiguous().double(), var.contiguous().double(), float(best))
+        if self._kind == "logei":
+            return _lib.log_ei(mean.contiguous().double(), var.contiguous().double(), float(best))
+        return _lib.acq_values(mean.contiguous().double(), var.contiguous().double(), float(best), self._kind, self._beta)
 
     __call__ = forward
+
+
+class ExpectedImprovement(LogExpectedImprovement):
+    """botorch ``ExpectedImprovement`` = utils.EI (reference utils.py:299-309) over ``model.posterior``:
+    sigma (phi(u) + u Phi(u)), evaluated by the CUDA library (stp_acq_values)."""
+
+    _kind = "ei"
+
+
+class UpperConfidenceBound(LogExpectedImprovement):
+    """botorch ``UpperConfidenceBound``: (mean if maximize else -mean) + sqrt(beta) sigma,
+    sigma = sqrt(max(var, 1e-12)); evaluated by the CUDA library (stp_acq_values)."""
+
+    _kind = "ucb"
+
+    def __init__(self, model, beta, posterior_transform=None, maximize: bool = True):
+        super().__init__(model, 0.0, posterior_transform, maximize)
+        self._beta = float(beta)
 
 
 def log_expected_improvement(model, test_X: torch.Tensor, best_f: torch.Tensor) -> torch.Tensor:
@@ -85,6 +108,11 @@ def log_expected_improvement_t(model, test_X: torch.Tensor, best_f: torch.Tensor
         std = std.expand(mean.shape) if std.shape != mean.shape else std
         df = df.expand(mean.shape) if df.shape != mean.shape else df
         mean, std, df = torch.mean(mean, dim=0), torch.mean(std, dim=0), torch.mean(df, dim=0)
+    if mean.is_cuda:   # device form (stp_log_ei_t): the same formula without the round trip through scipy
+        from . import _lib
+        out = _lib.log_ei_t(mean.double().contiguous(), std.double().contiguous(), df.double().contiguous(),
+                            float(torch.as_tensor(best_f)))
+        return out.to(device=test_X.device, dtype=test_X.dtype)
     mean_np, std_np = mean.detach().cpu().numpy(), std.detach().cpu().numpy()
     df_np = df.detach().cpu().numpy()
     best_np = torch.as_tensor(best_f).detach().cpu().numpy()

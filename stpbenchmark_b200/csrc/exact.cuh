@@ -47,6 +47,9 @@ struct ExactSmem {
   double* small;  // 64 doubles: theta (<=11), gradient (<=11), misc
   double* red;    // kRedDoubles reduction scratch
   int ld, cap;
+  int kern;          // kKernRBF / kKernMatern52 (set by the caller after the carve-up; 0 = the reference's RBF)
+  int acq_kind;      // kAcqLogEI / kAcqUCB / kAcqEI
+  double acq_beta;   // UCB's beta
 };
 
 STP_HD size_t exact_tile_doubles(int cap, int tc) {
@@ -61,6 +64,7 @@ STP_HD size_t exact_smem_doubles(int cap, int d, int tc, int nwarps) {
 
 STP_HD ExactSmem exact_smem_carve(double* base, int cap, int d, int tc, int nwarps) {
   ExactSmem s;
+  s.kern = 0; s.acq_kind = 0; s.acq_beta = 0.0;
   s.cap = cap;
   s.ld = odd_ld(cap + 1);
   double* p = base;
@@ -101,8 +105,25 @@ STP_HD uint8_t mask_byte(const uint8_t* mask, int i) {
 #endif
 }
 
+// Stationary ARD kernels as functions of r2 = ||(x - x') / l||^2.  RBF is what the reference uses (models.py:342-358);
+// Matern-5/2 (gpytorch MaternKernel(nu = 2.5): os (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r), r = sqrt(max(r2, 1e-30)))
+// is the alternative north_star names (row f4).
+enum { kKernRBF = 0, kKernMatern52 = 1 };
+STP_HD_NOINLINE double matern52_of_r2(double r2, double os) {
+  const double r = sqrt(r2 > 1e-30 ? r2 : 1e-30), sr = 2.23606797749978969641 * r;
+  return os * (1.0 + sr + (5.0 / 3.0) * r * r) * exp(-sr);
+}
+// d k / d l_k = kernel_dfactor * k * (x_k - x'_k)^2 / l_k^3:  1 for RBF, (5/3)(1 + sqrt5 r) / (1 + sqrt5 r + 5/3 r^2) for Matern-5/2
+STP_HD_NOINLINE double matern52_dfactor(double r2) {
+  const double r = sqrt(r2 > 1e-30 ? r2 : 1e-30), sr = 2.23606797749978969641 * r;
+  return (5.0 / 3.0) * (1.0 + sr) / (1.0 + sr + (5.0 / 3.0) * r * r);
+}
+STP_HD double kernel_of_r2(int kern, double r2, double os) {
+  return kern == kKernMatern52 ? matern52_of_r2(r2, os) : os * exp(-0.5 * r2);
+}
+
 // noise-free kernel value between training points i and j (direct differences, App. A.1)
-STP_HD double ard_rbf_tt(const double* Xt, int cap, int d, const double* invl, int i, int j, double os) {
+STP_HD double ard_rbf_tt(const double* Xt, int cap, int d, const double* invl, int i, int j, double os, int kern = 0) {
   double r2 = 0.0;
 #pragma unroll
   for (int k = 0; k < kMaxD; ++k)
@@ -110,7 +131,7 @@ STP_HD double ard_rbf_tt(const double* Xt, int cap, int d, const double* invl, i
       const double t = (Xt[k * cap + i] - Xt[k * cap + j]) * invl[k];
       r2 += t * t;
     }
-  return os * exp(-0.5 * r2);
+  return kernel_of_r2(kern, r2, os);
 }
 
 // Calls f(i, j) once for every pair of the strict lower triangle 0 <= j < i < n.  Row i of a triangle has i
@@ -165,7 +186,7 @@ STP_HD int exact_mll_fg(const Team& tm, const ExactSmem& s, int n, int d, const 
   STP_ROLLED for (int attempt = 0; attempt < kPsdSafeTries && fail; ++attempt) {
     const double diag = os + noise + psd_safe_jitter(attempt);
     for_each_lower_pair(tm, n, [&](int i, int j) {
-      const double kij = ard_rbf_tt(s.Xt, cap, d, invl, i, j, os);
+      const double kij = ard_rbf_tt(s.Xt, cap, d, invl, i, j, os, s.kern);
       s.A[i * ld + j] = kij;
       s.A[j * ld + i] = kij;
     });
@@ -200,15 +221,21 @@ STP_HD int exact_mll_fg(const Team& tm, const ExactSmem& s, int n, int d, const 
     acc[1] += ai * ai + s.A[i * ld + i];
     acc[2] += ai;
   }
+  const int kern = s.kern;
   for_each_lower_pair(tm, n, [&](int i, int j) {
     const double t = (arow[i] * arow[j] + s.A[i * ld + j]) * s.A[j * ld + i];
     acc[3] += t;
+    double dxv[kMaxD];
+    double r2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kMaxD; ++k) {
+      dxv[k] = (k < d) ? s.Xt[k * cap + i] - s.Xt[k * cap + j] : 0.0;
+      if (kern != kKernRBF && k < d) { const double u = dxv[k] * invl[k]; r2 += u * u; }
+    }
+    const double tl = (kern == kKernRBF) ? t : t * matern52_dfactor(r2);
 #pragma unroll
     for (int k = 0; k < kMaxD; ++k)
-      if (k < d) {
-        const double dx = s.Xt[k * cap + i] - s.Xt[k * cap + j];
-        acc[4 + k] += t * dx * dx;
-      }
+      if (k < d) acc[4 + k] += tl * dxv[k] * dxv[k];
   });
   STP_PHASE(5);
   tm.sum_vec(acc, 5 + d);
@@ -261,7 +288,7 @@ STP_HD int exact_factorize(const Team& tm, const ExactSmem& s, int n, int d, con
     for (int i = tm.warp(); i < n; i += tm.nwarps()) {
       double* row = s.A + i * ld;
       for (int j = tm.lane(); j <= i; j += W)
-        row[j] = (j == i) ? diag : ard_rbf_tt(s.Xt, cap, d, invl, i, j, os);
+        row[j] = (j == i) ? diag : ard_rbf_tt(s.Xt, cap, d, invl, i, j, os, s.kern);
     }
     fail = cholesky_inverse_fused(tm, s.A, ld, n, s.c1, s.c2, s.piv, (double*)nullptr, 0);
     if (fail) tm.sync();
@@ -416,7 +443,7 @@ STP_HD void exact_acquire(const Team& tm, const ExactSmem& s, int n, int d, cons
             const double t = (xc[k * TC + c] - s.Xt[k * cap + j]) * invl[k];
             r2 += t * t;
           }
-        v = os * exp(-0.5 * r2);
+        v = kernel_of_r2(s.kern, r2, os);
       }
       s.tile[j * TC + c] = v;
     }
@@ -430,7 +457,7 @@ STP_HD void exact_acquire(const Team& tm, const ExactSmem& s, int n, int d, cons
       for (int w = 0; w < n_mu; ++w) mu += s.part[(w * TC + c) * 2 + 1];
       const double mean = cst + mu;
       const double var = os - ssq + noise;
-      const double a = log_ei(mean, var, best_f);
+      const double a = acq_value(s.acq_kind, s.acq_beta, mean, var, best_f);
       const int gi = base + c;
       if (mean_out) mean_out[gi] = mean;
       if (var_out) var_out[gi] = var;

@@ -1,9 +1,11 @@
 // libstp_b200.so -- sm_100a kernels and C ABI (include/stp_b200.h) of the batched BO hot path.
-// One CTA owns one campaign; every matrix of a campaign stays in shared memory for the whole
-// launch (<= 64 KB per campaign at n = 89, so three campaigns are resident per SM).
+// One CTA owns one campaign; every matrix of an exact-GP campaign stays in shared memory for the whole
+// launch (43 KB at n <= 48, 65 KB at n <= 66, 106 KB at n <= 89: four, three or two campaigns resident per SM).
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+
+#include <mutex>
 
 #include "../../include/stp_b200.h"
 #include "exact_campaign.cuh"
@@ -57,6 +59,22 @@ size_t exact_smem_bytes(int n_cap, int d, int threads, bool with_optimizer) {
 }
 
 struct PriorArg { double v[6]; };
+struct ModelArg { int kernel, acquisition; double beta; };
+
+int fill_model(ModelArg& m, const stp_model_opts* o, bool kernel_allowed) {
+  m.kernel = 0; m.acquisition = 0; m.beta = 0.0;
+  if (!o) return 0;
+  if (o->kernel != STP_KERNEL_RBF && (o->kernel != STP_KERNEL_MATERN52 || !kernel_allowed))
+    return fail(kernel_allowed ? "unknown kernel" : "the variational entry points provide the RBF kernel only");
+  if (o->acquisition < STP_ACQ_LOGEI || o->acquisition > STP_ACQ_EI) return fail("unknown acquisition");
+  if (o->acquisition == STP_ACQ_UCB && !(o->beta >= 0.0)) return fail("UCB needs beta >= 0");
+  m.kernel = o->kernel; m.acquisition = o->acquisition; m.beta = o->beta;
+  return 0;
+}
+__device__ __forceinline__ ExactSmem with_model(ExactSmem s, const ModelArg& m) {
+  s.kern = m.kernel; s.acq_kind = m.acquisition; s.acq_beta = m.beta;
+  return s;
+}
 struct BoundsArg { double lb[kMaxP], ub[kMaxP], theta0[kMaxP]; };
 
 __device__ __forceinline__ ExactPrior to_prior(const PriorArg& p) {
@@ -70,11 +88,11 @@ __device__ __forceinline__ int fit_status_code(int s) {  // optimiser status -> 
 // ------------------------------------------------------------------------------------------
 __global__ void k_exact_mll_fg(int n_cap, int d, const double* __restrict__ X, const double* __restrict__ y,
                                const int32_t* __restrict__ n_arr, const double* __restrict__ theta, PriorArg prior,
-                               double* __restrict__ f, double* __restrict__ g, int32_t* __restrict__ status) {
+                               double* __restrict__ f, double* __restrict__ g, int32_t* __restrict__ status, ModelArg model) {
   extern __shared__ double smem[];
   const int b = blockIdx.x;
   const int n = n_arr ? n_arr[b] : n_cap;
-  const ExactSmem s = exact_smem_carve(smem, n_cap, d, kTC, blockDim.x >> 5);
+  const ExactSmem s = with_model(exact_smem_carve(smem, n_cap, d, kTC, blockDim.x >> 5), model);
   CtaTeam tm{s.red};
   const int np = d + 3;
   exact_load(tm, s, n, d, X + (size_t)b * n_cap * d, y + (size_t)b * n_cap);
@@ -89,12 +107,12 @@ __global__ void k_exact_mll_fg(int n_cap, int d, const double* __restrict__ X, c
 __global__ void __launch_bounds__(STP_EXACT_MAXT, STP_EXACT_MINB) k_exact_fit(int n_cap, int d, const double* __restrict__ X, const double* __restrict__ y,
                             const int32_t* __restrict__ n_arr, double* __restrict__ theta, BoundsArg bnd,
                             PriorArg prior, LbfgsbOpts opts, double* __restrict__ f_out, int32_t* __restrict__ nit,
-                            int32_t* __restrict__ nfev, int32_t* __restrict__ status) {
+                            int32_t* __restrict__ nfev, int32_t* __restrict__ status, ModelArg model) {
   extern __shared__ double smem[];
   const int b = blockIdx.x;
   const int n = n_arr ? n_arr[b] : n_cap;
   const int nw = blockDim.x >> 5;
-  const ExactSmem s = exact_smem_carve(smem, n_cap, d, kTC, nw);
+  const ExactSmem s = with_model(exact_smem_carve(smem, n_cap, d, kTC, nw), model);
   LbfgsbState* S = reinterpret_cast<LbfgsbState*>(smem + exact_smem_doubles(n_cap, d, kTC, nw));
   int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(S) + sizeof(LbfgsbState));
   CtaTeam tm{s.red};
@@ -119,11 +137,11 @@ __global__ void k_exact_acq(int n_cap, int d, int N, const double* __restrict__ 
                             const int32_t* __restrict__ n_arr, const double* __restrict__ theta,
                             const double* __restrict__ best_f, int32_t* __restrict__ out_idx,
                             double* __restrict__ out_acq, double* __restrict__ mean, double* __restrict__ var,
-                            double* __restrict__ acq, int32_t* __restrict__ status) {
+                            double* __restrict__ acq, int32_t* __restrict__ status, ModelArg model) {
   extern __shared__ double smem[];
   const int b = blockIdx.x;
   const int n = n_arr ? n_arr[b] : n_cap;
-  const ExactSmem s = exact_smem_carve(smem, n_cap, d, kTC, blockDim.x >> 5);
+  const ExactSmem s = with_model(exact_smem_carve(smem, n_cap, d, kTC, blockDim.x >> 5), model);
   CtaTeam tm{s.red};
   const int np = d + 3;
   exact_load(tm, s, n, d, X + (size_t)b * n_cap * d, y + (size_t)b * n_cap);
@@ -150,6 +168,7 @@ struct BoArgs {
   BoundsArg bnd; PriorArg prior; LbfgsbOpts opts;
   double* theta_out; double* acq_out; int32_t* nit; int32_t* nfev; int32_t* status;
   stp_turnover turn; double* work_acc; int32_t* iters_acc;
+  ModelArg model;
 };
 
 // One BO iteration of campaign b by the whole CTA.  CG: the campaign state may have been written by another SM
@@ -162,7 +181,7 @@ __device__ __forceinline__ int exact_bo_iteration(const BoArgs& a, double* smem,
   // n_cap: row capacity of the global arrays; s_cap <= n_cap - 1: what the shared-memory carve-up of this launch holds
   if (n >= n_cap || n < 1 || n > s_cap) { if (threadIdx.x == 0) a.status[b] = 2; return 2; }
   const int nw = blockDim.x >> 5;
-  const ExactSmem s = exact_smem_carve(smem, s_cap, d, kTC, nw);
+  const ExactSmem s = with_model(exact_smem_carve(smem, s_cap, d, kTC, nw), a.model);
   LbfgsbState* S = reinterpret_cast<LbfgsbState*>(smem + exact_smem_doubles(s_cap, d, kTC, nw));
   int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(S) + sizeof(LbfgsbState));
   CtaTeam tm{s.red};
@@ -378,7 +397,7 @@ __global__ void __launch_bounds__(256) k_var_acq(int n_cap, int d, int N, int li
                                                  double* __restrict__ acq, int update, const double* __restrict__ pool_y,
                                                  double* __restrict__ X, double* __restrict__ y, int32_t* __restrict__ trace,
                                                  int32_t* __restrict__ status, double* __restrict__ work,
-                                                 const int32_t* __restrict__ order) {
+                                                 const int32_t* __restrict__ order, ModelArg model) {
   extern __shared__ double smem[];
   const int b = order ? order[blockIdx.x] : blockIdx.x;
   if (status[b] != 0) { if (threadIdx.x == 0 && out_idx) out_idx[b] = -1; return; }
@@ -405,7 +424,7 @@ __global__ void __launch_bounds__(256) k_var_acq(int n_cap, int d, int N, int li
   int bi; double bv;
   var_acquire(tm, s, w, n, d, lik, tile, part, Pl, N, mb, best, S, eps ? eps + (size_t)b * N * S : nullptr, seed,
               (unsigned long long)b, &bi, &bv, mean ? mean + (size_t)b * N : nullptr,
-              var ? var + (size_t)b * N : nullptr, acq ? acq + (size_t)b * N : nullptr, !BIG);
+              var ? var + (size_t)b * N : nullptr, acq ? acq + (size_t)b * N : nullptr, !BIG, model.acquisition, model.beta);
   if (threadIdx.x == 0) { if (out_idx) out_idx[b] = bi; if (out_acq) out_acq[b] = bv; }
   if (!update) return;
   if (bi < 0) { if (threadIdx.x == 0) status[b] = 2; return; }
@@ -501,6 +520,20 @@ __global__ void k_design_snap(int Q, int Ne, int d, const double* __restrict__ P
   if (lane == 0) out[q] = bi;
 }
 
+__global__ void k_acq_values(long long count, const double* __restrict__ mean, const double* __restrict__ var,
+                             double best_f, ModelArg model, double* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = acq_value(model.acquisition, model.beta, mean[i], var[i], best_f);
+}
+
+__global__ void k_log_ei_t(long long count, const double* __restrict__ mean, const double* __restrict__ sd,
+                           const double* __restrict__ df, double best_f, double* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = log_ei_t(mean[i], sd[i], df[i], best_f);
+}
+
 // Opt in to > 48 KB of dynamic shared memory.  cudaFuncSetAttribute blocks while instances of the kernel are
 // running, which would serialise launches on different streams, so it is issued only when the requested size
 // grows (cached per kernel and device).
@@ -511,6 +544,8 @@ int set_smem(K kernel, size_t bytes) {
   struct Grant { const void* fn; int dev; size_t bytes; };
   static Grant table[64];
   static int used = 0;
+  static std::mutex guard;                       // the ABI may be called from one host thread per GPU
+  std::lock_guard<std::mutex> lock(guard);
   int dev = 0;
   cudaGetDevice(&dev);
   const void* fn = reinterpret_cast<const void*>(kernel);
@@ -567,7 +602,9 @@ const char* stp_last_error_string(void) { return g_err; }
 
 int stp_exact_mll_fg(int B, int n_cap, int d, const double* X, const double* y, const int32_t* n,
                      const double* theta, const double* prior, double* f, double* g, int32_t* status,
-                     void* stream) {
+                     const stp_model_opts* model, void* stream) {
+  ModelArg m;
+  if (fill_model(m, model, true)) return -1;
   if (check_dims(B, n_cap, d)) return -1;
   if (!X || !y || !theta || !prior || !f || !g || !status) return fail("null argument");
   if (B == 0) return 0;
@@ -575,13 +612,15 @@ int stp_exact_mll_fg(int B, int n_cap, int d, const double* X, const double* y, 
   const size_t smem = exact_smem_bytes(n_cap, d, threads, false);
   if (set_smem(k_exact_mll_fg, smem)) return -1;
   PriorArg p; memcpy(p.v, prior, sizeof(p.v));
-  k_exact_mll_fg<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, theta, p, f, g, status);
+  k_exact_mll_fg<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, theta, p, f, g, status, m);
   return after_launch("stp_exact_mll_fg");
 }
 
 int stp_exact_fit(int B, int n_cap, int d, const double* X, const double* y, const int32_t* n, double* theta,
                   const double* lower, const double* upper, const double* prior, const stp_lbfgsb_opts* opts,
-                  double* f_out, int32_t* nit, int32_t* nfev, int32_t* status, void* stream) {
+                  double* f_out, int32_t* nit, int32_t* nfev, int32_t* status, const stp_model_opts* model, void* stream) {
+  ModelArg m;
+  if (fill_model(m, model, true)) return -1;
   if (check_dims(B, n_cap, d)) return -1;
   if (!X || !y || !theta || !prior || !status) return fail("null argument");
   if (B == 0) return 0;
@@ -591,14 +630,16 @@ int stp_exact_fit(int B, int n_cap, int d, const double* X, const double* y, con
   PriorArg p; memcpy(p.v, prior, sizeof(p.v));
   BoundsArg bnd; fill_bounds(bnd, d, lower, upper, nullptr);
   k_exact_fit<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, theta, bnd, p, to_opts(opts), f_out, nit,
-                                                          nfev, status);
+                                                          nfev, status, m);
   return after_launch("stp_exact_fit");
 }
 
 int stp_exact_acq(int B, int n_cap, int d, int N, const double* pool, const int32_t* pool_id, const uint8_t* mask,
                   const double* X, const double* y, const int32_t* n, const double* theta, const double* best_f,
                   int32_t* out_idx, double* out_acq, double* mean, double* var, double* acq, int32_t* status,
-                  void* stream) {
+                  const stp_model_opts* model, void* stream) {
+  ModelArg m;
+  if (fill_model(m, model, true)) return -1;
   if (check_dims(B, n_cap, d)) return -1;
   if (N < 0) return fail("N < 0");
   if (!pool || !X || !y || !theta || !status) return fail("null argument");
@@ -607,7 +648,7 @@ int stp_exact_acq(int B, int n_cap, int d, int N, const double* pool, const int3
   const size_t smem = exact_smem_bytes(n_cap, d, threads, false);
   if (set_smem(k_exact_acq, smem)) return -1;
   k_exact_acq<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, N, pool, pool_id, mask, X, y, n, theta, best_f,
-                                                          out_idx, out_acq, mean, var, acq, status);
+                                                          out_idx, out_acq, mean, var, acq, status, m);
   return after_launch("stp_exact_acq");
 }
 
@@ -615,7 +656,9 @@ static int fill_bo_args(BoArgs& a, int B, int n_cap, int d, int N, const double*
                         const int32_t* pool_id, uint8_t* mask, double* X, double* y, int32_t* n, int32_t* trace,
                         const double* theta0, const double* lower, const double* upper, const double* prior,
                         const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
-                        int32_t* status, const stp_turnover* turnover, double* work_acc, int32_t* iters_acc, int n_max) {
+                        int32_t* status, const stp_turnover* turnover, double* work_acc, int32_t* iters_acc, int n_max,
+                        const stp_model_opts* model) {
+  if (fill_model(a.model, model, true)) return -1;
   if (check_dims(B, n_cap, d)) return -1;
   if (N < 1) return fail("N < 1");
   if (n_max < 0 || n_max >= n_cap) return fail("n_max must be 0 (unknown) or in [1, n_cap - 1]");
@@ -643,10 +686,10 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
                       const double* theta0, const double* lower, const double* upper, const double* prior,
                       const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
                       int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
-                      int32_t* iters_acc, int n_max, void* stream) {
+                      int32_t* iters_acc, int n_max, const stp_model_opts* model, void* stream) {
   BoArgs a;
   if (fill_bo_args(a, B, n_cap, d, N, pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upper, prior, opts,
-                   theta_out, acq_out, nit, nfev, status, turnover, work_acc, iters_acc, n_max)) return -1;
+                   theta_out, acq_out, nit, nfev, status, turnover, work_acc, iters_acc, n_max, model)) return -1;
   if (B == 0) return 0;
   const int threads = threads_for(a.s_cap);
   const size_t smem = exact_smem_bytes(a.s_cap, d, threads, true) + smem_pad();
@@ -660,10 +703,11 @@ int stp_exact_bo_run(int B, int n_cap, int d, int N, const double* pool, const d
                      const double* theta0, const double* lower, const double* upper, const double* prior,
                      const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
                      int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
-                     int32_t* iters_acc, int n_max, int32_t* iters_left, int32_t* sched, int max_ctas, void* stream) {
+                     int32_t* iters_acc, int n_max, int32_t* iters_left, int32_t* sched, int max_ctas,
+                     const stp_model_opts* model, void* stream) {
   BoArgs a;
   if (fill_bo_args(a, B, n_cap, d, N, pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upper, prior, opts,
-                   theta_out, acq_out, nit, nfev, status, turnover, work_acc, iters_acc, n_max)) return -1;
+                   theta_out, acq_out, nit, nfev, status, turnover, work_acc, iters_acc, n_max, model)) return -1;
   if (!iters_left || !sched) return fail("null argument");
   if (B == 0) return 0;
   const int threads = threads_for(a.s_cap);
@@ -765,7 +809,10 @@ int stp_var_acq(int B, int n_cap, int d, int N, int lik, const double* pool, con
                 const double* Z, const double* hyp, const double* nat1, const double* nat2, int32_t* n,
                 const double* best_f, int S, const double* eps, unsigned long long seed, int32_t* out_idx,
                 double* out_acq, double* mean, double* var, double* acq, int update, const double* pool_y, double* X,
-                double* y, int32_t* trace, int32_t* status, double* work, const int32_t* order, void* stream) {
+                double* y, int32_t* trace, int32_t* status, double* work, const int32_t* order,
+                const stp_model_opts* model, void* stream) {
+  ModelArg m;
+  if (fill_model(m, model, false)) return -1;
   if (check_dims(B, n_cap, d, STP_MAX_N_VAR)) return -1;
   if (N < 0 || S < 1) return fail("N < 0 or S < 1");
   if (lik < 0 || lik > 2) return fail("lik must be 0, 1 or 2");
@@ -780,12 +827,12 @@ int stp_var_acq(int B, int n_cap, int d, int N, int lik, const double* pool, con
     if (set_smem(k_var_acq<true>, smem)) return -1;
     k_var_acq<true><<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, N, lik, pool, pool_id, mask, ptrs, n, best_f, S, eps,
                                                             seed, out_idx, out_acq, mean, var, acq, update, pool_y, X, y,
-                                                            trace, status, work, order);
+                                                            trace, status, work, order, m);
   } else {
     if (set_smem(k_var_acq<false>, smem)) return -1;
     k_var_acq<false><<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, N, lik, pool, pool_id, mask, ptrs, n, best_f, S, eps,
                                                              seed, out_idx, out_acq, mean, var, acq, update, pool_y, X, y,
-                                                             trace, status, work, order);
+                                                             trace, status, work, order, m);
   }
   return after_launch("stp_var_acq");
 }
@@ -807,6 +854,28 @@ int stp_log_ei(long long count, const double* mean, const double* var, double be
   if (blocks > 148 * 16) blocks = 148 * 16;
   k_log_ei<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(count, mean, var, best_f, out);
   return after_launch("stp_log_ei");
+}
+
+int stp_acq_values(long long count, const double* mean, const double* var, double best_f, const stp_model_opts* model,
+                   double* out, void* stream) {
+  ModelArg m;
+  if (fill_model(m, model, true)) return -1;
+  if (count < 0 || !mean || !var || !out) return fail("bad argument");
+  if (count == 0) return 0;
+  long long blocks = (count + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_acq_values<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(count, mean, var, best_f, m, out);
+  return after_launch("stp_acq_values");
+}
+
+int stp_log_ei_t(long long count, const double* mean, const double* sd, const double* df, double best_f, double* out,
+                 void* stream) {
+  if (count < 0 || !mean || !sd || !df || !out) return fail("bad argument");
+  if (count == 0) return 0;
+  long long blocks = (count + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_log_ei_t<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(count, mean, sd, df, best_f, out);
+  return after_launch("stp_log_ei_t");
 }
 
 int stp_design_snap(int Q, int Ne, int d, const double* points, const double* eligible, int32_t* out_idx, void* stream) {

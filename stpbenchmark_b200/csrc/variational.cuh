@@ -782,7 +782,8 @@ template <class Team>
 STP_HD void var_acquire(const Team& tm, const VarSmem& s, const VarWork& w, int n, int d, int lik, double* tile,
                         double* part, const double* pool, int N, const uint8_t* mask, double best_f, int S,
                         const double* eps, uint64_t seed, uint64_t stream, int* best_idx, double* best_acq,
-                        double* mean_out, double* var_out, double* acq_out, bool packed = false) {
+                        double* mean_out, double* var_out, double* acq_out, bool packed = false,
+                        int acq_kind = kAcqLogEI, double acq_beta = 0.0) {
   const int cap = s.cap, TC = tm.warp_width(), nw = tm.nwarps();
   const int n16 = (n + 15) & ~15;                 // rows n .. n16 - 1 of the tile are zero (DMMA row tiles)
   const int slots = var_acq_slots(cap);           // partial-sum slots per candidate and quantity
@@ -793,6 +794,7 @@ STP_HD void var_acquire(const Team& tm, const VarSmem& s, const VarWork& w, int 
   const double lik_var = var_lik_variance(lik, noise, rho);
   const double sig_l = sqrt(lik_var > 1e-12 ? lik_var : 1e-12);
   const double log_sig_l = log(sig_l);
+  const double sqrt_beta = sqrt(acq_beta > 0.0 ? acq_beta : 0.0);
   double run_v = -INFINITY;
   int run_i = -1;
   for (int base = 0; base < N; base += TC) {
@@ -842,7 +844,7 @@ STP_HD void var_acquire(const Team& tm, const VarSmem& s, const VarWork& w, int 
     if (lik == kLikGaussian) {
       for (int c = tm.rank(); c < cnt; c += tm.size()) {
         const int gi = base + c;
-        const double a = log_ei(part[c], part[slots * TC + c] + noise, best_f);
+        const double a = acq_value(acq_kind, acq_beta, part[c], part[slots * TC + c] + noise, best_f);
         if (acq_out) acq_out[gi] = a;
         if ((!mask || mask[gi]) && acq_better(a, gi, run_v, run_i)) { run_v = a; run_i = gi; }
       }
@@ -855,16 +857,16 @@ STP_HD void var_acquire(const Team& tm, const VarSmem& s, const VarWork& w, int 
         double a = 0.0;
         if (eps) {
           const double* e = eps + (size_t)gi * S;
-          for (int q = tm.lane(); q < S; q += TC) a += log_h(((mean + sd * e[q]) - best_f) / sig_l);
+          for (int q = tm.lane(); q < S; q += TC) a += acq_sample(acq_kind, sqrt_beta, mean + sd * e[q], best_f, sig_l);
         } else {
           for (int q = tm.lane(); 2 * q < S; q += TC) {
             double z0, z1;
             philox_normal2(seed, stream, (uint64_t)gi * (uint64_t)((S + 1) / 2) + q, z0, z1);
-            a += log_h(((mean + sd * z0) - best_f) / sig_l);
-            if (2 * q + 1 < S) a += log_h(((mean + sd * z1) - best_f) / sig_l);
+            a += acq_sample(acq_kind, sqrt_beta, mean + sd * z0, best_f, sig_l);
+            if (2 * q + 1 < S) a += acq_sample(acq_kind, sqrt_beta, mean + sd * z1, best_f, sig_l);
           }
         }
-        a = tm.warp_sum(a) / S + log_sig_l;
+        a = tm.warp_sum(a) / S + (acq_kind == kAcqLogEI ? log_sig_l : 0.0);
         if (tm.lane() == 0) {
           if (acq_out) acq_out[gi] = a;
           if ((!mask || mask[gi]) && acq_better(a, gi, run_v, run_i)) { run_v = a; run_i = gi; }

@@ -34,13 +34,18 @@ class CampaignBatch:
                  init_indices: Sequence[Sequence[int]], n_cap: int, kind: str = "ExactGP",
                  device: Optional[torch.device] = None, epochs: int = 600, learning_rate: float = 0.01,
                  num_samples: int = 2048, seeds: Optional[Sequence[int]] = None,
-                 pool_sizes: Optional[Sequence[int]] = None, lengthscale_prior=None):
+                 pool_sizes: Optional[Sequence[int]] = None, lengthscale_prior=None, kernel: str = "rbf",
+                 acquisition: str = "logei", beta: float = 0.0):
         if not torch.cuda.is_available():
             raise RuntimeError("CampaignBatch needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         if pools.dim() == 2:
             pools, pool_ys = pools.unsqueeze(0), pool_ys.reshape(1, -1)
         self.kind = kind
+        # kernel / acquisition variants (row f4); None = RBF + LogEI, the reference's path
+        self.model_opts = _lib.ModelOpts.make(kernel, acquisition, beta)
+        if kind != "ExactGP" and str(kernel).lower() != "rbf":
+            raise NotImplementedError("the variational models provide the RBF kernel only")
         self.G, self.N, self.d = pools.shape
         self.B = len(pool_id)
         self.cap = int(n_cap)
@@ -118,7 +123,7 @@ class CampaignBatch:
                                self._theta0, self._lower, self._upper, self._prior, self.status,
                                theta_out=self.theta, acq_out=self.acq, nit=self.nit, nfev=self.nfev,
                                opts=self._opts, order=order, turnover=self._turnover, work_acc=self.work_acc,
-                               iters_acc=self.iters_acc, n_max=n_max)
+                               iters_acc=self.iters_acc, n_max=n_max, model=self.model_opts)
             self.launches += 1
             if self._n_host is not None:          # what the kernel does to n: +1, and the turnover's restart
                 self._n_host += 1
@@ -173,7 +178,7 @@ class CampaignBatch:
                           self._theta0, self._lower, self._upper, self._prior, self.status, self._iters_left, self._sched,
                           theta_out=self.theta, acq_out=self.acq, nit=self.nit, nfev=self.nfev, opts=self._opts,
                           turnover=self._turnover, work_acc=self.work_acc, iters_acc=self.iters_acc, n_max=n_max,
-                          max_ctas=max_ctas)
+                          max_ctas=max_ctas, model=self.model_opts)
         self.launches += 1
         self.iteration += int(iters)
         if self._n_host is not None:
@@ -251,13 +256,15 @@ class Campaign:
     """One campaign of a job: which pool, which model kind, its initial design and its budget."""
 
     __slots__ = ("key", "kind", "pool", "design", "n_trials", "epochs", "learning_rate", "num_samples",
-                 "lengthscale_prior", "rng_state", "seed", "n_initial")
+                 "lengthscale_prior", "rng_state", "seed", "n_initial", "kernel", "acquisition", "beta")
 
     def __init__(self, key, kind: str, pool: int, design: Optional[Sequence[int]], n_trials: int, epochs: int = 100,
                  learning_rate: float = 0.1, num_samples: int = 2048, lengthscale_prior=None, rng_state=None, seed: int = 0,
-                 n_initial: Optional[int] = None):
+                 n_initial: Optional[int] = None, kernel: str = "rbf", acquisition: str = "logei", beta: float = 0.0):
         """``design`` may be None until the rank that owns the campaign fills it in (``n_initial`` then says how long
-        it will be)."""
+        it will be).  ``kernel`` / ``acquisition`` / ``beta``: the variants of include/stp_b200.h's stp_model_opts
+        (defaults = the reference's RBF + LogEI)."""
+        self.kernel, self.acquisition, self.beta = str(kernel).lower(), str(acquisition).lower(), float(beta)
         self.key, self.kind, self.pool = key, kind, int(pool)
         self.design = None if design is None else [int(i) for i in design]
         self.n_initial = int(n_initial) if n_initial is not None else len(self.design)
@@ -267,7 +274,8 @@ class Campaign:
     def group_key(self, d: int):
         """Campaigns that can share launches: same kernel arguments and the same age at every step."""
         lp = None if self.lengthscale_prior is None else tuple(float(v) for v in self.lengthscale_prior)
-        return (self.kind, d, len(self.design), self.n_trials, self.epochs, self.learning_rate, self.num_samples, lp)
+        return (self.kind, d, len(self.design), self.n_trials, self.epochs, self.learning_rate, self.num_samples, lp,
+                self.kernel, self.acquisition, self.beta)
 
 
 class CampaignJob:
@@ -296,7 +304,7 @@ class CampaignJob:
             by_key.setdefault(c.group_key(d), []).append(c_id)
         self.groups = []
         for key, ids in by_key.items():
-            kind, d, n_init, n_trials, epochs, lr, S, lp = key
+            kind, d, n_init, n_trials, epochs, lr, S, lp, kernel, acquisition, beta = key
             used = sorted({self.campaigns[i].pool for i in ids})
             local = {g: k for k, g in enumerate(used)}
             sizes = [int(pools[g][0].shape[0]) for g in used]
@@ -314,7 +322,8 @@ class CampaignJob:
                 batch = CampaignBatch(PX, PY, [local[self.campaigns[i].pool] for i in ids],
                                       [self.campaigns[i].design for i in ids], n_cap=n_init + max(trials, 0) + 1, kind=kind,
                                       device=self.device, epochs=epochs, learning_rate=lr, num_samples=S,
-                                      seeds=[self.campaigns[i].seed for i in ids], pool_sizes=sizes, lengthscale_prior=lp)
+                                      seeds=[self.campaigns[i].seed for i in ids], pool_sizes=sizes, lengthscale_prior=lp,
+                                      kernel=kernel, acquisition=acquisition, beta=beta)
                 if kind != "ExactGP" and all(self.campaigns[i].rng_state is not None for i in ids):
                     batch._var.set_rng_states([self.campaigns[i].rng_state for i in ids])
             self.groups.append({"key": key, "ids": ids, "batch": batch, "stream": stream, "trials": max(trials, 0)})

@@ -155,10 +155,13 @@ def run_campaigns(pools, campaigns: List[Campaign], on_done: Optional[Callable] 
 
 def run_campaign_batch(X: torch.Tensor, y: torch.Tensor, model_class, seeds: Sequence[int], n_initial: int = 10,
                        n_trials: int = 25, epochs: int = 100, learning_rate: float = 0.1,
-                       num_samples: int = 2048, model_kwargs: Optional[dict] = None
+                       num_samples: int = 2048, model_kwargs: Optional[dict] = None, kernel: str = "rbf",
+                       acquisition: str = "logei", beta: float = 0.0
                        ) -> Tuple[List[List[int]], List[List[float]], List[int]]:
     """Advance one campaign per seed on the same pool, all together.  Returns
-    (indices per seed, values per seed, status per seed)."""
+    (indices per seed, values per seed, status per seed).  ``kernel`` ("rbf" | "matern52", ExactGP only) and
+    ``acquisition`` ("logei" | "ucb" | "ei", with UCB's ``beta``) select the variants of SURVEY section 8 row f4;
+    the defaults are what the reference's loop does (models.py:342-358, runners.py:88-90)."""
     X = X.double()
     y = y.double().flatten()
     kind = _kind_of(model_class)
@@ -168,7 +171,8 @@ def run_campaign_batch(X: torch.Tensor, y: torch.Tensor, model_class, seeds: Seq
     dev = "cuda" if torch.cuda.is_available() else None
     designs, states = initial_designs_batch(X, y, seeds, n_initial, 50.0, return_rng_states=True, device=dev)
     camps = [Campaign(s, kind, 0, designs[k].tolist(), n_trials, epochs, learning_rate, num_samples, prior,
-                      states[k], seed=s) for k, s in enumerate(seeds)]
+                      states[k], seed=s, kernel=kernel, acquisition=acquisition, beta=beta)
+             for k, s in enumerate(seeds)]
     res = run_campaigns([(X, y)], camps)
     y_host = y.cpu()
     out_idx = [res[k][0] for k in range(len(seeds))]

@@ -100,7 +100,8 @@ class VarBatchState:
                                for g in self.generators]).to(b.device)
         out = _lib.var_acq(b.pool, self.state, b.n, self.lik, b.status, self.work, best_f=None, mask=b.mask,
                            pool_id=b.pool_id, S=b.num_samples, eps=eps, seed=self.philox_seed + 104729 * b.iteration,
-                           update={"pool_y": b.pool_y, "X": b.X, "y": b.y, "trace": b.trace}, order=order)
+                           update={"pool_y": b.pool_y, "X": b.X, "y": b.y, "trace": b.trace}, order=order,
+                           model=getattr(b, "model_opts", None))
         b.acq = out["acq_best"]
         return 2
 

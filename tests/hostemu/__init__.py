@@ -34,4 +34,10 @@ def load():
         _lib.emu_log_ei.restype = ctypes.c_double
         _lib.emu_log_ei.argtypes = [ctypes.c_double] * 3
         _lib.emu_lbfgsb_new.restype = ctypes.c_void_p
+        _lib.emu_set_model.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double]
+        _lib.emu_set_model.restype = None
+        _lib.emu_acq_value.restype = ctypes.c_double
+        _lib.emu_acq_value.argtypes = [ctypes.c_int] + [ctypes.c_double] * 4
+        _lib.emu_log_ei_t.restype = ctypes.c_double
+        _lib.emu_log_ei_t.argtypes = [ctypes.c_double] * 4
     return _lib

@@ -17,11 +17,14 @@
 using namespace stp;
 
 namespace {
+int g_kern = 0, g_acq = 0;   // emu_set_model: kernel / acquisition variant of the next emu_exact_* calls
+double g_beta = 0.0;
 struct Scratch {
   std::vector<double> buf;
   ExactSmem s;
   Scratch(int cap, int d) : buf(exact_smem_doubles(cap, d, 1, 1) + 8, 0.0) {
     s = exact_smem_carve(buf.data(), cap, d, 1, 1);
+    s.kern = g_kern; s.acq_kind = g_acq; s.acq_beta = g_beta;
   }
 };
 ExactPrior prior_from(const double* p) { return ExactPrior{p[0], p[1], p[2], p[3], p[4], p[5]}; }
@@ -101,6 +104,11 @@ void emu_lbfgsb_result(void* h, double* f, int* nit, int* nfev, int* status) {
 }
 void emu_lbfgsb_free(void* h) { free(h); }
 
+void emu_set_model(int kern, int acq, double beta) { g_kern = kern; g_acq = acq; g_beta = beta; }
+double emu_acq_value(int kind, double beta, double mean, double var, double best_f) {
+  return acq_value(kind, beta, mean, var, best_f);
+}
+double emu_log_ei_t(double mean, double sd, double df, double best_f) { return log_ei_t(mean, sd, df, best_f); }
 double emu_log_h(double u) { return log_h(u); }
 double emu_log_ei(double mean, double var, double best_f) { return log_ei(mean, var, best_f); }
 

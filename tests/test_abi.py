@@ -30,17 +30,17 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_version_and_argument_rejection(lib):
-    assert lib.stp_version() == 1
+    assert lib.stp_version() == 2
     lib.stp_last_error_string.restype = ctypes.c_char_p
     # argument validation happens before any CUDA call, so it is testable without a GPU
-    rc = lib.stp_exact_mll_fg(1, 10, 99, None, None, None, None, None, None, None, None, None)
+    rc = lib.stp_exact_mll_fg(1, 10, 99, None, None, None, None, None, None, None, None, None, None)
     assert rc < 0 and b"d out of range" in lib.stp_last_error_string()
-    rc = lib.stp_exact_mll_fg(1, 100000, 3, None, None, None, None, None, None, None, None, None)
+    rc = lib.stp_exact_mll_fg(1, 100000, 3, None, None, None, None, None, None, None, None, None, None)
     assert rc < 0 and b"n_cap out of range" in lib.stp_last_error_string()
-    rc = lib.stp_exact_fit(1, 10, 3, None, None, None, None, None, None, None, None, None, None, None, None, None)
+    rc = lib.stp_exact_fit(1, 10, 3, None, None, None, None, None, None, None, None, None, None, None, None, None, None)
     assert rc < 0 and b"null argument" in lib.stp_last_error_string()
     assert lib.stp_exact_mll_fg(0, 10, 3, ctypes.c_void_p(8), ctypes.c_void_p(8), None, ctypes.c_void_p(8),
-                                (ctypes.c_double * 6)(), ctypes.c_void_p(8), ctypes.c_void_p(8), ctypes.c_void_p(8), None) == 0
+                                (ctypes.c_double * 6)(), ctypes.c_void_p(8), ctypes.c_void_p(8), ctypes.c_void_p(8), None, None) == 0
 
 
 def test_library_is_device_code_only():
@@ -74,5 +74,7 @@ def test_struct_layouts_match_the_header():
     from stpbenchmark_b200 import _lib
     assert C.sizeof(_lib.LbfgsbOpts) == 32 and _lib.LbfgsbOpts.factr.offset == 16
     assert C.sizeof(_lib.Turnover) == 48 and _lib.Turnover.bank.offset == 16 and _lib.Turnover.sink_count.offset == 40
+    assert C.sizeof(_lib.ModelOpts) == 16 and _lib.ModelOpts.beta.offset == 8
+    assert _lib.ModelOpts.make() is None and _lib.ModelOpts.make("matern52", "ucb", 4.0).acquisition == 1
     o = _lib.LbfgsbOpts.scipy_defaults()
     assert (o.m, o.maxiter, o.maxfun, o.maxls) == (10, 15000, 15000, 20) and abs(o.factr - 1e7) < 1e-6 and o.pgtol == 1e-5
