@@ -241,7 +241,7 @@ int stp_design_snap(int Q, int Ne, int d, const double* points, const double* el
 
 /* Diagnostic: per-phase cycle counters of stp_exact_bo_step (clock64 of thread 0 of every CTA, summed over CTAs;
  * ids in csrc/team.cuh).  Only in libraries built with -DSTP_PHASE_TIMERS (tools/gpu_phase_timers.py builds one
- * beside the shipped library); the shipped build returns an error.  out32: HOST array of 32 counters (may be
+ * beside the shipped library); the shipped build returns an error.  out32: HOST array of 64 counters (0-31 exact path, 32-63 variational epoch) (may be
  * NULL); reset != 0 zeroes them.  Synchronises the device. */
 int stp_phase_timers(unsigned long long* out32, int reset);
 

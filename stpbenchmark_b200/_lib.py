@@ -233,11 +233,17 @@ PHASE_NAMES = {0: "load", 1: "gram", 2: "sweep_A", 3: "sweep_B", 4: "sweep_C", 5
                14: "adv_ls_start", 15: "adv_ls_step", 19: "adv_entry", 20: "adv_copy_dot", 21: "adv_dcsrch", 22: "adv_projgr_tests", 16: "closures", 17: "sweep_blocks", 18: "campaigns"}
 
 
+# the same counters as charged by var_epoch (k_var_fit) in a -DSTP_PHASE_TIMERS build
+VAR_PHASE_NAMES = {33: "setup_sweep_P", 34: "Ct_Kzz_cholinv", 35: "write_LI_LT", 36: "c3_At", 37: "c4_Tt_qf",
+                   38: "quadrature_loss", 39: "c6_GS_ngd", 40: "c8_CBt", 41: "c9_LB", 42: "c10_PH", 43: "c11_U", 44: "c12_KB",
+                   45: "grad_pass", 46: "adam", 48: "epochs"}
+
+
 def phase_timers(reset: bool = False) -> dict:
     """Per-phase cycle counters of stp_exact_bo_step (only in a -DSTP_PHASE_TIMERS build, see stp_phase_timers)."""
-    out = (ctypes.c_ulonglong * 32)()
+    out = (ctypes.c_ulonglong * 64)()
     _check(lib().stp_phase_timers(out, int(bool(reset))), "stp_phase_timers")
-    return {name: int(out[i]) for i, name in PHASE_NAMES.items()}
+    return {name: int(out[i]) for i, name in list(PHASE_NAMES.items()) + list(VAR_PHASE_NAMES.items())}
 
 
 def acq_values(mean: torch.Tensor, var: torch.Tensor, best_f: float, acquisition: str = "logei", beta: float = 0.0):

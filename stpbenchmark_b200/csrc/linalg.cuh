@@ -234,8 +234,9 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // Per block step:
 //   (A) every warp eliminates the 8 x 8 block in registers (accumulator-fragment layout, warp shuffles only: no
 //       barrier on the critical path of 8 dependent pivots), giving X and 1 / Delta;
-//   (B) W, V, T by DMMA, 8 rows per warp; W replaces C in its panel, -V goes to a second panel, T is written
-//       straight into the pivot columns / rows of A (and into the next panel where it belongs);      -- barrier --
+//   (B) W, V, T by DMMA, 8 rows per warp; W replaces C in its panel (V = W / Delta is rebuilt from it where it is
+//       needed), T is written straight into the pivot columns / rows of A (and into the next panel where it
+//       belongs);                                                                                    -- barrier --
 //   (C) rank-8 update of the lower triangle in 16 x 16 tiles, 8 DMMA per tile; the store pass also collects the
 //       NEXT panel (columns K + 8, symmetric fill).                                                -- barrier --
 // i.e. 2 barriers per 8 pivots instead of 4, and ~8x fewer issued instructions per MAC than the pair sweep.
@@ -243,18 +244,33 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // `scratch`: sweep_blocked_scratch_doubles(m) doubles of shared memory.  Returns 0 or 1 + k for a bad pivot.
 // ---------------------------------------------------------------------------------------
 constexpr int kPanelLd = 12;   // 8 panel columns + 4 pad doubles: conflict-free fragment loads (24 g + 2 q words)
-STP_HD size_t sweep_blocked_scratch_doubles(int m) { return (size_t)3 * m * kPanelLd; }
+STP_HD size_t sweep_blocked_scratch_doubles(int m) { return (size_t)2 * m * kPanelLd; }
+
+// By-product of the blocked sweep of a positive-definite matrix (no border): its Cholesky factor and the inverse of
+// that factor.  Right before block K is eliminated, the panel rows c < K hold (A[K, :K] A[:K, :K]^-1)^T =
+// (L[K, :K] L[:K, :K]^-1)^T, so with D = Lu Delta Lu^T the product W = C Lu^-T already is, up to Delta^-1/2,
+//     L[i, K_b]       =  W[i][b] / sqrt(Delta_b)      (i >= K_b),
+//     L^-1[K_b, c]    = -W[c][b] / sqrt(Delta_b)      (c <  K),          L^-1[K_g, K_b] = X[g][b] / sqrt(Delta_g).
+// The sweep therefore replaces the column-by-column fused Cholesky + inverse (n barriers, one pass over the triangle
+// each) by n / 8 block steps.  Targets may be null; only the lower triangles (upper for LiT) are written.
+struct SweepCholExport {
+  double* L;     // lower Cholesky factor, row-major, leading dimension ld
+  double* Li;    // L^-1 (lower)
+  double* LiT;   // (L^-1)^T (upper)
+  int ld;
+};
 
 #if defined(__CUDACC__)
+template <bool EXPORT = false>
 __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double* A, int ld, int m, int npiv,
-                                                      double* scratch, double* piv) {
+                                                      double* scratch, double* piv,
+                                                      SweepCholExport ex = SweepCholExport{nullptr, nullptr, nullptr, 0}) {
   constexpr unsigned kFull = 0xffffffffu;
   constexpr int PL = kPanelLd;
   const int lane = tm.lane(), warp = tm.warp(), nw = tm.nwarps();
   const int g = lane >> 2, q = lane & 3;
   double* C = scratch;                           // current panel; rows outside K become W in step (B)
   double* Cn = scratch + (size_t)m * PL;         // next panel
-  double* Vn = scratch + (size_t)2 * m * PL;     // -V
   tm.sync();   // the caller's writes to A must be complete
   for (int idx = tm.rank(); idx < m * 8; idx += tm.size()) {
     const int i = idx >> 3, b = idx & 7;
@@ -278,6 +294,7 @@ __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double*
     double xm0 = (2 * q == g) ? 1.0 : 0.0, xm1 = (2 * q + 1 == g) ? 1.0 : 0.0;
     double ipa = 1.0, ipb = 1.0;     // 1 / Delta at columns 2q, 2q + 1
     double ipq0 = 1.0, ipq1 = 1.0;   // 1 / Delta at q, q + 4
+    double ipg = 1.0;                // 1 / Delta at g (EXPORT)
     int fail = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -300,6 +317,7 @@ __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double*
       if (2 * q + 1 == k) ipb = ip;
       if (q == k) ipq0 = ip;
       if (q + 4 == k) ipq1 = ip;
+      if (EXPORT && g == k) ipg = ip;
       if (warp == 0 && lane == 0 && k < r) piv[kb + k] = p;
     }
     if (fail) return fail;   // identical in every warp: the whole team leaves together
@@ -327,7 +345,20 @@ __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double*
         if (2 * q <= g) row[2 * q] = -s0;
         if (2 * q + 1 <= g) row[2 * q + 1] = -s1;
       }
+      if (EXPORT && g < r) {   // L^-1[K, K] = Delta^-1/2 X
+        const double sg = sqrt(ipg);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int b = 2 * q + e;
+          if (b <= g) {
+            const double v = (e ? xm1 : xm0) * sg;
+            if (ex.Li) ex.Li[(size_t)(kb + g) * ex.ld + kb + b] = v;
+            if (ex.LiT) ex.LiT[(size_t)(kb + b) * ex.ld + kb + g] = v;
+          }
+        }
+      }
     }
+    const double isa = EXPORT ? sqrt(ipa) : 0.0, isb = EXPORT ? sqrt(ipb) : 0.0;
     // ---- (B) W = C X^T, V = W / Delta, T = V X, 8 rows per warp
     for (int rt = warp; rt * 8 < m; rt += nw) {
       const int i = rt * 8 + g, ic = (i < m) ? i : m - 1;
@@ -343,11 +374,23 @@ __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double*
       double t0 = 0.0, t1 = 0.0;
       dmma884(t0, t1, va0, bt0);
       dmma884(t0, t1, va1, bt1);
+      if (EXPORT && i < npiv) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int b = 2 * q + e, j = kb + b;
+          if (b < r) {
+            const double v = (e ? w1 : w0) * (e ? isb : isa);
+            if (i >= j) { if (ex.L) ex.L[(size_t)i * ex.ld + j] = v; }
+            if (i < kb) {
+              if (ex.Li) ex.Li[(size_t)j * ex.ld + i] = -v;
+              if (ex.LiT) ex.LiT[(size_t)i * ex.ld + j] = -v;
+            }
+          }
+        }
+      }
       if (i < m && !((unsigned)(i - kb) < (unsigned)r)) {   // rows of K keep C (phase (A) of other warps reads them)
         C[i * PL + 2 * q] = w0;
         C[i * PL + 2 * q + 1] = w1;
-        Vn[i * PL + 2 * q] = -v0;
-        Vn[i * PL + 2 * q + 1] = -v1;
         const bool nxt = (unsigned)(i - kn) < 8u && i < npiv;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -379,8 +422,8 @@ __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double*
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
         const int i = ib + 8 * a + g, ic = (i < m) ? i : m - 1;
-        af[a][0] = Vn[ic * PL + q];
-        af[a][1] = Vn[ic * PL + 4 + q];
+        af[a][0] = -(C[ic * PL + q] * ipq0);        // -V = -W / Delta (bitwise what a stored -V panel would hold)
+        af[a][1] = -(C[ic * PL + 4 + q] * ipq1);
         const int j = jb + 8 * a + g, jc = (j < m) ? j : m - 1;
         bf[a][0] = C[jc * PL + q];
         bf[a][1] = C[jc * PL + 4 + q];
@@ -620,6 +663,191 @@ __device__ __forceinline__ void contract_mma(const CtaTeam& tm, int n_rows, int 
         }
       }
   }
+}
+#endif
+
+// ---------------------------------------------------------------------------------------
+// The same contraction with the operands STAGED THROUGH SHARED MEMORY (the product path of the variational epoch).
+// contract_mma lets every warp stream its own operand rows from global memory: a 16x16 tile reads 2 x 16 x n doubles,
+// n^3 / 8 doubles per contraction, and every 4-step waits for an L2 round trip (the work squares of a campaign are
+// L2 / HBM residents).  Here the CTA walks the output in blocks of up to 4 x 4 tiles (64 x 64); for
+// each block the K range is cut into chunks of kStageRC reduction indices whose two operand panels are copied by ALL
+// threads with cp.async (coalesced rows, 8-byte copies: the leading dimensions are odd) into a three-deep ring, so
+// the copy of chunk c + 2 is in flight while chunk c feeds the tensor cores: one barrier per chunk, ~10x less global
+// traffic per MAC, and no load latency on the DMMA chain.  Panel strides are = 4 mod 8 doubles, so
+// the m8n8k4 fragment loads (4 rows x 4 consecutive doubles per half warp, or the transpose) are bank-conflict free.
+// Every tile accumulates the SAME DMMA sequence over the same 4-steps as contract_mma (ranges widened to multiples
+// of 4, zeros beyond n_red): the two forms are bit-identical; -DSTP_NO_STAGE selects the old one for A/B runs.
+// `stage`: shared memory, contract_stage_doubles() doubles, free for the duration of the call.
+// ---------------------------------------------------------------------------------------
+#if !defined(STP_STAGE_MAXT)
+#define STP_STAGE_MAXT 2
+#endif
+#if !defined(STP_STAGE_CT)
+#define STP_STAGE_CT 4
+#endif
+constexpr int kStageMaxT = STP_STAGE_MAXT;      // tiles per warp and block
+constexpr int kStageCT = STP_STAGE_CT;          // column tiles of a block (rows: <= 4 tiles)
+constexpr int kStageRC = 16;                    // reduction indices per chunk
+constexpr int kStageLdK = kStageCT * 16 + 4;    // stride of a K-major panel (row = reduction index): = 4 mod 8
+constexpr int kStageLdR = kStageRC + 4;         // stride of a row-major L panel (row = output row): 20 = 4 mod 8
+constexpr int kStagePanel = (64 * kStageLdR > kStageRC * kStageLdK) ? 64 * kStageLdR : kStageRC * kStageLdK;
+constexpr int kStageDepth = 3;
+STP_HD size_t contract_stage_doubles() { return (size_t)kStageDepth * 2 * kStagePanel; }
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void cp_async_f64(double* dst_shared, const double* src_global) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool LT, bool SCALE, class RangeF, class StoreF>
+__device__ __forceinline__ void contract_staged(const CtaTeam& tm, int n_rows, int n_cols, int n_red, const double* Lp,
+                                                int ld_l, const double* Rp, int ld_r, const double* scale, RangeF range,
+                                                StoreF store, double* stage) {
+  const int lane = tm.lane(), nw = tm.nwarps(), wid = tm.warp(), tid = tm.rank(), nt = tm.size();
+  const int g = lane >> 2, q = lane & 3;
+  const int TR = (n_rows + 15) >> 4, TC = (n_cols + 15) >> 4;
+  // block shape: <= 4 x kStageCT tiles, a warp owns <= kStageMaxT of them, both edges evened out over the matrix
+  const int cap_t = kStageMaxT * nw;
+  const int ncb = (TC + kStageCT - 1) / kStageCT, BTC = (TC + ncb - 1) / ncb;
+  int btr_max = cap_t / BTC; btr_max = btr_max > 4 ? 4 : (btr_max < 1 ? 1 : btr_max);
+  const int nrb = (TR + btr_max - 1) / btr_max, BTR = (TR + nrb - 1) / nrb;
+  for (int rb = 0; rb < TR; rb += BTR)
+    for (int cb = 0; cb < TC; cb += BTC) {
+      const int btr = (TR - rb < BTR) ? TR - rb : BTR, btc = (TC - cb < BTC) ? TC - cb : BTC;
+      const int ntile = btr * btc;
+      // the block's reduction range: union over its tiles (every thread computes it: integer work only)
+      int R0 = 0x7fffffff, R1 = 0;
+      for (int t = 0; t < ntile; ++t) {
+        const int ib = (rb + t / btc) << 4, kb = (cb + t % btc) << 4;
+        int r0 = 0, r1 = 0;
+        range(ib, (ib + 15 < n_rows) ? ib + 15 : n_rows - 1, kb, (kb + 15 < n_cols) ? kb + 15 : n_cols - 1, r0, r1);
+        r0 &= ~3; r1 = (r1 + 3) & ~3;
+        if (r1 > r0) { R0 = r0 < R0 ? r0 : R0; R1 = r1 > R1 ? r1 : R1; }
+      }
+      // this warp's tiles (a block with an empty range still stores its zeros: triangular outputs rely on it)
+      int tib[kStageMaxT], tkb[kStageMaxT], tr0[kStageMaxT], tr1[kStageMaxT];
+      double c[kStageMaxT][2][2][2];
+#pragma unroll
+      for (int m = 0; m < kStageMaxT; ++m) {
+        const int t = wid + m * nw;
+        tr0[m] = 0; tr1[m] = 0; tib[m] = 0; tkb[m] = 0;
+        if (t < ntile) {
+          tib[m] = (t / btc) << 4; tkb[m] = (t % btc) << 4;      // offsets inside the block
+          const int ib = (rb << 4) + tib[m], kb = (cb << 4) + tkb[m];
+          int r0 = 0, r1 = 0;
+          range(ib, (ib + 15 < n_rows) ? ib + 15 : n_rows - 1, kb, (kb + 15 < n_cols) ? kb + 15 : n_cols - 1, r0, r1);
+          tr0[m] = r0 & ~3; tr1[m] = (r1 + 3) & ~3;
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) { c[m][a][b][0] = 0.0; c[m][a][b][1] = 0.0; }
+      }
+      const int i0 = rb << 4, k0 = cb << 4, rows = btr << 4, cols = btc << 4;
+      const int nchunk = (R1 > R0) ? (R1 - R0 + kStageRC - 1) / kStageRC : 0;
+      // Copy plan of this thread, fixed for the block: in a K-major panel (row = reduction index) the thread owns
+      // column `tid & (pw - 1)` of the rows (tid >> sh) + j (nt >> sh), the width padded to a power of two; in the
+      // row-major L panel it owns reduction index tid & 15 of the rows (tid >> 4) + j (nt >> 4).  Per chunk only the
+      // two source pointers move.
+      const int shl = rows > 32 ? 6 : 5, shr = cols > 64 ? 7 : (cols > 32 ? 6 : 5);
+      const int rk = tid & ((1 << shr) - 1), rrow = tid >> shr, rstep = nt >> shr;
+      const bool r_on = rk < cols, r_in = k0 + rk < n_cols;
+      const double* gR = Rp + (size_t)(R0 + rrow) * ld_r + k0 + rk;
+      const int dR = rrow * kStageLdK + rk;
+      const int lk = LT ? (tid & ((1 << shl) - 1)) : (tid & 15), lrow = LT ? (tid >> shl) : (tid >> 4);
+      const int lstep = LT ? (nt >> shl) : (nt >> 4);
+      const bool l_on = LT ? lk < rows : true, l_in = LT ? (i0 + lk < n_rows) : true;
+      const double* gL = LT ? Lp + (size_t)(R0 + lrow) * ld_l + i0 + lk : Lp + (size_t)(i0 + lrow) * ld_l + R0 + lk;
+      const int dL = LT ? lrow * kStageLdK + lk : lrow * kStageLdR + lk;
+      auto issue = [&](int ch) {
+        double* sL = stage + (size_t)(ch % kStageDepth) * (2 * kStagePanel);
+        double* sR = sL + kStagePanel;
+        const int r = R0 + ch * kStageRC;
+        if (r_on) {
+          const double* src = gR + (size_t)ch * kStageRC * ld_r;
+          double* dst = sR + dR;
+          const int lim = r_in ? n_red - r : 0;            // rows rr < lim are inside the matrix
+          for (int rr = rrow; rr < kStageRC; rr += rstep, src += (size_t)rstep * ld_r, dst += rstep * kStageLdK) {
+            if (rr < lim) cp_async_f64(dst, src); else *dst = 0.0;
+          }
+        }
+        if (LT) {       // L(i, r) = Lp[r * ld_l + i]: K-major panel sL[rr][i]
+          if (l_on) {
+            const double* src = gL + (size_t)ch * kStageRC * ld_l;
+            double* dst = sL + dL;
+            const int lim = l_in ? n_red - r : 0;
+            for (int rr = lrow; rr < kStageRC; rr += lstep, src += (size_t)lstep * ld_l, dst += lstep * kStageLdK) {
+              if (rr < lim) cp_async_f64(dst, src); else *dst = 0.0;
+            }
+          }
+        } else {        // row-major panel sL[i][rr]
+          const double* src = gL + ch * kStageRC;
+          double* dst = sL + dL;
+          const bool red_in = r + lk < n_red;
+          const int lim = red_in ? n_rows - i0 : 0;        // rows i < lim are inside the matrix
+          for (int i = lrow; i < rows; i += lstep, src += (size_t)lstep * ld_l, dst += lstep * kStageLdR) {
+            if (i < lim) cp_async_f64(dst, src); else *dst = 0.0;
+          }
+        }
+        cp_async_commit();
+      };
+      __syncthreads();                        // the ring is free (previous block / previous user of `stage`)
+      if (nchunk > 0) issue(0);
+      if (nchunk > 1) issue(1);
+      for (int ch = 0; ch < nchunk; ++ch) {
+        if (ch + 1 < nchunk) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();                      // chunk ch is visible; everyone is done with chunk ch - 1
+        if (ch + 2 < nchunk) issue(ch + 2);   // into the slot chunk ch - 1 occupied
+        const double* sL = stage + (size_t)(ch % kStageDepth) * (2 * kStagePanel);
+        const double* sR = sL + kStagePanel;
+        const int r = R0 + ch * kStageRC;
+#pragma unroll
+        for (int m = 0; m < kStageMaxT; ++m) {
+          if (tr1[m] <= tr0[m]) continue;
+          const double* pa = LT ? sL + q * kStageLdK + tib[m] + g : sL + (tib[m] + g) * kStageLdR + q;
+          const double* pb = sR + q * kStageLdK + tkb[m] + g;
+#pragma unroll
+          for (int kk = 0; kk < kStageRC; kk += 4) {
+            if (r + kk < tr0[m] || r + kk >= tr1[m]) continue;
+            double af[2], bf[2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) af[a] = LT ? pa[kk * kStageLdK + 8 * a] : pa[8 * a * kStageLdR + kk];
+#pragma unroll
+            for (int b = 0; b < 2; ++b) bf[b] = pb[kk * kStageLdK + 8 * b];
+            if (SCALE) {
+              const int rk2 = r + kk + q;
+              const double sc = scale[rk2 < n_red ? rk2 : n_red - 1];
+              bf[0] *= sc; bf[1] *= sc;
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+              for (int b = 0; b < 2; ++b) dmma884(c[m][a][b][0], c[m][a][b][1], af[a], bf[b]);
+          }
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < kStageMaxT; ++m) {
+        if (wid + m * nw >= ntile) continue;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int i = i0 + tib[m] + 8 * a + g;
+            const int j = k0 + tkb[m] + 8 * b + 2 * q;
+            if (i < n_rows) {
+              if (j < n_cols) store(i, j, c[m][a][b][0]);
+              if (j + 1 < n_cols) store(i, j + 1, c[m][a][b][1]);
+            }
+          }
+      }
+    }
+  __syncthreads();   // `stage` may be reused by the caller
 }
 #endif
 

@@ -336,8 +336,10 @@ __device__ __forceinline__ VarModel var_model_of(const VarPtrs& P, int b, int ca
 #endif
 // BIG: the working square M0 of a campaign lives in its global workspace (n_cap > kVarSmemSquareMax) instead of
 // shared memory; a template parameter so that each instantiation addresses M0 in one known address space.
+// BIG campaigns (M0 in the global workspace, 145 KB of shared memory: one CTA per SM) run with kVarBigThreads threads.
+constexpr int kVarBigThreads = 512;
 template <bool BIG>
-__global__ void __launch_bounds__(256, STP_VAR_MINB) k_var_fit(int n_cap, int d, const double* __restrict__ X,
+__global__ void __launch_bounds__(BIG ? kVarBigThreads : 256, BIG ? 1 : STP_VAR_MINB) k_var_fit(int n_cap, int d, const double* __restrict__ X,
                                                  const double* __restrict__ y, const int32_t* __restrict__ n_arr,
                                                  const double* __restrict__ init_noise, VarFitArgs args, int t0,
                                                  VarPtrs P, double* __restrict__ loss_hist, int32_t* __restrict__ status,
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(256, STP_VAR_MINB) k_var_fit(int n_cap, int d,
   if (args.fresh) var_init_state(tm, M, n, d, n_cap, Xb, init_noise ? init_noise + (size_t)b * n_cap : nullptr, args, b);
   int st = 0;
   for (int e = 0; e < args.epochs; ++e) {
-    const VarEpochOut r = var_epoch(tm, s, w, M, n, d, args.lik, args.prior, args.gh_x, args.gh_w, t0 + e + 1,
+    const VarEpochOut r = var_epoch<BIG>(tm, s, w, M, n, d, args.lik, args.prior, args.gh_x, args.gh_w, t0 + e + 1,
                                     args.lr_ngd, args.lr_adam, 1, (double*)nullptr);
     if (r.status) { st = r.status; break; }
     if (loss_hist && threadIdx.x == 0) loss_hist[(size_t)b * args.epochs + e] = r.loss;
@@ -382,13 +384,13 @@ __global__ void __launch_bounds__(256) k_var_elbo_fg(int n_cap, int d, int lik, 
   const VarModel M = var_model_of(P, b, n_cap, d);
   var_load(tm, s, n, d, X + (size_t)b * n_cap * d, y + (size_t)b * n_cap, standardise);
   const size_t G = (size_t)n_cap + (size_t)n_cap * n_cap + (size_t)n_cap * d + d + 4;
-  const VarEpochOut r = var_epoch(tm, s, w, M, n, d, lik, args.prior, args.gh_x, args.gh_w, 1, 0.0, 0.0, 0,
+  const VarEpochOut r = var_epoch<BIG>(tm, s, w, M, n, d, lik, args.prior, args.gh_x, args.gh_w, 1, 0.0, 0.0, 0,
                                   grads + (size_t)b * G);
   if (threadIdx.x == 0) { loss[b] = r.loss; status[b] = r.status; }
 }
 
 template <bool BIG>
-__global__ void __launch_bounds__(256) k_var_acq(int n_cap, int d, int N, int lik, const double* __restrict__ pool,
+__global__ void __launch_bounds__(BIG ? kVarBigThreads : 256) k_var_acq(int n_cap, int d, int N, int lik, const double* __restrict__ pool,
                                                  const int32_t* __restrict__ pool_id, uint8_t* __restrict__ mask,
                                                  VarPtrs P, int32_t* __restrict__ n_arr, const double* __restrict__ best_f,
                                                  int S, const double* __restrict__ eps, unsigned long long seed,
@@ -404,13 +406,17 @@ __global__ void __launch_bounds__(256) k_var_acq(int n_cap, int d, int N, int li
   const int n = n_arr ? n_arr[b] : n_cap;
   if (n < 1 || n > n_cap || (update && n >= n_cap)) { if (threadIdx.x == 0) status[b] = 2; return; }
   VarSmem s = var_smem_carve(smem, n_cap, d, false, BIG ? 0 : 1);
-  double* tile = smem + var_smem_doubles(n_cap, d);
+  // BIG: the working square is global, so the stage region (busy only inside var_prepare) also hosts the candidate tile
+  double* tile = BIG ? s.stage : smem + var_smem_doubles(n_cap, d);
   double* part = tile + (size_t)(((n_cap + 15) & ~15) + kMaxD) * kTC;
+#if !defined(STP_NO_DMMA)
+  s.panels = tile;   // the candidate tile is idle during var_prepare and larger than the two sweep panels
+#endif
   CtaTeam tm{s.red};
   const VarWork w = var_work_carve(work + (size_t)b * var_work_doubles(n_cap), n_cap);
   if (BIG) s.M0 = w.M0g;
   const VarModel M = var_model_of(P, b, n_cap, d);
-  const int st = var_prepare(tm, s, w, M, n, d, !BIG);
+  const int st = var_prepare<BIG>(tm, s, w, M, n, d, !BIG);
   if (st) { if (threadIdx.x == 0) { status[b] = st; if (out_idx) out_idx[b] = -1; if (out_acq) out_acq[b] = NAN; } return; }
   double best;
   if (best_f) best = best_f[b];
@@ -740,12 +746,14 @@ static int fill_var_args(VarFitArgs& a, int d, int lik, int epochs, int fresh, d
   return 0;
 }
 
-// The blocked sweep needs three panels next to the shared-memory square: use it while two CTAs still fit in an SM.
+// The blocked sweep (P, and K_ZZ with the Cholesky export) needs two panels of 12 doubles per row in shared memory:
+// 111 KB per CTA at n_cap = 91, d = 6 (two CTAs per SM), always carved on the device.
 static int var_use_panels(int n_cap, int d) {
+  (void)n_cap; (void)d;
 #if defined(STP_NO_DMMA)
   return 0;
 #else
-  return n_cap <= kVarSmemSquareMax && var_smem_doubles(n_cap, d, true) * sizeof(double) <= 113u * 1024u;
+  return 1;
 #endif
 }
 
@@ -771,7 +779,7 @@ int stp_var_fit(int B, int n_cap, int d, int lik, int epochs, double lr_ngd, dou
   const VarPtrs ptrs{Z, hyp, nat1, nat2, adam_m, adam_v};
   if (n_cap > kVarSmemSquareMax) {
     if (set_smem(k_var_fit<true>, smem)) return -1;
-    k_var_fit<true><<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, init_noise, a, t0, ptrs, loss_hist, status,
+    k_var_fit<true><<<B, kVarBigThreads, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, init_noise, a, t0, ptrs, loss_hist, status,
                                                             work, order, with_panels);
   } else {
     if (set_smem(k_var_fit<false>, smem)) return -1;
@@ -820,12 +828,16 @@ int stp_var_acq(int B, int n_cap, int d, int N, int lik, const double* pool, con
   if (update && (!pool_y || !X || !y || !trace || !mask || !n)) return fail("update needs pool_y, X, y, n, trace and mask");
   if (!best_f && !y) return fail("best_f or y required");
   if (B == 0) return 0;
-  const size_t smem = (var_smem_doubles(n_cap, d) + var_acq_smem_doubles(n_cap, kTC)) * sizeof(double);
+  size_t smem = (var_smem_doubles(n_cap, d) + var_acq_smem_doubles(n_cap, kTC)) * sizeof(double);
+  if (n_cap > kVarSmemSquareMax) {   // the tile aliases the stage region (see k_var_acq)
+    const size_t region = var_acq_smem_doubles(n_cap, kTC) > contract_stage_doubles() ? var_acq_smem_doubles(n_cap, kTC) : contract_stage_doubles();
+    smem = (var_smem_vector_doubles(n_cap, d) + region) * sizeof(double);
+  }
   const VarPtrs ptrs{const_cast<double*>(Z), const_cast<double*>(hyp), const_cast<double*>(nat1),
                      const_cast<double*>(nat2), nullptr, nullptr};
   if (n_cap > kVarSmemSquareMax) {
     if (set_smem(k_var_acq<true>, smem)) return -1;
-    k_var_acq<true><<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, N, lik, pool, pool_id, mask, ptrs, n, best_f, S, eps,
+    k_var_acq<true><<<B, kVarBigThreads, smem, (cudaStream_t)stream>>>(n_cap, d, N, lik, pool, pool_id, mask, ptrs, n, best_f, S, eps,
                                                             seed, out_idx, out_acq, mean, var, acq, update, pool_y, X, y,
                                                             trace, status, work, order, m);
   } else {
@@ -889,11 +901,11 @@ int stp_design_snap(int Q, int Ne, int d, const double* points, const double* el
 int stp_phase_timers(unsigned long long* out32, int reset) {
 #if defined(STP_PHASE_TIMERS)
   if (out32) {
-    const cudaError_t e = cudaMemcpyFromSymbol(out32, g_stp_phase, 32 * sizeof(unsigned long long));
+    const cudaError_t e = cudaMemcpyFromSymbol(out32, g_stp_phase, 64 * sizeof(unsigned long long));
     if (e != cudaSuccess) return fail_cuda("stp_phase_timers", e);
   }
   if (reset) {
-    unsigned long long zero[32] = {0};
+    unsigned long long zero[64] = {0};
     const cudaError_t e = cudaMemcpyToSymbol(g_stp_phase, zero, sizeof(zero));
     if (e != cudaSuccess) return fail_cuda("stp_phase_timers", e);
   }

@@ -36,7 +36,7 @@ constexpr int kMaxWarps = 32;
 // 15 line-search step + BFGS pair (from the closure's end to the start of the next iteration),
 // 16 closures (count), 17 sweep block steps (count), 18 campaigns (count).
 #if defined(__CUDACC__) && defined(STP_PHASE_TIMERS)
-__device__ unsigned long long g_stp_phase[32];
+__device__ unsigned long long g_stp_phase[64];
 __device__ __forceinline__ void phase_mark(int id) {
   __shared__ long long last;
   if (threadIdx.x == 0) {
@@ -124,6 +124,7 @@ struct SoloTeam {
   STP_HD void sync_warp() const {}
   STP_HD double sum(double v) const { return v; }
   STP_HD double warp_sum(double v) const { return v; }
+  STP_HD double quad_sum(double v) const { return v; }
   template <int KMAX>
   STP_HD void sum_vec(double (&v)[KMAX], int k) const {}
   // argmax with torch semantics (first maximal index; NaN wins, first NaN wins)
@@ -167,6 +168,12 @@ struct CtaTeam {
   __device__ __forceinline__ double warp_sum(double v) const {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  // sum over the four lanes 4p .. 4p + 3 of a quad, returned to all four
+  __device__ __forceinline__ double quad_sum(double v) const {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
   }
   // Block-wide sum, result returned to every thread.  Deterministic for a fixed block size.

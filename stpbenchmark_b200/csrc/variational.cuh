@@ -105,7 +105,9 @@ struct VarSmem {
   double* small; // 96
   double* red;   // 16 * kMaxWarps
   double* M0;    // (cap+1) x ld: the step-sequential routines (sweep, Cholesky, triangular inverse) run here
-  double* panels; // three panels of the blocked (DMMA) sweep, or nullptr: the pair sweep is used then
+  double* panels; // the two panels of the blocked (DMMA) sweep, or nullptr: the pair sweep is used then
+  double* stage;  // contract_stage_doubles(): operand ring of the staged contractions; aliases M0 (when M0 is in
+                  // shared memory) and the sweep panels: all dead between the factorisations of an epoch and the next
   int cap, ld;
 };
 
@@ -113,8 +115,15 @@ struct VarSmem {
 // campaign's global workspace (an eighth square, L2-resident); the routines are the same, only slower per step.
 constexpr int kVarSmemSquareMax = 144;
 STP_HD size_t var_smem_doubles(int cap, int d, bool with_panels = false) {
-  const size_t square = cap <= kVarSmemSquareMax ? (size_t)(cap + 1) * odd_ld(cap + 1) : 0;
-  return square + (with_panels ? sweep_blocked_scratch_doubles(cap + 1) : 0) + (size_t)2 * d * cap + (size_t)cap * 8 + 6 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
+  // the working square + the sweep panels double as the operand ring of the staged contractions
+  size_t square = (cap <= kVarSmemSquareMax ? (size_t)(cap + 1) * odd_ld(cap + 1) : 0) + (with_panels ? sweep_blocked_scratch_doubles(cap + 1) : 0);
+  if (cap > kVarSmemSquareMax && square < contract_stage_doubles()) square = contract_stage_doubles();   // staged contractions: BIG only
+  return square + (size_t)2 * d * cap + (size_t)cap * 4 + 6 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
+}
+
+// The part of var_smem_doubles() in front of the working square / stage region (vectors and point sets).
+STP_HD size_t var_smem_vector_doubles(int cap, int d) {
+  return (size_t)2 * d * cap + (size_t)cap * 4 + 6 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
 }
 
 // in_smem: where the working square lives (-1: decided by the capacity).  The kernels pass a compile-time constant
@@ -128,15 +137,13 @@ STP_HD VarSmem var_smem_carve(double* base, int cap, int d, bool with_panels = f
   s.Zt = p; p += (size_t)d * cap;
   s.ys = p; p += cap;
   s.mu = p; p += cap + 1;
-  s.c0 = p; p += cap + 1;
-  s.c1 = p; p += cap + 1;
-  s.c2 = p; p += cap + 1;
-  s.c3 = p; p += cap + 1;
   s.piv = p; p += cap + 1;
-  s.fm = p; p += cap;
-  s.fv = p; p += cap;
-  s.dm = p; p += cap;
-  s.dv = p; p += cap;
+  // the scratch columns of the step-sequential routines (dead once the factorisations of an epoch are done) share
+  // their storage with the per-point vectors of the likelihood pass (written after them)
+  s.c0 = s.fm = p; p += cap + 1;
+  s.c1 = s.fv = p; p += cap + 1;
+  s.c2 = s.dm = p; p += cap + 1;
+  s.c3 = s.dv = p; p += cap + 1;
   s.gmu = p; p += cap;
   s.gsm = p; p += cap;
   s.gZ = p; p += (size_t)cap * d;
@@ -144,6 +151,7 @@ STP_HD VarSmem var_smem_carve(double* base, int cap, int d, bool with_panels = f
   s.red = p; p += 16 * kMaxWarps;
   const bool square_here = in_smem < 0 ? (cap <= kVarSmemSquareMax) : (in_smem != 0);
   s.M0 = square_here ? p : nullptr;   // nullptr: bound to the workspace by var_bind()
+  s.stage = p;
   if (square_here) p += (size_t)(cap + 1) * s.ld;
   s.panels = with_panels ? p : nullptr;
   return s;
@@ -179,6 +187,91 @@ STP_HD int var_sweep(const Team& tm, const VarSmem& s, int n) {
 __device__ __forceinline__ int var_sweep(const CtaTeam& tm, const VarSmem& s, int n) {
   if (s.panels) return sweep_bordered_blocked(tm, s.M0, s.ld, n + 1, n, s.panels, s.piv);
   return sweep_bordered4(tm, s.M0, s.ld, n + 1, n, s.c0, s.c1, s.c2, s.c3, s.piv);
+}
+#endif
+
+// The O(n^3) contractions of the epoch.  STAGED (device, capacities above kVarSmemSquareMax: the n = 256 squares of
+// BASELINE config #5 live in HBM / L2): operand panels staged through shared memory by contract_staged.  Otherwise
+// every warp streams its operands straight from the L2-resident work squares (contract_mma) -- for n <= 144 the
+// staging overhead (one barrier per 16 reduction indices, the copy issue) costs more than it saves: measured 8.6 ms
+// against 9.4 ms per 40 epochs at n = 50 and 21.8 against 25.4 at n = 89, but 111 against 90 at n = 256
+// (profiles/r02_var_ab.md).  Host emulation: the register-tiled loop.
+template <bool STAGED, bool LT, bool SCALE, class Team, class RangeF, class StoreF>
+STP_HD void var_contract(const Team& tm, const VarSmem&, int n_rows, int n_cols, int n_red, const double* Lp, int ld_l,
+                         const double* Rp, int ld_r, const double* scale, RangeF range, StoreF store) {
+  contract_nn<LT, SCALE>(tm, n_rows, n_cols, n_red, Lp, ld_l, Rp, ld_r, scale, range, store);
+}
+#if defined(__CUDACC__) && !defined(STP_NO_DMMA) && !defined(STP_NO_STAGE)
+template <bool STAGED, bool LT, bool SCALE, class RangeF, class StoreF>
+__device__ __forceinline__ void var_contract(const CtaTeam& tm, const VarSmem& s, int n_rows, int n_cols, int n_red,
+                                             const double* Lp, int ld_l, const double* Rp, int ld_r, const double* scale,
+                                             RangeF range, StoreF store) {
+  if (STAGED) contract_staged<LT, SCALE>(tm, n_rows, n_cols, n_red, Lp, ld_l, Rp, ld_r, scale, range, store, s.stage);
+  else contract_nn<LT, SCALE>(tm, n_rows, n_cols, n_red, Lp, ld_l, Rp, ld_r, scale, range, store);
+}
+#endif
+
+// Cholesky factor L of the positive-definite matrix `fill(i, j, extra)` (j <= i; `extra` = the diagonal jitter of
+// the psd_safe_cholesky retry) and its inverse, written zero-filled to global memory: Lout (lower), LIout = L^-1
+// (lower), LTout = L^-T (upper); any of them may be null.  Works in s.M0.  Returns 0 or 1 (not PD after 3 retries).
+template <class Team, class FillF>
+STP_HD int var_factor_fused(const Team& tm, const VarSmem& s, int n, FillF fill, double* Lout, double* LIout,
+                            double* LTout, int ldo) {
+  const int ld = s.ld, W = tm.warp_width(), nw = tm.nwarps();
+  double* M0 = s.M0;
+  if (Lout)
+    for (int i = tm.warp(); i < n; i += nw)
+      for (int j = i + 1 + tm.lane(); j < n; j += W) Lout[i * ldo + j] = 0.0;
+  int chol_fail = 1;
+  STP_ROLLED for (int attempt = 0; attempt < kPsdSafeTries && chol_fail; ++attempt) {
+    const double extra = psd_safe_jitter(attempt);
+    for (int i = tm.warp(); i < n; i += nw) {
+      double* row = M0 + i * ld;
+      for (int j = tm.lane(); j <= i; j += W) row[j] = fill(i, j, extra);
+    }
+    chol_fail = cholesky_inverse_fused(tm, M0, ld, n, s.c0, s.c1, s.c2, Lout, ldo);
+    if (chol_fail) tm.sync();
+  }
+  if (chol_fail) return 1;
+  for (int i = tm.warp(); i < n; i += nw)
+    for (int j = tm.lane(); j < n; j += W) {
+      if (LIout) LIout[i * ldo + j] = (j <= i) ? M0[i * ld + j] : 0.0;
+      if (LTout) LTout[i * ldo + j] = (j >= i) ? M0[j * ld + i] : 0.0;
+    }
+  tm.sync();
+  return 0;
+}
+template <class Team, class FillF>
+STP_HD int var_factor(const Team& tm, const VarSmem& s, int n, FillF fill, double* Lout, double* LIout, double* LTout,
+                      int ldo) {
+  return var_factor_fused(tm, s, n, fill, Lout, LIout, LTout, ldo);
+}
+#if defined(__CUDACC__)
+// Device form: the blocked tensor-core sweep of the matrix exports L and L^-1 as a by-product (SweepCholExport):
+// n / 8 block steps of two barriers instead of n column steps.
+template <class FillF>
+__device__ __forceinline__ int var_factor(const CtaTeam& tm, const VarSmem& s, int n, FillF fill, double* Lout,
+                                          double* LIout, double* LTout, int ldo) {
+  if (!s.panels) return var_factor_fused(tm, s, n, fill, Lout, LIout, LTout, ldo);
+  const int ld = s.ld, nw = tm.nwarps();
+  double* M0 = s.M0;
+  for (int i = tm.warp(); i < n; i += nw)       // the parts the export never writes
+    for (int j = tm.lane(); j < n; j += 32) {
+      if (j > i) { if (Lout) Lout[i * ldo + j] = 0.0; if (LIout) LIout[i * ldo + j] = 0.0; }
+      if (j < i && LTout) LTout[i * ldo + j] = 0.0;
+    }
+  int fail = 1;
+  STP_ROLLED for (int attempt = 0; attempt < kPsdSafeTries && fail; ++attempt) {
+    const double extra = psd_safe_jitter(attempt);
+    for (int i = tm.warp(); i < n; i += nw) {
+      double* row = M0 + i * ld;
+      for (int j = tm.lane(); j <= i; j += 32) row[j] = fill(i, j, extra);
+    }
+    fail = sweep_bordered_blocked<true>(tm, M0, ld, n, n, s.panels, s.piv, SweepCholExport{Lout, LIout, LTout, ldo});
+    if (fail) tm.sync();
+  }
+  tm.sync();
+  return fail ? 1 : 0;
 }
 #endif
 
@@ -220,7 +313,7 @@ struct VarEpochOut {
 // untouched and the raw gradients are exported through `dbg` (tests): layout
 // [g_nat1 (cap) | g_nat2 (cap*cap) | gZ (cap*d) | g_c | g_ls (d) | g_os | g_noise | g_rho].
 // ------------------------------------------------------------------------------------------
-template <class Team>
+template <bool STAGED = false, class Team>
 STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w, const VarModel& M, int n, int d,
                              int lik, const VarHyperPrior& pr, const double* gh_x, const double* gh_w, int t,
                              double lr_ngd, double lr_adam, int apply, double* dbg) {
@@ -238,6 +331,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   double* ghyp = s.small + 32;    // gradient of hyp (d + 4)
   const int nh = d + 4;
   tm.sync();
+  STP_PHASE(-1); STP_COUNT(48);
   for (int k = tm.rank(); k < nh; k += tm.size()) hyp[k] = M.hyp[k];
   for (int idx = tm.rank(); idx < n * d; idx += tm.size()) {
     const int i = idx / d, k = idx - i * d;
@@ -273,6 +367,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   for (int i = tm.warp(); i < n; i += nw)
     for (int j = tm.lane(); j < n; j += W) S[i * ld + j] = (j <= i) ? -M0[i * ld + j] : -M0[j * ld + i];
   tm.sync();
+  STP_PHASE(33);
   // (2) K_ZZ + jitter: fused Cholesky + in-place inverse in shared memory (one barrier per column), L_K streamed
   //     out (strict upper zero-filled); then Linv (lower) and Linv^T (upper), zero-filled, to global memory; Ct
   for (int c = tm.warp(); c < n; c += nw) {
@@ -288,35 +383,22 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
       row[j] = os * exp(-0.5 * r2);
     }
   }
-  for (int i = tm.warp(); i < n; i += nw)
-    for (int j = i + 1 + tm.lane(); j < n; j += W) LK[i * ld + j] = 0.0;
   {
-    int chol_fail = 1;
-    STP_ROLLED for (int attempt = 0; attempt < kPsdSafeTries && chol_fail; ++attempt) {   // psd_safe_cholesky (jitter retry)
-      const double diag = os + kVarJitter + psd_safe_jitter(attempt);
-      for (int i = tm.warp(); i < n; i += nw) {
-        double* row = M0 + i * ld;
-        for (int j = tm.lane(); j <= i; j += W)
-          row[j] = (j < i) ? ard_rbf_tt(s.Zt, cap, d, invl, i, j, os) : diag;
-      }
-      chol_fail = cholesky_inverse_fused(tm, M0, ld, n, s.c0, s.c1, s.c2, LK, ld);
-      if (chol_fail) tm.sync();
-    }
-    if (chol_fail) { out.status = 1; return out; }
+    const double* Zt = s.Zt;
+    const double diag0 = os + kVarJitter;
+    if (var_factor(tm, s, n, [=](int i, int j, double extra) {
+          return (j < i) ? ard_rbf_tt(Zt, cap, d, invl, i, j, os) : diag0 + extra;
+        }, LK, LI, LT, ld)) { out.status = 1; return out; }
   }
-  for (int i = tm.warp(); i < n; i += nw)
-    for (int j = tm.lane(); j < n; j += W) {
-      LI[i * ld + j] = (j <= i) ? M0[i * ld + j] : 0.0;
-      LT[i * ld + j] = (j >= i) ? M0[j * ld + i] : 0.0;
-    }
-  tm.sync();
+  STP_PHASE(34); STP_PHASE(35);
   // (3) At[c][k] = sum_{j<=k} Ct[c][j] Linv^T[j][k]
-  contract_nn<false, false>(tm, n, n, n, Ct, ld, LT, ld, (const double*)nullptr,
+  var_contract<STAGED, false, false>(tm, s, n, n, n, Ct, ld, LT, ld, (const double*)nullptr,
                  [=](int, int, int, int k_hi, int& r0, int& r1) { r0 = 0; r1 = k_hi + 1; },
                  [=](int c, int k, double v) { At[c * ld + k] = v; });
   tm.sync();
+  STP_PHASE(36);
   // (4) Tt = At S ; Dt = Tt - At ; q(f): m_c = cst + At[c].mu ; v_c = os + jitter + At[c].Dt[c]
-  contract_nn<false, false>(tm, n, n, n, At, ld, S, ld, (const double*)nullptr,
+  var_contract<STAGED, false, false>(tm, s, n, n, n, At, ld, S, ld, (const double*)nullptr,
                  [=](int, int, int, int, int& r0, int& r1) { r0 = 0; r1 = n; },
                  [=](int c, int k, double v) { Dt[c * ld + k] = v - At[c * ld + k]; });
   tm.sync();
@@ -334,31 +416,52 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
     if (tm.lane() == 0) { s.fm[c] = cst + pm; s.fv[c] = os + kVarJitter + pv; }
   }
   tm.sync();
+  STP_PHASE(37);
   // (5) expected log-likelihood and its derivatives per training point
+  // likelihood constants (lgamma / digamma: thousands of fp64 instructions): thread 0 evaluates them, the others read
+  // them from shared memory instead of re-deriving them 256 times over on the shared fp64 pipe
   LikConst LC; LC.lik = lik; LC.noise = noise; LC.nu = 0.0; LC.lg_const = 0.0; LC.dnu_const = 0.0;
   double nu = 0.0;
   if (lik == kLikStudentT) {
-    nu = 2.0 + softplus(rho);
-    LC.nu = nu;
-    LC.lg_const = lgamma(0.5 * (nu + 1.0)) - lgamma(0.5 * nu) - 0.5 * log(nu * 3.14159265358979323846) - 0.5 * log(noise);
-    LC.dnu_const = 0.5 * digamma_pos(0.5 * (nu + 1.0)) - 0.5 * digamma_pos(0.5 * nu) - 0.5 / nu;
+    double* lc = s.small + 48;
+    if (tm.rank() == 0) {
+      const double nu0 = 2.0 + softplus(rho);
+      lc[0] = nu0;
+      lc[1] = lgamma(0.5 * (nu0 + 1.0)) - lgamma(0.5 * nu0) - 0.5 * log(nu0 * 3.14159265358979323846) - 0.5 * log(noise);
+      lc[2] = 0.5 * digamma_pos(0.5 * (nu0 + 1.0)) - 0.5 * digamma_pos(0.5 * nu0) - 0.5 / nu0;
+    }
+    tm.sync();
+    nu = lc[0];
+    LC.nu = nu; LC.lg_const = lc[1]; LC.dnu_const = lc[2];
   }
   const double inv_n = 1.0 / n;
   double lk_acc[4] = {0.0, 0.0, 0.0, 0.0};   // ell, d ell / d noise, d ell / d nu, sum dv
-  for (int i = tm.rank(); i < n; i += tm.size()) {
-    const double m = s.fm[i], v = s.fv[i], yy = s.ys[i];
-    double ell, dm_, dv_, dn_ = 0.0, dnu_ = 0.0;
-    if (lik == kLikGaussian) {
+  if (lik == kLikGaussian) {
+    for (int i = tm.rank(); i < n; i += tm.size()) {
+      const double m = s.fm[i], v = s.fv[i], yy = s.ys[i];
       const double r = yy - m;
-      ell = -0.5 * ((r * r + v) / noise + log(noise) + kLog2Pi);
-      dm_ = r / noise;
-      dv_ = -0.5 / noise;
-      dn_ = 0.5 * ((r * r + v) / (noise * noise) - 1.0 / noise);
-    } else {
+      const double ell = -0.5 * ((r * r + v) / noise + log(noise) + kLog2Pi);
+      const double dm_ = r / noise;
+      const double dv_ = -0.5 / noise;
+      const double dn_ = 0.5 * ((r * r + v) / (noise * noise) - 1.0 / noise);
+      s.dm[i] = -inv_n * dm_;
+      s.dv[i] = -inv_n * dv_;
+      lk_acc[0] += ell; lk_acc[1] += dn_; lk_acc[3] += -inv_n * dv_;
+    }
+  } else {
+    // Gauss-Hermite quadrature: four lanes share a training point, five of the 20 nodes each (a node costs a log1p
+    // and four divisions); a warp takes eight points at a time, the partial sums meet through two shuffles.
+    const double kInvSqrtPi = 0.56418958354775628695;
+    const int G4 = W >= 4 ? 4 : 1;                 // lanes per point (1 in the host emulation)
+    const int ppw = W / G4;                        // points per warp and pass
+    const int sub = tm.lane() % G4, slot = tm.lane() / G4;
+    for (int i0 = tm.warp() * ppw; i0 < n; i0 += nw * ppw) {
+      const int i = i0 + slot;
+      const bool on = i < n;
+      const double m = on ? s.fm[i] : 0.0, v = on ? s.fv[i] : 1.0, yy = on ? s.ys[i] : 0.0;
       const double sq = sqrt(2.0 * v);
-      const double kInvSqrtPi = 0.56418958354775628695;
-      ell = 0.0; dm_ = 0.0; dv_ = 0.0;
-      for (int q = 0; q < kGH; ++q) {
+      double ell = 0.0, dm_ = 0.0, dv_ = 0.0, dn_ = 0.0, dnu_ = 0.0;
+      for (int q = sub; q < kGH; q += G4) {
         const double f = sq * gh_x[q] + m;
         double lp, dlf, dln, dlnu;
         lik_node(LC, yy - f, lp, dlf, dln, dlnu);
@@ -369,11 +472,15 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
         dn_ += wq * dln;
         dnu_ += wq * dlnu;
       }
+      ell = tm.quad_sum(ell); dm_ = tm.quad_sum(dm_); dv_ = tm.quad_sum(dv_);
+      dn_ = tm.quad_sum(dn_); dnu_ = tm.quad_sum(dnu_);
       dv_ /= sq;
+      if (on && sub == 0) {
+        s.dm[i] = -inv_n * dm_;
+        s.dv[i] = -inv_n * dv_;
+        lk_acc[0] += ell; lk_acc[1] += dn_; lk_acc[2] += dnu_; lk_acc[3] += -inv_n * dv_;
+      }
     }
-    s.dm[i] = -inv_n * dm_;
-    s.dv[i] = -inv_n * dv_;
-    lk_acc[0] += ell; lk_acc[1] += dn_; lk_acc[2] += dnu_; lk_acc[3] += -inv_n * dv_;
   }
   tm.sum_vec(lk_acc, 4);
   // loss
@@ -386,6 +493,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   out.loss = -(lk_acc[0] - kl + lprior) * inv_n;
   if (!(out.loss == out.loss) || !(fabs(out.loss) <= 1.79e308)) { out.status = 2; return out; }
 
+  STP_PHASE(38);
   // (6) variational gradients: g_mu = A dm + mu/n ; G_S = A diag(dv) A^T + (I - P)/(2n)  (into R0)
   for (int k = tm.rank(); k < n; k += tm.size()) {
     double a = 0.0;
@@ -397,7 +505,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   {
     const double* dvv = s.dv;
     const double* nat2 = M.nat2;
-    contract_nn<true, true>(tm, n, n, n, At, ld, At, ld, dvv,
+    var_contract<STAGED, true, true>(tm, s, n, n, n, At, ld, At, ld, dvv,
                    [=](int, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = 0; r1 = (k_lo > i_hi) ? 0 : n; },
                    [=](int i, int k, double v) {
                      if (k <= i) {
@@ -431,6 +539,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
       for (int k = tm.lane(); k < n; k += W) M.nat2[(size_t)i * cap + k] -= step * GS[i * ld + k];
   }
   tm.sync();
+  STP_PHASE(39);
   // (7) Abar_t[c][k] = mu_k dm_c + 2 Dt[c][k] dv_c   (in place over Dt)
   for (int c = tm.warp(); c < n; c += nw) {
     double* drow = Dt + c * ld;
@@ -439,35 +548,45 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   }
   tm.sync();
   // (8) Cbar_t[c][j] = sum_{i>=j} Abar_t[c][i] Linv[i][j]   (into R0; G_S is dead)
+  //     and ET[j][c] = Cbar_t[c][j] Ct[c][j], the transposed elementwise product step (13) walks by rows (into R6;
+  //     Linv_K^T is dead after step 3)
   double* CBt = S;
-  contract_nn<false, false>(tm, n, n, n, Dt, ld, LI, ld, (const double*)nullptr,
+  double* ET = LT;
+  var_contract<STAGED, false, false>(tm, s, n, n, n, Dt, ld, LI, ld, (const double*)nullptr,
                  [=](int, int, int k_lo, int, int& r0, int& r1) { r0 = k_lo; r1 = n; },
-                 [=](int c, int j, double v) { CBt[c * ld + j] = v; });
+                 [=](int c, int j, double v) { CBt[c * ld + j] = v; ET[j * ld + c] = v * Ct[c * ld + j]; });
   tm.sync();
+  STP_PHASE(40);
   // (9) Lbar[i][k] = -sum_c Cbar_t[c][i] At[c][k], i >= k, zero above   (into R5, Abar_t is dead)
   double* LB = Dt;
-  contract_nn<true, false>(tm, n, n, n, CBt, ld, At, ld, (const double*)nullptr,
+  var_contract<STAGED, true, false>(tm, s, n, n, n, CBt, ld, At, ld, (const double*)nullptr,
                  [=](int, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = 0; r1 = (k_lo > i_hi) ? 0 : n; },
                  [=](int i, int k, double v) { LB[i * ld + k] = (k <= i) ? -v : 0.0; });
   tm.sync();
+  STP_PHASE(41);
   // (10) Phi[i][k] = sum_{r>=i} L[r][i] Lbar[r][k], i >= k, diagonal halved, zero above   (into R4, At is dead)
   double* PH = At;
-  contract_nn<true, false>(tm, n, n, n, LK, ld, LB, ld, (const double*)nullptr,
+  var_contract<STAGED, true, false>(tm, s, n, n, n, LK, ld, LB, ld, (const double*)nullptr,
                  [=](int i_lo, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = i_lo; r1 = (k_lo > i_hi) ? i_lo : n; },
                  [=](int i, int k, double v) { PH[i * ld + k] = (k < i) ? v : (k == i ? 0.5 * v : 0.0); });
   tm.sync();
+  STP_PHASE(42);
   // (11) U[i][k] = sum_{k<=r<=i} Phi[i][r] Linv[r][k], zero above   (into R5, Lbar is dead)
   double* U = Dt;
-  contract_nn<false, false>(tm, n, n, n, PH, ld, LI, ld, (const double*)nullptr,
+  var_contract<STAGED, false, false>(tm, s, n, n, n, PH, ld, LI, ld, (const double*)nullptr,
                  [=](int, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = k_lo; r1 = (k_lo > i_hi) ? k_lo : i_hi + 1; },
                  [=](int i, int k, double v) { U[i * ld + k] = (k <= i) ? v : 0.0; });
   tm.sync();
+  STP_PHASE(43);
   // (12) Kbar'[j][k] = sum_{i>=max(j,k)} Linv[i][j] U[i][k]   (into R4, Phi is dead)
+  //      and its transpose (into R1; L_K is dead after step 10) so that step (13) reads both by rows
   double* KB = At;
-  contract_nn<true, false>(tm, n, n, n, LI, ld, U, ld, (const double*)nullptr,
+  double* KBT = LK;
+  var_contract<STAGED, true, false>(tm, s, n, n, n, LI, ld, U, ld, (const double*)nullptr,
                  [=](int j_lo, int, int k_lo, int, int& r0, int& r1) { r0 = (j_lo > k_lo) ? j_lo : k_lo; r1 = n; },
-                 [=](int j, int k, double v) { KB[j * ld + k] = v; });
+                 [=](int j, int k, double v) { KB[j * ld + k] = v; KBT[k * ld + j] = v; });
   tm.sync();
+  STP_PHASE(44);
   // (13) kernel-parameter gradients.  Kbar = sym(Kbar'); K0 and C are re-evaluated on the fly.
   double acc[kMaxD + 4];
 #pragma unroll
@@ -481,7 +600,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
     for (int j = tm.lane(); j < n; j += W) {
       // K part: pair (i, j) of inducing points, i != j (the diagonal has no dependence on l or Z)
       if (j != i) {
-        const double kb = 0.5 * (KB[i * ld + j] + KB[j * ld + i]);
+        const double kb = 0.5 * (KB[i * ld + j] + KBT[i * ld + j]);
         const double k0 = ard_rbf_tt(s.Zt, cap, d, invl, i, j, os);
         const double tK = kb * k0;
         acc[0] += tK;
@@ -496,7 +615,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
         acc[0] += KB[i * ld + i] * os;
       }
       // C part: inducing point i against data point j : (Cbar . C)[i][j] = Cbar_t[j][i] Ct[j][i]
-      const double tC = CBt[j * ld + i] * Ct[j * ld + i];
+      const double tC = ET[i * ld + j];
       acc[0] += tC;
 #pragma unroll
       for (int k = 0; k < kMaxD; ++k)
@@ -514,6 +633,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
       }
   }
   tm.sum_vec(acc, 1 + d);
+  STP_PHASE(45);
   double csum = 0.0;
   for (int i = tm.rank(); i < n; i += tm.size()) csum += s.dm[i];
   csum = tm.sum(csum);
@@ -559,6 +679,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
     }
   }
   tm.sync();
+  STP_PHASE(46);
   return out;
 }
 
@@ -568,7 +689,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
 // v_* = os + jitter + ||G k||^2 - ||Linv_K k||^2, m_* = cst + k.w   (App. A.4 step 3 at a candidate)
 // Returns 0, 1 (not PD) or 2 (non-finite hyper-parameter).
 // ------------------------------------------------------------------------------------------
-template <class Team>
+template <bool STAGED = false, class Team>
 STP_HD int var_prepare(const Team& tm, const VarSmem& s, const VarWork& w, const VarModel& M, int n, int d,
                        bool pack_in_smem = false) {
   const int ld = w.ld, cap = s.cap, W = tm.warp_width(), nw = tm.nwarps();
@@ -591,26 +712,16 @@ STP_HD int var_prepare(const Team& tm, const VarSmem& s, const VarWork& w, const
   for (int k = 0; k < d; ++k) bad |= !(hyp[1 + k] == hyp[1 + k]) || hyp[1 + k] == 0.0;
   if (bad) return 2;
   tm.sync();
-  // chol(P)^-1 and chol(K_ZZ + jitter I)^-1, each factorised and inverted in shared memory, written out zero-filled
-  double* M0 = s.M0;
-  for (int pass = 0; pass < 2; ++pass) {
-    double* dst = pass == 0 ? LPI : LI;
-    int chol_fail = 1;
-    STP_ROLLED for (int attempt = 0; attempt < kPsdSafeTries && chol_fail; ++attempt) {   // psd_safe_cholesky (jitter retry)
-      const double extra = psd_safe_jitter(attempt);
-      for (int i = tm.warp(); i < n; i += nw) {
-        double* row = M0 + i * ld;
-        for (int j = tm.lane(); j <= i; j += W)
-          row[j] = pass == 0 ? -2.0 * M.nat2[(size_t)i * cap + j] + ((j == i) ? extra : 0.0)
-                             : ((j == i) ? os + kVarJitter + extra : ard_rbf_tt(s.Zt, cap, d, invl, i, j, os));
-      }
-      chol_fail = cholesky_inverse_fused(tm, M0, ld, n, s.c0, s.c1, s.c2, (double*)nullptr, 0);
-      if (chol_fail) tm.sync();
-    }
-    if (chol_fail) return 1;
-    for (int i = tm.warp(); i < n; i += nw)
-      for (int j = tm.lane(); j < n; j += W) dst[i * ld + j] = (j <= i) ? M0[i * ld + j] : 0.0;
-    tm.sync();
+  // chol(P)^-1 and chol(K_ZZ + jitter I)^-1 (factorised in s.M0, written out zero-filled)
+  {
+    const double* nat2 = M.nat2;
+    const double* Zt = s.Zt;
+    if (var_factor(tm, s, n, [=](int i, int j, double extra) {
+          return -2.0 * nat2[(size_t)i * cap + j] + ((j == i) ? extra : 0.0);
+        }, (double*)nullptr, LPI, (double*)nullptr, ld)) return 1;
+    if (var_factor(tm, s, n, [=](int i, int j, double extra) {
+          return (j == i) ? os + kVarJitter + extra : ard_rbf_tt(Zt, cap, d, invl, i, j, os);
+        }, (double*)nullptr, LI, (double*)nullptr, ld)) return 1;
   }
   // mu = S theta1 = LPI^T (LPI theta1)
   for (int i = tm.rank(); i < n; i += tm.size()) {
@@ -631,7 +742,7 @@ STP_HD int var_prepare(const Team& tm, const VarSmem& s, const VarWork& w, const
     for (int i = j; i < n; ++i) a += LI[i * ld + j] * s.mu[i];
     s.gmu[j] = a;
   }
-  contract_nn<false, false>(tm, n, n, n, LPI, ld, LI, ld, (const double*)nullptr,
+  var_contract<STAGED, false, false>(tm, s, n, n, n, LPI, ld, LI, ld, (const double*)nullptr,
                  [=](int, int i_hi, int k_lo, int, int& r0, int& r1) { r0 = k_lo; r1 = (k_lo > i_hi) ? k_lo : i_hi + 1; },
                  [=](int i, int k, double v) { G[i * ld + k] = (k <= i) ? v : 0.0; });
   tm.sync();
@@ -640,6 +751,7 @@ STP_HD int var_prepare(const Team& tm, const VarSmem& s, const VarWork& w, const
     // square (free after the factorisations) -- Linv_K in the lower triangle, G transposed in the upper one, shifted
     // by one column so that the two diagonals do not collide (ld >= n + 1):  M0[i][k] = Linv_K[i][k],
     // M0[k][i + 1] = G[i][k]  (k <= i).  No global load is left in the pool pass.
+    double* M0 = s.M0;
     for (int i = tm.warp(); i < n; i += nw)
       for (int k = tm.lane(); k <= i; k += W) {
         M0[i * ld + k] = LI[i * ld + k];

@@ -61,14 +61,21 @@ class CampaignBatch:
         mask = torch.ones(B, N, dtype=torch.uint8)
         trace = torch.full((B, cap), -1, dtype=torch.int32)
         n = torch.zeros(B, dtype=torch.int32)
-        for b, idx in enumerate(init_indices):
-            idx = [int(i) for i in idx]
-            if len(idx) > cap:
-                raise ValueError("initial design longer than n_cap")
-            t = torch.tensor(idx, dtype=torch.long)
-            mask[b, t] = 0
-            trace[b, : len(idx)] = t.to(torch.int32)
-            n[b] = len(idx)
+        lengths = {len(idx) for idx in init_indices}
+        if max(lengths, default=0) > cap:
+            raise ValueError("initial design longer than n_cap")
+        if len(lengths) == 1 and B > 0 and max(lengths) > 0:      # the usual case: one vectorised assembly
+            k = max(lengths)
+            t = torch.as_tensor(np.asarray(init_indices, dtype=np.int64).reshape(B, k))
+            mask.scatter_(1, t, 0)
+            trace[:, :k] = t.to(torch.int32)
+            n[:] = k
+        else:
+            for b, idx in enumerate(init_indices):
+                t = torch.tensor([int(i) for i in idx], dtype=torch.long)
+                mask[b, t] = 0
+                trace[b, : len(idx)] = t.to(torch.int32)
+                n[b] = len(idx)
         if pool_sizes is not None:      # ragged pools, zero-padded to N rows: the padding is never a candidate
             for b, g in enumerate(pool_id):
                 mask[b, int(pool_sizes[int(g)]):] = 0
@@ -292,7 +299,7 @@ class CampaignJob:
     """
 
     def __init__(self, pools: Sequence, campaigns: Sequence[Campaign], device: Optional[torch.device] = None,
-                 chunk: int = 16):
+                 chunk: int = 16, max_group: int = 256):
         if not torch.cuda.is_available():
             raise RuntimeError("CampaignJob needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -303,7 +310,16 @@ class CampaignJob:
             d = pools[c.pool][0].shape[1]
             by_key.setdefault(c.group_key(d), []).append(c_id)
         self.groups = []
+        # a launch cannot end before its slowest campaign: large ExactGP groups are cut into sub-groups of at most
+        # `max_group` campaigns on their own streams, so that the tail of one launch is filled by the others
+        parts = []
         for key, ids in by_key.items():
+            if key[0] == "ExactGP" and max_group > 0 and len(ids) > max_group:
+                pieces = -(-len(ids) // max_group)
+                parts += [(key, ids[p * len(ids) // pieces:(p + 1) * len(ids) // pieces]) for p in range(pieces)]
+            else:
+                parts.append((key, ids))
+        for key, ids in parts:
             kind, d, n_init, n_trials, epochs, lr, S, lp, kernel, acquisition, beta = key
             used = sorted({self.campaigns[i].pool for i in ids})
             local = {g: k for k, g in enumerate(used)}

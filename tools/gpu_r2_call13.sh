@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_variants.py -m gpu -q 2>&1 | tail -4
+python tools/gpu_phase_timers_var.py > gpurun_out/r2c13_var_phases.json 2> gpurun_out/r2c13_var_phases.err; echo rc=$?
+python tools/gpu_phase_timers_var.py cfg5 > gpurun_out/r2c13_var_phases_cfg5.json 2>> gpurun_out/r2c13_var_phases.err; echo rc=$?
+python tools/gpu_time_var.py 40 2>&1 | tail -8
+python tools/gpu_time_var.py 10 cfg5 2>&1 | tail -3
