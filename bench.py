@@ -450,9 +450,14 @@ def run_exact_arm(args):
             with torch.cuda.stream(gr.stream):
                 fn(gr)
 
+    chunk = max(1, int(args.chunk)) if args.schedule == "cohort" else 1
+
     def run_steps(k):
         if queue:
             all_groups(lambda gr: gr.batch.run_queue(k))
+        elif chunk > 1:      # cohorts advanced by persistent work-queue launches of `chunk` iterations (the product path's form)
+            for c in range(0, k, chunk):
+                all_groups(lambda gr: gr.batch.run_queue(min(chunk, k - c)))
         else:
             for _ in range(k):
                 all_groups(lambda gr: gr.batch.step())
@@ -462,6 +467,8 @@ def run_exact_arm(args):
                 int(sum(gr.batch.iters_acc.sum().item() for gr in groups)))
 
     # ---- device-resident arm: W warm-up + K timed steps ------------------------------------
+    if chunk > 1:
+        W = -(-W // chunk) * chunk      # whole chunks: a cohort then never crosses the end of its campaigns inside a launch
     run_steps(W)
     D.barrier()
     flops0, iters0 = totals()
@@ -498,7 +505,7 @@ def run_exact_arm(args):
     hbm_gbs = hbm_bytes / (elapsed_ms * 1e-3) / 1e9
     mean_closures = float(torch.cat([gr.batch.nfev for gr in groups]).double().mean().item())
     traffic = None
-    if all(v is not None for v in NCU_DRAM_BYTES_COHORT.values()) and args.schedule == "cohort":
+    if all(v is not None for v in NCU_DRAM_BYTES_COHORT.values()) and args.schedule == "cohort" and chunk == 1:
         # launches of the three block sizes in proportion to the ages a cohort spends at n_max <= 48 / 66 / 89
         w = {128: 38 / 80.0, 160: 18 / 80.0, 256: 24 / 80.0}
         traffic = sum(w[t] * NCU_DRAM_BYTES_COHORT[t] for t in w) * (B / NG) / 64.0
@@ -554,7 +561,7 @@ def run_exact_arm(args):
             "config": {"workload": WORKLOAD.format(B=B), "campaigns_per_gpu": B, "pool": N_POOL, "d": DIM,
                        "l2": "inputs are L2-resident by design (0.8 MB of pools); the kernel is FP64/latency bound, "
                              "no HBM stream to flush", "threads_per_campaign": os.environ.get("STP_THREADS", "auto"),
-                       "groups": NG, "schedule": args.schedule},
+                       "groups": NG, "schedule": args.schedule, "chunk": chunk},
             "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA mma.sync.m8n8k4.f64 + DFMA; same peak on B200)",
                          "achieved": achieved_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peaks["peak"],
                          "traffic": traffic,
@@ -900,6 +907,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--groups", type=int, default=16, help="campaign groups per GPU, one CUDA stream each (at most B / 16)")
+    ap.add_argument("--chunk", type=int, default=1,
+                    help="cohort schedule: BO iterations per launch (1 = stp_exact_bo_step, > 1 = stp_exact_bo_run)")
     ap.add_argument("--schedule", default="cohort", choices=["mixed", "cohort", "queue"],
                     help="cohort: the campaigns of a group share their age (groups staggered over the 80 trials), each launch "
                          "is sized for its own n; mixed: every group holds all ages; queue: ONE persistent work-queue launch "

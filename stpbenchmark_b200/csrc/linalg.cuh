@@ -688,7 +688,11 @@ __device__ __forceinline__ void contract_mma(const CtaTeam& tm, int n_rows, int 
 #endif
 constexpr int kStageMaxT = STP_STAGE_MAXT;      // tiles per warp and block
 constexpr int kStageCT = STP_STAGE_CT;          // column tiles of a block (rows: <= 4 tiles)
-constexpr int kStageRC = 16;                    // reduction indices per chunk
+#if !defined(STP_STAGE_RC_LOG)
+#define STP_STAGE_RC_LOG 5
+#endif
+constexpr int kStageRCLog = STP_STAGE_RC_LOG;
+constexpr int kStageRC = 1 << kStageRCLog;      // reduction indices per chunk
 constexpr int kStageLdK = kStageCT * 16 + 4;    // stride of a K-major panel (row = reduction index): = 4 mod 8
 constexpr int kStageLdR = kStageRC + 4;         // stride of a row-major L panel (row = output row): 20 = 4 mod 8
 constexpr int kStagePanel = (64 * kStageLdR > kStageRC * kStageLdK) ? 64 * kStageLdR : kStageRC * kStageLdK;
@@ -759,8 +763,8 @@ __device__ __forceinline__ void contract_staged(const CtaTeam& tm, int n_rows, i
       const bool r_on = rk < cols, r_in = k0 + rk < n_cols;
       const double* gR = Rp + (size_t)(R0 + rrow) * ld_r + k0 + rk;
       const int dR = rrow * kStageLdK + rk;
-      const int lk = LT ? (tid & ((1 << shl) - 1)) : (tid & 15), lrow = LT ? (tid >> shl) : (tid >> 4);
-      const int lstep = LT ? (nt >> shl) : (nt >> 4);
+      const int lk = LT ? (tid & ((1 << shl) - 1)) : (tid & (kStageRC - 1)), lrow = LT ? (tid >> shl) : (tid >> kStageRCLog);
+      const int lstep = LT ? (nt >> shl) : (nt >> kStageRCLog);
       const bool l_on = LT ? lk < rows : true, l_in = LT ? (i0 + lk < n_rows) : true;
       const double* gL = LT ? Lp + (size_t)(R0 + lrow) * ld_l + i0 + lk : Lp + (size_t)(i0 + lrow) * ld_l + R0 + lk;
       const int dL = LT ? lrow * kStageLdK + lk : lrow * kStageLdR + lk;

@@ -182,3 +182,32 @@ def test_scipy_lockstep_driver_reproduces_scipy_minimize(monkeypatch):
         ths, res = oexact.fit_exact(X[tr[:n]], y[tr[:n]])
         assert status[b] == 0 and (nit[b], nfev[b]) == (res.nit, res.nfev)
         assert np.abs(theta[b].numpy() - ths).max() <= 1e-7 * np.abs(ths).max()
+
+
+def test_fast_csv_writer_is_byte_identical_to_pandas(tmp_path):
+    """runners._csv_text replaces DataFrame.to_csv for plain trace frames: same bytes (ints, shortest-repr floats, NaN
+    as the empty cell, the three header rows), and anything unusual falls back to pandas."""
+    import numpy as np
+    import pandas as pd
+    from stpbenchmark_b200 import runners
+    rng = np.random.default_rng(0)
+    cols = {}
+    for k, sd in enumerate([3, 17, 45]):
+        x = rng.integers(0, 2000, 12).astype(np.int64) if k != 1 else np.r_[rng.integers(0, 2000, 7).astype(float), [np.nan] * 5]
+        y = rng.normal(size=12) * 10.0 ** rng.integers(-8, 8, 12)
+        if k == 1:
+            y[7:] = np.nan
+        y[:5] = [1e-5, 123456789.123456789, -0.0, 1e22, 5.0]
+        cols[(f"seed_{sd}", "x_index")] = x
+        cols[(f"seed_{sd}", "y_value")] = y
+    f = pd.DataFrame(cols, index=range(12))
+    f.columns = pd.MultiIndex.from_tuples(list(cols))
+    f.index.name = "iteration"
+    assert runners._csv_text(f) == f.to_csv()
+    path = str(tmp_path / "t.csv")
+    runners._save(f, path, invert_y=False)
+    assert open(path).read() == f.to_csv()
+    back = pd.read_csv(path, header=[0, 1], index_col=0)
+    assert back.shape == f.shape and np.allclose(back.to_numpy(dtype=float), f.to_numpy(dtype=float), equal_nan=True)
+    g = f.astype(object)
+    assert runners._csv_text(g) is None          # object columns: pandas writes them
