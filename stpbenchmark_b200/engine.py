@@ -19,6 +19,8 @@ State kept resident in HBM for the whole run (row-major, batch-major, fp64 / int
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -304,6 +306,10 @@ class CampaignJob:
             raise RuntimeError("CampaignJob needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.campaigns = list(campaigns)
+        # tuning knobs (defaults measured on cfg #4, profiles/r02_e2e_tuning.md): iterations per persistent launch and
+        # the largest ExactGP sub-group
+        chunk = int(os.environ.get("STP_JOB_CHUNK", chunk))
+        max_group = int(os.environ.get("STP_JOB_MAX_GROUP", max_group))
         self.chunk = int(chunk)
         by_key = {}
         for c_id, c in enumerate(self.campaigns):

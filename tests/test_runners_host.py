@@ -211,3 +211,28 @@ def test_fast_csv_writer_is_byte_identical_to_pandas(tmp_path):
     assert back.shape == f.shape and np.allclose(back.to_numpy(dtype=float), f.to_numpy(dtype=float), equal_nan=True)
     g = f.astype(object)
     assert runners._csv_text(g) is None          # object columns: pandas writes them
+
+
+def test_block_built_frame_equals_column_built_frame(tmp_path):
+    """A fresh job whose seeds all finish at once is assembled from two homogeneous blocks; a job that gets its seeds
+    one by one goes through the column path.  Same frame, same file."""
+    import numpy as np
+    import pandas as pd
+    import torch
+    from stpbenchmark_b200 import runners
+    from stpbenchmark_b200.models import ExactGP
+    rng = np.random.default_rng(1)
+    X = torch.rand(60, 3, dtype=torch.double); y = torch.rand(60, dtype=torch.double)
+    seeds = [5, 9, 2]
+    traces = [(s, [int(v) for v in rng.permutation(60)[:14]]) for s in seeds]
+    a = runners._CsvJob(X, y, ExactGP, seeds, str(tmp_path / "a.csv"), n_initial=4, n_trials=10)
+    a.record_many(traces); a.save()
+    b = runners._CsvJob(X, y, ExactGP, seeds, str(tmp_path / "b.csv"), n_initial=4, n_trials=10)
+    for item in traces:
+        b.record(*item)
+    b.save()
+    assert open(tmp_path / "a.csv").read() == open(tmp_path / "b.csv").read()
+    assert a.frame.shape == b.frame.shape == (14, 6)
+    assert list(a.frame.columns) == list(b.frame.columns)
+    assert (a.frame.to_numpy(dtype=float) == b.frame.to_numpy(dtype=float)).all()
+    assert pd.read_csv(tmp_path / "a.csv", header=[0, 1], index_col=0).shape == (14, 6)

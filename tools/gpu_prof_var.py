@@ -1,9 +1,14 @@
-"""One stp_var_fit launch (VarTGP, B=296, n=50, E=20) for ncu."""
+"""One stp_var_fit launch for ncu: VarTGP, B = 296 campaigns of n points on a cfg #4 pool (E = 20 epochs), or with
+`cfg5` B = 148 campaigns of n = 256 on a cfg #5 pool (pool 8192, d = 8; E = 3).  usage: gpu_prof_var.py [n] [cfg5]"""
 import sys, torch
 sys.path.insert(0, '/root/repo')
 from stpbenchmark_b200 import _lib, synthetic, varops
-dev = 'cuda'; X, y = synthetic.cfg4_pool(0); d = 6; N = 2048
-B, n, E = 296, int(sys.argv[1]) if len(sys.argv) > 1 else 50, 20
+CFG5 = "cfg5" in sys.argv
+dev = 'cuda'
+X, y = synthetic.cfg5_pool(0) if CFG5 else synthetic.cfg4_pool(0)
+d = X.shape[1]; N = X.shape[0]
+nums = [a for a in sys.argv[1:] if a.isdigit()]
+B, n, E = (148, 256, 3) if CFG5 else (296, int(nums[0]) if nums else 50, 20)
 cap = n + 1; g = torch.Generator().manual_seed(n)
 Xb = torch.zeros(B, cap, d, dtype=torch.double); yb = torch.zeros(B, cap, dtype=torch.double)
 for b in range(B):
