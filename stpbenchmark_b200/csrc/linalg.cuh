@@ -261,7 +261,10 @@ struct SweepCholExport {
 };
 
 #if defined(__CUDACC__)
-template <bool EXPORT = false>
+// FACTOR_ONLY (with EXPORT): the caller wants L and L^-1 but not the swept matrix, so the trailing update skips the
+// tiles that lie entirely above the pivot block -- the already inverted top-left part, which no later panel reads
+// (a third of the update's traffic over the whole sweep).  A is then garbage on exit.
+template <bool EXPORT = false, bool FACTOR_ONLY = false>
 __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double* A, int ld, int m, int npiv,
                                                       double* scratch, double* piv,
                                                       SweepCholExport ex = SweepCholExport{nullptr, nullptr, nullptr, 0}) {
@@ -417,6 +420,7 @@ __device__ __forceinline__ int sweep_bordered_blocked(const CtaTeam& tm, double*
       int I = 0, J = t;
       while (J > I) { J -= I + 1; ++I; }
       const int ib = I << 4, jb = J << 4;
+      if (FACTOR_ONLY && ib + 16 <= kb) continue;
       double c[2][2][2];
       double af[2][2], bf[2][2];
 #pragma unroll
@@ -686,16 +690,20 @@ __device__ __forceinline__ void contract_mma(const CtaTeam& tm, int n_rows, int 
 #if !defined(STP_STAGE_CT)
 #define STP_STAGE_CT 4
 #endif
+#if !defined(STP_STAGE_RT)
+#define STP_STAGE_RT 4
+#endif
 constexpr int kStageMaxT = STP_STAGE_MAXT;      // tiles per warp and block
-constexpr int kStageCT = STP_STAGE_CT;          // column tiles of a block (rows: <= 4 tiles)
+constexpr int kStageCT = STP_STAGE_CT;          // column tiles of a block
+constexpr int kStageRT = STP_STAGE_RT;          // row tiles of a block
 #if !defined(STP_STAGE_RC_LOG)
 #define STP_STAGE_RC_LOG 5
 #endif
 constexpr int kStageRCLog = STP_STAGE_RC_LOG;
 constexpr int kStageRC = 1 << kStageRCLog;      // reduction indices per chunk
-constexpr int kStageLdK = kStageCT * 16 + 4;    // stride of a K-major panel (row = reduction index): = 4 mod 8
+constexpr int kStageLdK = (kStageCT > kStageRT ? kStageCT : kStageRT) * 16 + 4;   // stride of a K-major panel (row = reduction index): = 4 mod 8
 constexpr int kStageLdR = kStageRC + 4;         // stride of a row-major L panel (row = output row): 20 = 4 mod 8
-constexpr int kStagePanel = (64 * kStageLdR > kStageRC * kStageLdK) ? 64 * kStageLdR : kStageRC * kStageLdK;
+constexpr int kStagePanel = (kStageRT * 16 * kStageLdR > kStageRC * kStageLdK) ? kStageRT * 16 * kStageLdR : kStageRC * kStageLdK;
 constexpr int kStageDepth = 3;
 STP_HD size_t contract_stage_doubles() { return (size_t)kStageDepth * 2 * kStagePanel; }
 
@@ -704,11 +712,25 @@ __device__ __forceinline__ void cp_async_f64(double* dst_shared, const double* s
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
 }
+__device__ __forceinline__ void cp_async_2f64(double* dst_shared, const double* src_global) {   // both 16-byte aligned
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src_global) : "memory");
+}
+// two consecutive doubles of which the first `nvalid` (0, 1, 2) exist; the others are zero-filled
+__device__ __forceinline__ void cp_async_pair(double* dst, const double* src, int nvalid) {
+  if (nvalid >= 2) cp_async_2f64(dst, src);
+  else {
+    if (nvalid == 1) cp_async_f64(dst, src); else dst[0] = 0.0;
+    dst[1] = 0.0;
+  }
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <bool LT, bool SCALE, class RangeF, class StoreF>
+// WIDE: 16-byte copies (two doubles per cp.async: half the LSU instructions, which are what bounds the 8-byte form);
+// needs even leading dimensions and 16-byte aligned operand bases / stage.
+template <bool LT, bool SCALE, bool WIDE = false, class RangeF, class StoreF>
 __device__ __forceinline__ void contract_staged(const CtaTeam& tm, int n_rows, int n_cols, int n_red, const double* Lp,
                                                 int ld_l, const double* Rp, int ld_r, const double* scale, RangeF range,
                                                 StoreF store, double* stage) {
@@ -718,7 +740,7 @@ __device__ __forceinline__ void contract_staged(const CtaTeam& tm, int n_rows, i
   // block shape: <= 4 x kStageCT tiles, a warp owns <= kStageMaxT of them, both edges evened out over the matrix
   const int cap_t = kStageMaxT * nw;
   const int ncb = (TC + kStageCT - 1) / kStageCT, BTC = (TC + ncb - 1) / ncb;
-  int btr_max = cap_t / BTC; btr_max = btr_max > 4 ? 4 : (btr_max < 1 ? 1 : btr_max);
+  int btr_max = cap_t / BTC; btr_max = btr_max > kStageRT ? kStageRT : (btr_max < 1 ? 1 : btr_max);
   const int nrb = (TR + btr_max - 1) / btr_max, BTR = (TR + nrb - 1) / nrb;
   for (int rb = 0; rb < TR; rb += BTR)
     for (int cb = 0; cb < TC; cb += BTC) {
@@ -758,7 +780,7 @@ __device__ __forceinline__ void contract_staged(const CtaTeam& tm, int n_rows, i
       // column `tid & (pw - 1)` of the rows (tid >> sh) + j (nt >> sh), the width padded to a power of two; in the
       // row-major L panel it owns reduction index tid & 15 of the rows (tid >> 4) + j (nt >> 4).  Per chunk only the
       // two source pointers move.
-      const int shl = rows > 32 ? 6 : 5, shr = cols > 64 ? 7 : (cols > 32 ? 6 : 5);
+      const int shl = rows > 64 ? 7 : (rows > 32 ? 6 : 5), shr = cols > 64 ? 7 : (cols > 32 ? 6 : 5);
       const int rk = tid & ((1 << shr) - 1), rrow = tid >> shr, rstep = nt >> shr;
       const bool r_on = rk < cols, r_in = k0 + rk < n_cols;
       const double* gR = Rp + (size_t)(R0 + rrow) * ld_r + k0 + rk;
@@ -768,7 +790,43 @@ __device__ __forceinline__ void contract_staged(const CtaTeam& tm, int n_rows, i
       const bool l_on = LT ? lk < rows : true, l_in = LT ? (i0 + lk < n_rows) : true;
       const double* gL = LT ? Lp + (size_t)(R0 + lrow) * ld_l + i0 + lk : Lp + (size_t)(i0 + lrow) * ld_l + R0 + lk;
       const int dL = LT ? lrow * kStageLdK + lk : lrow * kStageLdR + lk;
-      auto issue = [&](int ch) {
+      // WIDE plan: the same with column PAIRS (K-major panels) / reduction-index pairs (row-major L panel)
+      const int wrk = (tid & ((1 << (shr - 1)) - 1)) * 2, wrrow = tid >> (shr - 1), wrstep = nt >> (shr - 1);
+      const int wlk = LT ? (tid & ((1 << (shl - 1)) - 1)) * 2 : (tid & (kStageRC / 2 - 1)) * 2;
+      const int wlrow = LT ? (tid >> (shl - 1)) : (tid >> (kStageRCLog - 1));
+      const int wlstep = LT ? (nt >> (shl - 1)) : (nt >> (kStageRCLog - 1));
+      auto issue_wide = [&](int ch) {
+        double* sL = stage + (size_t)(ch % kStageDepth) * (2 * kStagePanel);
+        double* sR = sL + kStagePanel;
+        const int r = R0 + ch * kStageRC;
+        if (wrk < cols) {
+          const int nv = n_cols - (k0 + wrk);                  // valid columns of the pair: >= 2, 1 or <= 0
+          const double* src = Rp + (size_t)(r + wrrow) * ld_r + k0 + wrk;
+          double* dst = sR + wrrow * kStageLdK + wrk;
+          const int lim = n_red - r;
+          for (int rr = wrrow; rr < kStageRC; rr += wrstep, src += (size_t)wrstep * ld_r, dst += wrstep * kStageLdK)
+            cp_async_pair(dst, src, rr < lim ? nv : 0);
+        }
+        if (LT) {
+          if (wlk < rows) {
+            const int nv = n_rows - (i0 + wlk);
+            const double* src = Lp + (size_t)(r + wlrow) * ld_l + i0 + wlk;
+            double* dst = sL + wlrow * kStageLdK + wlk;
+            const int lim = n_red - r;
+            for (int rr = wlrow; rr < kStageRC; rr += wlstep, src += (size_t)wlstep * ld_l, dst += wlstep * kStageLdK)
+              cp_async_pair(dst, src, rr < lim ? nv : 0);
+          }
+        } else {
+          const int nv = n_red - (r + wlk);                    // valid reduction indices of the pair
+          const double* src = Lp + (size_t)(i0 + wlrow) * ld_l + r + wlk;
+          double* dst = sL + wlrow * kStageLdR + wlk;
+          const int lim = n_rows - i0;
+          for (int i = wlrow; i < rows; i += wlstep, src += (size_t)wlstep * ld_l, dst += wlstep * kStageLdR)
+            cp_async_pair(dst, src, i < lim ? nv : 0);
+        }
+        cp_async_commit();
+      };
+      auto issue_narrow = [&](int ch) {
         double* sL = stage + (size_t)(ch % kStageDepth) * (2 * kStagePanel);
         double* sR = sL + kStagePanel;
         const int r = R0 + ch * kStageRC;
@@ -800,6 +858,7 @@ __device__ __forceinline__ void contract_staged(const CtaTeam& tm, int n_rows, i
         }
         cp_async_commit();
       };
+      auto issue = [&](int ch) { if (WIDE) issue_wide(ch); else issue_narrow(ch); };
       __syncthreads();                        // the ring is free (previous block / previous user of `stage`)
       if (nchunk > 0) issue(0);
       if (nchunk > 1) issue(1);

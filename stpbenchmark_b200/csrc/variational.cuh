@@ -114,16 +114,21 @@ struct VarSmem {
 // Above this capacity the square M0 no longer fits in shared memory next to the vectors: it then lives in the
 // campaign's global workspace (an eighth square, L2-resident); the routines are the same, only slower per step.
 constexpr int kVarSmemSquareMax = 144;
-STP_HD size_t var_smem_doubles(int cap, int d, bool with_panels = false) {
-  // the working square + the sweep panels double as the operand ring of the staged contractions
-  size_t square = (cap <= kVarSmemSquareMax ? (size_t)(cap + 1) * odd_ld(cap + 1) : 0) + (with_panels ? sweep_blocked_scratch_doubles(cap + 1) : 0);
-  if (cap > kVarSmemSquareMax && square < contract_stage_doubles()) square = contract_stage_doubles();   // staged contractions: BIG only
-  return square + (size_t)2 * d * cap + (size_t)cap * 4 + 6 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
-}
-
+// Leading dimension of the work squares (global AND shared: the epoch addresses all of them with one stride): odd
+// where the working square is in shared memory (bank-conflict-free row and column walks), EVEN above -- the squares
+// are then all global, banks do not matter, and even rows are what the 16-byte cp.async copies of contract_staged need.
+STP_HD int var_ld(int cap) { return cap > kVarSmemSquareMax ? ((cap + 2) & ~1) : odd_ld(cap + 1); }
 // The part of var_smem_doubles() in front of the working square / stage region (vectors and point sets).
 STP_HD size_t var_smem_vector_doubles(int cap, int d) {
-  return (size_t)2 * d * cap + (size_t)cap * 4 + 6 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
+  const size_t v = (size_t)2 * d * cap + (size_t)cap * 4 + 6 * (size_t)(cap + 1) + (size_t)cap * d + 96 + 16 * kMaxWarps;
+  return (v + 1) & ~(size_t)1;      // the square / stage region starts on a 16-byte boundary
+}
+
+STP_HD size_t var_smem_doubles(int cap, int d, bool with_panels = false) {
+  // the working square + the sweep panels double as the operand ring of the staged contractions
+  size_t square = (cap <= kVarSmemSquareMax ? (size_t)(cap + 1) * var_ld(cap) : 0) + (with_panels ? sweep_blocked_scratch_doubles(cap + 1) : 0);
+  if (cap > kVarSmemSquareMax && square < contract_stage_doubles()) square = contract_stage_doubles();   // staged contractions: BIG only
+  return square + var_smem_vector_doubles(cap, d);
 }
 
 // in_smem: where the working square lives (-1: decided by the capacity).  The kernels pass a compile-time constant
@@ -131,7 +136,7 @@ STP_HD size_t var_smem_vector_doubles(int cap, int d) {
 // generic loads / stores in the step-sequential routines: measured 6 % of the VarTGP bench).
 STP_HD VarSmem var_smem_carve(double* base, int cap, int d, bool with_panels = false, int in_smem = -1) {
   VarSmem s;
-  s.cap = cap; s.ld = odd_ld(cap + 1);
+  s.cap = cap; s.ld = var_ld(cap);
   double* p = base;
   s.Xt = p; p += (size_t)d * cap;
   s.Zt = p; p += (size_t)d * cap;
@@ -149,6 +154,7 @@ STP_HD VarSmem var_smem_carve(double* base, int cap, int d, bool with_panels = f
   s.gZ = p; p += (size_t)cap * d;
   s.small = p; p += 96;
   s.red = p; p += 16 * kMaxWarps;
+  p = base + var_smem_vector_doubles(cap, d);
   const bool square_here = in_smem < 0 ? (cap <= kVarSmemSquareMax) : (in_smem != 0);
   s.M0 = square_here ? p : nullptr;   // nullptr: bound to the workspace by var_bind()
   s.stage = p;
@@ -160,7 +166,7 @@ STP_HD VarSmem var_smem_carve(double* base, int cap, int d, bool with_panels = f
 // Per-campaign global workspace: 7 squares of (cap+1) rows x ld doubles (+ 1 for M0 above kVarSmemSquareMax).
 constexpr int kVarSquares = 7;
 STP_HD size_t var_work_doubles(int cap) {
-  return (size_t)(kVarSquares + (cap > kVarSmemSquareMax ? 1 : 0)) * (cap + 1) * odd_ld(cap + 1);
+  return (size_t)(kVarSquares + (cap > kVarSmemSquareMax ? 1 : 0)) * (cap + 1) * var_ld(cap);
 }
 
 struct VarWork {
@@ -170,7 +176,7 @@ struct VarWork {
 };
 STP_HD VarWork var_work_carve(double* base, int cap) {
   VarWork w;
-  w.ld = odd_ld(cap + 1);
+  w.ld = var_ld(cap);
   for (int q = 0; q < kVarSquares; ++q) w.R[q] = base + (size_t)q * (cap + 1) * w.ld;
   w.M0g = cap > kVarSmemSquareMax ? base + (size_t)kVarSquares * (cap + 1) * w.ld : nullptr;
   return w;
@@ -206,7 +212,7 @@ template <bool STAGED, bool LT, bool SCALE, class RangeF, class StoreF>
 __device__ __forceinline__ void var_contract(const CtaTeam& tm, const VarSmem& s, int n_rows, int n_cols, int n_red,
                                              const double* Lp, int ld_l, const double* Rp, int ld_r, const double* scale,
                                              RangeF range, StoreF store) {
-  if (STAGED) contract_staged<LT, SCALE>(tm, n_rows, n_cols, n_red, Lp, ld_l, Rp, ld_r, scale, range, store, s.stage);
+  if (STAGED) contract_staged<LT, SCALE, true>(tm, n_rows, n_cols, n_red, Lp, ld_l, Rp, ld_r, scale, range, store, s.stage);
   else contract_nn<LT, SCALE>(tm, n_rows, n_cols, n_red, Lp, ld_l, Rp, ld_r, scale, range, store);
 }
 #endif
@@ -267,7 +273,7 @@ __device__ __forceinline__ int var_factor(const CtaTeam& tm, const VarSmem& s, i
       double* row = M0 + i * ld;
       for (int j = tm.lane(); j <= i; j += 32) row[j] = fill(i, j, extra);
     }
-    fail = sweep_bordered_blocked<true>(tm, M0, ld, n, n, s.panels, s.piv, SweepCholExport{Lout, LIout, LTout, ldo});
+    fail = sweep_bordered_blocked<true, true>(tm, M0, ld, n, n, s.panels, s.piv, SweepCholExport{Lout, LIout, LTout, ldo});
     if (fail) tm.sync();
   }
   tm.sync();
