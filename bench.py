@@ -45,9 +45,9 @@ METRIC, UNIT = "bo_iterations_per_sec", "it/s"
 WORKLOAD = ("cfg4: synthetic pools N=2048 d=6 (Hartmann-6 + t3 noise), {B} concurrent ExactGP campaigns per GPU, "
             "n_initial=10, 80 trials, ages staggered over n=10..89 (continuous batching)")
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE cohort launch (64 campaigns) of k_exact_bo_step, ncu --set full
-# (profiles/r02_ncu_cohort_launches.txt): keyed by the launch's block size (128 / 160 / 256 threads <-> n_max <= 48 / 66 / 89)
+# (profiles/r02_ncu_cohort_n40.txt, _n60.txt, _n85.txt): keyed by the launch's block size (128 / 160 / 256 threads <-> n_max <= 48 / 66 / 89)
 NCU_DRAM_BYTES_COHORT = {128: 1.238016e6 + 256, 160: 1.313024e6 + 5888, 256: 1.40032e6 + 8704}
-NCU_DRAM_BYTES_VARFIT = 52.59904e6 + 1.294605e9     # k_var_fit, B = 296, n = 60, 20 epochs (profiles/r02_ncu_varfit.txt)
+NCU_DRAM_BYTES_VARFIT = 55.64544e6 + 1.42416e9     # k_var_fit, B = 296, n = 60, 20 epochs (profiles/r02_ncu_final_varfit_n60.txt)
 
 
 # ------------------------------------------------------------------------------------------
@@ -567,7 +567,7 @@ def run_exact_arm(args):
                          "traffic": traffic,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of single cohort launches of "
                                            "k_exact_bo_step (64 campaigns, block sizes 128 / 160 / 256), ncu --set full, "
-                                           "profiles/r02_ncu_cohort_launches.txt, weighted by the share of the 80 ages each "
+                                           "profiles/r02_ncu_cohort_n40/60/85.txt, weighted by the share of the 80 ages each "
                                            f"block size serves; algorithmic bytes per launch: {hbm_bytes / max(gpu_launches, 1):.3g}",
                          "kernel": "k_exact_bo_step", **peaks,
                          "hbm": {"achieved": hbm_gbs, "peak": measured_hbm_peak(), "unit": "GB/s"}},
@@ -750,7 +750,7 @@ def run_var_arm(args):
             "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA + DFMA)", "achieved": achieved, "unit": "TFLOP/s",
                          "frac": achieved / peaks["peak"], "traffic": NCU_DRAM_BYTES_VARFIT,
                          "traffic_source": ("dram bytes of one k_var_fit launch (B = 296, n = 60, 20 epochs), ncu --set full, "
-                                            "profiles/r02_ncu_varfit.txt") if NCU_DRAM_BYTES_VARFIT else None,
+                                            "profiles/r02_ncu_final_varfit_n60.txt") if NCU_DRAM_BYTES_VARFIT else None,
                          "kernel": "k_var_fit + k_var_acq", **peaks},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks,
             "frozen_campaigns": bad, "streams": len(batch.streams), "setup_s": setup_s}), flush=True)
