@@ -707,8 +707,12 @@ STP_HD_NOINLINE int lb_advance_once(const LN& L, LbfgsbState& S, double f, const
   }
   // inside a line search: (f, g) belong to x = t + stp d
   if (!finite) {
-    // a non-finite objective cannot be handled by the cubic interpolation: give up on this
-    // campaign (the reference's closure would raise and the trace would be NaN-padded)
+    // A non-finite objective cannot be handled by the cubic interpolation: the fit ends with status 3 and the caller
+    // freezes the campaign.  Upstream differs here ("Fit failures"): botorch's closure turns a failed
+    // evaluation into a NaN loss that scipy's dcsrch keeps stepping on, and _fit_fallback then retries the whole fit
+    // from resampled hyper-parameters (up to 5 attempts) before run_single_loop's except-branch returns the partial
+    // trace.  With psd_safe_cholesky's jitter retries inside the closure this branch was not reached in any of the 250
+    // golden ExactGP campaigns nor in the bench workloads (frozen_campaigns = 0).
     lb_restore_iterate(L, S);
     return lb_finish(L, S, 3, 0);
   }

@@ -77,23 +77,26 @@ if vt:
 # ncu launch list
 f = os.path.join(G, "r2f_launches.csv")
 if os.path.exists(f):
-    shutil.copy(f, os.path.join(P, "r02_launches_bench_steps3.csv"))
-    tot = {}
-    rows = [r for r in csv.reader(open(f)) if len(r) > 6]
+    shutil.copy(f, os.path.join(P, "r02_launches_bench_steps12.csv"))
+    rows = [r for r in csv.reader(open(f)) if len(r) > 10]
     head = next((r for r in rows if "Kernel Name" in r), None)
     if head:
-        ki, vi = head.index("Kernel Name"), head.index("Metric Value")
+        ki, vi, bi, gi = head.index("Kernel Name"), head.index("Metric Value"), head.index("Block Size"), head.index("Grid Size")
+        tot = {}
         for r in rows:
-            if r is head or len(r) <= vi:
+            if r is head:
                 continue
             try:
-                tot.setdefault(r[ki][:60], []).append(float(r[vi].replace(",", "")))
+                tot.setdefault((r[ki][:48], r[bi], r[gi]), []).append(float(r[vi].replace(",", "")))
             except ValueError:
                 pass
         all_t = sum(sum(v) for v in tot.values()) or 1.0
-        lines.append("## ncu launch list of `bench.py --steps 3 --warmup 3` (r02_launches_bench_steps3.csv; launches 40..240, serialised by ncu)\n")
-        for k, v in sorted(tot.items(), key=lambda kv: -sum(kv[1]))[:6]:
-            lines.append(f"* {k}: {len(v)} launches, {sum(v) / 1e6:.1f} ms, {100 * sum(v) / all_t:.1f} % of the listed kernel time")
+        lines.append("## ncu launch list of `bench.py --steps 12 --warmup 3` (`-k regex:k_exact`, launches 160..; r02_launches_bench_steps12.csv)\n")
+        lines.append("Only `k_exact_bo_step` runs inside the timed region (one launch per cohort and step: its share of the step is 100 %).  ncu serialises "
+                     "the launches: a step is 16 launches of 64 campaigns, 16 x ~8 ms one after another against 14.6 ms per step measured with the 16 streams "
+                     "overlapping (r2f_exact_steps12.json: 70 015 it/s at 12 steps; a single 1024-campaign launch per step, `--groups 1 --schedule mixed`: 22.5 ms, 45 422 it/s).\n")
+        for k, v in sorted(tot.items(), key=lambda kv: -sum(kv[1])):
+            lines.append(f"* {k[0]} block {k[1]} grid {k[2]}: {len(v)} launches, mean {sum(v) / len(v) / 1e6:.2f} ms, {100 * sum(v) / all_t:.1f} % of the listed kernel time")
         lines.append("")
 
 # ncu --set full summaries
