@@ -110,13 +110,15 @@ def _shard_order(campaigns: List[Campaign]) -> List[int]:
 
 
 def run_campaigns(pools, campaigns: List[Campaign], on_done: Optional[Callable] = None, _executor=None,
-                  prepare: Optional[Callable] = None):
+                  prepare: Optional[Callable] = None, on_local: Optional[Callable] = None):
     """Run every campaign; under an initialised ``torch.distributed`` group the campaign list is sharded in
     contiguous blocks over the ranks (one process per GPU, no data-path collective) and the traces are gathered
     on rank 0 at the end.  Returns {campaign index: (indices, status)} on rank 0 (all campaigns)
     and on the other ranks (their own shard).  ``on_done`` receives finished groups on the rank that ran them, or,
     with several ranks, the complete result once on rank 0.  ``prepare(ids)`` is called with the indices this rank
-    owns before they run (run_sweep computes the initial designs of its own shard only)."""
+    owns before they run (run_sweep computes the initial designs of its own shard only).  ``on_local(res)`` (several
+    ranks only) is called on EVERY rank with the results of its own shard before the gather: run_sweep uses it to write
+    the CSV files of the jobs a rank ran completely on that rank, in parallel, instead of all of them on rank 0."""
     import torch.distributed as dist
     execute = _executor or _execute_on_device
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -131,6 +133,8 @@ def run_campaigns(pools, campaigns: List[Campaign], on_done: Optional[Callable] 
     if prepare is not None:
         prepare(mine)
     local = execute(pools, [campaigns[i] for i in mine], None)
+    if on_local is not None:
+        on_local({mine[row]: local[row] for row in range(len(mine))})
     T = max((c.n_initial + c.n_trials for c in campaigns), default=0) + 1
     use_cuda = dist.get_backend() == "nccl"
     dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
@@ -147,7 +151,7 @@ def run_campaigns(pools, campaigns: List[Campaign], on_done: Optional[Callable] 
     out = {}
     for pos, c_id in enumerate(order):
         row = gt[pos]
-        out[c_id] = ([int(v) for v in row[row >= 0]], int(gs[pos, 0]))
+        out[c_id] = (row[row >= 0].tolist(), int(gs[pos, 0]))
     if on_done is not None:
         on_done(out)
     return out
@@ -408,22 +412,52 @@ def run_sweep(jobs: Sequence[dict], _executor=None) -> List[pd.DataFrame]:
                 camps[i].design = designs[k].tolist()
                 camps[i].rng_state = states[k]
 
-    def on_done(res: Dict[int, tuple]):
-        if rank != 0:
-            return
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    # With several ranks a job whose pending campaigns all fall into ONE rank's shard is written by that rank (the
+    # files of a sweep are then written in parallel); rank 0 still records every trace for the frames it returns.
+    whole_on: Dict[int, int] = {}
+    if world > 1 and camps:
+        order = _shard_order(camps)
+        rank_of = {}
+        for r in range(world):
+            lo, hi = sdist.shard_bounds(len(order), world, r)
+            for c_id in order[lo:hi]:
+                rank_of[c_id] = r
+        ranks_of_job: Dict[int, set] = {}
+        for c_id, (j, _) in enumerate(owner):
+            ranks_of_job.setdefault(j, set()).add(rank_of[c_id])
+        whole_on = {j: next(iter(rs)) for j, rs in ranks_of_job.items() if len(rs) == 1}
+
+    def record(res: Dict[int, tuple], save_if: Callable[[int], bool], verbose: bool):
         per_job: Dict[int, list] = {}
         for c_id, (indices, status) in res.items():
             j, s = owner[c_id]
-            if status != 0:
+            if status != 0 and verbose:
                 print(f"Error occurred at iteration {len(indices)}: campaign (job {j}, seed {s}) stopped with status {status}")
             per_job.setdefault(j, []).append((s, indices))
         for j, items in per_job.items():
+            if world > 1:      # the gather returns the campaigns in shard order: back to the job's seed order
+                pos = {s: k for k, s in enumerate(csv_jobs[j].remaining)}
+                items.sort(key=lambda it: pos.get(it[0], len(pos)))
             csv_jobs[j].record_many(items)
-            csv_jobs[j].save()
+            if save_if(j):
+                csv_jobs[j].save()
+
+    def on_local(res: Dict[int, tuple]):
+        if rank == 0:
+            return             # rank 0 records its own shard with everybody else's in on_done
+        mine = {c_id: v for c_id, v in res.items() if whole_on.get(owner[c_id][0]) == rank}
+        record(mine, lambda j: True, verbose=False)
+
+    def on_done(res: Dict[int, tuple]):
+        if rank != 0:
+            return
+        record(res, lambda j: whole_on.get(j, 0) == 0, verbose=True)
 
     if camps:
         try:
-            run_campaigns(pools, camps, on_done=on_done, _executor=_executor, prepare=prepare)
+            run_campaigns(pools, camps, on_done=on_done, _executor=_executor, prepare=prepare,
+                          on_local=on_local if world > 1 else None)
         except Exception as e:
             print(f"Error in sweep: {str(e)}")
             if rank == 0:

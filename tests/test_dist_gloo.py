@@ -65,7 +65,8 @@ def _fake_executor(pools, campaigns, on_done=None):
 
 def _sweep_worker(rank, world, port, tmp, q):
     """The product path under torch.distributed: runners.run_sweep shards the campaigns of ALL jobs over the ranks,
-    gathers the traces on rank 0, and rank 0 alone writes the CSVs."""
+    gathers the traces on rank 0; a job that ran entirely on one rank is written by that rank (here b.csv by rank 1), the
+    others by rank 0."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from stpbenchmark_b200 import runners
@@ -82,7 +83,7 @@ def _sweep_worker(rank, world, port, tmp, q):
     dist.destroy_process_group()
 
 
-def test_run_sweep_shards_over_two_ranks_and_rank0_writes_the_csvs(tmp_path):
+def test_run_sweep_shards_over_two_ranks_and_owning_ranks_write_the_csvs(tmp_path):
     import pandas as pd
     from stpbenchmark_b200 import runners, utils
     with socket.socket() as s:
