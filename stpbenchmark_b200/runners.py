@@ -148,10 +148,10 @@ def run_campaigns(pools, campaigns: List[Campaign], on_done: Optional[Callable] 
     if got is None:
         return {mine[row]: local[row] for row in range(len(mine))}
     gt, gs = got[0].cpu(), got[1].cpu()
+    rows, counts, stat = gt.tolist(), (gt >= 0).sum(dim=1).tolist(), gs[:, 0].tolist()   # one conversion each: 8192 campaigns at N = 8
     out = {}
     for pos, c_id in enumerate(order):
-        row = gt[pos]
-        out[c_id] = (row[row >= 0].tolist(), int(gs[pos, 0]))
+        out[c_id] = (rows[pos][: counts[pos]], int(stat[pos]))
     if on_done is not None:
         on_done(out)
     return out
