@@ -668,7 +668,11 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   if (apply) {
     // (14) Adam (torch.optim.Adam defaults; lr = 0.01 hard-coded at optim.py:140)
     const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
-    const double bc1 = 1.0 - pow(b1, (double)t), bc2s = sqrt(1.0 - pow(b2, (double)t));
+    // the two bias corrections (an fp64 pow each) once per CTA, not once per thread
+    double* bc = s.small + 52;
+    if (tm.rank() == 0) { bc[0] = 1.0 - pow(b1, (double)t); bc[1] = sqrt(1.0 - pow(b2, (double)t)); }
+    tm.sync();
+    const double bc1 = bc[0], bc2s = bc[1];
     const double step_size = lr_adam / bc1;
     const int nadam = (lik == kLikStudentT) ? nh : nh - 1;
     for (int idx = tm.rank(); idx < n * d + nadam; idx += tm.size()) {
