@@ -392,8 +392,16 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   {
     const double* Zt = s.Zt;
     const double diag0 = os + kVarJitter;
+    // the factorisations only touch the lower triangle of the working square: when it lives in shared memory its strict
+    // upper triangle keeps the noise-free K_ZZ entries for the kernel-gradient pass of step (13) (one exp per pair saved)
+    double* keep = STAGED ? nullptr : M0;
     if (var_factor(tm, s, n, [=](int i, int j, double extra) {
-          return (j < i) ? ard_rbf_tt(Zt, cap, d, invl, i, j, os) : diag0 + extra;
+          if (j < i) {
+            const double k = ard_rbf_tt(Zt, cap, d, invl, i, j, os);
+            if (keep) keep[j * ld + i] = k;
+            return k;
+          }
+          return diag0 + extra;
         }, LK, LI, LT, ld)) { out.status = 1; return out; }
   }
   STP_PHASE(34); STP_PHASE(35);
@@ -607,7 +615,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
       // K part: pair (i, j) of inducing points, i != j (the diagonal has no dependence on l or Z)
       if (j != i) {
         const double kb = 0.5 * (KB[i * ld + j] + KBT[i * ld + j]);
-        const double k0 = ard_rbf_tt(s.Zt, cap, d, invl, i, j, os);
+        const double k0 = STAGED ? ard_rbf_tt(s.Zt, cap, d, invl, i, j, os) : ((i < j) ? M0[i * ld + j] : M0[j * ld + i]);
         const double tK = kb * k0;
         acc[0] += tK;
 #pragma unroll
