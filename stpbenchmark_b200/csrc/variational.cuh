@@ -67,9 +67,16 @@ STP_HD void philox_normal2(uint64_t seed, uint64_t stream, uint64_t counter, dou
   const double u0 = (((uint64_t)o[0] << 21) ^ (uint64_t)(o[1] >> 11)) * (1.0 / 9007199254740992.0);  // [0,1)
   const double u1 = (((uint64_t)o[2] << 21) ^ (uint64_t)(o[3] >> 11)) * (1.0 / 9007199254740992.0);
   const double rad = sqrt(-2.0 * log(1.0 - u0));   // 1 - u0 in (0, 1]
+#if defined(__CUDA_ARCH__)
+  double sn, cs;
+  sincospi(2.0 * u1, &sn, &cs);                    // cos / sin of 2 pi u1 without the 2 pi product and its range reduction
+  z0 = rad * cs;
+  z1 = rad * sn;
+#else
   const double ang = 6.283185307179586476925 * u1;
   z0 = rad * cos(ang);
   z1 = rad * sin(ang);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
