@@ -31,6 +31,8 @@ def load():
         _lib = ctypes.CDLL(_SO)
         _lib.emu_log_h.restype = ctypes.c_double
         _lib.emu_log_h.argtypes = [ctypes.c_double]
+        _lib.emu_log_h_mc.restype = ctypes.c_double
+        _lib.emu_log_h_mc.argtypes = [ctypes.c_double]
         _lib.emu_log_ei.restype = ctypes.c_double
         _lib.emu_log_ei.argtypes = [ctypes.c_double] * 3
         _lib.emu_lbfgsb_new.restype = ctypes.c_void_p

@@ -110,6 +110,7 @@ double emu_acq_value(int kind, double beta, double mean, double var, double best
 }
 double emu_log_ei_t(double mean, double sd, double df, double best_f) { return log_ei_t(mean, sd, df, best_f); }
 double emu_log_h(double u) { return log_h(u); }
+double emu_log_h_mc(double u) { return log_h_mc(u); }
 double emu_log_ei(double mean, double var, double best_f) { return log_ei(mean, var, best_f); }
 
 #include "hostemu_var.inc"

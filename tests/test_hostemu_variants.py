@@ -93,3 +93,18 @@ def test_student_t_logei_against_scipy():
             assert got == ref[i]
         else:
             assert abs(got - ref[i]) <= 1e-9 * max(1.0, abs(ref[i])), (i, mean[i], sd[i], df[i], got, ref[i])
+
+
+def test_log_h_of_the_monte_carlo_path_equals_botorchs_form():
+    """log_h_mc (log1p(-t) for every u < 0) against the oracle's restatement of botorch's three-branch _log_ei_helper:
+    the same function to round-off over the whole range the sampled values can reach."""
+    lib = hostemu.load()
+    u = np.concatenate([-np.logspace(-9, 7, 3000), np.linspace(-3, 6, 2000), [0.0, -1.0, -1e6, -1.0000001e6, 30.0]])
+    ref = oacq.log_ei_helper(torch.tensor(u)).numpy()
+    got = np.array([lib.emu_log_h_mc(float(x)) for x in u])
+    assert np.isfinite(got).all()
+    # 1 - t cancels ~2 log10|u| digits for |u| >> 1 in BOTH forms (log t near 0 in botorch's): 1e-13 at |u| = 35
+    assert (np.abs(got - ref) <= 2e-12 * np.maximum(1.0, np.abs(ref))).all()
+    mid = np.abs(u) < 5
+    assert (np.abs(got[mid] - ref[mid]) <= 1e-14 * np.maximum(1.0, np.abs(ref[mid]))).all()
+    assert np.isnan(lib.emu_log_h_mc(float("nan")))
