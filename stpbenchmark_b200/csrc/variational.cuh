@@ -995,6 +995,17 @@ STP_HD void var_acquire(const Team& tm, const VarSmem& s, const VarWork& w, int 
         if (eps) {
           const double* e = eps + (size_t)gi * S;
           for (int q = tm.lane(); q < S; q += TC) a += acq_sample(acq_kind, sqrt_beta, mean + sd * e[q], best_f, sig_l);
+        } else if (acq_kind == kAcqLogEI) {
+          // u = ((mean + sd z) - best_f) / sigma_l as one FMA per sample: the division (and two more operations) per
+          // sample are hoisted to the candidate (in-kernel stream only; the explicit-eps parity path keeps the
+          // reference's operation order)
+          const double inv = 1.0 / sig_l, ua = (mean - best_f) * inv, ub = sd * inv;
+          for (int q = tm.lane(); 2 * q < S; q += TC) {
+            double z0, z1;
+            philox_normal2(seed, stream, (uint64_t)gi * (uint64_t)((S + 1) / 2) + q, z0, z1);
+            a += log_h_mc(fma(ub, z0, ua));
+            if (2 * q + 1 < S) a += log_h_mc(fma(ub, z1, ua));
+          }
         } else {
           for (int q = tm.lane(); 2 * q < S; q += TC) {
             double z0, z1;
