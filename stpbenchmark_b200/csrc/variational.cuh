@@ -293,23 +293,26 @@ struct LikConst {   // per-epoch constants of the likelihood
   int lik;
   double noise, nu, lg_const;   // lg_const: lgamma((nu+1)/2) - lgamma(nu/2) - 0.5 log(nu pi) - 0.5 log noise
   double dnu_const;             // 0.5 psi((nu+1)/2) - 0.5 psi(nu/2) - 1/(2 nu)
+  double inv_noise, inv_nu, inv_sqrt_noise;   // reciprocals of the per-epoch constants: one division per node is left
 };
 
 STP_HD void lik_node(const LikConst& L, double r, double& lp, double& dlf, double& dln, double& dlnu) {
   if (L.lik == kLikStudentT) {
+    // with den = nu noise + r^2:  z2n = r^2 / (nu noise),  1 / (1 + z2n) = nu noise / den  -- one division per node
     const double r2 = r * r;
-    const double den = L.nu * L.noise + r2;
-    const double z2n = r2 / (L.noise * L.nu);
-    lp = L.lg_const - 0.5 * (L.nu + 1.0) * log1p(z2n);
-    dlf = (L.nu + 1.0) * r / den;
-    dln = -0.5 / L.noise + (L.nu + 1.0) * r2 / (2.0 * L.noise * den);
-    dlnu = L.dnu_const - 0.5 * log1p(z2n) + 0.5 * (L.nu + 1.0) * (z2n / L.nu) / (1.0 + z2n);
+    const double nn = L.nu * L.noise;
+    const double inv_den = 1.0 / (nn + r2);
+    const double z2n = r2 * (L.inv_nu * L.inv_noise);
+    const double l1p = log1p(z2n);
+    lp = L.lg_const - 0.5 * (L.nu + 1.0) * l1p;
+    dlf = (L.nu + 1.0) * r * inv_den;
+    dln = -0.5 * L.inv_noise + 0.5 * (L.nu + 1.0) * r2 * L.inv_noise * inv_den;
+    dlnu = L.dnu_const - 0.5 * l1p + 0.5 * (L.nu + 1.0) * (z2n * L.inv_nu) * (nn * inv_den);
   } else {  // Laplace, b = sqrt(noise)
-    const double b = sqrt(L.noise);
     const double a = fabs(r);
-    lp = -log(2.0 * b) - a / b;
-    dlf = (r > 0.0 ? 1.0 : (r < 0.0 ? -1.0 : 0.0)) / b;
-    dln = -0.5 / L.noise + a / (2.0 * L.noise * b);
+    lp = L.lg_const - a * L.inv_sqrt_noise;          // lg_const = -log(2 b) for the Laplace likelihood
+    dlf = (r > 0.0 ? 1.0 : (r < 0.0 ? -1.0 : 0.0)) * L.inv_sqrt_noise;
+    dln = -0.5 * L.inv_noise + 0.5 * a * L.inv_noise * L.inv_sqrt_noise;
     dlnu = 0.0;
   }
 }
@@ -442,6 +445,8 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
   // likelihood constants (lgamma / digamma: thousands of fp64 instructions): thread 0 evaluates them, the others read
   // them from shared memory instead of re-deriving them 256 times over on the shared fp64 pipe
   LikConst LC; LC.lik = lik; LC.noise = noise; LC.nu = 0.0; LC.lg_const = 0.0; LC.dnu_const = 0.0;
+  LC.inv_noise = 1.0 / noise; LC.inv_nu = 0.0; LC.inv_sqrt_noise = 1.0 / sqrt(noise);
+  if (lik == kLikLaplace) LC.lg_const = -log(2.0 * sqrt(noise));
   double nu = 0.0;
   if (lik == kLikStudentT) {
     double* lc = s.small + 48;
@@ -453,7 +458,7 @@ STP_HD VarEpochOut var_epoch(const Team& tm, const VarSmem& s, const VarWork& w,
     }
     tm.sync();
     nu = lc[0];
-    LC.nu = nu; LC.lg_const = lc[1]; LC.dnu_const = lc[2];
+    LC.nu = nu; LC.lg_const = lc[1]; LC.dnu_const = lc[2]; LC.inv_nu = 1.0 / nu;
   }
   const double inv_n = 1.0 / n;
   double lk_acc[4] = {0.0, 0.0, 0.0, 0.0};   // ell, d ell / d noise, d ell / d nu, sum dv
