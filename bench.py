@@ -47,7 +47,7 @@ WORKLOAD = ("cfg4: synthetic pools N=2048 d=6 (Hartmann-6 + t3 noise), {B} concu
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE cohort launch (64 campaigns) of k_exact_bo_step, ncu --set full
 # (profiles/r02_ncu_cohort_n40.txt, _n60.txt, _n85.txt): keyed by the launch's block size (128 / 160 / 256 threads <-> n_max <= 48 / 66 / 89)
 NCU_DRAM_BYTES_COHORT = {128: 1.238016e6 + 256, 160: 1.313024e6 + 5888, 256: 1.40032e6 + 8704}
-NCU_DRAM_BYTES_VARFIT = 55.64544e6 + 1.42416e9     # k_var_fit, B = 296, n = 60, 20 epochs (profiles/r02_ncu_final_varfit_n60.txt)
+NCU_DRAM_BYTES_VARFIT = 46.688512e6 + 1.44043e9     # k_var_fit, B = 296, n = 60, 20 epochs (profiles/r02_ncu_final_varfit_n60.txt)
 
 
 # ------------------------------------------------------------------------------------------
