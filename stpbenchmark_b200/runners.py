@@ -262,15 +262,19 @@ def _csv_text(frame: pd.DataFrame) -> Optional[str]:
     Byte-for-byte equality with pandas is checked in tests/test_runners_host.py."""
     if frame.columns.nlevels != 2 or frame.index.name != "iteration" or len(frame.columns) == 0:
         return None
-    cols = []
-    for c in frame.columns:
-        v = frame[c].to_numpy()
-        if v.dtype == np.int64:
-            cols.append([str(x) for x in v.tolist()])
-        elif v.dtype == np.float64:
-            cols.append([repr(x) if x == x else "" for x in v.tolist()])
-        else:
-            return None
+    dt = frame.dtypes.to_numpy()
+    int_pos = np.flatnonzero(dt == np.dtype(np.int64))
+    flt_pos = np.flatnonzero(dt == np.dtype(np.float64))
+    if len(int_pos) + len(flt_pos) != len(dt):
+        return None
+    cols: List[Optional[list]] = [None] * len(dt)
+    # one positional take per dtype (a label lookup per column costs 0.1 ms on a two-level index: 25 ms per file)
+    if len(int_pos):
+        for c, col in zip(int_pos.tolist(), frame.iloc[:, int_pos].to_numpy().T.tolist()):
+            cols[c] = list(map(str, col))
+    if len(flt_pos):
+        for c, col in zip(flt_pos.tolist(), frame.iloc[:, flt_pos].to_numpy().T.tolist()):
+            cols[c] = [repr(x) if x == x else "" for x in col]
     idx = frame.index.to_numpy()
     if idx.dtype != np.int64:
         return None
@@ -325,11 +329,11 @@ class _CsvJob:
             # a fresh job whose seeds all finished at once with full traces (the batched engine's normal case): two
             # homogeneous blocks (int64 indices, float64 values) instead of 2 x len(seeds) single-column ones
             xi = np.asarray([ix[: self.total] for _, ix in items], dtype=np.int64).T
-            names = [f"seed_{s}" for s in self.seeds]
-            fx = pd.DataFrame(np.ascontiguousarray(xi), columns=pd.MultiIndex.from_product([names, ["x_index"]]))
-            fy = pd.DataFrame(np.ascontiguousarray(y_host[xi]), columns=pd.MultiIndex.from_product([names, ["y_value"]]))
-            order = [(nm, m) for nm in names for m in ("x_index", "y_value")]
-            frame = pd.concat([fx, fy], axis=1)[order]
+            S = len(self.seeds)
+            names = np.repeat(np.array([f"seed_{s}" for s in self.seeds], dtype=object), 2)
+            both = pd.concat([pd.DataFrame(np.ascontiguousarray(xi)), pd.DataFrame(np.ascontiguousarray(y_host[xi]))], axis=1)
+            frame = both.iloc[:, np.arange(2 * S).reshape(2, S).T.reshape(-1)]          # x_0, y_0, x_1, y_1, ... (positional)
+            frame.columns = pd.MultiIndex.from_arrays([names, np.tile(np.array(["x_index", "y_value"], dtype=object), S)])
             frame.index.name = "iteration"
             self._frame = frame
             return
