@@ -325,7 +325,19 @@ class CampaignJob:
                 parts += [(key, ids[p * len(ids) // pieces:(p + 1) * len(ids) // pieces]) for p in range(pieces)]
             else:
                 parts.append((key, ids))
-        for key, ids in parts:
+        # earlier groups get the higher stream priority: their CTAs win the SM slots that free up, they finish first,
+        # and the host-side work on their traces (frames, CSV files) overlaps with the device work of the later ones
+        prio_levels = 1
+        lo_p = 0
+        try:
+            if os.environ.get("STP_JOB_PRIORITIES", "1") == "0":
+                raise RuntimeError("priorities disabled")
+            a_p, b_p = torch.cuda.Stream.priority_range()        # least and greatest priority (lower number = higher)
+            lo_p, hi_p = max(a_p, b_p), min(a_p, b_p)
+            prio_levels = max(1, lo_p - hi_p + 1)
+        except Exception:
+            prio_levels, lo_p = 1, 0
+        for part_no, (key, ids) in enumerate(parts):
             kind, d, n_init, n_trials, epochs, lr, S, lp, kernel, acquisition, beta = key
             used = sorted({self.campaigns[i].pool for i in ids})
             local = {g: k for k, g in enumerate(used)}
@@ -339,7 +351,8 @@ class CampaignJob:
             trials = min(n_trials, min(sizes) - n_init)      # runners.py:62 (per pool; equal budgets share a group)
             if any(min(n_trials, sz - n_init) != trials for sz in sizes):
                 raise ValueError("pools of one group must leave the same number of trials (runners.py:62)")
-            stream = torch.cuda.Stream(device=self.device)
+            rank_p = min(len(parts) - 1 - part_no, prio_levels - 1) if len(parts) > 1 else 0
+            stream = torch.cuda.Stream(device=self.device, priority=lo_p - rank_p)
             with torch.cuda.stream(stream):
                 batch = CampaignBatch(PX, PY, [local[self.campaigns[i].pool] for i in ids],
                                       [self.campaigns[i].design for i in ids], n_cap=n_init + max(trials, 0) + 1, kind=kind,

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -c "import torch; print('priority range', torch.cuda.Stream.priority_range())"
+python -m pytest tests/test_gpu_exact.py -m gpu -x -q -k "one_device_job or persistent or cfg1" 2>&1 | tail -2
+for rep in 1 2; do
+python bench.py --no-cpu-baseline > gpurun_out/r2c40_exact_$rep.json 2>/dev/null; python - <<PY
+import json
+d=json.loads(open('gpurun_out/r2c40_exact_$rep.json').read().strip().splitlines()[-1])
+print('exact', round(d['value'],1), {k:(round(v,3) if isinstance(v,float) else v) for k,v in d['e2e'].items() if k!='what'})
+PY
+done
+python tools/gpu_profile_e2e.py 2>&1 | head -14 | cut -c1-150
