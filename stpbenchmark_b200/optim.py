@@ -120,7 +120,11 @@ def train_exact_model(model, X, y, epochs=100, lr=0.01, verbose=False, y_standar
         y = TorchStandardScaler().fit_transform(y)
     model.train()
     model.likelihood.train()
-    Xd, yd = _exact_batch(model)
+    # optim.py:49-51: the loss is -mll(model(X), y) with the y handed in -- STANDARDISED when y_standardize is set
+    # (unlike the botorch path, whose closure reads model.train_targets, i.e. raw y: SURVEY App. D-1)
+    dev = model.train_inputs[0].device
+    Xd = X.detach().to(dev).double().unsqueeze(0).contiguous()
+    yd = y.detach().to(dev).double().reshape(1, -1).contiguous()
     params = [model.likelihood.noise_covar.raw_noise, model.mean_module.raw_constant,
               model.covar_module.raw_outputscale, model.covar_module.base_kernel.raw_lengthscale]
     opt = torch.optim.Adam(model.parameters(), lr=lr)

@@ -171,17 +171,15 @@ def train_natural(model, X, y, epochs=500, lr=0.05, y_standardize=True, init_noi
     work = _lib.var_workspace(1, cap, dev)
     hist = torch.zeros(1, max(int(epochs), 1), dtype=torch.double, device=dev)
     nn = torch.tensor([n], dtype=torch.int32, device=dev)
-    t0 = getattr(model, "_adam_steps", 0)
-    if t0:
-        st["adam_m"], st["adam_v"] = model._adam_state
+    # optim.py:131-143 builds a fresh NGD and a fresh Adam optimiser on EVERY call: step count and moments start at
+    # zero even when the same model is trained again (the packed state's moments are zero-initialised)
+    t0 = 0
     _lib.var_fit(Xd, yd, nn, st, _LIK_OF_KIND[model.likelihood.kind], int(epochs), float(lr), ADAM_LR, var_hyp0(d, ls_prior),
                  var_prior_vector(ls_prior), gauss_hermite_table(), status, work, fresh=False, t0=t0, loss_hist=hist)
     code = int(status.item())
     if code != 0:
         raise RuntimeError("variational fit failed: " + _lib.STATUS_TEXT.get(code, str(code)))
     _unpack(model, st, n, d)
-    model._adam_steps = t0 + int(epochs)
-    model._adam_state = (st["adam_m"], st["adam_v"])
     mean = yd.mean()
     model._y_scaler = (float(mean), float(yd.std(unbiased=False)) + 1e-10)
     losses = hist[0, : int(epochs)].cpu().tolist()

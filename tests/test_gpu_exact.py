@@ -451,3 +451,28 @@ def test_largest_supported_exact_campaigns(L):
     assert ((out["var"][0].cpu() - var).abs() / var.abs()).max() <= 1e-7
     ref = acq.clone(); ref[mask[0] == 0] = -float("inf")
     assert out["idx"][0].item() == int(torch.argmax(ref))
+
+
+def test_train_exact_model_adam_uses_the_standardised_targets():
+    """optim.train_exact_model (reference optim.py:35-58): plain Adam on -mll(model(X), y) with the STANDARDISED y.
+    Loss history against torch.optim.Adam on the oracle's neg_mll (autograd) with the same targets."""
+    from stpbenchmark_b200 import optim, priors, utils
+    from stpbenchmark_b200.models import ExactGP
+    X, y = dataset("AgNP")
+    sel = trace("gold1", "ExactGP", "AgNP", 45)[:22]
+    Xt, yt = X[sel], y[sel]
+    model = ExactGP(Xt, yt).double()
+    hist = optim.train_exact_model(model, Xt, yt, epochs=6, lr=0.01, verbose=True)
+    ys = utils.TorchStandardScaler().fit_transform(yt)
+    theta = torch.tensor(priors.exact_theta0(X.shape[1]), dtype=torch.double, requires_grad=True)
+    opt = torch.optim.Adam([theta], lr=0.01)
+    want = []
+    for _ in range(6):
+        opt.zero_grad()
+        loss = oexact.neg_mll(theta, Xt, ys)
+        want.append(float(loss.detach()))
+        loss.backward()
+        opt.step()
+    assert np.abs(np.array(hist) - np.array(want)).max() <= 1e-9 * np.abs(want).max()
+    raw = float(oexact.neg_mll(torch.tensor(priors.exact_theta0(X.shape[1]), dtype=torch.double), Xt, yt))
+    assert abs(hist[0] - raw) > 1e-3          # and it is NOT the raw-y loss
