@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: bash tools/gpu_r2_call30.sh N  -- smoke() + the default bench arm and its reference arm under torchrun at N ranks
+# usage: bash tools/gpu_ngpu_check.sh N  -- smoke() + the default bench arm and its reference arm under torchrun at N ranks
 N=${1:-2}
 mkdir -p gpurun_out
 P=29531
