@@ -389,8 +389,12 @@ __global__ void __launch_bounds__(256) k_var_elbo_fg(int n_cap, int d, int lik, 
   if (threadIdx.x == 0) { loss[b] = r.loss; status[b] = r.status; }
 }
 
-template <bool BIG>
-__global__ void __launch_bounds__(BIG ? kVarBigThreads : 256) k_var_acq(int n_cap, int d, int N, int lik, const double* __restrict__ pool,
+// T512: 512-thread CTAs -- always for BIG, and for the smaller capacities whenever the shared-memory footprint leaves
+// room for one CTA per SM only (n_cap > ~75): the Monte-Carlo acquisition is 97 % of this kernel and runs at the rate
+// the fp64 pipe is kept fed, i.e. with the number of resident warps (ncu: 23 % warps active, 42 % of the samples on
+// fixed-latency waits with 8 warps per SM).  Otherwise 256 threads with at most 85 registers: three CTAs per SM.
+template <bool BIG, bool T512 = BIG>
+__global__ void __launch_bounds__(T512 ? kVarBigThreads : 256, T512 ? 1 : 3) k_var_acq(int n_cap, int d, int N, int lik, const double* __restrict__ pool,
                                                  const int32_t* __restrict__ pool_id, uint8_t* __restrict__ mask,
                                                  VarPtrs P, int32_t* __restrict__ n_arr, const double* __restrict__ best_f,
                                                  int S, const double* __restrict__ eps, unsigned long long seed,
@@ -841,10 +845,17 @@ int stp_var_acq(int B, int n_cap, int d, int N, int lik, const double* pool, con
                                                             seed, out_idx, out_acq, mean, var, acq, update, pool_y, X, y,
                                                             trace, status, work, order, m);
   } else {
-    if (set_smem(k_var_acq<false>, smem)) return -1;
-    k_var_acq<false><<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, N, lik, pool, pool_id, mask, ptrs, n, best_f, S, eps,
-                                                             seed, out_idx, out_acq, mean, var, acq, update, pool_y, X, y,
-                                                             trace, status, work, order, m);
+    if (smem > 113u * 1024u) {     // one CTA per SM anyway: give it 16 warps
+      if (set_smem(k_var_acq<false, true>, smem)) return -1;
+      k_var_acq<false, true><<<B, kVarBigThreads, smem, (cudaStream_t)stream>>>(n_cap, d, N, lik, pool, pool_id, mask, ptrs, n, best_f, S,
+                                                                                eps, seed, out_idx, out_acq, mean, var, acq, update, pool_y,
+                                                                                X, y, trace, status, work, order, m);
+    } else {
+      if (set_smem(k_var_acq<false, false>, smem)) return -1;
+      k_var_acq<false, false><<<B, 256, smem, (cudaStream_t)stream>>>(n_cap, d, N, lik, pool, pool_id, mask, ptrs, n, best_f, S, eps,
+                                                                      seed, out_idx, out_acq, mean, var, acq, update, pool_y, X, y,
+                                                                      trace, status, work, order, m);
+    }
   }
   return after_launch("stp_var_acq");
 }

@@ -392,3 +392,32 @@ def test_train_variational_model_plain_adam(cls_name):
     assert rel(model.variational_strategy.inducing_points.detach().cpu().numpy(), ost.Z.detach().numpy()) <= 1e-5
     assert rel(model.covar_module.base_kernel.lengthscale.detach().cpu().numpy().ravel(), ost.ls.detach().numpy().ravel()) <= 1e-6
     assert abs(float(model.likelihood.noise.detach()) - ost.noise.item()) <= 1e-6 * ost.noise.item()
+
+
+@pytest.mark.parametrize("kind", ["VarGP", "VarTGP"])
+def test_pool_pass_is_the_same_with_256_and_512_thread_ctas(kind):
+    """stp_var_acq picks its CTA shape from the shared-memory footprint: 256 threads (three CTAs per SM) for small
+    row capacities, 512 threads once only one CTA fits (n_cap > ~75).  The same campaigns at n_cap = 42 and
+    n_cap = 100 -- identical data, identical fits, the in-kernel Philox stream -- give the same posterior and acquisition
+    (partial sums are grouped differently: 1e-11) and the same pick."""
+    from stpbenchmark_b200 import _lib, varops
+    ns = [25, 40]
+    out = {}
+    for cap in (42, 100):
+        X, y, sels, Xb, yb, nb, cap = _sets(ns, cap=cap)
+        d = X.shape[1]
+        st = varops.alloc_state(len(ns), cap, d, "cuda")
+        status = torch.zeros(len(ns), dtype=torch.int32, device="cuda"); work = _lib.var_workspace(len(ns), cap, "cuda")
+        noise = torch.zeros(len(ns), cap, dtype=torch.double)
+        noise[:, :40] = torch.randn(len(ns), 40, dtype=torch.double, generator=torch.Generator().manual_seed(9))
+        _lib.var_fit(Xb, yb, nb, st, LIK[kind], 25, 0.01, 0.01, varops.var_hyp0(d), PRIOR, GH, status, work, fresh=True,
+                     init_noise=noise.cuda())
+        best = torch.stack([y[s].max() for s in sels]).cuda()
+        out[cap] = _lib.var_acq(X.cuda().unsqueeze(0).contiguous(), st, nb, LIK[kind], status, work, best_f=best, S=512, seed=31,
+                                want_pointwise=True)
+        assert status.tolist() == [0, 0]
+    a, b = out[42], out[100]
+    for key, tol in (("mean", 1e-11), ("var", 1e-10), ("acq", 1e-9)):
+        ref = a[key].cpu()
+        assert ((b[key].cpu() - ref).abs() <= tol * ref.abs().clamp_min(1.0)).all(), key
+    assert a["idx"].tolist() == b["idx"].tolist()
