@@ -15,6 +15,7 @@ python tools/gpu_phase_timers_var.py cfg5 > gpurun_out/r2f_var_phases_cfg5.json 
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_exact --launch-skip 160 -c 200 --csv --log-file gpurun_out/r2f_launches.csv python bench.py --steps 12 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2f_ncu_launch.log 2>&1; tail -2 gpurun_out/r2f_launches.csv | cut -c1-200
 python bench.py --steps 12 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2f_exact_steps12.json 2>/dev/null
 python bench.py --groups 1 --schedule mixed --steps 12 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2f_exact_groups1.json 2>/dev/null
+[ -n "$SKIP_NCU_FULL" ] && exit 0     # the three captures below are ~20 MB each: gpurun brings back at most 64 MiB per call
 ncu --set full --clock-control none --import-source on -k regex:k_exact_bo_step -s 1 -c 1 -f -o gpurun_out/prof_r2f_cohort_n60 python tools/gpu_single_n.py --n 60 --B 64 > gpurun_out/r2f_ncu_cohort_n60.log 2>&1; tail -1 gpurun_out/r2f_ncu_cohort_n60.log
 ncu --set full --clock-control none --import-source on -k regex:k_var_fit -s 1 -c 1 -f -o gpurun_out/prof_r2f_varfit_n60 python tools/gpu_prof_var.py 60 > gpurun_out/r2f_ncu_varfit_n60.log 2>&1; tail -1 gpurun_out/r2f_ncu_varfit_n60.log
 ncu --set full --clock-control none --import-source on -k regex:k_var_fit -s 1 -c 1 -f -o gpurun_out/prof_r2f_varfit_cfg5 python tools/gpu_prof_var.py 256 cfg5 > gpurun_out/r2f_ncu_varfit_cfg5.log 2>&1; tail -1 gpurun_out/r2f_ncu_varfit_cfg5.log

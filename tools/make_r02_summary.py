@@ -92,9 +92,12 @@ if os.path.exists(f):
                 pass
         all_t = sum(sum(v) for v in tot.values()) or 1.0
         lines.append("## ncu launch list of `bench.py --steps 12 --warmup 3` (`-k regex:k_exact`, launches 160..; r02_launches_bench_steps12.csv)\n")
+        s12, g1 = last_json(os.path.join(G, "r2f_exact_steps12.json")) or {}, last_json(os.path.join(G, "r2f_exact_groups1.json")) or {}
         lines.append("Only `k_exact_bo_step` runs inside the timed region (one launch per cohort and step: its share of the step is 100 %).  ncu serialises "
-                     "the launches: a step is 16 launches of 64 campaigns, 16 x ~8 ms one after another against 14.6 ms per step measured with the 16 streams "
-                     "overlapping (r2f_exact_steps12.json: 70 015 it/s at 12 steps; a single 1024-campaign launch per step, `--groups 1 --schedule mixed`: 22.5 ms, 45 422 it/s).\n")
+                     f"the launches: a step is 16 launches of 64 campaigns, 16 x ~8 ms one after another against {s12.get('ms_per_step', float('nan')):.1f} ms per step "
+                     f"measured with the 16 streams overlapping (the same command without ncu: {s12.get('value', float('nan')):.0f} it/s at 12 steps; a single "
+                     f"1024-campaign launch per step, `--groups 1 --schedule mixed`: {g1.get('ms_per_step', float('nan')):.1f} ms, {g1.get('value', float('nan')):.0f} it/s; "
+                     "both lines are committed as r02_bench_exact_steps12_*.json / r02_bench_exact_groups1_*.json).\n")
         for k, v in sorted(tot.items(), key=lambda kv: -sum(kv[1])):
             lines.append(f"* {k[0]} block {k[1]} grid {k[2]}: {len(v)} launches, mean {sum(v) / len(v) / 1e6:.2f} ms, {100 * sum(v) / all_t:.1f} % of the listed kernel time")
         lines.append("")
