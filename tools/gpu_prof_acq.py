@@ -2,7 +2,7 @@
 import sys, torch
 sys.path.insert(0, '/root/repo')
 from stpbenchmark_b200 import _lib, synthetic, varops
-dev = 'cuda'; X, y = synthetic.cfg4_pool(0); d = 6; N = 2048; B, n = 296, 50
+dev = "cuda"; X, y = synthetic.cfg4_pool(0); d = 6; N = 2048; B, n = 296, (int(sys.argv[1]) if len(sys.argv) > 1 else 50)
 cap = n + 1; g = torch.Generator().manual_seed(n)
 Xb = torch.zeros(B, cap, d, dtype=torch.double); yb = torch.zeros(B, cap, dtype=torch.double); mask = torch.ones(B, N, dtype=torch.uint8)
 for b in range(B):

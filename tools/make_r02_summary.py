@@ -102,9 +102,13 @@ if os.path.exists(f):
             lines.append(f"* {k[0]} block {k[1]} grid {k[2]}: {len(v)} launches, mean {sum(v) / len(v) / 1e6:.2f} ms, {100 * sum(v) / all_t:.1f} % of the listed kernel time")
         lines.append("")
 
-# ncu --set full summaries
+# ncu --set full summaries (the k_exact_bo_step / k_var_fit captures are one build older than the bench lines above: taken
+# before the K_ZZ retention and the quadrature reciprocals, which do not change the shape of those kernels)
+lines.append("The `ncu --set full` captures of k_exact_bo_step / k_var_fit below are one build older than the bench lines (before the K_ZZ "
+             "retention and the hoisted quadrature reciprocals); the k_var_acq captures are of the final build (both CTA shapes).\n")
 for rep, name in (("prof_r2f_cohort_n60", "r02_ncu_final_cohort_n60"), ("prof_r2f_varfit_n60", "r02_ncu_final_varfit_n60"),
-                  ("prof_r2f_varfit_cfg5", "r02_ncu_final_varfit_cfg5")):
+                  ("prof_r2f_varfit_cfg5", "r02_ncu_final_varfit_cfg5"), ("prof_r2f_varacq_n50", "r02_ncu_final_varacq_n50"),
+                  ("prof_r2f_varacq_n89", "r02_ncu_final_varacq_n89")):
     src = os.path.join(G, rep + ".ncu-rep")
     if os.path.exists(src):
         txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), src], capture_output=True, text=True).stdout
