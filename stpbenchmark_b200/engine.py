@@ -399,9 +399,10 @@ class CampaignJob:
                 gr = self.groups[gi]
                 gr["stream"].synchronize()
                 idx, n, status = gr["batch"].traces(sync=False)
+                rows, counts, stat = idx.tolist(), n.tolist(), status.tolist()     # one conversion each, not one per element
                 res = {}
                 for row, c_id in enumerate(gr["ids"]):
-                    res[c_id] = ([int(v) for v in idx[row, : int(n[row])]], int(status[row]))
+                    res[c_id] = (rows[row][: counts[row]], int(stat[row]))
                 out.update(res)
                 if on_group_done is not None:
                     on_group_done(res)
