@@ -421,3 +421,44 @@ def test_pool_pass_is_the_same_with_256_and_512_thread_ctas(kind):
         ref = a[key].cpu()
         assert ((b[key].cpu() - ref).abs() <= tol * ref.abs().clamp_min(1.0)).all(), key
     assert a["idx"].tolist() == b["idx"].tolist()
+
+
+def test_odd_sizes_just_above_the_shared_memory_capacity():
+    """n_cap = 153 > 144 with odd n, odd d (AgNP: d = 5): the working square is global with an EVEN leading dimension
+    (16-byte operand copies of the staged contractions must cope with pairs that straddle n), blocked sweeps with the
+    Cholesky export on global memory, 512-thread CTAs.  ELBO value and gradients, then a short fit, against the oracle."""
+    from stpbenchmark_b200 import _lib, varops
+    kind, E = "VarTGP", 4
+    X, y = dataset("AgNP")
+    d, N = X.shape[1], len(X)
+    ns, cap = [151, 147], 153
+    B = len(ns)
+    g = torch.Generator().manual_seed(3)
+    sels = [torch.randperm(N, generator=g)[:n] for n in ns]
+    Xb = torch.zeros(B, cap, d, dtype=torch.double); yb = torch.zeros(B, cap, dtype=torch.double)
+    for b, sel in enumerate(sels):
+        Xb[b, :ns[b]] = X[sel]; yb[b, :ns[b]] = y[sel]
+    Xb, yb = Xb.cuda(), yb.cuda()
+    nb = torch.tensor(ns, dtype=torch.int32, device="cuda")
+    work = _lib.var_workspace(B, cap, "cuda")
+    states = [perturbed_state(X[s], kind, seed=b + 1) for b, s in enumerate(sels)]
+    dev = _dev_state([pack(st, cap) for st in states], cap, d)
+    loss, grads, status = _lib.var_elbo_fg(Xb, yb, nb, dev, LIK[kind], PRIOR, GH, work)
+    assert status.tolist() == [0] * B
+    for b, (n, sel, st) in enumerate(zip(ns, sels, states)):
+        lo, ref = ov.epoch(st, X[sel], ov.standardise(y[sel]), lr=0.0)
+        assert abs(loss[b].item() - lo) <= 1e-9 * max(1.0, abs(lo))
+        check_grads(split_grads(grads[b].cpu().numpy(), n, d, cap), ref, d, 1e-7)
+    noise = torch.zeros(B, cap, dtype=torch.double)
+    for b, n in enumerate(ns):
+        noise[b, :n] = torch.randn(n, dtype=torch.double, generator=torch.Generator().manual_seed(20 + b))
+    st = varops.alloc_state(B, cap, d, "cuda")
+    status = torch.zeros(B, dtype=torch.int32, device="cuda")
+    hist = torch.zeros(B, E, dtype=torch.double, device="cuda")
+    _lib.var_fit(Xb, yb, nb, st, LIK[kind], E, 0.01, 0.01, varops.var_hyp0(d), PRIOR, GH, status, work, fresh=True,
+                 init_noise=noise.cuda(), loss_hist=hist)
+    assert status.tolist() == [0] * B
+    for b, (n, sel) in enumerate(zip(ns, sels)):
+        ost = ov.train_natural(X[sel], y[sel], kind, E, 0.01, init_noise=noise[b, :n])
+        assert rel(hist[b].cpu().numpy(), ost.losses) <= 1e-7
+        assert rel(st["nat2"][b, :n, :n].cpu().numpy(), ost.nat2.numpy()) <= 1e-5
