@@ -38,8 +38,11 @@ extern "C" {
 #define STP_MAX_N 144   /* exact-GP entry points: (n_cap + 1)^2 doubles + the pool tile must fit in 227 KB of shared memory;
                            stp_exact_fit / stp_exact_bo_step also hold the optimiser state there: n_cap <= 142, beyond
                            that they return an error ("campaign does not fit in shared memory") */
-#define STP_MAX_N_VAR 272   /* variational entry points: above 144 the working square moves to the global workspace */
-#define STP_ABI_VERSION 2
+#define STP_MAX_N_VAR 512   /* variational entry points: above 144 the working square moves to the global workspace; the
+                               vectors and the sweep panels / pool tile still have to fit in 227 KB of shared memory
+                               (n_cap = 480 fits for d <= 5, n_cap = 272 for d = 8), otherwise the call returns an error */
+#define STP_MAX_N_LARGE 512 /* stp_exact_*_large: the working square lives in a caller-owned global workspace */
+#define STP_ABI_VERSION 3
 
 /* L-BFGS-B options; scipy.optimize.minimize(method="L-BFGS-B") defaults are
  * {10, 15000, 15000, 20, ftol / DBL_EPSILON with ftol = 2.220446049250313e-09, 1e-5}. */
@@ -115,6 +118,26 @@ int stp_exact_acq(int B, int n_cap, int d, int N, const double* pool, const int3
                   int32_t* out_idx, double* out_acq, double* mean, double* var, double* acq, int32_t* status,
                   const stp_model_opts* model, void* stream);
 
+/* The same three operations for training sets beyond STP_MAX_N (the 80/20 fit-and-predict
+ * study benchmark_predictions.py:19-75 fits ExactGP on up to 480 points and predicts the held-out 20 % through
+ * model.posterior, :59-67).  The (n_cap + 1)^2 working square of each campaign lives in `work`, a device buffer of
+ * stp_exact_large_workspace_bytes(B, n_cap) bytes owned by the caller (no hidden allocation; contents are scratch,
+ * nothing is carried between calls); vectors, sweep panels, pool tile and optimiser state stay in shared memory.
+ * Arguments, results, status codes and arithmetic are those of stp_exact_mll_fg / stp_exact_fit / stp_exact_acq;
+ * any 1 <= n_cap <= STP_MAX_N_LARGE is accepted (small capacities run too, just slower than the shared-memory form). */
+size_t stp_exact_large_workspace_bytes(int B, int n_cap);
+int stp_exact_mll_fg_large(int B, int n_cap, int d, const double* X, const double* y, const int32_t* n,
+                           const double* theta, const double* prior, double* f, double* g, int32_t* status,
+                           const stp_model_opts* model, void* work, void* stream);
+int stp_exact_fit_large(int B, int n_cap, int d, const double* X, const double* y, const int32_t* n, double* theta,
+                        const double* lower, const double* upper, const double* prior, const stp_lbfgsb_opts* opts,
+                        double* f_out, int32_t* nit, int32_t* nfev, int32_t* status, const stp_model_opts* model,
+                        void* work, void* stream);
+int stp_exact_acq_large(int B, int n_cap, int d, int N, const double* pool, const int32_t* pool_id, const uint8_t* mask,
+                        const double* X, const double* y, const int32_t* n, const double* theta, const double* best_f,
+                        int32_t* out_idx, double* out_acq, double* mean, double* var, double* acq, int32_t* status,
+                        const stp_model_opts* model, void* work, void* stream);
+
 /* One whole BO iteration (the loop body runners.py:64-109) for B campaigns in ONE launch:
  * fresh theta0 -> L-BFGS-B fit -> factorise -> pool pass -> argmax -> append the pick to
  * (X, y, n, trace) and clear its mask byte.  pool_y: [G, N].  trace: int32[B, n_cap] receives
@@ -165,6 +188,11 @@ int stp_exact_bo_run(int B, int n_cap, int d, int N, const double* pool, const d
  * Host tables: hyp0 [d+4] construction values; prior [8] = (ls_loc, ls_scale, os_loc, os_scale, noise_loc,
  * noise_scale, df_concentration, df_rate); gh [40] = 20 Gauss-Hermite nodes then 20 weights. */
 size_t stp_var_workspace_bytes(int B, int n_cap);
+/* Smallest capacity n_cap >= n that EVERY variational entry point can launch with for input dimension d, or -1.
+ * The shared-memory budget has a gap just below 144 (the working square, the vectors and the pool tile of stp_var_acq
+ * together exceed 227 KB from n_cap = 138 at d = 5) that ends where the square moves to the global workspace (145):
+ * a caller that needs n = 143 rows (benchmark_predictions.py's 80 % split of the 178 P3HT points) allocates 145. */
+int stp_var_capacity(int n, int d);
 
 /* train_natural_variational_model (optim.py:105-181): `epochs` full-batch steps in ONE persistent launch --
  * ELBO forward (20-point Gauss-Hermite for Student-T / Laplace), hand-derived backward, natural-gradient step

@@ -19,8 +19,10 @@ LIB_PATH = os.environ.get("STP_LIB") or os.path.join(_PKG, "libstp_b200.so")
 _lib = None
 
 MAX_D = 8
-MAX_N = 144        # STP_MAX_N: exact-GP entry points
-MAX_N_VAR = 272    # STP_MAX_N_VAR: variational entry points
+MAX_N = 144        # STP_MAX_N: exact-GP entry points with the campaign in shared memory
+MAX_N_FIT = 142    # ... of which stp_exact_fit also keeps the optimiser state there
+MAX_N_LARGE = 512  # STP_MAX_N_LARGE: stp_exact_*_large (working square in a global workspace; row f3)
+MAX_N_VAR = 512    # STP_MAX_N_VAR: variational entry points (subject to the shared-memory check of the launch)
 
 STATUS_TEXT = {
     0: "ok", 1: "matrix not positive definite", 2: "non-finite parameter or objective",
@@ -79,6 +81,7 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         L.stp_version.restype = ctypes.c_int
         L.stp_last_error_string.restype = ctypes.c_char_p
+        L.stp_exact_large_workspace_bytes.restype = ctypes.c_size_t
         _lib = L
     return _lib
 
@@ -115,10 +118,27 @@ def _bounds(lower, upper, np_):
     return _host(lo), _host(hi)
 
 
-def exact_mll_fg(X, y, theta, prior, n=None, model: Optional[ModelOpts] = None):
-    """f [B], g [B, d+3], status [B] for X [B, n_cap, d], y [B, n_cap], theta [B, d+3]."""
+def exact_large_work(B: int, n_cap: int, device) -> torch.Tensor:
+    """Scratch for the stp_exact_*_large entry points: the working squares of B campaigns of capacity n_cap."""
+    nbytes = lib().stp_exact_large_workspace_bytes(int(B), int(n_cap))
+    if nbytes == 0 and B > 0:
+        raise ValueError(f"n_cap = {n_cap} is beyond STP_MAX_N_LARGE = {MAX_N_LARGE}")
+    return torch.empty(max(nbytes // 8, 1), dtype=torch.double, device=device)
+
+
+def exact_mll_fg(X, y, theta, prior, n=None, model: Optional[ModelOpts] = None, large: Optional[bool] = None):
+    """f [B], g [B, d+3], status [B] for X [B, n_cap, d], y [B, n_cap], theta [B, d+3].  ``large``: run with the working
+    square in a global workspace (default: when n_cap > MAX_N; the model-level entry points only)."""
     _require_cuda(X, y, theta, n)
     B, n_cap, d = X.shape
+    if (n_cap > MAX_N) if large is None else large:
+        f = torch.empty(B, dtype=torch.double, device=X.device)
+        g = torch.empty(B, d + 3, dtype=torch.double, device=X.device)
+        status = torch.zeros(B, dtype=torch.int32, device=X.device)
+        work = exact_large_work(B, n_cap, X.device)
+        _check(lib().stp_exact_mll_fg_large(B, n_cap, d, _p(X), _p(y), _p(n), _p(theta), _host(prior), _p(f), _p(g),
+                                            _p(status), _m(model), _p(work), _stream()), "stp_exact_mll_fg_large")
+        return f, g, status
     f = torch.empty(B, dtype=torch.double, device=X.device)
     g = torch.empty(B, d + 3, dtype=torch.double, device=X.device)
     status = torch.zeros(B, dtype=torch.int32, device=X.device)
@@ -128,8 +148,9 @@ def exact_mll_fg(X, y, theta, prior, n=None, model: Optional[ModelOpts] = None):
 
 
 def exact_fit(X, y, theta, lower, upper, prior, n=None, opts: Optional[LbfgsbOpts] = None,
-              model: Optional[ModelOpts] = None):
-    """In-place device L-BFGS-B fit of theta [B, d+3]; returns (f, nit, nfev, status)."""
+              model: Optional[ModelOpts] = None, large: Optional[bool] = None):
+    """In-place device L-BFGS-B fit of theta [B, d+3]; returns (f, nit, nfev, status).  ``large`` as in exact_mll_fg
+    (default: when n_cap > MAX_N_FIT)."""
     _require_cuda(X, y, theta, n)
     B, n_cap, d = X.shape
     f = torch.empty(B, dtype=torch.double, device=X.device)
@@ -138,15 +159,21 @@ def exact_fit(X, y, theta, lower, upper, prior, n=None, opts: Optional[LbfgsbOpt
     status = torch.zeros(B, dtype=torch.int32, device=X.device)
     lo, hi = _bounds(lower, upper, d + 3)
     o = opts or LbfgsbOpts.scipy_defaults()
+    if (n_cap > MAX_N_FIT) if large is None else large:
+        work = exact_large_work(B, n_cap, X.device)
+        _check(lib().stp_exact_fit_large(B, n_cap, d, _p(X), _p(y), _p(n), _p(theta), lo, hi, _host(prior), ctypes.byref(o),
+                                         _p(f), _p(nit), _p(nfev), _p(status), _m(model), _p(work), _stream()),
+               "stp_exact_fit_large")
+        return f, nit, nfev, status
     _check(lib().stp_exact_fit(B, n_cap, d, _p(X), _p(y), _p(n), _p(theta), lo, hi, _host(prior), ctypes.byref(o),
                                _p(f), _p(nit), _p(nfev), _p(status), _m(model), _stream()), "stp_exact_fit")
     return f, nit, nfev, status
 
 
 def exact_acq(pool, X, y, theta, best_f=None, mask=None, pool_id=None, n=None, want_pointwise=False,
-              model: Optional[ModelOpts] = None):
+              model: Optional[ModelOpts] = None, large: Optional[bool] = None):
     """Fused predictive + LogEI + argmax.  pool [G, N, d].  Returns dict(idx, acq_best, status
-    [, mean, var, acq])."""
+    [, mean, var, acq]).  ``large`` as in exact_mll_fg."""
     _require_cuda(pool, X, y, theta, best_f, mask, pool_id, n)
     B, n_cap, d = X.shape
     N = pool.shape[-2]
@@ -159,9 +186,15 @@ def exact_acq(pool, X, y, theta, best_f=None, mask=None, pool_id=None, n=None, w
         mean = torch.empty(B, N, dtype=torch.double, device=dev)
         var = torch.empty(B, N, dtype=torch.double, device=dev)
         acq = torch.empty(B, N, dtype=torch.double, device=dev)
-    _check(lib().stp_exact_acq(B, n_cap, d, N, _p(pool), _p(pool_id), _p(mask), _p(X), _p(y), _p(n), _p(theta),
-                               _p(best_f), _p(idx), _p(best), _p(mean), _p(var), _p(acq), _p(status), _m(model), _stream()),
-           "stp_exact_acq")
+    if (n_cap > MAX_N) if large is None else large:
+        work = exact_large_work(B, n_cap, dev)
+        _check(lib().stp_exact_acq_large(B, n_cap, d, N, _p(pool), _p(pool_id), _p(mask), _p(X), _p(y), _p(n), _p(theta),
+                                         _p(best_f), _p(idx), _p(best), _p(mean), _p(var), _p(acq), _p(status), _m(model),
+                                         _p(work), _stream()), "stp_exact_acq_large")
+    else:
+        _check(lib().stp_exact_acq(B, n_cap, d, N, _p(pool), _p(pool_id), _p(mask), _p(X), _p(y), _p(n), _p(theta),
+                                   _p(best_f), _p(idx), _p(best), _p(mean), _p(var), _p(acq), _p(status), _m(model),
+                                   _stream()), "stp_exact_acq")
     return {"idx": idx, "acq_best": best, "status": status, "mean": mean, "var": var, "acq": acq}
 
 
@@ -310,6 +343,16 @@ def var_workspace(B: int, n_cap: int, device) -> torch.Tensor:
     L.stp_var_workspace_bytes.restype = ctypes.c_size_t
     nbytes = L.stp_var_workspace_bytes(B, n_cap)
     return torch.empty(nbytes // 8, dtype=torch.double, device=device)
+
+
+def var_capacity(n: int, d: int) -> int:
+    """Smallest n_cap >= n every variational entry point can launch with (stp_var_capacity): n itself except in the
+    shared-memory gap just below 144, where it is 145 (the global-square path)."""
+    cap = int(lib().stp_var_capacity(int(n), int(d)))
+    if cap < 0:
+        raise ValueError(f"no variational capacity holds n = {n} training points at d = {d} "
+                         f"(STP_MAX_N_VAR = {MAX_N_VAR}, 227 KB of shared memory)")
+    return cap
 
 
 def _u64(v: int):

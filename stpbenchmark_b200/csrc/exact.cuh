@@ -84,6 +84,37 @@ STP_HD ExactSmem exact_smem_carve(double* base, int cap, int d, int tc, int nwar
   return s;
 }
 
+// Large capacities (benchmark_predictions.py:19-75 fits 80 % of a dataset, n up to 480): the
+// working square no longer fits in shared memory next to the vectors, so it lives in a per-campaign GLOBAL workspace
+// (L2-resident: 1.9 MB at n = 480) while the vectors, the training inputs, the sweep panels / pool tile and the
+// optimiser state stay in shared memory.  Every routine addresses the square through s.A / s.ld, so the arithmetic
+// (and its order) is the one of the shared-memory path; barriers order the global accesses of a CTA.
+STP_HD size_t exact_large_work_doubles(int cap) { return (size_t)(cap + 1) * odd_ld(cap + 1); }
+STP_HD size_t exact_large_smem_doubles(int cap, int d, int tc) {
+  return (size_t)d * cap + cap + 5 * (size_t)(cap + 9) + cap + exact_tile_doubles(cap, tc) + 64 + 16 * kMaxWarps;
+}
+STP_HD ExactSmem exact_smem_carve_large(double* base, double* square, int cap, int d, int tc) {
+  ExactSmem s;
+  s.kern = 0; s.acq_kind = 0; s.acq_beta = 0.0;
+  s.cap = cap;
+  s.ld = odd_ld(cap + 1);
+  s.A = square;
+  double* p = base;
+  s.Xt = p;     p += (size_t)d * cap;
+  s.y = p;      p += cap;
+  s.c0 = p;     p += cap + 9;
+  s.c1 = p;     p += cap + 9;
+  s.c2 = p;     p += cap + 9;
+  s.c3 = p;     p += cap + 9;
+  s.piv = p;    p += cap + 9;
+  s.alpha = p;  p += cap;
+  s.tile = p;   p += exact_tile_doubles(cap, tc);
+  s.small = p;  p += 64;
+  s.red = p;
+  s.part = p;
+  return s;
+}
+
 // Copy one campaign's training set into shared memory (X row-major [n,d] -> Xt [d][cap]).
 template <class Team>
 STP_HD void exact_load(const Team& tm, const ExactSmem& s, int n, int d, const double* X, const double* y) {

@@ -58,6 +58,22 @@ size_t exact_smem_bytes(int n_cap, int d, int threads, bool with_optimizer) {
   return b;
 }
 
+// Large capacities (n_cap > STP_MAX_N; row f3): square in the global workspace, kExactLargeThreads threads, one CTA per SM.
+constexpr int kExactLargeThreads = 512;
+int threads_large() {
+  const char* env = getenv("STP_THREADS_LARGE");
+  if (env) {
+    const int t = atoi(env);
+    if (t >= 32 && t <= kExactLargeThreads && t % 32 == 0) return t;
+  }
+  return kExactLargeThreads;
+}
+size_t exact_large_smem_bytes(int n_cap, int d, bool with_optimizer) {
+  size_t b = exact_large_smem_doubles(n_cap, d, kTC) * sizeof(double);
+  if (with_optimizer) b += sizeof(LbfgsbState) + 16;
+  return b;
+}
+
 struct PriorArg { double v[6]; };
 struct ModelArg { int kernel, acquisition; double beta; };
 
@@ -86,13 +102,23 @@ __device__ __forceinline__ int fit_status_code(int s) {  // optimiser status -> 
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void k_exact_mll_fg(int n_cap, int d, const double* __restrict__ X, const double* __restrict__ y,
-                               const int32_t* __restrict__ n_arr, const double* __restrict__ theta, PriorArg prior,
-                               double* __restrict__ f, double* __restrict__ g, int32_t* __restrict__ status, ModelArg model) {
-  extern __shared__ double smem[];
+// LARGE (all three model-level kernels): the working square of campaign b is work + b * exact_large_work_doubles(n_cap).
+template <bool LARGE>
+__device__ __forceinline__ ExactSmem exact_carve_for(double* smem, double* work, int b, int n_cap, int d, int nwarps) {
+  if (LARGE) return exact_smem_carve_large(smem, work + (size_t)b * exact_large_work_doubles(n_cap), n_cap, d, kTC);
+  return exact_smem_carve(smem, n_cap, d, kTC, nwarps);
+}
+
+template <bool LARGE>
+__device__ __forceinline__ void exact_mll_fg_body(double* smem, int n_cap, int d, const double* __restrict__ X,
+                                                  const double* __restrict__ y, const int32_t* __restrict__ n_arr,
+                                                  const double* __restrict__ theta, const PriorArg& prior,
+                                                  double* __restrict__ f, double* __restrict__ g,
+                                                  int32_t* __restrict__ status, const ModelArg& model,
+                                                  double* __restrict__ work) {
   const int b = blockIdx.x;
   const int n = n_arr ? n_arr[b] : n_cap;
-  const ExactSmem s = with_model(exact_smem_carve(smem, n_cap, d, kTC, blockDim.x >> 5), model);
+  const ExactSmem s = with_model(exact_carve_for<LARGE>(smem, work, b, n_cap, d, blockDim.x >> 5), model);
   CtaTeam tm{s.red};
   const int np = d + 3;
   exact_load(tm, s, n, d, X + (size_t)b * n_cap * d, y + (size_t)b * n_cap);
@@ -103,17 +129,34 @@ __global__ void k_exact_mll_fg(int n_cap, int d, const double* __restrict__ X, c
   if (threadIdx.x == 0) { f[b] = fv; status[b] = st; }
   if (threadIdx.x < np) g[b * np + threadIdx.x] = st ? NAN : s.small[16 + threadIdx.x];
 }
+__global__ void k_exact_mll_fg(int n_cap, int d, const double* __restrict__ X, const double* __restrict__ y,
+                               const int32_t* __restrict__ n_arr, const double* __restrict__ theta, PriorArg prior,
+                               double* __restrict__ f, double* __restrict__ g, int32_t* __restrict__ status, ModelArg model) {
+  extern __shared__ double smem[];
+  exact_mll_fg_body<false>(smem, n_cap, d, X, y, n_arr, theta, prior, f, g, status, model, nullptr);
+}
+__global__ void __launch_bounds__(kExactLargeThreads, 1)
+k_exact_mll_fg_large(int n_cap, int d, const double* __restrict__ X, const double* __restrict__ y,
+                     const int32_t* __restrict__ n_arr, const double* __restrict__ theta, PriorArg prior,
+                     double* __restrict__ f, double* __restrict__ g, int32_t* __restrict__ status, ModelArg model,
+                     double* __restrict__ work) {
+  extern __shared__ double smem[];
+  exact_mll_fg_body<true>(smem, n_cap, d, X, y, n_arr, theta, prior, f, g, status, model, work);
+}
 
-__global__ void __launch_bounds__(STP_EXACT_MAXT, STP_EXACT_MINB) k_exact_fit(int n_cap, int d, const double* __restrict__ X, const double* __restrict__ y,
-                            const int32_t* __restrict__ n_arr, double* __restrict__ theta, BoundsArg bnd,
-                            PriorArg prior, LbfgsbOpts opts, double* __restrict__ f_out, int32_t* __restrict__ nit,
-                            int32_t* __restrict__ nfev, int32_t* __restrict__ status, ModelArg model) {
+template <bool LARGE>
+__global__ void __launch_bounds__(LARGE ? kExactLargeThreads : STP_EXACT_MAXT, LARGE ? 1 : STP_EXACT_MINB)
+k_exact_fit(int n_cap, int d, const double* __restrict__ X, const double* __restrict__ y,
+            const int32_t* __restrict__ n_arr, double* __restrict__ theta, BoundsArg bnd,
+            PriorArg prior, LbfgsbOpts opts, double* __restrict__ f_out, int32_t* __restrict__ nit,
+            int32_t* __restrict__ nfev, int32_t* __restrict__ status, ModelArg model, double* __restrict__ work) {
   extern __shared__ double smem[];
   const int b = blockIdx.x;
   const int n = n_arr ? n_arr[b] : n_cap;
   const int nw = blockDim.x >> 5;
-  const ExactSmem s = with_model(exact_smem_carve(smem, n_cap, d, kTC, nw), model);
-  LbfgsbState* S = reinterpret_cast<LbfgsbState*>(smem + exact_smem_doubles(n_cap, d, kTC, nw));
+  const ExactSmem s = with_model(exact_carve_for<LARGE>(smem, work, b, n_cap, d, nw), model);
+  LbfgsbState* S = reinterpret_cast<LbfgsbState*>(
+      smem + (LARGE ? exact_large_smem_doubles(n_cap, d, kTC) : exact_smem_doubles(n_cap, d, kTC, nw)));
   int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(S) + sizeof(LbfgsbState));
   CtaTeam tm{s.red};
   const int np = d + 3;
@@ -131,17 +174,17 @@ __global__ void __launch_bounds__(STP_EXACT_MAXT, STP_EXACT_MINB) k_exact_fit(in
   }
 }
 
-__global__ void k_exact_acq(int n_cap, int d, int N, const double* __restrict__ pool,
-                            const int32_t* __restrict__ pool_id, const uint8_t* __restrict__ mask,
-                            const double* __restrict__ X, const double* __restrict__ y,
-                            const int32_t* __restrict__ n_arr, const double* __restrict__ theta,
-                            const double* __restrict__ best_f, int32_t* __restrict__ out_idx,
-                            double* __restrict__ out_acq, double* __restrict__ mean, double* __restrict__ var,
-                            double* __restrict__ acq, int32_t* __restrict__ status, ModelArg model) {
-  extern __shared__ double smem[];
+template <bool LARGE>
+__device__ __forceinline__ void exact_acq_body(double* smem, int n_cap, int d, int N, const double* __restrict__ pool,
+            const int32_t* __restrict__ pool_id, const uint8_t* __restrict__ mask,
+            const double* __restrict__ X, const double* __restrict__ y,
+            const int32_t* __restrict__ n_arr, const double* __restrict__ theta,
+            const double* __restrict__ best_f, int32_t* __restrict__ out_idx,
+            double* __restrict__ out_acq, double* __restrict__ mean, double* __restrict__ var,
+            double* __restrict__ acq, int32_t* __restrict__ status, const ModelArg& model, double* __restrict__ work) {
   const int b = blockIdx.x;
   const int n = n_arr ? n_arr[b] : n_cap;
-  const ExactSmem s = with_model(exact_smem_carve(smem, n_cap, d, kTC, blockDim.x >> 5), model);
+  const ExactSmem s = with_model(exact_carve_for<LARGE>(smem, work, b, n_cap, d, blockDim.x >> 5), model);
   CtaTeam tm{s.red};
   const int np = d + 3;
   exact_load(tm, s, n, d, X + (size_t)b * n_cap * d, y + (size_t)b * n_cap);
@@ -158,6 +201,29 @@ __global__ void k_exact_acq(int n_cap, int d, int N, const double* __restrict__ 
                 &bv, mean ? mean + (size_t)b * N : nullptr, var ? var + (size_t)b * N : nullptr,
                 acq ? acq + (size_t)b * N : nullptr);
   if (threadIdx.x == 0) { status[b] = 0; if (out_idx) out_idx[b] = bi; if (out_acq) out_acq[b] = bv; }
+}
+__global__ void k_exact_acq(int n_cap, int d, int N, const double* __restrict__ pool,
+                            const int32_t* __restrict__ pool_id, const uint8_t* __restrict__ mask,
+                            const double* __restrict__ X, const double* __restrict__ y,
+                            const int32_t* __restrict__ n_arr, const double* __restrict__ theta,
+                            const double* __restrict__ best_f, int32_t* __restrict__ out_idx,
+                            double* __restrict__ out_acq, double* __restrict__ mean, double* __restrict__ var,
+                            double* __restrict__ acq, int32_t* __restrict__ status, ModelArg model) {
+  extern __shared__ double smem[];
+  exact_acq_body<false>(smem, n_cap, d, N, pool, pool_id, mask, X, y, n_arr, theta, best_f, out_idx, out_acq, mean, var,
+                        acq, status, model, nullptr);
+}
+__global__ void __launch_bounds__(kExactLargeThreads, 1)
+k_exact_acq_large(int n_cap, int d, int N, const double* __restrict__ pool,
+                  const int32_t* __restrict__ pool_id, const uint8_t* __restrict__ mask,
+                  const double* __restrict__ X, const double* __restrict__ y,
+                  const int32_t* __restrict__ n_arr, const double* __restrict__ theta,
+                  const double* __restrict__ best_f, int32_t* __restrict__ out_idx,
+                  double* __restrict__ out_acq, double* __restrict__ mean, double* __restrict__ var,
+                  double* __restrict__ acq, int32_t* __restrict__ status, ModelArg model, double* __restrict__ work) {
+  extern __shared__ double smem[];
+  exact_acq_body<true>(smem, n_cap, d, N, pool, pool_id, mask, X, y, n_arr, theta, best_f, out_idx, out_acq, mean, var,
+                       acq, status, model, work);
 }
 
 // Arguments of one BO iteration (the whole loop body runners.py:64-109) shared by the two exact-GP campaign kernels.
@@ -411,7 +477,8 @@ __global__ void __launch_bounds__(T512 ? kVarBigThreads : 256, T512 ? 1 : 3) k_v
   if (n < 1 || n > n_cap || (update && n >= n_cap)) { if (threadIdx.x == 0) status[b] = 2; return; }
   VarSmem s = var_smem_carve(smem, n_cap, d, false, BIG ? 0 : 1);
   // BIG: the working square is global, so the stage region (busy only inside var_prepare) also hosts the candidate tile
-  double* tile = BIG ? s.stage : smem + var_smem_doubles(n_cap, d);
+  // (the tile starts on gZ, which only the training epoch uses)
+  double* tile = BIG ? smem + var_smem_acq_vector_doubles(n_cap, d) : smem + var_smem_doubles(n_cap, d);
   double* part = tile + (size_t)(((n_cap + 15) & ~15) + kMaxD) * kTC;
 #if !defined(STP_NO_DMMA)
   s.panels = tile;   // the candidate tile is idle during var_prepare and larger than the two sweep panels
@@ -574,8 +641,10 @@ int set_smem(K kernel, size_t bytes) {
 int check_dims(int B, int n_cap, int d, int n_limit = STP_MAX_N) {
   if (B < 0) return fail("B < 0");
   if (d < 1 || d > STP_MAX_D) return fail("d out of range [1, STP_MAX_D]");
-  if (n_cap < 1 || n_cap > n_limit) return fail(n_limit == STP_MAX_N ? "n_cap out of range [1, STP_MAX_N]"
-                                                                      : "n_cap out of range [1, STP_MAX_N_VAR]");
+  if (n_cap < 1 || n_cap > n_limit)
+    return fail(n_limit == STP_MAX_N ? "n_cap out of range [1, STP_MAX_N] (larger training sets: the stp_exact_*_large entry points)"
+                                     : (n_limit == STP_MAX_N_VAR ? "n_cap out of range [1, STP_MAX_N_VAR]"
+                                                                 : "n_cap out of range [1, STP_MAX_N_LARGE]"));
   return 0;
 }
 
@@ -610,56 +679,138 @@ extern "C" {
 int stp_version(void) { return STP_ABI_VERSION; }
 const char* stp_last_error_string(void) { return g_err; }
 
+// Shared bodies of the model-level exact entry points: work == nullptr -> the campaign lives in shared memory
+// (n_cap <= STP_MAX_N), else its square is in `work` (n_cap <= STP_MAX_N_LARGE).
+static int exact_check(int B, int n_cap, int d, const double* work, bool large) {
+  if (check_dims(B, n_cap, d, large ? STP_MAX_N_LARGE : STP_MAX_N)) return -1;
+  if (large && !work && B > 0) return fail("null workspace (stp_exact_large_workspace_bytes)");
+  if (large && ((uintptr_t)work & 7)) return fail("workspace must be 8-byte aligned");
+  return 0;
+}
+
+static int exact_mll_fg_impl(const char* what, bool large, int B, int n_cap, int d, const double* X, const double* y,
+                             const int32_t* n, const double* theta, const double* prior, double* f, double* g,
+                             int32_t* status, const stp_model_opts* model, double* work, void* stream) {
+  ModelArg m;
+  if (fill_model(m, model, true)) return -1;
+  if (exact_check(B, n_cap, d, work, large)) return -1;
+  if (!X || !y || !theta || !prior || !f || !g || !status) return fail("null argument");
+  if (B == 0) return 0;
+  PriorArg p; memcpy(p.v, prior, sizeof(p.v));
+  if (large) {
+    const size_t smem = exact_large_smem_bytes(n_cap, d, false);
+    if (set_smem(k_exact_mll_fg_large, smem)) return -1;
+    k_exact_mll_fg_large<<<B, threads_large(), smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, theta, p, f, g, status, m, work);
+  } else {
+    const int threads = threads_for(n_cap);
+    const size_t smem = exact_smem_bytes(n_cap, d, threads, false);
+    if (set_smem(k_exact_mll_fg, smem)) return -1;
+    k_exact_mll_fg<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, theta, p, f, g, status, m);
+  }
+  return after_launch(what);
+}
+
+static int exact_fit_impl(const char* what, bool large, int B, int n_cap, int d, const double* X, const double* y,
+                          const int32_t* n, double* theta, const double* lower, const double* upper,
+                          const double* prior, const stp_lbfgsb_opts* opts, double* f_out, int32_t* nit, int32_t* nfev,
+                          int32_t* status, const stp_model_opts* model, double* work, void* stream) {
+  ModelArg m;
+  if (fill_model(m, model, true)) return -1;
+  if (exact_check(B, n_cap, d, work, large)) return -1;
+  if (!X || !y || !theta || !prior || !status) return fail("null argument");
+  if (B == 0) return 0;
+  PriorArg p; memcpy(p.v, prior, sizeof(p.v));
+  BoundsArg bnd; fill_bounds(bnd, d, lower, upper, nullptr);
+  if (large) {
+    const size_t smem = exact_large_smem_bytes(n_cap, d, true);
+    if (set_smem(k_exact_fit<true>, smem)) return -1;
+    k_exact_fit<true><<<B, threads_large(), smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, theta, bnd, p, to_opts(opts),
+                                                                          f_out, nit, nfev, status, m, work);
+  } else {
+    const int threads = threads_for(n_cap);
+    const size_t smem = exact_smem_bytes(n_cap, d, threads, true);
+    if (set_smem(k_exact_fit<false>, smem)) return -1;
+    k_exact_fit<false><<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, theta, bnd, p, to_opts(opts), f_out,
+                                                                   nit, nfev, status, m, nullptr);
+  }
+  return after_launch(what);
+}
+
+static int exact_acq_impl(const char* what, bool large, int B, int n_cap, int d, int N, const double* pool,
+                          const int32_t* pool_id, const uint8_t* mask, const double* X, const double* y,
+                          const int32_t* n, const double* theta, const double* best_f, int32_t* out_idx,
+                          double* out_acq, double* mean, double* var, double* acq, int32_t* status,
+                          const stp_model_opts* model, double* work, void* stream) {
+  ModelArg m;
+  if (fill_model(m, model, true)) return -1;
+  if (exact_check(B, n_cap, d, work, large)) return -1;
+  if (N < 0) return fail("N < 0");
+  if (!pool || !X || !y || !theta || !status) return fail("null argument");
+  if (B == 0) return 0;
+  if (large) {
+    const size_t smem = exact_large_smem_bytes(n_cap, d, false);
+    if (set_smem(k_exact_acq_large, smem)) return -1;
+    k_exact_acq_large<<<B, threads_large(), smem, (cudaStream_t)stream>>>(n_cap, d, N, pool, pool_id, mask, X, y, n, theta,
+                                                                          best_f, out_idx, out_acq, mean, var, acq, status,
+                                                                          m, work);
+  } else {
+    const int threads = threads_for(n_cap);
+    const size_t smem = exact_smem_bytes(n_cap, d, threads, false);
+    if (set_smem(k_exact_acq, smem)) return -1;
+    k_exact_acq<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, N, pool, pool_id, mask, X, y, n, theta, best_f,
+                                                            out_idx, out_acq, mean, var, acq, status, m);
+  }
+  return after_launch(what);
+}
+
 int stp_exact_mll_fg(int B, int n_cap, int d, const double* X, const double* y, const int32_t* n,
                      const double* theta, const double* prior, double* f, double* g, int32_t* status,
                      const stp_model_opts* model, void* stream) {
-  ModelArg m;
-  if (fill_model(m, model, true)) return -1;
-  if (check_dims(B, n_cap, d)) return -1;
-  if (!X || !y || !theta || !prior || !f || !g || !status) return fail("null argument");
-  if (B == 0) return 0;
-  const int threads = threads_for(n_cap);
-  const size_t smem = exact_smem_bytes(n_cap, d, threads, false);
-  if (set_smem(k_exact_mll_fg, smem)) return -1;
-  PriorArg p; memcpy(p.v, prior, sizeof(p.v));
-  k_exact_mll_fg<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, theta, p, f, g, status, m);
-  return after_launch("stp_exact_mll_fg");
+  return exact_mll_fg_impl("stp_exact_mll_fg", false, B, n_cap, d, X, y, n, theta, prior, f, g, status, model, nullptr, stream);
 }
 
 int stp_exact_fit(int B, int n_cap, int d, const double* X, const double* y, const int32_t* n, double* theta,
                   const double* lower, const double* upper, const double* prior, const stp_lbfgsb_opts* opts,
                   double* f_out, int32_t* nit, int32_t* nfev, int32_t* status, const stp_model_opts* model, void* stream) {
-  ModelArg m;
-  if (fill_model(m, model, true)) return -1;
-  if (check_dims(B, n_cap, d)) return -1;
-  if (!X || !y || !theta || !prior || !status) return fail("null argument");
-  if (B == 0) return 0;
-  const int threads = threads_for(n_cap);
-  const size_t smem = exact_smem_bytes(n_cap, d, threads, true);
-  if (set_smem(k_exact_fit, smem)) return -1;
-  PriorArg p; memcpy(p.v, prior, sizeof(p.v));
-  BoundsArg bnd; fill_bounds(bnd, d, lower, upper, nullptr);
-  k_exact_fit<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, X, y, n, theta, bnd, p, to_opts(opts), f_out, nit,
-                                                          nfev, status, m);
-  return after_launch("stp_exact_fit");
+  return exact_fit_impl("stp_exact_fit", false, B, n_cap, d, X, y, n, theta, lower, upper, prior, opts, f_out, nit, nfev,
+                        status, model, nullptr, stream);
 }
 
 int stp_exact_acq(int B, int n_cap, int d, int N, const double* pool, const int32_t* pool_id, const uint8_t* mask,
                   const double* X, const double* y, const int32_t* n, const double* theta, const double* best_f,
                   int32_t* out_idx, double* out_acq, double* mean, double* var, double* acq, int32_t* status,
                   const stp_model_opts* model, void* stream) {
-  ModelArg m;
-  if (fill_model(m, model, true)) return -1;
-  if (check_dims(B, n_cap, d)) return -1;
-  if (N < 0) return fail("N < 0");
-  if (!pool || !X || !y || !theta || !status) return fail("null argument");
-  if (B == 0) return 0;
-  const int threads = threads_for(n_cap);
-  const size_t smem = exact_smem_bytes(n_cap, d, threads, false);
-  if (set_smem(k_exact_acq, smem)) return -1;
-  k_exact_acq<<<B, threads, smem, (cudaStream_t)stream>>>(n_cap, d, N, pool, pool_id, mask, X, y, n, theta, best_f,
-                                                          out_idx, out_acq, mean, var, acq, status, m);
-  return after_launch("stp_exact_acq");
+  return exact_acq_impl("stp_exact_acq", false, B, n_cap, d, N, pool, pool_id, mask, X, y, n, theta, best_f, out_idx,
+                        out_acq, mean, var, acq, status, model, nullptr, stream);
+}
+
+// ---- large capacities (row f3): the same three operations with the working square in a caller-owned workspace
+size_t stp_exact_large_workspace_bytes(int B, int n_cap) {
+  if (B <= 0 || n_cap < 1 || n_cap > STP_MAX_N_LARGE) return 0;
+  return (size_t)B * exact_large_work_doubles(n_cap) * sizeof(double);
+}
+
+int stp_exact_mll_fg_large(int B, int n_cap, int d, const double* X, const double* y, const int32_t* n,
+                           const double* theta, const double* prior, double* f, double* g, int32_t* status,
+                           const stp_model_opts* model, void* work, void* stream) {
+  return exact_mll_fg_impl("stp_exact_mll_fg_large", true, B, n_cap, d, X, y, n, theta, prior, f, g, status, model,
+                           (double*)work, stream);
+}
+
+int stp_exact_fit_large(int B, int n_cap, int d, const double* X, const double* y, const int32_t* n, double* theta,
+                        const double* lower, const double* upper, const double* prior, const stp_lbfgsb_opts* opts,
+                        double* f_out, int32_t* nit, int32_t* nfev, int32_t* status, const stp_model_opts* model,
+                        void* work, void* stream) {
+  return exact_fit_impl("stp_exact_fit_large", true, B, n_cap, d, X, y, n, theta, lower, upper, prior, opts, f_out, nit,
+                        nfev, status, model, (double*)work, stream);
+}
+
+int stp_exact_acq_large(int B, int n_cap, int d, int N, const double* pool, const int32_t* pool_id, const uint8_t* mask,
+                        const double* X, const double* y, const int32_t* n, const double* theta, const double* best_f,
+                        int32_t* out_idx, double* out_acq, double* mean, double* var, double* acq, int32_t* status,
+                        const stp_model_opts* model, void* work, void* stream) {
+  return exact_acq_impl("stp_exact_acq_large", true, B, n_cap, d, N, pool, pool_id, mask, X, y, n, theta, best_f,
+                        out_idx, out_acq, mean, var, acq, status, model, (double*)work, stream);
 }
 
 static int fill_bo_args(BoArgs& a, int B, int n_cap, int d, int N, const double* pool, const double* pool_y,
@@ -761,6 +912,28 @@ static int var_use_panels(int n_cap, int d) {
 #endif
 }
 
+// shared memory of a stp_var_acq launch
+static size_t var_acq_smem_bytes(int n_cap, int d) {
+  size_t smem = (var_smem_doubles(n_cap, d) + var_acq_smem_doubles(n_cap, kTC)) * sizeof(double);
+  if (n_cap > kVarSmemSquareMax) {   // the tile aliases gZ and the stage region (see k_var_acq)
+    const size_t with_tile = var_smem_acq_vector_doubles(n_cap, d) + var_acq_smem_doubles(n_cap, kTC);
+    const size_t with_stage = var_smem_vector_doubles(n_cap, d) + contract_stage_doubles();
+    smem = (with_tile > with_stage ? with_tile : with_stage) * sizeof(double);
+  }
+  return smem;
+}
+
+int stp_var_capacity(int n, int d) {
+  if (n < 1 || d < 1 || d > STP_MAX_D) return -1;
+  const size_t limit = 227 * 1024;
+  for (int cap = n; cap <= STP_MAX_N_VAR; ++cap) {
+    const size_t fit = var_smem_doubles(cap, d, var_use_panels(cap, d) != 0) * sizeof(double);
+    const size_t fg = var_smem_doubles(cap, d, false) * sizeof(double);
+    if (fit <= limit && fg <= limit && var_acq_smem_bytes(cap, d) <= limit) return cap;
+  }
+  return -1;
+}
+
 size_t stp_var_workspace_bytes(int B, int n_cap) {
   if (B < 0 || n_cap < 1) return 0;
   return (size_t)B * var_work_doubles(n_cap) * sizeof(double);
@@ -832,11 +1005,7 @@ int stp_var_acq(int B, int n_cap, int d, int N, int lik, const double* pool, con
   if (update && (!pool_y || !X || !y || !trace || !mask || !n)) return fail("update needs pool_y, X, y, n, trace and mask");
   if (!best_f && !y) return fail("best_f or y required");
   if (B == 0) return 0;
-  size_t smem = (var_smem_doubles(n_cap, d) + var_acq_smem_doubles(n_cap, kTC)) * sizeof(double);
-  if (n_cap > kVarSmemSquareMax) {   // the tile aliases the stage region (see k_var_acq)
-    const size_t region = var_acq_smem_doubles(n_cap, kTC) > contract_stage_doubles() ? var_acq_smem_doubles(n_cap, kTC) : contract_stage_doubles();
-    smem = (var_smem_vector_doubles(n_cap, d) + region) * sizeof(double);
-  }
+  const size_t smem = var_acq_smem_bytes(n_cap, d);
   const VarPtrs ptrs{const_cast<double*>(Z), const_cast<double*>(hyp), const_cast<double*>(nat1),
                      const_cast<double*>(nat2), nullptr, nullptr};
   if (n_cap > kVarSmemSquareMax) {

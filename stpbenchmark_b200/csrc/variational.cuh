@@ -131,6 +131,13 @@ STP_HD size_t var_smem_vector_doubles(int cap, int d) {
   return (v + 1) & ~(size_t)1;      // the square / stage region starts on a 16-byte boundary
 }
 
+// The same without gZ (the last vector): all var_prepare / var_acquire need.  Large capacities start the candidate tile
+// of the pool pass here, which is what lets n_cap = 481 (benchmark_predictions.py's 80 % split of 600 points) fit.
+STP_HD size_t var_smem_acq_vector_doubles(int cap, int d) {
+  const size_t v = (size_t)2 * d * cap + (size_t)cap * 4 + 6 * (size_t)(cap + 1) + 96 + 16 * kMaxWarps;
+  return (v + 1) & ~(size_t)1;
+}
+
 STP_HD size_t var_smem_doubles(int cap, int d, bool with_panels = false) {
   // the working square + the sweep panels double as the operand ring of the staged contractions
   size_t square = (cap <= kVarSmemSquareMax ? (size_t)(cap + 1) * var_ld(cap) : 0) + (with_panels ? sweep_blocked_scratch_doubles(cap + 1) : 0);
@@ -158,9 +165,9 @@ STP_HD VarSmem var_smem_carve(double* base, int cap, int d, bool with_panels = f
   s.c3 = s.dv = p; p += cap + 1;
   s.gmu = p; p += cap;
   s.gsm = p; p += cap;
-  s.gZ = p; p += (size_t)cap * d;
   s.small = p; p += 96;
   s.red = p; p += 16 * kMaxWarps;
+  s.gZ = p; p += (size_t)cap * d;   // last: the pool pass never touches it and lets its candidate tile start here
   p = base + var_smem_vector_doubles(cap, d);
   const bool square_here = in_smem < 0 ? (cap <= kVarSmemSquareMax) : (in_smem != 0);
   s.M0 = square_here ? p : nullptr;   // nullptr: bound to the workspace by var_bind()

@@ -113,7 +113,7 @@ def _pack(model, cap=None):
     """Model parameters -> state dict (batch of one) on the model's device."""
     Z = model.variational_strategy.inducing_points.detach().double()
     n, d = Z.shape
-    cap = cap or n
+    cap = cap or _lib.var_capacity(n, d)
     dev = Z.device
     st = alloc_state(1, cap, d, dev)
     st["Z"][0, :n] = Z

@@ -19,11 +19,19 @@ using namespace stp;
 namespace {
 int g_kern = 0, g_acq = 0;   // emu_set_model: kernel / acquisition variant of the next emu_exact_* calls
 double g_beta = 0.0;
+int g_large = 0;             // emu_set_large: carve the campaign as the stp_exact_*_large entry points do
 struct Scratch {
-  std::vector<double> buf;
+  std::vector<double> buf, square;
   ExactSmem s;
-  Scratch(int cap, int d) : buf(exact_smem_doubles(cap, d, 1, 1) + 8, 0.0) {
-    s = exact_smem_carve(buf.data(), cap, d, 1, 1);
+  Scratch(int cap, int d) {
+    if (g_large) {   // stp_exact_*_large: the working square in its own ("global") buffer
+      buf.assign(exact_large_smem_doubles(cap, d, 1) + 8, 0.0);
+      square.assign(exact_large_work_doubles(cap), 0.0);
+      s = exact_smem_carve_large(buf.data(), square.data(), cap, d, 1);
+    } else {
+      buf.assign(exact_smem_doubles(cap, d, 1, 1) + 8, 0.0);
+      s = exact_smem_carve(buf.data(), cap, d, 1, 1);
+    }
     s.kern = g_kern; s.acq_kind = g_acq; s.acq_beta = g_beta;
   }
 };
@@ -31,6 +39,8 @@ ExactPrior prior_from(const double* p) { return ExactPrior{p[0], p[1], p[2], p[3
 }  // namespace
 
 extern "C" {
+
+void emu_set_large(int on) { g_large = on; }
 
 int emu_exact_mll_fg(int B, int n_max, int d, const double* X, const double* y, const int* n_arr,
                      const double* theta, const double* prior, double* f, double* g, int* status) {

@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_version_and_argument_rejection(lib):
-    assert lib.stp_version() == 2
+    assert lib.stp_version() == 3
     lib.stp_last_error_string.restype = ctypes.c_char_p
     # argument validation happens before any CUDA call, so it is testable without a GPU
     rc = lib.stp_exact_mll_fg(1, 10, 99, None, None, None, None, None, None, None, None, None, None)

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def L():
     from stpbenchmark_b200 import _lib
-    assert _lib.lib().stp_version() == 2
+    assert _lib.lib().stp_version() == 3
     return _lib
 
 
