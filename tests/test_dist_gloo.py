@@ -1,5 +1,7 @@
 """world_size-2 gloo test of the multi-GPU plumbing: static sharding + the final trace gather."""
+import datetime
 import os
+import queue
 import socket
 
 import torch
@@ -22,7 +24,7 @@ def test_shard_bounds_cover_everything_once():
 
 def _worker(rank, world, port, B, T, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=120))
     lo, hi = sd.shard_bounds(B, world, rank)
     trace = (torch.arange(lo, hi).unsqueeze(1) * 100 + torch.arange(T).unsqueeze(0)).to(torch.int32)
     vals = trace.double() / 7.0
@@ -35,17 +37,29 @@ def _worker(rank, world, port, B, T, q):
     dist.destroy_process_group()
 
 
+def _first_result(q, procs, seconds=240):
+    """What rank 0 put on the queue; a rank that died (or a rendezvous that never completes) fails the test instead of
+    blocking the suite."""
+    try:
+        return q.get(timeout=seconds)
+    except queue.Empty:
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+        raise AssertionError(f"no result within {seconds} s (exit codes {[p.exitcode for p in procs]})")
+
+
 def test_gather_traces_world2_ragged():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     B, T = 7, 5                        # 4 + 3 campaigns: ragged shards
     ctx = mp.get_context("spawn")
-    q = ctx.SimpleQueue()
+    q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, B, T, q)) for r in range(2)]
     for p in procs:
         p.start()
-    tr, vals = q.get()
+    tr, vals = _first_result(q, procs)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
@@ -68,7 +82,7 @@ def _sweep_worker(rank, world, port, tmp, q):
     gathers the traces on rank 0; a job that ran entirely on one rank is written by that rank (here b.csv by rank 1), the
     others by rank 0."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=120))
     from stpbenchmark_b200 import runners
     g = torch.Generator().manual_seed(0)
     jobs = []
@@ -90,11 +104,11 @@ def test_run_sweep_shards_over_two_ranks_and_owning_ranks_write_the_csvs(tmp_pat
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
-    q = ctx.SimpleQueue()
+    q = ctx.Queue()
     procs = [ctx.Process(target=_sweep_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
     for p in procs:
         p.start()
-    assert q.get() == "done"
+    assert _first_result(q, procs) == "done"
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
