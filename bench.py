@@ -4,6 +4,7 @@
   python bench.py [--gpus N] [--steps K] [--warmup W]                    # headline: BASELINE configs[3] ("cfg4")
   python bench.py --model VarTGP                                         # north-star VarTGP shape (pool 2048, d = 6)
   python bench.py --config cfg5 | cfg2 | cfg3                            # the other BASELINE configs
+  python bench.py --config f3                                            # benchmark_predictions.py study
   python bench.py --impl reference [--config ...] [--steps K] [--warmup W]   # CPU arm: the oracle on the host cores
   (N > 1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
 
@@ -16,6 +17,8 @@ Workloads:
   cfg5  pools N = 8192, d = 8, 512 VarTGP campaigns per GPU (4096 over 8 GPUs), n_initial = M = 256, 4 trials.
   cfg2  VarTGP x the 5 materials datasets x the 50 seeds of random_seeds.txt through run_benchmark's path (one device job).
   cfg3  Hartmann-6 fit-and-predict (test_hartmann.py scenario), 256 seeds x {ExactGP, VarGP, VarLGP, VarTGP}.
+  f3    benchmark_predictions.py's study: {VarTGP, VarGP, ExactGP} x 5 datasets x 25 seeds, fit on 80 % (n up to 480), MAE
+        on the rest; device-resident per (model, dataset) pair + end to end through evaluate_model_across_datasets.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.  The CPU legs (cpu_baseline of the CUDA
 arms, the whole --impl reference arm) run oracle/ in a SEPARATE interpreter started with OMP/MKL/OPENBLAS_NUM_THREADS=1
@@ -66,7 +69,7 @@ def _cpu_init():
     ov.acquisition(st, X[12:], y[:12].max(), eps=torch.zeros(28, 8, dtype=torch.double))
 
 
-def _pool_of(name, g):
+def _pool_of(name, g, raw_y=False):
     import torch
     from stpbenchmark_b200 import synthetic
     if name == "cfg4":
@@ -76,7 +79,7 @@ def _pool_of(name, g):
     import numpy as np
     z = np.load(os.path.join(ROOT, "tests", "golden", "datasets.npz"))       # the reference's data/*.csv, preprocessed
     X = torch.tensor(z[f"{name}_X"], dtype=torch.double); y = torch.tensor(z[f"{name}_y"], dtype=torch.double)
-    return X, (1.0 / y if name in ("AgNP", "Perovskite") else y)            # run_benchmark.py:27-28
+    return X, (1.0 / y if name in ("AgNP", "Perovskite") and not raw_y else y)            # run_benchmark.py:27-28
 
 
 def _aged_training_set(X, y, seed, n_initial, age):
@@ -146,6 +149,26 @@ def _cpu_job(job):
             m, _ = ov.latent_posterior(st, Xte)
             mean = m * (ytr.std(unbiased=False) + 1e-10) + ytr.mean()
         return [time.perf_counter() - t0, float((mean - yte).abs().mean())]
+    if t == "predict_fit":          # benchmark_predictions.py:19-75 on one 80/20 split; `epochs` of 600 timed (variational)
+        from oracle import exact as oexact, variational as ov
+        from stpbenchmark_b200 import benchmark_predictions as bp
+        X, y = _pool_of(job["pool"], 0, raw_y=True)
+        tr, te = bp.split_indices(len(X), job["seed"])
+        mu, sd = y[tr].mean(), y[tr].std(unbiased=False) + 1e-10
+        ys = (y[tr] - mu) / sd
+        if job["kind"] != "ExactGP":
+            ov.train_natural(X[tr], ys, job["kind"], 1, 0.01)     # untimed: first-call costs must not be extrapolated
+        t0 = time.perf_counter()
+        if job["kind"] == "ExactGP":
+            theta, _res = oexact.fit_exact(X[tr], ys)
+            mean, _ = oexact.posterior_exact(theta, X[tr], ys, X[te])
+            t1 = t2 = time.perf_counter()
+        else:
+            st = ov.train_natural(X[tr], ys, job["kind"], job["epochs"], 0.01)
+            t1 = time.perf_counter()
+            mean, _ = ov.latent_posterior(st, X[te])
+            t2 = time.perf_counter()
+        return [t1 - t0, t2 - t1, len(tr), float(((mean * sd + mu) - y[te]).abs().mean())]
     raise ValueError(t)
 
 
@@ -896,13 +919,136 @@ def run_cfg3_arm(args):
     D.close()
 
 
+# ------------------------------------------------------------------------------------------
+# f3: the fit-and-predict study of benchmark_predictions.py (3 models x 5 datasets x 25 seeds, 80/20 splits, n up to 480)
+# ------------------------------------------------------------------------------------------
+F3_WORKLOAD = ("f3: benchmark_predictions.py study: {{VarTGP, VarGP, ExactGP}} x 5 materials datasets x {S} seeds, fit on an 80 % "
+               "split (n = 76, 80, 132, 143, 480), {E} epochs NGD+Adam / L-BFGS-B, MAE of posterior.mean on the other 20 %")
+
+
+def run_f3_arm(args):
+    import numpy as np
+    import torch
+    D = Dist()
+    from stpbenchmark_b200 import benchmark_predictions as bp
+    from stpbenchmark_b200.models import ExactGP, VarGP, VarTGP
+    names = ["AgNP", "AutoAM", "CrossedBarrel", "P3HT", "Perovskite"]
+    S_ = 25 if args.campaigns == 1024 else args.campaigns
+    E = args.epochs
+    seeds = [int(s) for s in np.load(os.path.join(ROOT, "tests", "golden", "traces.npz"))["seeds"]][:S_]   # random_seeds.txt
+    z = np.load(os.path.join(ROOT, "tests", "golden", "datasets.npz"))
+    kinds = [("VarTGP", VarTGP), ("VarGP", VarGP), ("ExactGP", ExactGP)]
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in names:                           # the reference's data/*.csv
+            tab = z[f"{name}_raw"]
+            np.savetxt(os.path.join(tmp, f"{name}_dataset.csv"), tab, delimiter=",",
+                       header=",".join(f"c{i}" for i in range(tab.shape[1])), comments="")
+        files = [f"{n}_dataset.csv" for n in names]
+        for _k, cls in kinds:                        # warm-up: library, allocator, shared-memory grants
+            bp.evaluate_model_across_datasets(cls, n_seeds=2, epochs=5, data_dir=tmp, seeds=seeds, verbose=False, dataset_files=files)
+        # (1) per (model, dataset) pair alone on the device (diagnostic table): CUDA events around fit + predict
+        flops, serial_ms, launches, per, dev_in = 0.0, 0.0, 0, {}, {}
+        sampler = ClockSampler(D.local_rank); sampler.start()
+        for name in names:
+            X, y = _pool_of(name, 0, raw_y=True)
+            tr, te = zip(*[bp.split_indices(len(X), s_) for s_ in seeds])
+            tr, te = torch.stack(tr), torch.stack(te)
+            Xtr, ytr, Xte = X[tr].to(D.dev), y[tr].to(D.dev), X[te].to(D.dev)
+            dev_in[name] = (Xtr, ytr, Xte)
+            n, d, m = Xtr.shape[1], Xtr.shape[2], Xte.shape[1]
+            for k, _cls in kinds:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                res = bp.fit_predict_batch(k, Xtr, ytr, Xte, epochs=E, lr=0.01)
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                serial_ms += ms
+                if k == "ExactGP":
+                    w = sum(float(F) * (n ** 3 + n * n * (3 * d + 6)) + n ** 3 / 3 + m * (n * n + n * (3 * d + 8) + 60)
+                            for F in res["nfev"].tolist())
+                else:
+                    w = S_ * (E * (9 * n ** 3 + n * n * (14 * d + 12) + 800 * n) + 3 * n ** 3 + m * (n * (3 * d + 4) + 2 * n * n + 60))
+                flops += w
+                per[f"{k}/{name}"] = {"n": n, "ms": ms, "fits_per_sec": S_ / (ms * 1e-3), "tflops": w / (ms * 1e-3) / 1e12,
+                                      "bad": int((res["status"] != 0).sum())}
+        # (2) the timed step: all pairs in flight together, inputs resident in HBM, one CUDA stream per pair (what the
+        #     product path does), longest pairs first; device time from the start event to the last stream's end event
+        order = sorted(((k, nm) for k, _c in kinds for nm in names),
+                       key=lambda p_: -(dev_in[p_[1]][0].shape[1] ** 3) * (E if p_[0] != "ExactGP" else 100.0))
+        torch.cuda.synchronize()
+        ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
+        ends, keep = [], []
+        for k, nm in order:
+            st = torch.cuda.Stream(); st.wait_event(ev0)
+            with torch.cuda.stream(st):
+                keep.append(bp.launch_fit_predict(k, *dev_in[nm], epochs=E, lr=0.01))
+                e = torch.cuda.Event(enable_timing=True); e.record(st); ends.append(e)
+            launches += 2
+        torch.cuda.synchronize()
+        dev_ms = max(ev0.elapsed_time(e) for e in ends)
+        del keep
+        # (3) end to end through the product API: CSV files -> result dictionaries (host buffers both ways)
+        D.barrier()
+        t0 = time.perf_counter()
+        r = bp.evaluate_models_across_datasets([c for _k, c in kinds], n_seeds=S_, epochs=E, lr=0.01, data_dir=tmp, seeds=seeds,
+                                               verbose=False, dataset_files=files)
+        maes = {k: {ds.replace("_dataset", ""): v["mean_mae"] for ds, v in r[c.__name__].items()} for k, c in kinds}
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+    fits = len(kinds) * len(names) * S_ * D.world      # under torchrun every rank runs the whole study (replicas only)
+    dev_ms = D.reduce(dev_ms, "max"); wall = D.reduce(wall, "max")
+    sizes = {n_: z[f"{n_}_X"].shape for n_ in names}
+    h2d = len(kinds) * S_ * sum(sizes[n_][0] * (sizes[n_][1] + 1) * 8 for n_ in names)
+    d2h = len(kinds) * S_ * sum(int(0.2 * sizes[n_][0]) * 16 + 4 for n_ in names)
+    peaks = fp64_peaks()
+    cpu = None
+    if D.rank == 0 and not args.no_cpu_baseline:
+        cores = min(host_cores(), 64)
+        E_s = 60                                      # 60 of the 600 epochs timed (a 600-epoch fit at n = 480 is ~36 s per core)
+        order = [(k, n_) for n_ in names for k, _c in kinds]
+        cj = [dict(type="predict_fit", pool=order[c % len(order)][1], kind=order[c % len(order)][0], seed=seeds[c % S_],
+                   epochs=E_s) for c in range(cores)]
+        r = run_cpu_jobs(cj, cores)
+        # seconds of one full fit + predict per (kind, dataset), extrapolated to E epochs; the study = S_ x their sum
+        full = {}
+        for j, x in zip(cj, r["results"]):
+            t_fit = x[0] if j["kind"] == "ExactGP" else x[0] * (E / E_s)
+            full.setdefault((j["kind"], j["pool"]), []).append(t_fit + x[1])
+        mean_s = {kd: sum(v) / len(v) for kd, v in full.items()}
+        covered = [kd for kd in order if kd in mean_s]
+        study_core_s = S_ * sum(mean_s[kd] for kd in covered) * (len(order) / max(len(covered), 1))
+        cpu = {"value": fits / (study_core_s / cores), "unit": "fits/s", "cores": cores, "kind": "port",
+               "per_core": fits / study_core_s,
+               "sample": f"{cores} fits, one per core, (model, dataset) pairs round-robin ({len(covered)} of {len(order)} covered); "
+                         f"variational fits EXTRAPOLATED from {E_s} of {E} epochs; value = {fits} fits / (summed single-core seconds of "
+                         f"the study / cores); oracle/; wall {r['wall']:.1f}s",
+               "seconds_per_fit": {f"{k}/{n_}": mean_s[(k, n_)] for (k, n_) in covered}}
+    if D.rank == 0:
+        print(json.dumps({
+            "metric": "model_fits_per_sec", "value": fits / (dev_ms * 1e-3), "unit": "fits/s", "n_gpus": D.world, "steps": 1, "warmup": 1,
+            "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "the reference's data/*.csv (tests/golden/datasets.npz raw tables written back as CSV)",
+            "config": {"workload": F3_WORKLOAD.format(S=S_, E=E), "fits": fits, "multi_gpu": "replicas only (every rank runs the study)",
+                       "l2": "each campaign's working squares (1.9 - 15 MB at n = 480) are L2-resident; FP64 / latency bound"},
+            "per_pair": per, "serial_ms": serial_ms, "mean_mae": maes,
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA + DFMA)", "achieved": flops / (dev_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                         "frac": flops / (dev_ms * 1e-3) / 1e12 / peaks["peak"], "traffic": None,
+                         "kernel": "k_var_fit<BIG> (CrossedBarrel, n = 480: 25 CTAs on 148 SMs)", **peaks},
+            "cpu_baseline": cpu,
+            "e2e": {"value": fits / wall, "unit": "fits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "wall_s": wall,
+                    "api": "benchmark_predictions.evaluate_models_across_datasets on CSV files"},
+            "gpu_launches": launches, "clocks": clocks}), flush=True)
+    D.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg5", "cfg2", "cfg3"])
+    ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg5", "cfg2", "cfg3", "f3"])
     ap.add_argument("--campaigns", type=int, default=1024, help="campaigns per GPU (cfg5: 512, cfg3: 256 seeds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -935,6 +1081,8 @@ def main():
         run_cfg2_arm(args)
     elif args.config == "cfg3":
         run_cfg3_arm(args)
+    elif args.config == "f3":
+        run_f3_arm(args)
     elif variational:
         args.steps = min(args.steps, 10)
         run_var_arm(args)
