@@ -163,6 +163,16 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
                       int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
                       int32_t* iters_acc, int n_max, const stp_model_opts* model, void* stream);
 
+/* stp_exact_bo_step for campaigns beyond the shared-memory capacity (n_cap up to STP_MAX_N_LARGE: a BO loop with more
+ * than ~130 trials, runners.py:64-109 with a large n_trials): identical arguments and semantics, the working square
+ * of every campaign in `work` (stp_exact_large_workspace_bytes(B, n_cap) bytes, scratch). */
+int stp_exact_bo_step_large(int B, int n_cap, int d, int N, const double* pool, const double* pool_y,
+                            const int32_t* pool_id, uint8_t* mask, double* X, double* y, int32_t* n, int32_t* trace,
+                            const double* theta0, const double* lower, const double* upper, const double* prior,
+                            const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
+                            int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
+                            int32_t* iters_acc, int n_max, const stp_model_opts* model, void* work, void* stream);
+
 /* The same loop body as a PERSISTENT launch over a work queue: one CTA per SM slot (as many as are resident at the
  * launch's shared-memory footprint, at most max_ctas if max_ctas > 0) serves the B campaigns from a ticket ring; a
  * work item is one BO iteration of one campaign, and campaign b is advanced until iters_left[b] (int32[B], in/out,

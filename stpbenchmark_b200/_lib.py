@@ -217,6 +217,23 @@ def exact_bo_step(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, up
                                    ctypes.c_int(int(n_max)), _m(model), _stream()), "stp_exact_bo_step")
 
 
+def exact_bo_step_large(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upper, prior, status, work,
+                        theta_out=None, acq_out=None, nit=None, nfev=None, opts: Optional[LbfgsbOpts] = None, order=None,
+                        work_acc=None, iters_acc=None, n_max: int = 0, model: Optional[ModelOpts] = None):
+    """exact_bo_step for row capacities beyond MAX_N (stp_exact_bo_step_large); ``work`` = exact_large_work(B, n_cap)."""
+    _require_cuda(pool, pool_y, pool_id, mask, X, y, n, trace, status, work, theta_out, acq_out, nit, nfev, order, work_acc,
+                  iters_acc)
+    B, n_cap, d = X.shape
+    N = pool.shape[-2]
+    lo, hi = _bounds(lower, upper, d + 3)
+    o = opts or LbfgsbOpts.scipy_defaults()
+    _check(lib().stp_exact_bo_step_large(B, n_cap, d, N, _p(pool), _p(pool_y), _p(pool_id), _p(mask), _p(X), _p(y), _p(n),
+                                         _p(trace), _host(theta0), lo, hi, _host(prior), ctypes.byref(o), _p(theta_out),
+                                         _p(acq_out), _p(nit), _p(nfev), _p(status), _p(order), None, _p(work_acc),
+                                         _p(iters_acc), ctypes.c_int(int(n_max)), _m(model), _p(work), _stream()),
+           "stp_exact_bo_step_large")
+
+
 def exact_bo_run(pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upper, prior, status, iters_left, sched,
                  theta_out=None, acq_out=None, nit=None, nfev=None, opts: Optional[LbfgsbOpts] = None, order=None,
                  turnover: Optional[Turnover] = None, work_acc=None, iters_acc=None, n_max: int = 0, max_ctas: int = 0,

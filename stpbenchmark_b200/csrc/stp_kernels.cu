@@ -235,20 +235,22 @@ struct BoArgs {
   double* theta_out; double* acq_out; int32_t* nit; int32_t* nfev; int32_t* status;
   stp_turnover turn; double* work_acc; int32_t* iters_acc;
   ModelArg model;
+  double* work;   // LARGE only: the working squares (stp_exact_large_workspace_bytes)
 };
 
 // One BO iteration of campaign b by the whole CTA.  CG: the campaign state may have been written by another SM
 // during this launch (persistent kernel), so it is read through the L2 (ld.global.cg), never through this SM's L1.
 // Returns 0 when the iteration completed, non-zero when the campaign stopped (status[b] set).
-template <bool CG>
+template <bool CG, bool LARGE = false>
 __device__ __forceinline__ int exact_bo_iteration(const BoArgs& a, double* smem, int b) {
   const int n_cap = a.n_cap, d = a.d, N = a.N, s_cap = a.s_cap;
   const int n = CG ? __ldcg(a.n_arr + b) : a.n_arr[b];
   // n_cap: row capacity of the global arrays; s_cap <= n_cap - 1: what the shared-memory carve-up of this launch holds
   if (n >= n_cap || n < 1 || n > s_cap) { if (threadIdx.x == 0) a.status[b] = 2; return 2; }
   const int nw = blockDim.x >> 5;
-  const ExactSmem s = with_model(exact_smem_carve(smem, s_cap, d, kTC, nw), a.model);
-  LbfgsbState* S = reinterpret_cast<LbfgsbState*>(smem + exact_smem_doubles(s_cap, d, kTC, nw));
+  const ExactSmem s = with_model(exact_carve_for<LARGE>(smem, a.work, b, s_cap, d, nw), a.model);
+  LbfgsbState* S = reinterpret_cast<LbfgsbState*>(
+      smem + (LARGE ? exact_large_smem_doubles(s_cap, d, kTC) : exact_smem_doubles(s_cap, d, kTC, nw)));
   int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(S) + sizeof(LbfgsbState));
   CtaTeam tm{s.red};
   const int np = d + 3;
@@ -341,6 +343,14 @@ __global__ void __launch_bounds__(STP_EXACT_MAXT, STP_EXACT_MINB) k_exact_bo_ste
   const int b = order ? order[blockIdx.x] : blockIdx.x;   // longest-first scheduling: CTAs are issued in blockIdx order
   if (a.status[b] != 0) return;  // frozen campaign
   exact_bo_iteration<false>(a, smem, b);
+}
+
+// The same for campaigns beyond the shared-memory capacity (n_cap > STP_MAX_N): working squares in a.work.
+__global__ void __launch_bounds__(kExactLargeThreads, 1) k_exact_bo_step_large(BoArgs a, const int32_t* __restrict__ order) {
+  extern __shared__ double smem[];
+  const int b = order ? order[blockIdx.x] : blockIdx.x;
+  if (a.status[b] != 0) return;  // frozen campaign
+  exact_bo_iteration<false, true>(a, smem, b);
 }
 
 // Persistent form: gridDim.x resident CTAs serve B campaigns from a ticket ring until every campaign has done its
@@ -818,9 +828,10 @@ static int fill_bo_args(BoArgs& a, int B, int n_cap, int d, int N, const double*
                         const double* theta0, const double* lower, const double* upper, const double* prior,
                         const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
                         int32_t* status, const stp_turnover* turnover, double* work_acc, int32_t* iters_acc, int n_max,
-                        const stp_model_opts* model) {
+                        const stp_model_opts* model, int n_limit = STP_MAX_N) {
+  a.work = nullptr;
   if (fill_model(a.model, model, true)) return -1;
-  if (check_dims(B, n_cap, d)) return -1;
+  if (check_dims(B, n_cap, d, n_limit)) return -1;
   if (N < 1) return fail("N < 1");
   if (n_max < 0 || n_max >= n_cap) return fail("n_max must be 0 (unknown) or in [1, n_cap - 1]");
   memset(&a.turn, 0, sizeof(a.turn));
@@ -857,6 +868,24 @@ int stp_exact_bo_step(int B, int n_cap, int d, int N, const double* pool, const 
   if (set_smem(k_exact_bo_step, smem)) return -1;
   k_exact_bo_step<<<B, threads, smem, (cudaStream_t)stream>>>(a, order);
   return after_launch("stp_exact_bo_step");
+}
+
+int stp_exact_bo_step_large(int B, int n_cap, int d, int N, const double* pool, const double* pool_y,
+                            const int32_t* pool_id, uint8_t* mask, double* X, double* y, int32_t* n, int32_t* trace,
+                            const double* theta0, const double* lower, const double* upper, const double* prior,
+                            const stp_lbfgsb_opts* opts, double* theta_out, double* acq_out, int32_t* nit, int32_t* nfev,
+                            int32_t* status, const int32_t* order, const stp_turnover* turnover, double* work_acc,
+                            int32_t* iters_acc, int n_max, const stp_model_opts* model, void* work, void* stream) {
+  BoArgs a;
+  if (fill_bo_args(a, B, n_cap, d, N, pool, pool_y, pool_id, mask, X, y, n, trace, theta0, lower, upper, prior, opts,
+                   theta_out, acq_out, nit, nfev, status, turnover, work_acc, iters_acc, n_max, model, STP_MAX_N_LARGE)) return -1;
+  if (B == 0) return 0;
+  if (!work || ((uintptr_t)work & 7)) return fail("null or misaligned workspace (stp_exact_large_workspace_bytes)");
+  a.work = (double*)work;
+  const size_t smem = exact_large_smem_bytes(a.s_cap, d, true);
+  if (set_smem(k_exact_bo_step_large, smem)) return -1;
+  k_exact_bo_step_large<<<B, threads_large(), smem, (cudaStream_t)stream>>>(a, order);
+  return after_launch("stp_exact_bo_step_large");
 }
 
 int stp_exact_bo_run(int B, int n_cap, int d, int N, const double* pool, const double* pool_y,

@@ -51,9 +51,16 @@ class CampaignBatch:
         self.G, self.N, self.d = pools.shape
         self.B = len(pool_id)
         self.cap = int(n_cap)
-        max_n = _lib.MAX_N if kind == "ExactGP" else _lib.MAX_N_VAR
-        if self.cap > max_n or self.d > _lib.MAX_D:
-            raise ValueError(f"n_cap <= {max_n} and d <= {_lib.MAX_D} required for {kind}")
+        if self.d > _lib.MAX_D:
+            raise ValueError(f"d <= {_lib.MAX_D} required")
+        if kind == "ExactGP":
+            # beyond the shared-memory capacity the working squares live in a global workspace (stp_exact_bo_step_large)
+            self.large = self.cap > _lib.MAX_N
+            if self.cap > _lib.MAX_N_LARGE:
+                raise ValueError(f"n_cap <= {_lib.MAX_N_LARGE} required for ExactGP")
+        else:
+            self.large = False
+            self.cap = _lib.var_capacity(self.cap, self.d)      # the smallest launchable capacity (raises beyond the limit)
         dev = self.device
         self.pool = pools.to(dev, torch.double).contiguous()
         self.pool_y = pool_ys.to(dev, torch.double).contiguous()
@@ -110,6 +117,7 @@ class CampaignBatch:
             self._lower, self._upper = priors.exact_bounds(d)
             self._prior = priors.exact_prior_vector(d)
             self._opts = _lib.LbfgsbOpts.scipy_defaults()
+            self._work = _lib.exact_large_work(B, cap, dev) if self.large else None
         else:
             from . import varops
             self._var = varops.VarBatchState(self)
@@ -128,6 +136,19 @@ class CampaignBatch:
             # longest-first: a fit costs ~ closures x n^3, so the biggest training sets go first (no host sync)
             order = torch.argsort(self.n, descending=True, stable=True).to(torch.int32) if self.ragged else None
             n_max = 0 if self._n_host is None else int(min(self._n_host.max(), self.cap - 1))
+            if self.large:
+                if self._turnover is not None:
+                    raise NotImplementedError("continuous batching is provided for the shared-memory step only")
+                _lib.exact_bo_step_large(self.pool, self.pool_y, self.pool_id, self.mask, self.X, self.y, self.n, self.trace,
+                                         self._theta0, self._lower, self._upper, self._prior, self.status, self._work,
+                                         theta_out=self.theta, acq_out=self.acq, nit=self.nit, nfev=self.nfev,
+                                         opts=self._opts, order=order, work_acc=self.work_acc, iters_acc=self.iters_acc,
+                                         n_max=n_max, model=self.model_opts)
+                self.launches += 1
+                if self._n_host is not None:
+                    self._n_host += 1
+                self.iteration += 1
+                return
             _lib.exact_bo_step(self.pool, self.pool_y, self.pool_id, self.mask, self.X, self.y, self.n, self.trace,
                                self._theta0, self._lower, self._upper, self._prior, self.status,
                                theta_out=self.theta, acq_out=self.acq, nit=self.nit, nfev=self.nfev,
@@ -166,6 +187,12 @@ class CampaignBatch:
         is an int or one count per campaign."""
         if self.kind != "ExactGP":
             raise NotImplementedError("the persistent work-queue launch is provided for the ExactGP step")
+        if self.large:          # no persistent form beyond the shared-memory capacity: one launch per iteration
+            if not isinstance(iters, int):
+                raise NotImplementedError("per-campaign iteration counts need the shared-memory work-queue kernel")
+            for _ in range(iters):
+                self.step()
+            return
         if not hasattr(self, "_sched"):
             self._sched = torch.zeros(self.B + 1, dtype=torch.int32, device=self.device)
             self._iters_left = torch.zeros(self.B, dtype=torch.int32, device=self.device)
