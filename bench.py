@@ -216,6 +216,21 @@ def run_reference_arm(args):
     W, K = args.warmup, args.steps
     cfg = args.config if args.model == "ExactGP" or args.config != "cfg4" else "vartgp"
     note = ""
+    if cfg == "f3":
+        import numpy as np
+        names = ["AgNP", "AutoAM", "CrossedBarrel", "P3HT", "Perovskite"]
+        S_ = 25 if args.campaigns == 1024 else args.campaigns
+        seeds = [int(s) for s in np.load(os.path.join(ROOT, "tests", "golden", "traces.npz"))["seeds"]][:S_]
+        fits = 3 * len(names) * S_
+        cpu = f3_cpu_leg(["VarTGP", "VarGP", "ExactGP"], names, seeds, S_, args.epochs, fits, cores)
+        print(json.dumps({
+            "impl": "reference", "metric": "model_fits_per_sec", "value": cpu["value"], "unit": "fits/s", "n_gpus": args.gpus,
+            "steps": 1, "warmup": 0, "ms_per_step": 1e3 * cpu["study_core_seconds"] / cores, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "the reference's data/*.csv",
+            "config": {"workload": F3_WORKLOAD.format(S=S_, E=args.epochs), "sample": cpu["sample"]}, "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}), flush=True)
+        return
     if cfg == "cfg4":
         # a step = iteration t of `cores` campaigns (one per core, bounded sample of the 1024-campaign workload); the
         # campaigns start at ages spread over the 80 trials so that n covers 10..89 like the GPU mix; W + K = 80 is
@@ -926,6 +941,29 @@ F3_WORKLOAD = ("f3: benchmark_predictions.py study: {{VarTGP, VarGP, ExactGP}} x
                "split (n = 76, 80, 132, 143, 480), {E} epochs NGD+Adam / L-BFGS-B, MAE of posterior.mean on the other 20 %")
 
 
+def f3_cpu_leg(kind_names, names, seeds, S_, E, fits, cores):
+    """The study on the host cores with the oracle: one fit + predict per core, (model, dataset) pairs round-robin,
+    variational fits extrapolated from E_s of E epochs; value = fits / (summed single-core seconds of the study / cores)."""
+    E_s = min(60, E)                                  # 60 of the 600 epochs timed (a 600-epoch fit at n = 480 is ~36 s per core)
+    order = [(k, n_) for n_ in names for k in kind_names]
+    cj = [dict(type="predict_fit", pool=order[c % len(order)][1], kind=order[c % len(order)][0], seed=seeds[c % S_],
+               epochs=E_s) for c in range(max(cores, len(order)))]       # every pair at least once
+    r = run_cpu_jobs(cj, cores)
+    full = {}
+    for j, x in zip(cj, r["results"]):
+        t_fit = x[0] if j["kind"] == "ExactGP" else x[0] * (E / E_s)
+        full.setdefault((j["kind"], j["pool"]), []).append(t_fit + x[1])
+    mean_s = {kd: sum(v) / len(v) for kd, v in full.items()}
+    covered = [kd for kd in order if kd in mean_s]
+    study_core_s = S_ * sum(mean_s[kd] for kd in covered) * (len(order) / max(len(covered), 1))
+    return {"value": fits / (study_core_s / cores), "unit": "fits/s", "cores": cores, "kind": "port",
+            "per_core": fits / study_core_s,
+            "sample": f"{len(cj)} fits on {cores} cores, (model, dataset) pairs round-robin ({len(covered)} of {len(order)} covered); "
+                      f"variational fits EXTRAPOLATED from {E_s} of {E} epochs; value = {fits} fits / (summed single-core seconds of "
+                      f"the study / cores); oracle/; wall {r['wall']:.1f}s",
+            "seconds_per_fit": {f"{k}/{n_}": mean_s[(k, n_)] for (k, n_) in covered}, "study_core_seconds": study_core_s}
+
+
 def run_f3_arm(args):
     import numpy as np
     import torch
@@ -1005,25 +1043,7 @@ def run_f3_arm(args):
     cpu = None
     if D.rank == 0 and not args.no_cpu_baseline:
         cores = min(host_cores(), 64)
-        E_s = 60                                      # 60 of the 600 epochs timed (a 600-epoch fit at n = 480 is ~36 s per core)
-        order = [(k, n_) for n_ in names for k, _c in kinds]
-        cj = [dict(type="predict_fit", pool=order[c % len(order)][1], kind=order[c % len(order)][0], seed=seeds[c % S_],
-                   epochs=E_s) for c in range(cores)]
-        r = run_cpu_jobs(cj, cores)
-        # seconds of one full fit + predict per (kind, dataset), extrapolated to E epochs; the study = S_ x their sum
-        full = {}
-        for j, x in zip(cj, r["results"]):
-            t_fit = x[0] if j["kind"] == "ExactGP" else x[0] * (E / E_s)
-            full.setdefault((j["kind"], j["pool"]), []).append(t_fit + x[1])
-        mean_s = {kd: sum(v) / len(v) for kd, v in full.items()}
-        covered = [kd for kd in order if kd in mean_s]
-        study_core_s = S_ * sum(mean_s[kd] for kd in covered) * (len(order) / max(len(covered), 1))
-        cpu = {"value": fits / (study_core_s / cores), "unit": "fits/s", "cores": cores, "kind": "port",
-               "per_core": fits / study_core_s,
-               "sample": f"{cores} fits, one per core, (model, dataset) pairs round-robin ({len(covered)} of {len(order)} covered); "
-                         f"variational fits EXTRAPOLATED from {E_s} of {E} epochs; value = {fits} fits / (summed single-core seconds of "
-                         f"the study / cores); oracle/; wall {r['wall']:.1f}s",
-               "seconds_per_fit": {f"{k}/{n_}": mean_s[(k, n_)] for (k, n_) in covered}}
+        cpu = f3_cpu_leg([k for k, _c in kinds], names, seeds, S_, E, fits // D.world, cores)
     if D.rank == 0:
         print(json.dumps({
             "metric": "model_fits_per_sec", "value": fits / (dev_ms * 1e-3), "unit": "fits/s", "n_gpus": D.world, "steps": 1, "warmup": 1,
