@@ -11,7 +11,7 @@
 Workloads:
   cfg4  synthetic pools N = 2048, d = 6 (negated Hartmann-6 + 0.05 t_3 noise, 8 pools), 1024 concurrent ExactGP
         campaigns PER GPU, n_initial = 10, 80 trials.  Device-resident arm: campaigns at staggered ages (continuous
-        batching), 16 age cohorts on 16 CUDA streams, one stp_exact_bo_step launch per cohort and step.  e2e arm: the
+        batching), 24 age cohorts on 24 CUDA streams, one stp_exact_bo_step launch per cohort and step.  e2e arm: the
         SAME 1024 x 80 job through the product API (runners.run_sweep: host tensors in, CSV traces out).
   VarTGP the same pools, 1024 concurrent VarTGP campaigns, n = 10..89 mix, 600 epochs, S = 2048 in-kernel Philox.
   cfg5  pools N = 8192, d = 8, 512 VarTGP campaigns per GPU (4096 over 8 GPUs), n_initial = M = 256, 4 trials.
@@ -44,6 +44,8 @@ sys.path.insert(0, ROOT)
 N_POOL, DIM, N_POOLS = 2048, 6, 8
 N_INITIAL, N_TRIALS = 10, 80
 CAP = N_INITIAL + N_TRIALS + 1
+DEFAULT_GROUPS = 24   # age cohorts (CUDA streams) of the device-resident arm: 16 / 24 / 32 -> 71.7 / 73.7 / 73.5 k it/s at
+                      # --steps 20 --warmup 5 (profiles/r02_ab_groups.log); 40 streams and more serialise (52 - 58 k)
 METRIC, UNIT = "bo_iterations_per_sec", "it/s"
 WORKLOAD = ("cfg4: synthetic pools N=2048 d=6 (Hartmann-6 + t3 noise), {B} concurrent ExactGP campaigns per GPU, "
             "n_initial=10, 80 trials, ages staggered over n=10..89 (continuous batching)")
@@ -435,7 +437,7 @@ def run_exact_arm(args):
     pool_id = [min(b // per_pool, N_POOLS - 1) if per_pool else 0 for b in range(B)]
     NG = max(1, min(args.groups, B // 16 if B >= 16 else 1))
     queue = args.schedule == "queue"           # persistent work-queue kernel: K iterations per campaign in ONE launch
-    if queue and args.groups == 16:
+    if queue and args.groups == DEFAULT_GROUPS:
         NG = 1
     bounds = [(g * B // NG, (g + 1) * B // NG) for g in range(NG)]
     if args.schedule == "cohort":                             # one age per group, groups evenly staggered
@@ -1072,7 +1074,8 @@ def main():
     ap.add_argument("--campaigns", type=int, default=1024, help="campaigns per GPU (cfg5: 512, cfg3: 256 seeds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--groups", type=int, default=16, help="campaign groups per GPU, one CUDA stream each (at most B / 16)")
+    ap.add_argument("--groups", type=int, default=DEFAULT_GROUPS,
+                    help="campaign groups per GPU, one CUDA stream each (at most B / 16; beyond 32 streams launches serialise)")
     ap.add_argument("--chunk", type=int, default=1,
                     help="cohort schedule: BO iterations per launch (1 = stp_exact_bo_step, > 1 = stp_exact_bo_run)")
     ap.add_argument("--schedule", default="cohort", choices=["mixed", "cohort", "queue"],
