@@ -236,3 +236,19 @@ def test_block_built_frame_equals_column_built_frame(tmp_path):
     assert list(a.frame.columns) == list(b.frame.columns)
     assert (a.frame.to_numpy(dtype=float) == b.frame.to_numpy(dtype=float)).all()
     assert pd.read_csv(tmp_path / "a.csv", header=[0, 1], index_col=0).shape == (14, 6)
+
+
+def test_csv_text_corner_values_equal_pandas():
+    """The value-table form of the CSV writer: signed zeros, NaN, infinities, denormals, large indices."""
+    import numpy as np
+    import pandas as pd
+    from stpbenchmark_b200 import runners
+    cols = pd.MultiIndex.from_tuples([("seed_3", "x_index"), ("seed_3", "y_value"), ("seed_1", "x_index"), ("seed_1", "y_value")])
+    f = pd.DataFrame({cols[0]: np.array([0, 5, 1048575, 7], dtype=np.int64), cols[1]: np.array([-0.0, 0.0, np.nan, 1e22]),
+                      cols[2]: np.array([3, 2, 1, 2000000], dtype=np.int64), cols[3]: np.array([1e-5, 0.1 + 0.2, -np.inf, 5e-324])})
+    f.columns = cols
+    f.index.name = "iteration"
+    assert runners._csv_text(f) == f.to_csv()
+    g = f.copy()
+    g[cols[0]] = np.array([-1, 5, 2, 7], dtype=np.int64)          # negative indices: the plain path
+    assert runners._csv_text(g) == g.to_csv()
