@@ -1,5 +1,5 @@
 """One batched ExactGP fit + predict of CrossedBarrel's 80 % splits (n = 480, 25 seeds) through the large entry points:
-the ncu target for k_exact_fit<LARGE> / k_exact_acq_large (tools/gpu_r2_large3.sh)."""
+the ncu target for k_exact_fit<LARGE> / k_exact_acq_large (tools/gpu_r2_large_evidence.sh)."""
 import os
 import sys
 
