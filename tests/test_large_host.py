@@ -48,6 +48,20 @@ def test_large_carve_up_is_the_same_arithmetic(large_mode):
         assert np.array_equal(a1[k], a0[k])
 
 
+def test_large_carve_up_fit_is_the_same_trajectory(large_mode):
+    """The device L-BFGS-B on the large carve-up (optimiser state behind the vectors, square elsewhere): same theta,
+    objective and (nit, nfev) as on the shared-memory carve-up, bit for bit."""
+    Xt, yt, _, _ = _split("P3HT", 45, 40)
+    d = Xt.shape[1]
+    lo, hi = priors.exact_bounds(d)
+    args = (Xt.numpy()[None], yt.numpy()[None], priors.exact_theta0(d), lo, hi, priors.exact_prior_vector(d))
+    th1, f1, nit1, nfev1, st1 = _emu.exact_fit(*args)
+    large_mode.emu_set_large(0)
+    th0, f0, nit0, nfev0, st0 = _emu.exact_fit(*args)
+    assert st1.tolist() == st0.tolist() == [0] and nit1.tolist() == nit0.tolist() and nfev1.tolist() == nfev0.tolist()
+    assert np.array_equal(th1, th0) and np.array_equal(f1, f0) and nit0[0] > 3
+
+
 def test_large_carve_up_against_the_oracle_at_n200(large_mode):
     Xt, yt, Xs, _ = _split("CrossedBarrel", 359, 200)
     d = Xt.shape[1]
